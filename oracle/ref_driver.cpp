@@ -1,0 +1,200 @@
+// ref_driver.cpp -- C entry points around the UNMODIFIED reference library.
+//
+// TEST INFRASTRUCTURE ONLY (see sj_oracle.h).  Compiled by oracle/Makefile
+// together with /root/reference/singleheader/simdjson.cpp (from where it lies;
+// no reference source is copied into this repo) into oracle/_ref/libsj_ref.so.
+// It reaches the hot path exactly the way SURVEY.md section 8(c) describes:
+//   get_available_implementations()[name]->create_dom_parser_implementation()
+//   parser->stage1(buf,len,mode)   (include/simdjson/internal/dom_parser_implementation.h L80)
+//   impl->minify / impl->validate_utf8 (include/simdjson/implementation.h L116, L128)
+#include "simdjson.h"
+
+#include <atomic>
+#include <chrono>
+#include <cstring>
+#include <memory>
+#include <thread>
+#include <vector>
+
+using namespace simdjson;
+
+#define SJR_API extern "C" __attribute__((visibility("default")))
+
+static const implementation *find_impl(const char *name) {
+  if (name == nullptr || name[0] == 0) {
+    // best CPU kernel this host supports (icelake > haswell > westmere > fallback)
+    for (const char *n : {"icelake", "haswell", "westmere", "fallback"}) {
+      auto impl = get_available_implementations()[n];
+      if (impl && impl->supported_by_runtime_system()) return impl;
+    }
+    return nullptr;
+  }
+  auto impl = get_available_implementations()[name];
+  if (!impl || !impl->supported_by_runtime_system()) return nullptr;
+  return impl;
+}
+
+SJR_API int sjr_supported(const char *name) { return find_impl(name) != nullptr; }
+
+SJR_API const char *sjr_best_name() {
+  static std::string s;
+  auto impl = find_impl(nullptr);
+  s = impl ? impl->name() : "";
+  return s.c_str();
+}
+
+// Returns the error_code, or -1 if the implementation is not usable here.
+// idx_out receives min(max_words, ROUNDUP(capacity,64)+9) words of the
+// parser's structural_indexes; *n_inout is loaded into the parser before the
+// call (the reference leaves it untouched on its early-return paths) and read
+// back after.
+SJR_API int sjr_stage1(const char *name, const uint8_t *buf, size_t len, size_t capacity, int mode,
+                       uint32_t *idx_out, size_t max_words, uint32_t *n_inout) {
+  auto impl = find_impl(name);
+  if (!impl) return -1;
+  std::unique_ptr<internal::dom_parser_implementation> p;
+  auto err = impl->create_dom_parser_implementation(capacity, 1024, p);
+  if (err) return int(err);
+  p->n_structural_indexes = *n_inout;
+  err = p->stage1(buf, len, stage1_mode(mode));
+  *n_inout = p->n_structural_indexes;
+  size_t words = SIMDJSON_ROUNDUP_N(capacity, 64) + 9;
+  if (words > max_words) words = max_words;
+  if (idx_out && words) std::memcpy(idx_out, p->structural_indexes.get(), words * sizeof(uint32_t));
+  return int(err);
+}
+
+SJR_API int sjr_minify(const char *name, const uint8_t *buf, size_t len, uint8_t *dst, size_t *dst_len) {
+  auto impl = find_impl(name);
+  if (!impl) return -1;
+  size_t n = 0;
+  auto err = impl->minify(buf, len, dst, n);
+  *dst_len = n;
+  return int(err);
+}
+
+SJR_API int sjr_validate_utf8(const char *name, const uint8_t *buf, size_t len) {
+  auto impl = find_impl(name);
+  if (!impl) return -1;
+  return impl->validate_utf8(reinterpret_cast<const char *>(buf), len) ? 1 : 0;
+}
+
+// ---------------------------------------------------------------- timing ---
+// The reference has no intra-call parallelism: one
+// stage-1 call runs on one core.  "All host threads" therefore means T
+// independent parsers, each running the whole call on the same read-only
+// buffer; aggregate bytes/s = T*len / wall.  op: 0 stage1, 1 minify, 2 utf8.
+// Returns seconds for the best of `iters` rounds (each round = every thread
+// doing one call), after one warm-up round; negative on error.
+SJR_API double sjr_time(const char *name, int op, const uint8_t *buf, size_t len, int mode, int threads,
+                        int iters, int *err_out) {
+  auto impl = find_impl(name);
+  if (!impl) return -1.0;
+  if (threads < 1) threads = 1;
+  struct worker_state {
+    std::unique_ptr<internal::dom_parser_implementation> parser;
+    std::unique_ptr<uint8_t[]> dst;
+    int err{0};
+  };
+  std::vector<worker_state> ws(threads);
+  for (auto &w : ws) {
+    if (op == 0) {
+      if (impl->create_dom_parser_implementation(len, 1024, w.parser)) return -2.0;
+    } else if (op == 1) {
+      w.dst.reset(new uint8_t[len + SIMDJSON_PADDING]);
+    }
+  }
+  auto one_call = [&](worker_state &w) {
+    if (op == 0) {
+      w.err = int(w.parser->stage1(buf, len, stage1_mode(mode)));
+    } else if (op == 1) {
+      size_t n = 0;
+      w.err = int(impl->minify(buf, len, w.dst.get(), n));
+    } else {
+      w.err = impl->validate_utf8(reinterpret_cast<const char *>(buf), len) ? 0 : int(UTF8_ERROR);
+    }
+  };
+  double best = 1e30;
+  for (int it = 0; it < iters + 1; it++) {
+    std::atomic<int> ready{0};
+    std::atomic<bool> go{false};
+    std::vector<std::thread> th;
+    for (int t = 1; t < threads; t++) {
+      th.emplace_back([&, t] {
+        ready++;
+        while (!go.load(std::memory_order_acquire)) {}
+        one_call(ws[t]);
+      });
+    }
+    while (ready.load() < threads - 1) {}
+    auto t0 = std::chrono::steady_clock::now();
+    go.store(true, std::memory_order_release);
+    one_call(ws[0]);
+    for (auto &t : th) t.join();
+    auto t1 = std::chrono::steady_clock::now();
+    double s = std::chrono::duration<double>(t1 - t0).count();
+    if (it > 0 && s < best) best = s;  // round 0 is the warm-up
+  }
+  if (err_out) *err_out = ws[0].err;
+  return best;
+}
+
+// ------------------------------------------------- DOM-level reference hooks
+// Used by the drop-in tests to get what dom::parser::parse / parse_many /
+// simdjson::minify produce through a CPU implementation, for comparison with
+// the same calls routed through the b200 plug-in.
+
+// Parses one document with implementation `name` and writes its minified
+// re-serialisation (simdjson::minify(element)) to out; returns error code.
+SJR_API int sjr_dom_roundtrip(const char *name, const uint8_t *buf, size_t len, char *out, size_t out_cap,
+                              size_t *out_len) {
+  auto impl = find_impl(name);
+  if (!impl) return -1;
+  const implementation *saved = get_active_implementation();
+  get_active_implementation() = impl;
+  dom::parser parser;
+  dom::element doc;
+  auto err = parser.parse(buf, len, true).get(doc);
+  int rc = int(err);
+  *out_len = 0;
+  if (!err) {
+    std::string s = simdjson::minify(doc);
+    *out_len = s.size();
+    if (s.size() <= out_cap) std::memcpy(out, s.data(), s.size());
+  }
+  get_active_implementation() = saved;
+  return rc;
+}
+
+// parse_many: returns number of documents successfully iterated, writes first
+// error (0 if none) and the concatenated minified documents separated by '\n'.
+SJR_API long sjr_dom_parse_many(const char *name, const uint8_t *buf, size_t len, size_t batch_size, char *out,
+                                size_t out_cap, size_t *out_len, int *first_err) {
+  auto impl = find_impl(name);
+  if (!impl) return -1;
+  const implementation *saved = get_active_implementation();
+  get_active_implementation() = impl;
+  long ndocs = 0;
+  *first_err = 0;
+  std::string acc;
+  {
+    dom::parser parser;
+    dom::document_stream stream;
+    auto err = parser.parse_many(buf, len, batch_size).get(stream);
+    if (err) {
+      *first_err = int(err);
+    } else {
+      for (auto it = stream.begin(); it != stream.end(); ++it) {
+        auto doc = *it;
+        if (doc.error()) { *first_err = int(doc.error()); break; }
+        acc += simdjson::minify(doc.value_unsafe());
+        acc.push_back('\n');
+        ndocs++;
+      }
+    }
+  }
+  *out_len = acc.size();
+  if (acc.size() <= out_cap) std::memcpy(out, acc.data(), acc.size());
+  get_active_implementation() = saved;
+  return ndocs;
+}

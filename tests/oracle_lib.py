@@ -1,0 +1,192 @@
+"""ctypes bindings for the two CPU checkers under oracle/ (test infrastructure only).
+
+  port : oracle/libsj_oracle.so    -- our byte-at-a-time C restatement (always built)
+  ref  : oracle/_ref/libsj_ref.so  -- the unmodified reference compiled from
+                                      /root/reference/singleheader (may be absent)
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+PORT_SO = os.path.join(ORACLE_DIR, "libsj_oracle.so")
+REF_SO = os.path.join(ORACLE_DIR, "_ref", "libsj_ref.so")
+JSONEXAMPLES = os.path.join(ORACLE_DIR, "_ref", "jsonexamples")
+
+SUCCESS, CAPACITY, MEMALLOC, UTF8_ERROR, EMPTY, UNESCAPED_CHARS, UNCLOSED_STRING, UNEXPECTED_ERROR = 0, 1, 2, 11, 13, 14, 15, 24
+REGULAR, STREAMING_PARTIAL, STREAMING_FINAL, JSON_SEQUENCE_PARTIAL, JSON_SEQUENCE_FINAL, COMMA_DELIMITED_PARTIAL, COMMA_DELIMITED_FINAL = range(7)
+ALL_MODES = list(range(7))
+
+# error codes after which the reference has written n_structural_indexes and the sentinels
+# (json_structural_indexer.h L264-287): everything except the early returns.
+N_SENTINEL = 0xDEADBEEF
+
+
+def index_capacity(capacity):
+    return ((capacity + 63) // 64) * 64 + 9
+
+
+def _u8(buf):
+    if isinstance(buf, (bytes, bytearray)):
+        return np.frombuffer(bytes(buf), dtype=np.uint8)
+    return np.ascontiguousarray(buf, dtype=np.uint8)
+
+
+def _ptr(a, t=C.c_uint8):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class Stage1Result:
+    __slots__ = ("err", "n", "idx")
+
+    def __init__(self, err, n, idx):
+        self.err, self.n, self.idx = err, n, idx
+
+    @property
+    def wrote(self):
+        """True when the call got far enough to store n and the sentinels."""
+        return self.n != N_SENTINEL
+
+    def words(self):
+        """the (n+3) words the parity bar compares"""
+        return self.idx[: self.n + 3]
+
+
+def _build_port():
+    if not os.path.exists(PORT_SO) or os.path.getmtime(PORT_SO) < os.path.getmtime(os.path.join(ORACLE_DIR, "sj_oracle.c")):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, os.path.join(ORACLE_DIR, "libsj_oracle.so")], stdout=subprocess.DEVNULL)
+
+
+class Port:
+    def __init__(self):
+        _build_port()
+        L = C.CDLL(PORT_SO)
+        L.sjo_stage1.restype = C.c_int
+        L.sjo_stage1.argtypes = [C.POINTER(C.c_uint8), C.c_size_t, C.c_size_t, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.sjo_minify.restype = C.c_int
+        L.sjo_minify.argtypes = [C.POINTER(C.c_uint8), C.c_size_t, C.POINTER(C.c_uint8), C.POINTER(C.c_size_t)]
+        L.sjo_validate_utf8.restype = C.c_int
+        L.sjo_validate_utf8.argtypes = [C.POINTER(C.c_uint8), C.c_size_t]
+        L.sjo_trim_partial_utf8.restype = C.c_size_t
+        L.sjo_trim_partial_utf8.argtypes = [C.POINTER(C.c_uint8), C.c_size_t]
+        self.L = L
+        self.name = "port"
+
+    def stage1(self, buf, mode=REGULAR, capacity=None):
+        a = _u8(buf)
+        n = len(a)
+        cap = n if capacity is None else capacity
+        idx = np.zeros(index_capacity(max(cap, n)), dtype=np.uint32)
+        nn = C.c_uint32(N_SENTINEL)
+        pa = _ptr(a) if n else C.cast(C.c_void_p(0), C.POINTER(C.c_uint8))
+        err = self.L.sjo_stage1(pa, n, cap, mode, _ptr(idx, C.c_uint32), C.byref(nn))
+        return Stage1Result(err, nn.value, idx)
+
+    def minify(self, buf):
+        a = _u8(buf)
+        dst = np.zeros(max(len(a), 1), dtype=np.uint8)
+        dl = C.c_size_t(0)
+        err = self.L.sjo_minify(_ptr(a), len(a), _ptr(dst), C.byref(dl))
+        return err, bytes(dst[: dl.value])
+
+    def validate_utf8(self, buf):
+        a = _u8(buf)
+        return bool(self.L.sjo_validate_utf8(_ptr(a), len(a)))
+
+
+class Ref:
+    """the unmodified reference; impl = "icelake" | "haswell" | "westmere" | "fallback" | "" (best)."""
+
+    def __init__(self, impl=""):
+        L = C.CDLL(REF_SO)
+        L.sjr_supported.restype = C.c_int
+        L.sjr_supported.argtypes = [C.c_char_p]
+        L.sjr_best_name.restype = C.c_char_p
+        L.sjr_stage1.restype = C.c_int
+        L.sjr_stage1.argtypes = [C.c_char_p, C.POINTER(C.c_uint8), C.c_size_t, C.c_size_t, C.c_int, C.POINTER(C.c_uint32), C.c_size_t, C.POINTER(C.c_uint32)]
+        L.sjr_minify.restype = C.c_int
+        L.sjr_minify.argtypes = [C.c_char_p, C.POINTER(C.c_uint8), C.c_size_t, C.POINTER(C.c_uint8), C.POINTER(C.c_size_t)]
+        L.sjr_validate_utf8.restype = C.c_int
+        L.sjr_validate_utf8.argtypes = [C.c_char_p, C.POINTER(C.c_uint8), C.c_size_t]
+        L.sjr_time.restype = C.c_double
+        L.sjr_time.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_uint8), C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.sjr_dom_roundtrip.restype = C.c_int
+        L.sjr_dom_roundtrip.argtypes = [C.c_char_p, C.POINTER(C.c_uint8), C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.sjr_dom_parse_many.restype = C.c_long
+        L.sjr_dom_parse_many.argtypes = [C.c_char_p, C.POINTER(C.c_uint8), C.c_size_t, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
+        self.L = L
+        self.impl = impl.encode()
+        if not L.sjr_supported(self.impl):
+            raise RuntimeError(f"reference implementation {impl!r} not supported on this host")
+        self.name = impl or L.sjr_best_name().decode()
+
+    def stage1(self, buf, mode=REGULAR, capacity=None):
+        a = _u8(buf)
+        n = len(a)
+        cap = n if capacity is None else capacity
+        words = index_capacity(cap)
+        idx = np.zeros(words, dtype=np.uint32)
+        nn = C.c_uint32(N_SENTINEL)
+        # the reference may read up to SIMDJSON_PADDING bytes past len in stage 2 only; stage 1 never over-reads
+        err = self.L.sjr_stage1(self.impl, _ptr(a), n, cap, mode, _ptr(idx, C.c_uint32), words, C.byref(nn))
+        return Stage1Result(err, nn.value, idx)
+
+    def minify(self, buf):
+        a = _u8(buf)
+        dst = np.zeros(len(a) + 64, dtype=np.uint8)
+        dl = C.c_size_t(0)
+        err = self.L.sjr_minify(self.impl, _ptr(a), len(a), _ptr(dst), C.byref(dl))
+        return err, bytes(dst[: dl.value])
+
+    def validate_utf8(self, buf):
+        a = _u8(buf)
+        return bool(self.L.sjr_validate_utf8(self.impl, _ptr(a), len(a)))
+
+    def time(self, op, buf, mode=REGULAR, threads=1, iters=3):
+        a = _u8(buf)
+        err = C.c_int(0)
+        s = self.L.sjr_time(self.impl, op, _ptr(a), len(a), mode, threads, iters, C.byref(err))
+        return s, err.value
+
+    def dom_roundtrip(self, buf):
+        a = _u8(buf)
+        cap = 4 * len(a) + 64
+        out = C.create_string_buffer(cap)
+        ol = C.c_size_t(0)
+        err = self.L.sjr_dom_roundtrip(self.impl, _ptr(a), len(a), out, cap, C.byref(ol))
+        return err, out.raw[: ol.value]
+
+    def dom_parse_many(self, buf, batch_size=1000000):
+        a = _u8(buf)
+        cap = 4 * len(a) + 64
+        out = C.create_string_buffer(cap)
+        ol = C.c_size_t(0)
+        fe = C.c_int(0)
+        nd = self.L.sjr_dom_parse_many(self.impl, _ptr(a), len(a), batch_size, out, cap, C.byref(ol), C.byref(fe))
+        return nd, fe.value, out.raw[: ol.value]
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+def ref_impls():
+    """reference CPU kernels usable on this host, best first"""
+    if not have_ref():
+        return []
+    L = C.CDLL(REF_SO)
+    L.sjr_supported.restype = C.c_int
+    L.sjr_supported.argtypes = [C.c_char_p]
+    return [n for n in ("icelake", "haswell", "westmere", "fallback") if L.sjr_supported(n.encode())]
+
+
+def same_stage1(a, b):
+    """the parity bar: error code, n, and the (n+3) words when they were written"""
+    if a.err != b.err or a.n != b.n:
+        return False
+    if a.wrote:
+        return bool(np.array_equal(a.words(), b.words()))
+    return True
