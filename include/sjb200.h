@@ -1,0 +1,141 @@
+/*
+ * sjb200.h -- C ABI of the B200 (sm_100a) stage-1 / minify / validate_utf8 library.
+ *
+ * This is the drop-in boundary for ONE hot path of simdjson: it exports exactly
+ * what a `simdjson::implementation` / `internal::dom_parser_implementation` back-end has to provide
+ * for stage 1, minify and validate_utf8.  Plain pointers and sizes only; no C++ / torch types.
+ * Every function returns a simdjson::error_code value as int (include/simdjson/error.h L19-54) and
+ * never throws, prints or aborts (the reference's virtuals are all noexcept,
+ * include/simdjson/implementation.h L97-128, internal/dom_parser_implementation.h L64-165).
+ *
+ * There is NO CPU fallback: if the CUDA runtime, the device (compute capability 10.x) or the kernel
+ * image is unavailable, sjb200_create fails with SJB200_UNSUPPORTED_ARCHITECTURE, like
+ * `unsupported_implementation` does (src/implementation.cpp L245-268).
+ *
+ * Reference interface each entry point replaces (paths relative to the simdjson tree):
+ *   sjb200_create / _destroy / _set_capacity
+ *        implementation::create_dom_parser_implementation   include/simdjson/implementation.h L97-101
+ *        dom_parser_implementation::set_capacity             include/simdjson/generic/dom_parser_implementation.h L66-82
+ *   sjb200_stage1
+ *        dom_parser_implementation::stage1(buf,len,mode)     include/simdjson/internal/dom_parser_implementation.h L80
+ *        (= json_structural_indexer::index<128>              src/generic/stage1/json_structural_indexer.h L193-397)
+ *   sjb200_minify
+ *        implementation::minify(buf,len,dst,dst_len)         include/simdjson/implementation.h L116
+ *   sjb200_validate_utf8
+ *        implementation::validate_utf8(buf,len)              include/simdjson/implementation.h L128
+ * The *_dev variants take device pointers (input already resident in HBM); they are what the
+ * roofline metric times.  The sharded variant is the per-GPU piece of a multi-GPU scan (section 8e).
+ */
+#ifndef SJB200_H
+#define SJB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define SJB200_API __attribute__((visibility("default")))
+#else
+#define SJB200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* simdjson::error_code values used by this path */
+enum {
+  SJB200_SUCCESS = 0,
+  SJB200_CAPACITY = 1,
+  SJB200_MEMALLOC = 2,
+  SJB200_UTF8_ERROR = 11,
+  SJB200_EMPTY = 13,
+  SJB200_UNESCAPED_CHARS = 14,
+  SJB200_UNCLOSED_STRING = 15,
+  SJB200_UNSUPPORTED_ARCHITECTURE = 16,
+  SJB200_UNEXPECTED_ERROR = 24
+};
+
+/* simdjson::stage1_mode (include/simdjson/internal/dom_parser_implementation.h L22-27) */
+enum {
+  SJB200_REGULAR = 0,
+  SJB200_STREAMING_PARTIAL = 1,
+  SJB200_STREAMING_FINAL = 2,
+  SJB200_JSON_SEQUENCE_PARTIAL = 3,
+  SJB200_JSON_SEQUENCE_FINAL = 4,
+  SJB200_COMMA_DELIMITED_PARTIAL = 5,
+  SJB200_COMMA_DELIMITED_FINAL = 6
+};
+
+typedef struct sjb200_ctx sjb200_ctx;
+
+/* ---- lifetime: one context per dom_parser_implementation instance (own stream + scratch; contexts
+ * are independent, so two parsers may run from two host threads concurrently, as document_stream's
+ * stage-1 worker requires: include/simdjson/dom/document_stream-inl.h L16-85). */
+SJB200_API int sjb200_create(int device, size_t capacity_bytes, sjb200_ctx **out);
+SJB200_API void sjb200_destroy(sjb200_ctx *ctx);
+SJB200_API int sjb200_set_capacity(sjb200_ctx *ctx, size_t capacity_bytes); /* > 0xFFFFFFFF -> CAPACITY */
+SJB200_API size_t sjb200_capacity(const sjb200_ctx *ctx);
+/* number of uint32 words of an index buffer for `capacity`: ROUNDUP(capacity,64)+9 */
+SJB200_API size_t sjb200_index_words(size_t capacity_bytes);
+SJB200_API int sjb200_device(const sjb200_ctx *ctx);
+/* last CUDA error string seen by this context ("" if none); for diagnostics only */
+SJB200_API const char *sjb200_last_cuda_error(const sjb200_ctx *ctx);
+/* tuning knobs, mostly for tests and bench: "use_tma" (0/1), "grid" (CTAs, 0 = auto), "chunk_bytes",
+ * "time_kernel" (0/1: record CUDA events around the scan kernel on its launch stream) */
+SJB200_API int sjb200_set_option(sjb200_ctx *ctx, const char *key, long value);
+/* "kernel_ms" (last scan kernel, needs time_kernel=1), "launches" (kernels launched by this context so far),
+ * "grid_index", "sm_count"; negative when unavailable */
+SJB200_API double sjb200_get_stat(sjb200_ctx *ctx, const char *key);
+
+/* ---- host-pointer entry points (copy in, scan, copy out).
+ * idx_out: at least sjb200_index_words(capacity) words; on success and on UTF8_ERROR / EMPTY(after scan)
+ * it holds n indexes followed by the reference's three sentinel words.  *n_inout is the parser's
+ * n_structural_indexes: untouched on the early-return paths exactly like the reference
+ * (CAPACITY, len==0, UNCLOSED_STRING, UNESCAPED_CHARS). */
+SJB200_API int sjb200_stage1(sjb200_ctx *ctx, const uint8_t *buf, size_t len, int mode, uint32_t *idx_out, uint32_t *n_inout);
+/* dst needs len bytes (the reference's tests give it exactly len: tests/dom/basictests.cpp L1916). */
+SJB200_API int sjb200_minify(sjb200_ctx *ctx, const uint8_t *buf, size_t len, uint8_t *dst, size_t *dst_len);
+/* returns 1 valid / 0 invalid; a CUDA failure reports 0 and sets sjb200_last_cuda_error. */
+SJB200_API int sjb200_validate_utf8(sjb200_ctx *ctx, const uint8_t *buf, size_t len);
+
+/* ---- device-resident entry points.  d_* are device pointers on the context's device; `stream` is a
+ * cudaStream_t (NULL = the context's own stream).  The calls return after the result is known
+ * (they synchronise the stream once).  d_idx needs sjb200_index_words(len) words. */
+SJB200_API int sjb200_stage1_dev(sjb200_ctx *ctx, const uint8_t *d_buf, size_t len, int mode, uint32_t *d_idx, uint32_t *n_inout,
+                      void *stream);
+SJB200_API int sjb200_minify_dev(sjb200_ctx *ctx, const uint8_t *d_buf, size_t len, uint8_t *d_dst, size_t *dst_len, void *stream);
+SJB200_API int sjb200_validate_utf8_dev(sjb200_ctx *ctx, const uint8_t *d_buf, size_t len, void *stream);
+
+/* split form of the same calls for pipelining / timing: enqueue returns as soon as the work is on the
+ * stream, finish waits for it and completes the reference's finish() logic. */
+SJB200_API int sjb200_stage1_dev_enqueue(sjb200_ctx *ctx, const uint8_t *d_buf, size_t len, int mode, uint32_t *d_idx, void *stream);
+SJB200_API int sjb200_stage1_dev_finish(sjb200_ctx *ctx, uint32_t *n_inout);
+SJB200_API int sjb200_minify_dev_enqueue(sjb200_ctx *ctx, const uint8_t *d_buf, size_t len, uint8_t *d_dst, void *stream);
+SJB200_API int sjb200_minify_dev_finish(sjb200_ctx *ctx, size_t *dst_len);
+SJB200_API int sjb200_validate_utf8_dev_enqueue(sjb200_ctx *ctx, const uint8_t *d_buf, size_t len, void *stream);
+SJB200_API int sjb200_validate_utf8_dev_finish(sjb200_ctx *ctx);
+
+/* ---- multi-GPU: one shard of a document per GPU.
+ * A shard is scanned with a given incoming scanner state (bit0 escape, bit1 in-string, bit2
+ * previous-byte-was-scalar); the call reports the shard's 6-bit carry transducer, which is
+ * independent of the incoming state, so ranks can all-gather {ttable,count} once, fold their true
+ * incoming state, and re-scan only if their speculation (state 0) was wrong.
+ * Shards must be cut where the next byte is not a UTF-8 continuation byte (sjb200_shard_cut). */
+typedef struct {
+  uint32_t ttable;     /* T(e): bit0 esc(0) bit1 parity(0) bit2 scalar(0) bit3 esc(1) bit4 parity(1) bit5 scalar(1) */
+  uint32_t state_out;  /* ttable applied to state_in */
+  uint32_t flags;      /* bit0 utf-8 error, bit1 unescaped control char in string, bit2 internal error */
+  uint32_t reserved;
+  uint64_t count;      /* structurals found in this shard (indexes are shard-relative) */
+} sjb200_shard_result;
+SJB200_API int sjb200_stage1_shard_dev(sjb200_ctx *ctx, const uint8_t *d_buf, size_t len, uint32_t state_in, int last_shard,
+                            uint32_t *d_idx, sjb200_shard_result *out, void *stream);
+/* fold: state entering shard r given the ttables of shards 0..r-1 and the document's initial state 0 */
+SJB200_API uint32_t sjb200_fold_state(const uint32_t *ttables, int nshards_before);
+/* largest cut <= nominal such that buf[cut] is not a UTF-8 continuation byte (host pointer) */
+SJB200_API size_t sjb200_shard_cut(const uint8_t *buf, size_t len, size_t nominal);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SJB200_H */

@@ -1,0 +1,752 @@
+// sjb200_capi.cu -- the C ABI (include/sjb200.h): contexts, copies, launches and the host epilogue.
+// No torch, no CPU fallback: every scan runs in sjb200_kernels.cu or the call fails.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/sjb200.h"
+#include "sjb200_bits.cuh"
+#include "sjb200_finish.h"
+#include "sjb200_kernels.cuh"
+
+using namespace sjb200;
+
+namespace {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+constexpr size_t kMaxBytes = 0xFFFFFFFFull;  // SIMDJSON_MAXSIZE_BYTES (include/simdjson/base.h L23)
+
+struct PendingCall {
+  int kind = -1;
+  int mode = 0;
+  int early_error = -1;  // >= 0: the call already failed / finished before any launch
+  size_t len = 0;        // (trimmed) length scanned
+  const uint8_t *d_buf = nullptr;
+  uint32_t *d_idx = nullptr;
+  uint8_t *d_dst = nullptr;
+  cudaStream_t stream = nullptr;
+  int carry_slot = 0;    // h_carry/d_carry slot holding the final carry
+};
+
+}  // namespace
+
+struct sjb200_ctx {
+  int device = 0;
+  int sm_count = 0;
+  size_t capacity = 0;
+  cudaStream_t stream = nullptr;      // compute
+  cudaStream_t copy_stream = nullptr; // H2D of the chunked host path
+  std::vector<cudaEvent_t> chunk_events;
+  // scratch
+  uint8_t *d_in = nullptr;    size_t d_in_bytes = 0;
+  uint32_t *d_idx = nullptr;  size_t d_idx_words = 0;
+  uint8_t *d_out = nullptr;   size_t d_out_bytes = 0;
+  Carry *d_carry = nullptr;   // [2] ping-pong
+  uint32_t *d_flags = nullptr;
+  uint32_t *d_ticket = nullptr;
+  uint32_t *d_state_desc = nullptr;
+  unsigned long long *d_count_desc = nullptr;
+  size_t desc_tiles = 0;
+  uint8_t *d_chars = nullptr; size_t d_chars_bytes = 0;
+  // pinned host mirrors
+  Carry *h_carry = nullptr;     // [2]
+  uint32_t *h_flags = nullptr;
+  uint8_t *h_small = nullptr;   // 64 B scratch
+  uint8_t *h_chars = nullptr;   size_t h_chars_bytes = 0;
+  uint32_t *h_window = nullptr; size_t h_window_words = 0;
+  uint32_t epoch = 0;
+  int grid[3] = {0, 0, 0};
+  long opt_use_tma = 1, opt_grid = 0, opt_chunk_bytes = 16 << 20, opt_time_kernel = 0;
+  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // around the scan kernel when opt_time_kernel is set
+  bool ev_valid = false;
+  unsigned long long launches = 0;               // kernels of ours launched by this context
+  PFN_encodeTiled encode = nullptr;
+  PendingCall pending;
+  std::string last_error;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+bool ok(sjb200_ctx *c, cudaError_t e, const char *what) {
+  if (e == cudaSuccess) return true;
+  c->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  (void)cudaGetLastError();
+  return false;
+}
+
+size_t index_words(size_t capacity) { return ((capacity + 63) / 64) * 64 + 9; }
+uint32_t tiles_of(size_t len) { return uint32_t((len + kTileBytes - 1) / kTileBytes); }
+
+template <typename T>
+bool dev_alloc(sjb200_ctx *c, T **p, size_t count, const char *what) {
+  void *q = nullptr;
+  if (!ok(c, cudaMalloc(&q, count * sizeof(T)), what)) return false;
+  *p = static_cast<T *>(q);
+  return true;
+}
+
+void free_sized(sjb200_ctx *c) {
+  cudaFree(c->d_in); c->d_in = nullptr; c->d_in_bytes = 0;
+  cudaFree(c->d_idx); c->d_idx = nullptr; c->d_idx_words = 0;
+  cudaFree(c->d_out); c->d_out = nullptr; c->d_out_bytes = 0;
+  cudaFree(c->d_state_desc); c->d_state_desc = nullptr;
+  cudaFree(c->d_count_desc); c->d_count_desc = nullptr;
+  c->desc_tiles = 0;
+}
+
+// look-back descriptors: sized for the capacity, zeroed once (epoch tags make them reusable)
+bool ensure_desc(sjb200_ctx *c, size_t len) {
+  const size_t need = std::max<size_t>(tiles_of(len), 1);
+  if (need <= c->desc_tiles) return true;
+  cudaFree(c->d_state_desc); c->d_state_desc = nullptr;
+  cudaFree(c->d_count_desc); c->d_count_desc = nullptr;
+  c->desc_tiles = 0;
+  const size_t n = std::max(need, size_t(tiles_of(c->capacity)) + 1);
+  if (!dev_alloc(c, &c->d_state_desc, n, "cudaMalloc(state_desc)")) return false;
+  if (!dev_alloc(c, &c->d_count_desc, n, "cudaMalloc(count_desc)")) return false;
+  if (!ok(c, cudaMemsetAsync(c->d_state_desc, 0, n * sizeof(uint32_t), c->stream), "memset desc")) return false;
+  if (!ok(c, cudaMemsetAsync(c->d_count_desc, 0, n * sizeof(unsigned long long), c->stream), "memset desc")) return false;
+  if (!ok(c, cudaStreamSynchronize(c->stream), "sync")) return false;
+  c->desc_tiles = n;
+  c->epoch = 0;
+  return true;
+}
+
+uint32_t next_epoch(sjb200_ctx *c) {
+  c->epoch++;
+  if (c->epoch >= (1u << 24)) {  // 24-bit tag wrapped: wipe the descriptors once
+    cudaMemsetAsync(c->d_state_desc, 0, c->desc_tiles * sizeof(uint32_t), c->stream);
+    cudaMemsetAsync(c->d_count_desc, 0, c->desc_tiles * sizeof(unsigned long long), c->stream);
+    cudaStreamSynchronize(c->stream);
+    c->epoch = 1;
+  }
+  return c->epoch;
+}
+
+bool ensure_host_scratch(sjb200_ctx *c, uint8_t **p, size_t *have, size_t need) {
+  if (*have >= need) return true;
+  if (*p) cudaFreeHost(*p);
+  *p = nullptr; *have = 0;
+  void *q = nullptr;
+  if (!ok(c, cudaMallocHost(&q, need), "cudaMallocHost")) return false;
+  *p = static_cast<uint8_t *>(q);
+  *have = need;
+  return true;
+}
+
+bool make_tensor_map(sjb200_ctx *c, CUtensorMap *map, const uint8_t *d_buf, size_t len, bool *usable) {
+  memset(map, 0, sizeof(*map));
+  *usable = false;
+  const uint64_t rows = len / 128;
+  if (!c->opt_use_tma || c->encode == nullptr || rows == 0) return true;
+  if ((reinterpret_cast<uintptr_t>(d_buf) & 15u) != 0) return true;  // TMA needs a 16-byte aligned base
+  cuuint64_t dims[2] = {128, rows};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {128, (cuuint32_t)kTileRows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = c->encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t *>(d_buf), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    c->last_error = "cuTensorMapEncodeTiled failed (" + std::to_string(int(r)) + "); using plain loads";
+    return true;
+  }
+  *usable = true;
+  return true;
+}
+
+int grid_for(sjb200_ctx *c, int kind, uint32_t ntiles) {
+  if (c->grid[kind] == 0) c->grid[kind] = scan_max_ctas_per_sm(kind) * c->sm_count;
+  int g = c->opt_grid > 0 ? int(c->opt_grid) : c->grid[kind];
+  return int(std::max<uint32_t>(1, std::min<uint32_t>(uint32_t(g), ntiles)));
+}
+
+// Enqueue the scan of document tiles [tile_begin, tile_begin+ntiles) of (d_buf,len).
+bool enqueue_scan(sjb200_ctx *c, int kind, const CUtensorMap *map, bool tma, const uint8_t *d_buf, size_t len, uint32_t tile_begin,
+                  uint32_t ntiles, bool has_last_tile, uint32_t prev_word, uint32_t *d_idx, uint8_t *d_dst, int carry_in_slot,
+                  cudaStream_t stream) {
+  ScanParams p;
+  memset(&p, 0, sizeof(p));
+  p.buf = d_buf;
+  p.len = len;
+  p.pos_base = 0;
+  p.prev_word = prev_word;
+  p.check_eof = has_last_tile ? 1u : 0u;
+  p.use_tma = tma ? 1u : 0u;
+  p.tile_begin = tile_begin;
+  p.ntiles = ntiles;
+  p.full_tiles = uint32_t((len / 128) / kTileRows);
+  p.epoch = next_epoch(c);
+  p.idx_out = d_idx;
+  p.dst = d_dst;
+  p.carry_in = c->d_carry + carry_in_slot;
+  p.carry_out = c->d_carry + (carry_in_slot ^ 1);
+  p.flags = c->d_flags;
+  p.state_desc = c->d_state_desc;
+  p.count_desc = c->d_count_desc;
+  p.ticket = c->d_ticket;
+  if (c->opt_time_kernel) {
+    if (!c->ev_k0) { cudaEventCreate(&c->ev_k0); cudaEventCreate(&c->ev_k1); }
+    cudaEventRecord(c->ev_k0, stream);
+  }
+  const bool launched = ok(c, launch_scan(kind, map, p, grid_for(c, kind, ntiles), stream), "launch scan");
+  if (c->opt_time_kernel) { cudaEventRecord(c->ev_k1, stream); c->ev_valid = launched; }
+  c->launches += launched ? 1 : 0;
+  return launched;
+}
+
+// ---- structural characters of a device-resident index array, fetched in growing windows from the end
+class DeviceTailReader final : public StructuralReader {
+ public:
+  DeviceTailReader(sjb200_ctx *c, const uint8_t *d_buf, const uint32_t *d_idx, uint32_t n, cudaStream_t s)
+      : c_(c), d_buf_(d_buf), d_idx_(d_idx), n_(n), s_(s), lo_(n), hi_(n) {}
+  bool failed() const { return failed_; }
+  uint32_t position(uint32_t i) override { return fetch(i) ? c_->h_window[i - lo_] : 0; }
+  uint8_t character(uint32_t i) override { return fetch(i) ? c_->h_chars[i - lo_] : 0; }
+
+ private:
+  bool fetch(uint32_t i) {
+    if (failed_) return false;
+    if (i >= lo_ && i < hi_) return true;
+    // (re)load [new_lo, n): window doubles every time the walk runs off its low end
+    uint32_t want = std::max<uint32_t>(1024, 2 * (n_ - std::min(i, lo_)));
+    uint32_t new_lo = (want >= n_) ? 0 : n_ - want;
+    if (i < new_lo) new_lo = i;
+    const uint32_t count = n_ - new_lo;
+    size_t hw = c_->h_window_words * 4;
+    uint8_t *hwp = reinterpret_cast<uint8_t *>(c_->h_window);
+    if (!ensure_host_scratch(c_, &hwp, &hw, size_t(count) * 4)) { failed_ = true; return false; }
+    c_->h_window = reinterpret_cast<uint32_t *>(hwp);
+    c_->h_window_words = hw / 4;
+    if (!ensure_host_scratch(c_, &c_->h_chars, &c_->h_chars_bytes, count)) { failed_ = true; return false; }
+    if (c_->d_chars_bytes < count) {
+      cudaFree(c_->d_chars);
+      c_->d_chars = nullptr; c_->d_chars_bytes = 0;
+      if (!dev_alloc(c_, &c_->d_chars, count, "cudaMalloc(chars)")) { failed_ = true; return false; }
+      c_->d_chars_bytes = count;
+    }
+    bool good = ok(c_, launch_gather_chars(d_buf_, d_idx_, new_lo, count, c_->d_chars, s_), "gather") &&
+                ok(c_, cudaMemcpyAsync(c_->h_chars, c_->d_chars, count, cudaMemcpyDeviceToHost, s_), "D2H chars") &&
+                ok(c_, cudaMemcpyAsync(c_->h_window, d_idx_ + new_lo, size_t(count) * 4, cudaMemcpyDeviceToHost, s_), "D2H idx") &&
+                ok(c_, cudaStreamSynchronize(s_), "sync");
+    if (!good) { failed_ = true; return false; }
+    lo_ = new_lo;
+    hi_ = n_;
+    return true;
+  }
+  sjb200_ctx *c_;
+  const uint8_t *d_buf_;
+  const uint32_t *d_idx_;
+  uint32_t n_;
+  cudaStream_t s_;
+  uint32_t lo_, hi_;
+  bool failed_ = false;
+};
+
+__global__ void final_fixup_kernel(uint32_t *idx, uint32_t m, uint32_t len) {
+  idx[m + 1] = idx[m];
+  idx[m] = len;
+}
+
+class DeviceIndexWriter final : public IndexWriter {
+ public:
+  DeviceIndexWriter(sjb200_ctx *c, uint32_t *d_idx, cudaStream_t s) : c_(c), d_idx_(d_idx), s_(s) {}
+  bool set3(uint32_t n, uint32_t a, uint32_t b, uint32_t cc) override {
+    c_->launches++;
+    return ok(c_, launch_write_sentinels(d_idx_, n, a, b, cc, s_), "sentinels");
+  }
+  bool final_fixup(uint32_t m, uint32_t len) override {
+    c_->launches++;
+    final_fixup_kernel<<<1, 1, 0, s_>>>(d_idx_, m, len);
+    return ok(c_, cudaGetLastError(), "fixup");
+  }
+
+ private:
+  sjb200_ctx *c_;
+  uint32_t *d_idx_;
+  cudaStream_t s_;
+};
+
+bool is_filter_mode(int mode) { return mode >= SJB200_JSON_SEQUENCE_PARTIAL; }
+
+bool reset_document_state(sjb200_ctx *c, cudaStream_t s) {
+  return ok(c, cudaMemsetAsync(c->d_flags, 0, sizeof(uint32_t), s), "memset flags") &&
+         ok(c, cudaMemsetAsync(c->d_carry, 0, 2 * sizeof(Carry), s), "memset carry");
+}
+
+bool fetch_result(sjb200_ctx *c, cudaStream_t s) {
+  return ok(c, cudaMemcpyAsync(c->h_carry, c->d_carry, 2 * sizeof(Carry), cudaMemcpyDeviceToHost, s), "D2H carry") &&
+         ok(c, cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, s), "D2H flags");
+}
+
+}  // namespace
+
+// =============================================================================== lifetime
+extern "C" size_t sjb200_index_words(size_t capacity) { return index_words(capacity); }
+
+extern "C" int sjb200_create(int device, size_t capacity, sjb200_ctx **out) {
+  if (!out) return SJB200_UNEXPECTED_ERROR;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    (void)cudaGetLastError();
+    return SJB200_UNSUPPORTED_ARCHITECTURE;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+    (void)cudaGetLastError();
+    return SJB200_UNSUPPORTED_ARCHITECTURE;  // the kernel image is sm_100a only
+  }
+  sjb200_ctx *c = new (std::nothrow) sjb200_ctx();
+  if (!c) return SJB200_MEMALLOC;
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  DeviceGuard g(device);
+  bool good = ok(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "stream") &&
+              ok(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "stream") &&
+              dev_alloc(c, &c->d_carry, 2, "cudaMalloc(carry)") && dev_alloc(c, &c->d_flags, 1, "cudaMalloc(flags)") &&
+              dev_alloc(c, &c->d_ticket, 2, "cudaMalloc(ticket)") &&
+              ok(c, cudaMemset(c->d_ticket, 0, 2 * sizeof(uint32_t)), "memset ticket");
+  void *hp = nullptr;
+  good = good && ok(c, cudaMallocHost(&hp, 2 * sizeof(Carry)), "cudaMallocHost");
+  c->h_carry = static_cast<Carry *>(hp);
+  good = good && ok(c, cudaMallocHost(&hp, sizeof(uint32_t)), "cudaMallocHost");
+  c->h_flags = static_cast<uint32_t *>(hp);
+  good = good && ok(c, cudaMallocHost(&hp, 64), "cudaMallocHost");
+  c->h_small = static_cast<uint8_t *>(hp);
+  if (good) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      c->encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    else
+      (void)cudaGetLastError();
+  }
+  if (!good) {
+    sjb200_destroy(c);
+    return SJB200_MEMALLOC;
+  }
+  int rc = sjb200_set_capacity(c, capacity);
+  if (rc != SJB200_SUCCESS) {
+    sjb200_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return SJB200_SUCCESS;
+}
+
+extern "C" void sjb200_destroy(sjb200_ctx *c) {
+  if (!c) return;
+  DeviceGuard g(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  free_sized(c);
+  cudaFree(c->d_carry); cudaFree(c->d_flags); cudaFree(c->d_ticket); cudaFree(c->d_chars);
+  if (c->h_carry) cudaFreeHost(c->h_carry);
+  if (c->h_flags) cudaFreeHost(c->h_flags);
+  if (c->h_small) cudaFreeHost(c->h_small);
+  if (c->h_chars) cudaFreeHost(c->h_chars);
+  if (c->h_window) cudaFreeHost(c->h_window);
+  if (c->ev_k0) { cudaEventDestroy(c->ev_k0); cudaEventDestroy(c->ev_k1); }
+  for (auto e : c->chunk_events) cudaEventDestroy(e);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  delete c;
+}
+
+extern "C" int sjb200_set_capacity(sjb200_ctx *c, size_t capacity) {
+  if (!c) return SJB200_UNEXPECTED_ERROR;
+  if (capacity > kMaxBytes) return SJB200_CAPACITY;  // generic/dom_parser_implementation.h L67
+  DeviceGuard g(c->device);
+  if (capacity != c->capacity) {
+    cudaStreamSynchronize(c->stream);
+    free_sized(c);  // host-path staging buffers are re-created lazily at the new size
+  }
+  c->capacity = capacity;
+  if (!ensure_desc(c, capacity)) return SJB200_MEMALLOC;
+  return SJB200_SUCCESS;
+}
+
+extern "C" size_t sjb200_capacity(const sjb200_ctx *c) { return c ? c->capacity : 0; }
+extern "C" int sjb200_device(const sjb200_ctx *c) { return c ? c->device : -1; }
+extern "C" const char *sjb200_last_cuda_error(const sjb200_ctx *c) { return c ? c->last_error.c_str() : ""; }
+
+extern "C" double sjb200_get_stat(sjb200_ctx *c, const char *key) {
+  if (!c || !key) return -1.0;
+  if (!strcmp(key, "kernel_ms")) {  // duration of the last scan kernel (needs option time_kernel=1 and a finished call)
+    if (!c->ev_valid) return -1.0;
+    DeviceGuard g(c->device);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev_k0, c->ev_k1) != cudaSuccess) { (void)cudaGetLastError(); return -1.0; }
+    return double(ms);
+  }
+  if (!strcmp(key, "launches")) return double(c->launches);
+  if (!strcmp(key, "grid_index")) return double(grid_for(c, kIndex, 0xFFFFFFFFu));
+  if (!strcmp(key, "sm_count")) return double(c->sm_count);
+  return -1.0;
+}
+
+extern "C" int sjb200_set_option(sjb200_ctx *c, const char *key, long value) {
+  if (!c || !key) return SJB200_UNEXPECTED_ERROR;
+  if (!strcmp(key, "use_tma")) c->opt_use_tma = value;
+  else if (!strcmp(key, "grid")) c->opt_grid = value;
+  else if (!strcmp(key, "time_kernel")) c->opt_time_kernel = value;
+  else if (!strcmp(key, "chunk_bytes")) c->opt_chunk_bytes = std::max<long>(kTileBytes, (value / kTileBytes) * kTileBytes);
+  else return SJB200_UNEXPECTED_ERROR;
+  return SJB200_SUCCESS;
+}
+
+// =============================================================================== device-resident
+extern "C" int sjb200_stage1_dev_enqueue(sjb200_ctx *c, const uint8_t *d_buf, size_t len, int mode, uint32_t *d_idx, void *stream) {
+  if (!c) return SJB200_UNEXPECTED_ERROR;
+  DeviceGuard g(c->device);
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+  PendingCall &pc = c->pending;
+  pc = PendingCall();
+  pc.kind = kIndex; pc.mode = mode; pc.d_buf = d_buf; pc.d_idx = d_idx; pc.stream = s; pc.len = len;
+  if (mode < SJB200_REGULAR || mode > SJB200_COMMA_DELIMITED_FINAL) { pc.early_error = SJB200_UNEXPECTED_ERROR; return SJB200_SUCCESS; }
+  if (len > c->capacity) { pc.early_error = SJB200_CAPACITY; return SJB200_SUCCESS; }   // json_structural_indexer.h L195
+  if (len == 0) { pc.early_error = SJB200_EMPTY; return SJB200_SUCCESS; }                // L197
+  if (mode != SJB200_REGULAR) {                                                           // L198-204
+    const size_t k = std::min<size_t>(3, len);
+    if (!ok(c, cudaMemcpyAsync(c->h_small, d_buf + len - k, k, cudaMemcpyDeviceToHost, s), "D2H tail") ||
+        !ok(c, cudaStreamSynchronize(s), "sync"))
+      { pc.early_error = SJB200_UNEXPECTED_ERROR; return SJB200_SUCCESS; }
+    len = trim_partial_utf8_tail(c->h_small, k, len);
+    pc.len = len;
+    if (len == 0) { pc.early_error = SJB200_UTF8_ERROR; return SJB200_SUCCESS; }
+  }
+  if (!ensure_desc(c, len)) { pc.early_error = SJB200_MEMALLOC; return SJB200_SUCCESS; }
+  CUtensorMap map;
+  bool tma = false;
+  make_tensor_map(c, &map, d_buf, len, &tma);
+  if (!reset_document_state(c, s) ||
+      !enqueue_scan(c, kIndex, &map, tma, d_buf, len, 0, tiles_of(len), true, 0x20202020u, d_idx, nullptr, 0, s) ||
+      !fetch_result(c, s))
+    pc.early_error = SJB200_UNEXPECTED_ERROR;
+  pc.carry_slot = 1;
+  return SJB200_SUCCESS;
+}
+
+extern "C" int sjb200_stage1_dev_finish(sjb200_ctx *c, uint32_t *n_inout) {
+  if (!c || c->pending.kind != kIndex) return SJB200_UNEXPECTED_ERROR;
+  DeviceGuard g(c->device);
+  PendingCall pc = c->pending;
+  c->pending.kind = -1;
+  if (pc.early_error >= 0) return pc.early_error;
+  if (!ok(c, cudaStreamSynchronize(pc.stream), "sync")) return SJB200_UNEXPECTED_ERROR;
+  FinishInput in;
+  in.mode = pc.mode; in.len = pc.len;
+  in.count = c->h_carry[pc.carry_slot].count;
+  in.state = c->h_carry[pc.carry_slot].state;
+  in.flags = *c->h_flags;
+  DeviceIndexWriter writer(c, pc.d_idx, pc.stream);
+  int rc;
+  uint32_t n_local = n_inout ? *n_inout : 0;
+  if (is_filter_mode(pc.mode)) {
+    // RS / comma-delimited streams: the serial filters run on host copies, then go back
+    const uint32_t n = uint32_t(in.count);
+    std::vector<uint8_t> hbuf(pc.len);
+    std::vector<uint32_t> hidx(size_t(n) + 3);
+    if (!ok(c, cudaMemcpyAsync(hbuf.data(), pc.d_buf, pc.len, cudaMemcpyDeviceToHost, pc.stream), "D2H buf") ||
+        !ok(c, cudaMemcpyAsync(hidx.data(), pc.d_idx, size_t(n) * 4, cudaMemcpyDeviceToHost, pc.stream), "D2H idx") ||
+        !ok(c, cudaStreamSynchronize(pc.stream), "sync"))
+      return SJB200_UNEXPECTED_ERROR;
+    HostStructuralReader reader(hbuf.data(), hidx.data());
+    HostIndexWriter hw(hidx.data());
+    bool dirty = false;
+    rc = finish_stage1(in, reader, hw, &n_local, hbuf.data(), hidx.data(), &dirty);
+    const bool wrote = !(rc == SJB200_UNCLOSED_STRING && pc.mode == SJB200_REGULAR) && rc != SJB200_UNESCAPED_CHARS && rc != SJB200_UNEXPECTED_ERROR;
+    if (wrote) {
+      if (!ok(c, cudaMemcpyAsync(pc.d_idx, hidx.data(), (size_t(n) + 3) * 4, cudaMemcpyHostToDevice, pc.stream), "H2D idx") ||
+          !ok(c, cudaStreamSynchronize(pc.stream), "sync"))
+        return SJB200_UNEXPECTED_ERROR;
+    }
+  } else {
+    DeviceTailReader reader(c, pc.d_buf, pc.d_idx, uint32_t(in.count), pc.stream);
+    bool dirty = false;
+    rc = finish_stage1(in, reader, writer, &n_local, nullptr, nullptr, &dirty);
+    if (reader.failed()) return SJB200_UNEXPECTED_ERROR;
+    if (!ok(c, cudaStreamSynchronize(pc.stream), "sync")) return SJB200_UNEXPECTED_ERROR;
+  }
+  if (n_inout) *n_inout = n_local;
+  return rc;
+}
+
+extern "C" int sjb200_stage1_dev(sjb200_ctx *c, const uint8_t *d_buf, size_t len, int mode, uint32_t *d_idx, uint32_t *n_inout,
+                                 void *stream) {
+  int rc = sjb200_stage1_dev_enqueue(c, d_buf, len, mode, d_idx, stream);
+  if (rc != SJB200_SUCCESS) return rc;
+  return sjb200_stage1_dev_finish(c, n_inout);
+}
+
+extern "C" int sjb200_minify_dev_enqueue(sjb200_ctx *c, const uint8_t *d_buf, size_t len, uint8_t *d_dst, void *stream) {
+  if (!c) return SJB200_UNEXPECTED_ERROR;
+  DeviceGuard g(c->device);
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+  PendingCall &pc = c->pending;
+  pc = PendingCall();
+  pc.kind = kMinify; pc.d_buf = d_buf; pc.d_dst = d_dst; pc.stream = s; pc.len = len;
+  if (len > kMaxBytes) { pc.early_error = SJB200_CAPACITY; return SJB200_SUCCESS; }
+  if (len == 0) { pc.early_error = SJB200_SUCCESS; return SJB200_SUCCESS; }  // json_minifier.h: nothing to do, dst_len = 0
+  if (!ensure_desc(c, len)) { pc.early_error = SJB200_MEMALLOC; return SJB200_SUCCESS; }
+  CUtensorMap map;
+  bool tma = false;
+  make_tensor_map(c, &map, d_buf, len, &tma);
+  if (!reset_document_state(c, s) ||
+      !enqueue_scan(c, kMinify, &map, tma, d_buf, len, 0, tiles_of(len), true, 0x20202020u, nullptr, d_dst, 0, s) ||
+      !fetch_result(c, s))
+    pc.early_error = SJB200_UNEXPECTED_ERROR;
+  pc.carry_slot = 1;
+  return SJB200_SUCCESS;
+}
+
+extern "C" int sjb200_minify_dev_finish(sjb200_ctx *c, size_t *dst_len) {
+  if (!c || c->pending.kind != kMinify) return SJB200_UNEXPECTED_ERROR;
+  DeviceGuard g(c->device);
+  PendingCall pc = c->pending;
+  c->pending.kind = -1;
+  if (dst_len) *dst_len = 0;
+  if (pc.early_error >= 0) return pc.early_error;
+  if (!ok(c, cudaStreamSynchronize(pc.stream), "sync")) return SJB200_UNEXPECTED_ERROR;
+  if (*c->h_flags & kFlagInternal) return SJB200_UNEXPECTED_ERROR;
+  if ((c->h_carry[pc.carry_slot].state >> 1) & 1u) return SJB200_UNCLOSED_STRING;  // json_minifier.h L42-47
+  if (dst_len) *dst_len = size_t(c->h_carry[pc.carry_slot].count);
+  return SJB200_SUCCESS;
+}
+
+extern "C" int sjb200_minify_dev(sjb200_ctx *c, const uint8_t *d_buf, size_t len, uint8_t *d_dst, size_t *dst_len, void *stream) {
+  int rc = sjb200_minify_dev_enqueue(c, d_buf, len, d_dst, stream);
+  if (rc != SJB200_SUCCESS) return rc;
+  return sjb200_minify_dev_finish(c, dst_len);
+}
+
+extern "C" int sjb200_validate_utf8_dev_enqueue(sjb200_ctx *c, const uint8_t *d_buf, size_t len, void *stream) {
+  if (!c) return SJB200_UNEXPECTED_ERROR;
+  DeviceGuard g(c->device);
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+  PendingCall &pc = c->pending;
+  pc = PendingCall();
+  pc.kind = kUtf8; pc.d_buf = d_buf; pc.stream = s; pc.len = len;
+  if (len == 0) { pc.early_error = SJB200_SUCCESS; return SJB200_SUCCESS; }  // utf8_validator.h L27-28: empty is valid
+  if (len > kMaxBytes) { pc.early_error = SJB200_CAPACITY; return SJB200_SUCCESS; }
+  CUtensorMap map;
+  bool tma = false;
+  make_tensor_map(c, &map, d_buf, len, &tma);
+  if (!reset_document_state(c, s) ||
+      !enqueue_scan(c, kUtf8, &map, tma, d_buf, len, 0, tiles_of(len), true, 0x20202020u, nullptr, nullptr, 0, s) ||
+      !fetch_result(c, s))
+    pc.early_error = SJB200_UNEXPECTED_ERROR;
+  return SJB200_SUCCESS;
+}
+
+// returns 1 valid, 0 invalid, negative = CUDA failure
+extern "C" int sjb200_validate_utf8_dev_finish(sjb200_ctx *c) {
+  if (!c || c->pending.kind != kUtf8) return -1;
+  DeviceGuard g(c->device);
+  PendingCall pc = c->pending;
+  c->pending.kind = -1;
+  if (pc.early_error == SJB200_SUCCESS) return 1;
+  if (pc.early_error > 0) return -1;
+  if (!ok(c, cudaStreamSynchronize(pc.stream), "sync")) return -1;
+  if (*c->h_flags & kFlagInternal) return -1;
+  return (*c->h_flags & kFlagUtf8) ? 0 : 1;
+}
+
+extern "C" int sjb200_validate_utf8_dev(sjb200_ctx *c, const uint8_t *d_buf, size_t len, void *stream) {
+  if (sjb200_validate_utf8_dev_enqueue(c, d_buf, len, stream) != SJB200_SUCCESS) return -1;
+  return sjb200_validate_utf8_dev_finish(c);
+}
+
+// =============================================================================== host pointers
+namespace {
+
+// host staging: input buffer on the device sized to the capacity (+ slack so the last 16-byte vector load is in bounds)
+bool ensure_input(sjb200_ctx *c, size_t len) {
+  const size_t need = std::max(len, c->capacity) + 256;
+  if (c->d_in_bytes >= need) return true;
+  cudaFree(c->d_in); c->d_in = nullptr; c->d_in_bytes = 0;
+  if (!dev_alloc(c, &c->d_in, need, "cudaMalloc(input)")) return false;
+  c->d_in_bytes = need;
+  return true;
+}
+bool ensure_index(sjb200_ctx *c, size_t len) {
+  const size_t need = index_words(std::max(len, c->capacity));
+  if (c->d_idx_words >= need) return true;
+  cudaFree(c->d_idx); c->d_idx = nullptr; c->d_idx_words = 0;
+  if (!dev_alloc(c, &c->d_idx, need, "cudaMalloc(index)")) return false;
+  c->d_idx_words = need;
+  return true;
+}
+bool ensure_output(sjb200_ctx *c, size_t len) {
+  const size_t need = len + 256;
+  if (c->d_out_bytes >= need) return true;
+  cudaFree(c->d_out); c->d_out = nullptr; c->d_out_bytes = 0;
+  if (!dev_alloc(c, &c->d_out, need, "cudaMalloc(output)")) return false;
+  c->d_out_bytes = need;
+  return true;
+}
+
+// Copy the document to the device chunk by chunk and chain one scan launch per chunk behind its copy:
+// the scan of chunk k overlaps the H2D copy of chunk k+1.  Returns the carry slot with the final state.
+bool scan_host_document(sjb200_ctx *c, int kind, const uint8_t *buf, size_t len, uint32_t *d_idx, uint8_t *d_dst, int *final_slot) {
+  const size_t chunk = size_t(c->opt_chunk_bytes);
+  const size_t nchunks = (len + chunk - 1) / chunk;
+  while (c->chunk_events.size() < nchunks) {
+    cudaEvent_t e;
+    if (!ok(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event")) return false;
+    c->chunk_events.push_back(e);
+  }
+  CUtensorMap map;
+  bool tma = false;
+  make_tensor_map(c, &map, c->d_in, len, &tma);
+  if (!reset_document_state(c, c->stream)) return false;
+  // the copy stream must not overwrite d_in while an earlier call's kernels still read it: calls are synchronous, so it is idle
+  int slot = 0;
+  for (size_t k = 0; k < nchunks; k++) {
+    const size_t off = k * chunk;
+    const size_t bytes = std::min(chunk, len - off);
+    if (!ok(c, cudaMemcpyAsync(c->d_in + off, buf + off, bytes, cudaMemcpyHostToDevice, c->copy_stream), "H2D chunk")) return false;
+    if (!ok(c, cudaEventRecord(c->chunk_events[k], c->copy_stream), "event record")) return false;
+    if (!ok(c, cudaStreamWaitEvent(c->stream, c->chunk_events[k], 0), "wait event")) return false;
+    const uint32_t tile_begin = uint32_t(off / kTileBytes);
+    const uint32_t ntiles = tiles_of(bytes);
+    const bool last = (k + 1 == nchunks);
+    if (!enqueue_scan(c, kind, &map, tma, c->d_in, len, tile_begin, ntiles, last, 0x20202020u, d_idx, d_dst, slot, c->stream)) return false;
+    slot ^= 1;
+  }
+  *final_slot = slot;
+  return fetch_result(c, c->stream);
+}
+
+}  // namespace
+
+extern "C" int sjb200_stage1(sjb200_ctx *c, const uint8_t *buf, size_t len, int mode, uint32_t *idx_out, uint32_t *n_inout) {
+  if (!c || !idx_out || !n_inout) return SJB200_UNEXPECTED_ERROR;
+  if (mode < SJB200_REGULAR || mode > SJB200_COMMA_DELIMITED_FINAL) return SJB200_UNEXPECTED_ERROR;
+  if (len > c->capacity) return SJB200_CAPACITY;                                  // json_structural_indexer.h L195
+  if (len == 0) return SJB200_EMPTY;                                              // L197
+  if (mode != SJB200_REGULAR) {                                                   // L198-204
+    const size_t k = std::min<size_t>(3, len);
+    len = trim_partial_utf8_tail(buf + len - k, k, len);
+    if (len == 0) return SJB200_UTF8_ERROR;
+  }
+  DeviceGuard g(c->device);
+  if (!ensure_input(c, len) || !ensure_index(c, len) || !ensure_desc(c, len)) return SJB200_MEMALLOC;
+  int slot = 0;
+  if (!scan_host_document(c, kIndex, buf, len, c->d_idx, nullptr, &slot)) return SJB200_UNEXPECTED_ERROR;
+  if (!ok(c, cudaStreamSynchronize(c->stream), "sync")) return SJB200_UNEXPECTED_ERROR;
+  FinishInput in;
+  in.mode = mode; in.len = len;
+  in.count = c->h_carry[slot].count;
+  in.state = c->h_carry[slot].state;
+  in.flags = *c->h_flags;
+  const bool unclosed = (in.state >> 1) & 1u;
+  const bool early = (in.flags & kFlagInternal) || (mode == SJB200_REGULAR && unclosed) || (in.flags & kFlagCtl);
+  if (!early && in.count > 0) {
+    // pageable destination: a plain synchronous copy of exactly the n indexes found
+    if (!ok(c, cudaMemcpyAsync(idx_out, c->d_idx, size_t(in.count) * 4, cudaMemcpyDeviceToHost, c->stream), "D2H idx") ||
+        !ok(c, cudaStreamSynchronize(c->stream), "sync"))
+      return SJB200_UNEXPECTED_ERROR;
+  }
+  HostStructuralReader reader(buf, idx_out);
+  HostIndexWriter writer(idx_out);
+  bool dirty = false;
+  return finish_stage1(in, reader, writer, n_inout, buf, idx_out, &dirty);
+}
+
+extern "C" int sjb200_minify(sjb200_ctx *c, const uint8_t *buf, size_t len, uint8_t *dst, size_t *dst_len) {
+  if (!c || !dst_len) return SJB200_UNEXPECTED_ERROR;
+  *dst_len = 0;
+  if (len == 0) return SJB200_SUCCESS;
+  if (len > kMaxBytes) return SJB200_CAPACITY;
+  DeviceGuard g(c->device);
+  if (!ensure_input(c, len) || !ensure_output(c, len) || !ensure_desc(c, len)) return SJB200_MEMALLOC;
+  int slot = 0;
+  if (!scan_host_document(c, kMinify, buf, len, nullptr, c->d_out, &slot)) return SJB200_UNEXPECTED_ERROR;
+  if (!ok(c, cudaStreamSynchronize(c->stream), "sync")) return SJB200_UNEXPECTED_ERROR;
+  if (*c->h_flags & kFlagInternal) return SJB200_UNEXPECTED_ERROR;
+  if ((c->h_carry[slot].state >> 1) & 1u) return SJB200_UNCLOSED_STRING;
+  const size_t kept = size_t(c->h_carry[slot].count);
+  if (kept > 0) {
+    if (!ok(c, cudaMemcpyAsync(dst, c->d_out, kept, cudaMemcpyDeviceToHost, c->stream), "D2H out") ||
+        !ok(c, cudaStreamSynchronize(c->stream), "sync"))
+      return SJB200_UNEXPECTED_ERROR;
+  }
+  *dst_len = kept;
+  return SJB200_SUCCESS;
+}
+
+extern "C" int sjb200_validate_utf8(sjb200_ctx *c, const uint8_t *buf, size_t len) {
+  if (!c) return 0;
+  if (len == 0) return 1;
+  if (len > kMaxBytes) return 0;
+  DeviceGuard g(c->device);
+  if (!ensure_input(c, len)) return 0;
+  int slot = 0;
+  if (!scan_host_document(c, kUtf8, buf, len, nullptr, nullptr, &slot)) return 0;
+  if (!ok(c, cudaStreamSynchronize(c->stream), "sync")) return 0;
+  if (*c->h_flags & kFlagInternal) return 0;
+  return (*c->h_flags & kFlagUtf8) ? 0 : 1;
+}
+
+// =============================================================================== shards (multi-GPU)
+extern "C" int sjb200_stage1_shard_dev(sjb200_ctx *c, const uint8_t *d_buf, size_t len, uint32_t state_in, int last_shard,
+                                       uint32_t *d_idx, sjb200_shard_result *out, void *stream) {
+  if (!c || !out) return SJB200_UNEXPECTED_ERROR;
+  memset(out, 0, sizeof(*out));
+  if (len == 0 || len > kMaxBytes) return SJB200_UNEXPECTED_ERROR;
+  DeviceGuard g(c->device);
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+  if (!ensure_desc(c, len)) return SJB200_MEMALLOC;
+  CUtensorMap map;
+  bool tma = false;
+  make_tensor_map(c, &map, d_buf, len, &tma);
+  c->h_carry[0].count = 0; c->h_carry[0].state = state_in & 7u; c->h_carry[0].ttable = 0;
+  (void)last_shard;  // every shard checks its own end: cuts are at character boundaries (sjb200_shard_cut)
+  if (!ok(c, cudaMemsetAsync(c->d_flags, 0, sizeof(uint32_t), s), "memset flags") ||
+      !ok(c, cudaMemcpyAsync(c->d_carry, c->h_carry, sizeof(Carry), cudaMemcpyHostToDevice, s), "H2D carry") ||
+      !enqueue_scan(c, kIndex, &map, tma, d_buf, len, 0, tiles_of(len), true, 0x20202020u, d_idx, nullptr, 0, s) ||
+      !fetch_result(c, s) || !ok(c, cudaStreamSynchronize(s), "sync"))
+    return SJB200_UNEXPECTED_ERROR;
+  out->ttable = c->h_carry[1].ttable;
+  out->state_out = c->h_carry[1].state;
+  out->flags = *c->h_flags;
+  out->count = c->h_carry[1].count;
+  return (out->flags & kFlagInternal) ? SJB200_UNEXPECTED_ERROR : SJB200_SUCCESS;
+}
+
+extern "C" uint32_t sjb200_fold_state(const uint32_t *ttables, int nshards_before) {
+  uint32_t state = 0;
+  for (int i = 0; i < nshards_before; i++) state = tt_apply(ttables[i], state);
+  return state;
+}
+
+extern "C" size_t sjb200_shard_cut(const uint8_t *buf, size_t len, size_t nominal) {
+  if (nominal >= len) return len;
+  size_t cut = nominal;
+  for (int k = 0; k < 3 && cut > 0 && (buf[cut] & 0xC0) == 0x80; k++) cut--;
+  return cut;
+}

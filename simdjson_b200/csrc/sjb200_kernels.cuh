@@ -1,0 +1,61 @@
+// sjb200_kernels.cuh -- shared declarations between the kernels and the C-ABI host code.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "sjb200_common.h"
+
+namespace sjb200 {
+
+// ---- geometry (one "tile" is what one CTA scans per loop iteration)
+constexpr int kUnitsPerLane = 4;                     // 32-byte transposition units per lane
+constexpr int kLaneBytes = 32 * kUnitsPerLane;       // 128 B = one TMA 128B-swizzle row
+constexpr int kWarpBytes = 32 * kLaneBytes;          // 4 KiB
+constexpr int kWarps = 8;
+constexpr int kThreads = 32 * kWarps;
+constexpr int kTileBytes = kWarps * kWarpBytes;      // 32 KiB
+constexpr int kTileRows = kTileBytes / 128;          // 256 rows of 128 B (max TMA box dim)
+constexpr int kStages = 2;
+constexpr int kSmemBytes = kStages * kTileBytes + 1024 /*alignment slack*/ + 512 /*control block*/;
+
+// ---- scan kinds
+enum : int { kIndex = 0, kMinify = 1, kUtf8 = 2 };
+
+// Scanner state between consecutive launches of one document (chunked streaming,
+// multi-GPU shards).  state: bit0 escape, bit1 in_string, bit2 prev_scalar.
+struct Carry {
+  uint64_t count;     // structurals (kIndex) or kept bytes (kMinify) emitted so far
+  uint32_t state;
+  uint32_t ttable;    // out only: the 6-bit transducer T(e) of everything this launch scanned
+};
+
+struct ScanParams {
+  const uint8_t *buf;       // device pointer to byte 0 of the document (or shard)
+  uint64_t len;             // document length in bytes (<= 4 GiB - 1); bytes past it read as 0x20
+  uint32_t pos_base;        // added to every emitted index (0: positions relative to buf)
+  uint32_t prev_word;       // the 4 bytes that precede buf[0] (0x20202020 at start of document)
+  uint32_t check_eof;       // 1: this launch scans the last tile -> flag a truncated UTF-8 sequence
+  uint32_t use_tma;         // 1: full tiles arrive by cp.async.bulk.tensor (buf 16 B aligned)
+  uint32_t tile_begin;      // first document tile of this launch (chunked streaming)
+  uint32_t ntiles;          // tiles in this launch: document tiles [tile_begin, tile_begin+ntiles)
+  uint32_t full_tiles;      // document tiles that lie entirely inside floor(len/128) rows
+  uint32_t epoch;           // tags look-back descriptors so they need no per-launch reset
+  uint32_t *idx_out;        // kIndex: device index array
+  uint8_t *dst;             // kMinify: device output
+  const Carry *carry_in;
+  Carry *carry_out;
+  uint32_t *flags;          // accumulated with atomicOr
+  uint32_t *state_desc;     // [ntiles]  look-back chain 1 (transducer)
+  unsigned long long *count_desc;  // [ntiles] look-back chain 2 (output offsets)
+  uint32_t *ticket;         // [0] next tile, [1] CTAs finished
+};
+
+// launchers (defined in sjb200_kernels.cu)
+cudaError_t launch_scan(int kind, const CUtensorMap *tmap, const ScanParams &p, int grid, cudaStream_t stream);
+int scan_max_ctas_per_sm(int kind);
+cudaError_t launch_gather_chars(const uint8_t *buf, const uint32_t *idx, uint32_t first, uint32_t count, uint8_t *out,
+                                cudaStream_t stream);
+cudaError_t launch_write_sentinels(uint32_t *idx, uint32_t n, uint32_t a, uint32_t b, uint32_t c, cudaStream_t stream);
+
+}  // namespace sjb200

@@ -1,0 +1,379 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle
+(oracle/libsj_oracle.so, pinned to the reference by test_oracle_pinning.py) and against the
+committed golden vectors the reference itself produced.  Bar: bit-exact error code,
+n_structural_indexes and the (n+3) index words; minified bytes; UTF-8 verdict."""
+import hashlib
+import json
+import os
+import random
+import threading
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import simdjson_b200 as sj
+from simdjson_b200 import corpus
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+TILE = 32768
+
+
+@pytest.fixture(scope="module")
+def port():
+    return O.Port()
+
+
+@pytest.fixture(scope="module")
+def parser():
+    rc, p = sj.get_active_implementation().create_dom_parser_implementation(8 << 20)
+    assert rc == sj.SUCCESS, sj.ERROR_NAMES.get(rc, rc)
+    yield p
+    p.close()
+
+
+def _load(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)
+
+
+def run_stage1(p, buf, mode):
+    """host-pointer call; returns an oracle_lib.Stage1Result-alike"""
+    p.n_structural_indexes = O.N_SENTINEL
+    err = p.stage1(buf, mode)
+    return O.Stage1Result(err, p.n_structural_indexes, p.structural_indexes)
+
+
+def assert_same(got, want, ctx=None):
+    assert got.err == want.err, (ctx, got.err, want.err, got.n, want.n)
+    assert got.n == want.n, (ctx, got.err, got.n, want.n)
+    if want.wrote:
+        a, b = got.words(), want.words()
+        if not np.array_equal(a, b):
+            k = int(np.argmax(a != b))
+            raise AssertionError((ctx, "first differing word", k, a[max(0, k - 3):k + 4], b[max(0, k - 3):k + 4]))
+
+
+# --------------------------------------------------------------------------- golden vectors
+def test_golden_stage1(parser):
+    for c in _load("stage1.json")["cases"]:
+        r = run_stage1(parser, bytes.fromhex(c["hex"]), c["mode"])
+        assert r.err == c["err"], c
+        if c["n"] is None:
+            assert r.n == O.N_SENTINEL, c
+        else:
+            assert r.n == c["n"], c
+            assert [int(x) for x in r.words()] == c["words"], c
+
+
+def test_golden_minify_and_utf8(parser):
+    impl = sj.get_active_implementation()
+    for c in _load("minify.json")["cases"]:
+        err, out = impl.minify(bytes.fromhex(c["hex"]))
+        assert (err, bytes(out).hex()) == (c["err"], c["out"]), c
+    for c in _load("utf8.json")["cases"]:
+        assert impl.validate_utf8(bytes.fromhex(c["hex"])) == c["valid"], c
+
+
+@pytest.mark.skipif(not os.path.isdir(O.JSONEXAMPLES), reason="reference corpora not staged")
+def test_golden_corpora(parser):
+    import torch
+    impl = sj.get_active_implementation()
+    for f in _load("corpora.json")["files"]:
+        data = np.fromfile(os.path.join(O.JSONEXAMPLES, f["file"]), dtype=np.uint8)
+        r = run_stage1(parser, data, f["mode"])
+        assert (r.err, r.n) == (f["err"], f["n"]), f["file"]
+        assert hashlib.sha256(r.words().tobytes()).hexdigest() == f["idx_sha256"], f["file"]
+        # device-resident call gives the same array
+        d = torch.from_numpy(data).cuda()
+        parser.n_structural_indexes = O.N_SENTINEL
+        rc = parser.stage1_device(d, f["mode"])
+        got = parser.device_index_buffer().cpu().numpy().view(np.uint32)
+        assert (rc, parser.n_structural_indexes) == (f["err"], f["n"])
+        assert hashlib.sha256(got[: f["n"] + 3].tobytes()).hexdigest() == f["idx_sha256"], f["file"]
+        err, out = impl.minify(data)
+        assert (err, len(out), hashlib.sha256(bytes(out)).hexdigest()) == (f["minify_err"], f["minify_len"], f["minify_sha256"])
+        assert impl.validate_utf8(data) == f["utf8"]
+
+
+# --------------------------------------------------------------------------- seeded fuzz vs the oracle
+def _fuzz_inputs(rng, n):
+    for i in range(n):
+        kind = i % 4
+        if kind == 0:
+            yield corpus.adversarial(rng), rng.choice(O.ALL_MODES)
+        elif kind == 1:
+            yield corpus.multi_document(rng), rng.choice([1, 2])
+        elif kind == 2:
+            yield b"\x1e" + corpus.multi_document(rng, sep=b"\x1e"), rng.choice([3, 4])
+        else:
+            yield corpus.multi_document(rng, sep=b","), rng.choice([5, 6])
+
+
+@pytest.mark.parametrize("use_tma", [1, 0])
+def test_fuzz_small_all_modes(parser, port, use_tma):
+    parser.set_option("use_tma", use_tma)
+    try:
+        rng = random.Random(corpus.SEED + use_tma)
+        impl = sj.get_active_implementation()
+        for k, (b, mode) in enumerate(_fuzz_inputs(rng, 1500)):
+            assert_same(run_stage1(parser, b, mode), port.stage1(b, mode), (b, mode))
+            if k % 4 == 0:
+                err, out = impl.minify(b)
+                assert (err, bytes(out)) == port.minify(b), b
+                assert impl.validate_utf8(b) == port.validate_utf8(b), b
+    finally:
+        parser.set_option("use_tma", 1)
+
+
+def _big_adversarial(rng, nbytes):
+    """many adversarial snippets, with backslash runs and quotes planted on lane / warp / tile boundaries"""
+    out = bytearray()
+    while len(out) < nbytes:
+        out += corpus.adversarial(rng, 900)
+    out = out[:nbytes]
+    for boundary in range(128, nbytes - 300, 128):
+        r = rng.random()
+        if boundary % TILE == 0 or boundary % 4096 == 0 or r < 0.05:
+            run = rng.choice([1, 2, 3, 5, 127, 128, 129, 255, 256, 4095, 4096, 4097])
+            if rng.random() < 0.7:
+                run = rng.choice([1, 2, 3, 4, 5])
+            start = max(0, boundary - rng.randint(0, run))
+            out[start:start + run] = b"\\" * run
+            if rng.random() < 0.7:
+                out[start + run:start + run + 1] = b'"'
+        elif r < 0.10:
+            s = rng.choice([b"\xe2\x82\xac", b"\xf0\x9f\x98\x80", b"\xc3\xa9", b"\xf0\x9f\x98", b"\xe2\x82"])
+            at = boundary - rng.randint(0, len(s))
+            out[at:at + len(s)] = s
+    return bytes(out[:nbytes])
+
+
+@pytest.mark.parametrize("use_tma", [1, 0])
+def test_fuzz_multi_tile(parser, port, use_tma):
+    parser.set_option("use_tma", use_tma)
+    try:
+        rng = random.Random(corpus.SEED ^ 0x77 ^ use_tma)
+        impl = sj.get_active_implementation()
+        sizes = [TILE - 1, TILE, TILE + 1, 2 * TILE, 3 * TILE + 17, 5 * TILE - 128, 9 * TILE + 4095, 40 * TILE + 1, 64 * TILE]
+        for n in sizes:
+            for rep in range(3):
+                b = _big_adversarial(rng, n)
+                for mode in (0, 2):
+                    assert_same(run_stage1(parser, b, mode), port.stage1(b, mode), (n, rep, mode))
+                err, out = impl.minify(b)
+                werr, wout = port.minify(b)
+                assert err == werr and bytes(out) == wout, (n, rep)
+                assert impl.validate_utf8(b) == port.validate_utf8(b), (n, rep)
+    finally:
+        parser.set_option("use_tma", 1)
+
+
+def test_valid_documents_and_streams(parser, port):
+    impl = sj.get_active_implementation()
+    d = corpus.random_json(3 * (1 << 20) + 12345)
+    assert_same(run_stage1(parser, d, 0), port.stage1(d, 0))
+    err, out = impl.minify(d)
+    werr, wout = port.minify(d)
+    assert err == werr == 0 and bytes(out) == wout
+    nd = corpus.ndjson_rows(2 << 20)
+    for mode in (1, 2):
+        assert_same(run_stage1(parser, nd, mode), port.stage1(nd, mode))
+    cut = nd[: (1 << 20) + 123]  # mid-row: streaming_partial must stop at the last complete row
+    r = run_stage1(parser, cut, 1)
+    assert_same(r, port.stage1(cut, 1))
+    assert r.err == 0 and r.idx[r.n] < len(cut)
+    u = corpus.random_utf8(1 << 20)
+    assert impl.validate_utf8(u)
+    for pos in (0, 1, len(u) // 2, 32767, 32768, len(u) - 2, len(u) - 1):
+        v = u.copy()
+        v[pos] = 0xFF
+        assert not impl.validate_utf8(v), pos
+    t = u.copy()  # truncated sequence exactly at the end of the input
+    t[-3:] = np.frombuffer(b"\xf0\x9f\x98", dtype=np.uint8)
+    assert impl.validate_utf8(t) == port.validate_utf8(t) is False
+
+
+def test_capacity_and_empty(parser, port):
+    doc = b'{"a":[1,2,3]}'
+    rc, small = sj.get_active_implementation().create_dom_parser_implementation(8)
+    assert rc == 0
+    small.n_structural_indexes = 77
+    assert small.stage1(doc, 0) == sj.CAPACITY and small.n_structural_indexes == 77  # untouched, like the reference
+    assert small.stage1(b"", 0) == sj.EMPTY and small.n_structural_indexes == 77
+    assert small.set_capacity(1 << 33) == sj.CAPACITY
+    assert small.set_capacity(64) == 0 and small.stage1(doc, 0) == 0
+    small.close()
+    for b in (b" ", b"   \n\t ", b'"', b'"abc', b'["a\x01b"]', b'["a\xffb"]', b"\xe2\x82", b"\\"):
+        for mode in O.ALL_MODES:
+            assert_same(run_stage1(parser, b, mode), port.stage1(b, mode), (b, mode))
+
+
+# --------------------------------------------------------------------------- entry-point variants
+def test_device_resident_matches_host_path(parser, port):
+    import torch
+    rng = random.Random(99)
+    for n in (1, 63, 64, 65, 4097, TILE + 5, 7 * TILE + 1234):
+        b = _big_adversarial(rng, max(n, 400))[:n]
+        for mode in (0, 1, 2, 3, 6):
+            want = port.stage1(b, mode)
+            d = torch.from_numpy(np.frombuffer(b, dtype=np.uint8).copy()).cuda()
+            parser.n_structural_indexes = O.N_SENTINEL
+            rc = parser.stage1_device(d, mode)
+            got = O.Stage1Result(rc, parser.n_structural_indexes, parser.device_index_buffer().cpu().numpy().view(np.uint32))
+            assert_same(got, want, (n, mode))
+        # minify / utf8 device entry points
+        d = torch.from_numpy(np.frombuffer(b, dtype=np.uint8).copy()).cuda()
+        dst = torch.empty(max(n, 1), dtype=torch.uint8, device="cuda")
+        rc, dl = parser.minify_device(d, dst)
+        werr, wout = port.minify(b)
+        assert rc == werr and bytes(dst[:dl].cpu().numpy()) == wout
+        assert parser.validate_utf8_device(d) == int(port.validate_utf8(b))
+
+
+def test_unaligned_device_pointer(parser, port):
+    """a device buffer that is not 16-byte aligned cannot use TMA; the plain-load path must agree"""
+    import torch
+    b = np.frombuffer(_big_adversarial(random.Random(5), 3 * TILE + 100), dtype=np.uint8)
+    base = torch.zeros(len(b) + 64, dtype=torch.uint8, device="cuda")
+    for off in (1, 3, 8, 13):
+        view = base[off: off + len(b)]
+        view.copy_(torch.from_numpy(b.copy()))
+        want = port.stage1(b, 0)
+        parser.n_structural_indexes = O.N_SENTINEL
+        rc = parser.stage1_device(view, 0)
+        got = O.Stage1Result(rc, parser.n_structural_indexes, parser.device_index_buffer().cpu().numpy().view(np.uint32))
+        assert_same(got, want, off)
+        assert parser.validate_utf8_device(view) == int(port.validate_utf8(b))
+
+
+def test_chunked_host_pipeline_carries(port):
+    """host path with tiny chunks: every chunk boundary exercises the carry hand-off between launches"""
+    rc, p = sj.get_active_implementation().create_dom_parser_implementation(1 << 20)
+    assert rc == 0
+    rng = random.Random(1234)
+    for chunk in (TILE, 2 * TILE, 8 * TILE):
+        p.set_option("chunk_bytes", chunk)
+        b = _big_adversarial(rng, 11 * TILE + 77)
+        for mode in (0, 2):
+            assert_same(run_stage1(p, b, mode), port.stage1(b, mode), (chunk, mode))
+        err, out = p._minify_host(b)
+        werr, wout = port.minify(b)
+        assert err == werr and bytes(out) == wout, chunk
+        assert p._validate_utf8_host(b) == port.validate_utf8(b), chunk
+    p.close()
+
+
+def test_sharded_scan_matches_single_scan(port):
+    """section 8(e): byte-range shards + a fold of 6-bit transducers == one scan of the whole buffer"""
+    import torch
+    L = sj.implementation.lib()
+    rng = random.Random(4242)
+    rc, p = sj.get_active_implementation().create_dom_parser_implementation(4 << 20)
+    assert rc == 0
+    docs = [np.frombuffer(_big_adversarial(rng, 6 * TILE + 999), dtype=np.uint8), corpus.random_json(1 << 20), corpus.ndjson_rows(1 << 20)]
+    for doc in docs:
+        want = port.stage1(doc, 2)  # streaming_final tolerates an unclosed tail; gives the raw structurals
+        raw_n = int(np.count_nonzero(want.idx[: want.n] < 2**32)) if want.wrote else 0
+        for nshards in (2, 3, 8):
+            cuts = [0]
+            for k in range(1, nshards):
+                nominal = (len(doc) * k) // nshards
+                cuts.append(int(L.sjb200_shard_cut(doc.ctypes.data, len(doc), nominal)))
+            cuts.append(len(doc))
+            shards = [doc[cuts[k]: cuts[k + 1]] for k in range(nshards)]
+            tts, counts, idxs, flags = [], [], [], 0
+            for k, sh in enumerate(shards):
+                d = torch.from_numpy(sh.copy()).cuda()
+                rc, res = p.stage1_shard_device(d, 0, k == nshards - 1)
+                assert rc == 0
+                tts.append(res.ttable)
+                import ctypes as C
+                state_in = L.sjb200_fold_state((C.c_uint32 * len(tts))(*tts), k)
+                if state_in != 0:  # speculation was wrong for this shard: scan again with the true state
+                    rc, res = p.stage1_shard_device(d, state_in, k == nshards - 1)
+                    assert rc == 0 and res.ttable == tts[-1]
+                counts.append(res.count)
+                flags |= res.flags
+                idxs.append(p.device_index_buffer().cpu().numpy().view(np.uint32)[: res.count].astype(np.int64) + cuts[k])
+            allidx = np.concatenate(idxs) if idxs else np.zeros(0, np.int64)
+            # compare with the single-scan raw structural list (before the streaming fix-ups trimmed the tail)
+            single = port.stage1(doc, 0)
+            if single.err in (0, sj.UTF8_ERROR, sj.EMPTY) and single.wrote:
+                assert len(allidx) == single.n and np.array_equal(allidx, single.idx[: single.n].astype(np.int64)), nshards
+                assert bool(flags & 1) == (not port.validate_utf8(doc))
+            _ = raw_n
+    p.close()
+
+
+def test_two_parsers_in_two_threads(port):
+    """document_stream's stage-1 worker runs a second parser concurrently (dom/document_stream-inl.h L16-85)"""
+    impl = sj.get_active_implementation()
+    docs = [bytes(corpus.random_json(700000 + 4096 * k, seed=k)) for k in range(2)]
+    wants = [port.stage1(d, 0) for d in docs]
+    errors = []
+
+    def work(k):
+        try:
+            rc, p = impl.create_dom_parser_implementation(1 << 20)
+            assert rc == 0
+            for _ in range(20):
+                assert_same(run_stage1(p, docs[k], 0), wants[k], k)
+            p.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errors, errors
+
+
+# --------------------------------------------------------------------------- BASELINE.json sizes
+def test_config2_64mib_random_json(port):
+    """configs[1]: synthetic 64 MiB random-structure JSON, stage1 on 1xB200 -- full array compared"""
+    import torch
+    doc = corpus.random_json(64 << 20)
+    want = port.stage1(doc, 0)
+    rc, p = sj.get_active_implementation().create_dom_parser_implementation(len(doc))
+    assert rc == 0
+    d = torch.from_numpy(doc).cuda()
+    rc = p.stage1_device(d, 0)
+    got = p.device_index_buffer().cpu().numpy().view(np.uint32)
+    assert rc == want.err == 0 and p.n_structural_indexes == want.n
+    assert np.array_equal(got[: want.n + 3], want.words())
+    # size-independent properties: strictly increasing, every index addresses a non-whitespace byte
+    idx = got[: want.n].astype(np.int64)
+    assert np.all(np.diff(idx) > 0)
+    assert not np.any(np.isin(doc[idx], [0x20, 0x0A, 0x0D, 0x09]))
+    # the host-pointer path (chunked H2D pipeline) agrees
+    assert_same(run_stage1(p, doc, 0), want)
+    # minify: idempotent and equal to the oracle
+    dst = torch.empty(len(doc), dtype=torch.uint8, device="cuda")
+    rc, dl = p.minify_device(d, dst)
+    werr, wout = port.minify(doc)
+    assert rc == werr == 0 and dl == len(wout)
+    assert bytes(dst[:dl].cpu().numpy()) == wout
+    dst2 = torch.empty(dl, dtype=torch.uint8, device="cuda")
+    rc, dl2 = p.minify_device(dst[:dl].clone(), dst2)
+    assert rc == 0 and dl2 == dl and torch.equal(dst2[:dl2], dst[:dl])
+    p.close()
+
+
+def test_config4_utf8_256mib(port):
+    """configs[3]: validate_utf8 on 256 MiB mixed ASCII/UTF-8; valid -> true, three corrupted copies -> false"""
+    import torch
+    u = corpus.random_utf8(256 << 20)
+    rc, p = sj.get_active_implementation().create_dom_parser_implementation(0)
+    assert rc == 0
+    d = torch.from_numpy(u).cuda()
+    assert p.validate_utf8_device(d) == 1
+    for pos in (0, len(u) // 2 + 1, len(u) - 2):
+        saved = int(d[pos])
+        d[pos] = 0xFF
+        assert p.validate_utf8_device(d) == 0, pos
+        d[pos] = saved
+    assert p.validate_utf8_device(d) == 1
+    p.close()
+    assert port.validate_utf8(u[: 1 << 20])
