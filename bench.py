@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- stage-1 structural indexing throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one stage-1 pass (structural indexing + UTF-8 validation) over one synthetic
+document per GPU.  Workload at N=1: configs[1] of BASELINE.json, "synthetic 64 MiB
+random-structure JSON, stage1 index on 1xB200" (seeded generator simdjson_b200/corpus.py,
+SURVEY.md section 8(d) item 2).  At N>1 every rank holds one 64 MiB shard of an N x 64 MiB stream
+(byte-range sharding): each rank scans its shard with a speculated incoming
+scanner state, the ranks all-gather {6-bit carry transducer, count} over NCCL (the path's one
+real exchange step), fold their true incoming state / index base, and re-scan only if the
+speculation was wrong -> weak scaling.
+
+The JSON line carries:
+  value     input GB/s with the input resident in HBM (device-timed, max over ranks)
+  e2e       the same metric through the host-pointer C-ABI call (pinned host input, H2D copy and
+            D2H of the n indexes inside the timed region)
+  roofline  algorithmic bytes (1 B read per input byte + 4 B written per structural + 12 B of
+            sentinels) / the scan kernel's mean duration, measured with CUDA events
+            recorded around the kernel on its launch stream, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the reference's own CPU stage 1 (oracle/_ref, compiled from the unmodified
+            reference) timed on this box's host cores on the same document (bounded sample)
+`--impl reference` times that CPU implementation as its own arm (rank 0 only).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DOC_BYTES = 64 << 20
+ROTATE = 4  # distinct 64 MiB inputs used round-robin: 256 MiB > 126 MB of L2, so no step finds its input in L2
+METRIC = "stage1 GB/s (bytes in / s) vs HBM roofline at 1/2/4/8 B200; CPU ref GB/s"
+UNIT = "GB/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop, self.th = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def make_doc(seed_offset):
+    from simdjson_b200 import corpus
+    return corpus.random_json(DOC_BYTES, seed=corpus.SEED + 7919 * seed_offset)
+
+
+# =============================================================================== reference arm
+def run_reference(args, rank):
+    """the reference's own CPU stage 1 (oracle/_ref = unmodified reference, compiled in the build
+    container) on this box's host cores; else the oracle port.  Rank 0 only."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    doc = make_doc(0)
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, int(os.environ.get("SJB200_REF_THREADS", cores))))
+    if O.have_ref():
+        ref = O.Ref("")
+        kind, name = "reference", ref.name
+        # bounded sample: every thread runs one full 64 MiB stage-1 call per round (independent parsers, the only
+        # way the reference can use more than one core for this path); `steps` rounds after `warmup` rounds
+        for _ in range(max(0, args.warmup - 1)):
+            ref.time(0, doc, 0, threads, 1)
+        t0 = time.perf_counter()
+        best, err = ref.time(0, doc, 0, threads, max(1, args.steps))
+        wall = time.perf_counter() - t0
+        gbs = threads * len(doc) / best / 1e9
+        one, _ = ref.time(0, doc, 0, 1, 2)
+        sample = f"{threads} threads x one {DOC_BYTES >> 20} MiB stage1 call per round, best of {args.steps} rounds ({wall:.1f} s wall); 1 thread: {len(doc)/one/1e9:.2f} GB/s"
+    else:
+        port = O.Port()
+        kind, name, threads = "port", "oracle port (scalar C)", 1
+        t0 = time.perf_counter()
+        r = port.stage1(doc[: 16 << 20], 0)
+        best = time.perf_counter() - t0
+        gbs = (16 << 20) / best / 1e9
+        err = r.err
+        sample = "1 thread x 16 MiB prefix of the document, one pass"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(gbs, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(best * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "synthetic 64 MiB random-structure JSON, stage1 (CPU reference, %s kernel)" % name, "bytes_per_call": DOC_BYTES, "threads": threads},
+        "cpu_baseline": {"value": round(gbs, 3), "unit": UNIT, "cores": threads, "kind": kind, "sample": sample, "error_code": err},
+        "e2e": {"value": round(gbs, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# =============================================================================== our arm
+def run_ours(args, rank, world):
+    import torch
+    import torch.distributed as dist
+
+    import simdjson_b200 as sj
+    from simdjson_b200 import capi
+
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    impl = sj.get_active_implementation(local)
+    L = sj.lib()
+
+    # ---- workload: ROTATE distinct documents per rank, resident in HBM before the timed region
+    docs = [make_doc(rank * ROTATE + k) for k in range(ROTATE)]
+    # (N>1: rank r's document is shard r of the stream doc_0 doc_1 ... doc_{N-1}; every shard is a complete document)
+    d_docs = [torch.from_numpy(d.copy()).to(dev) for d in docs]
+    pinned = [torch.from_numpy(d.copy()).pin_memory() for d in docs]
+    parsers = []
+    for _ in range(2):  # two parser contexts so one call is always queued behind the other (no idle GPU between steps)
+        rc, p = impl.create_dom_parser_implementation(DOC_BYTES)
+        if rc != sj.SUCCESS:
+            raise RuntimeError("create_dom_parser_implementation failed: " + capi.ERROR_NAMES.get(rc, str(rc)))
+        p.set_option("time_kernel", 1)
+        p.device_index_buffer(DOC_BYTES)
+        parsers.append(p)
+    stream = torch.cuda.current_stream()
+    gather_in = torch.zeros(4, dtype=torch.int64, device=dev)
+    gather_out = torch.zeros(4 * world, dtype=torch.int64, device=dev) if world > 1 else None
+
+    kernel_ms, n_struct = [], []
+
+    def step_enqueue(i):
+        p = parsers[i % 2]
+        if world == 1:
+            rc = p.stage1_device_enqueue(d_docs[i % ROTATE], sj.REGULAR, stream=stream)
+            assert rc == 0
+        return p
+
+    def step_finish(i, p):
+        if world == 1:
+            rc = p.stage1_device_finish()
+            if rc != sj.SUCCESS:
+                raise RuntimeError("stage1 failed: " + capi.ERROR_NAMES.get(rc, str(rc)) + " " + p.last_cuda_error())
+            return p.n_structural_indexes
+        return None
+
+    def sharded_step(i):
+        """one sharded pass: scan with speculated state 0, exchange, re-scan if the speculation was wrong"""
+        p = parsers[i % 2]
+        rc, res = p.stage1_shard_device(d_docs[i % ROTATE], 0, rank == world - 1, stream=stream)
+        if rc != 0:
+            raise RuntimeError("shard scan failed")
+        gather_in[0], gather_in[1], gather_in[2] = int(res.ttable), int(res.count), int(res.flags)
+        dist.all_gather_into_tensor(gather_out, gather_in)
+        g = gather_out.view(world, 4).cpu().numpy()
+        tts = (C.c_uint32 * world)(*[int(x) for x in g[:, 0]])
+        state_in = L.sjb200_fold_state(tts, rank)
+        if state_in != 0:  # wrong speculation: scan again with the true state, then publish the corrected count
+            rc, res = p.stage1_shard_device(d_docs[i % ROTATE], state_in, rank == world - 1, stream=stream)
+            gather_in[1] = int(res.count)
+        if np.any([L.sjb200_fold_state(tts, r) != 0 for r in range(world)]):
+            dist.all_gather_into_tensor(gather_out, gather_in)
+            g = gather_out.view(world, 4).cpu().numpy()
+        base = int(g[:rank, 1].sum())  # global index base of this shard (indexes stay shard-relative + base)
+        return int(res.count), base
+
+    def run_steps(k, record):
+        t_ev0, t_ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t_ev0.record(stream)
+        if world == 1:
+            inflight = step_enqueue(0)
+            for i in range(k):
+                nxt = step_enqueue(i + 1) if i + 1 < k else None
+                n = step_finish(i, inflight)
+                if record:
+                    kernel_ms.append(inflight.get_stat("kernel_ms"))
+                    n_struct.append(n)
+                inflight = nxt
+        else:
+            for i in range(k):
+                n, _base = sharded_step(i)
+                if record:
+                    kernel_ms.append(parsers[i % 2].get_stat("kernel_ms"))
+                    n_struct.append(n)
+        t_ev1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        return t_ev0.elapsed_time(t_ev1)
+
+    launches0 = sum(p.get_stat("launches") for p in parsers)
+    run_steps(max(3, args.warmup), False)
+    launches1 = sum(p.get_stat("launches") for p in parsers)
+    with ClockSampler(local) as clocks:
+        total_ms = run_steps(args.steps, True)
+    launches2 = sum(p.get_stat("launches") for p in parsers)
+    _ = launches0
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * DOC_BYTES / (ms_per_step * 1e-3) / 1e9
+
+    # ---- e2e through the host-pointer C-ABI call (pinned host input; H2D + D2H inside the timed region)
+    p = parsers[0]
+    hosts = [x.numpy() for x in pinned]
+    for i in range(3):
+        p.stage1(hosts[i % ROTATE], sj.REGULAR)
+    e2e_steps = max(3, min(args.steps, 10))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e2e_n = 0
+    for i in range(e2e_steps):
+        rc = p.stage1(hosts[i % ROTATE], sj.REGULAR)
+        assert rc == 0, rc
+        e2e_n = p.n_structural_indexes
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * DOC_BYTES * e2e_steps / float(te.item()) / 1e9
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        kms = float(np.mean(kernel_ms))
+        nmean = float(np.mean(n_struct))
+        algo_bytes = DOC_BYTES + 4.0 * nmean + 12.0
+        achieved = algo_bytes / (kms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "synthetic 64 MiB random-structure JSON, stage1 index on 1xB200 (BASELINE.json configs[1])" if world == 1 else
+                       f"{world} x 64 MiB shards of one random-structure JSON stream, stage1 sharded by byte range + NCCL carry/offset all-gather",
+                       "bytes_per_gpu_per_step": DOC_BYTES, "mode": "regular" if world == 1 else "shard", "structurals_per_step": int(nmean),
+                       "l2": f"{ROTATE} distinct inputs used round-robin ({ROTATE * DOC_BYTES >> 20} MiB > 126 MB L2)",
+                       "pipelining": "two parser contexts, the next call is enqueued before the previous one is finished"},
+            "clocks": clocks.summary(),
+            "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": DOC_BYTES, "d2h_bytes_per_step": int(4 * e2e_n + 24), "steps": e2e_steps},
+            "gpu_launches": int(launches2 - launches1),
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                         "peak_source": peak_src, "kernel": "sjb200::scan_kernel<kIndex>", "kernel_ms": round(kms, 5), "algorithmic_bytes": int(algo_bytes),
+                         "input_gbs_kernel_only": round(DOC_BYTES / (kms * 1e-3) / 1e9, 1)},
+        }
+        line["cpu_baseline"] = cpu_baseline(docs[0])
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(doc):
+    """rank 0, N=1 style bounded sample of the reference's CPU stage 1 on this host"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    cores = os.cpu_count() or 1
+    if O.have_ref():
+        ref = O.Ref("")
+        one, _ = ref.time(0, doc, 0, 1, 3)
+        threads = max(1, min(cores, int(os.environ.get("SJB200_REF_THREADS", cores))))
+        many, _ = ref.time(0, doc, 0, threads, 3)
+        return {"value": round(threads * len(doc) / many / 1e9, 3), "unit": UNIT, "cores": threads, "kind": "reference",
+                "sample": f"{ref.name} kernel; {threads} threads x one 64 MiB stage1 call, best of 3 rounds; single thread: {len(doc)/one/1e9:.2f} GB/s"}
+    port = O.Port()
+    t0 = time.perf_counter()
+    port.stage1(doc[: 16 << 20], 0)
+    dt = time.perf_counter() - t0
+    return {"value": round((16 << 20) / dt / 1e9, 3), "unit": UNIT, "cores": 1, "kind": "port", "sample": "scalar C port, 16 MiB prefix, one pass"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus and args.gpus > 1:
+        sys.stderr.write(f"bench.py: --gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})\n")
+    run_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -11,6 +11,6 @@ There is no CPU fallback anywhere in this package.
 from .capi import (CAPACITY, COMMA_DELIMITED_FINAL, COMMA_DELIMITED_PARTIAL, EMPTY, ERROR_NAMES, JSON_SEQUENCE_FINAL,  # noqa: F401
                    JSON_SEQUENCE_PARTIAL, MEMALLOC, REGULAR, STREAMING_FINAL, STREAMING_PARTIAL, SUCCESS, UNCLOSED_STRING,
                    UNESCAPED_CHARS, UNEXPECTED_ERROR, UNSUPPORTED_ARCHITECTURE, UTF8_ERROR)
-from .implementation import (dom_parser_implementation, get_active_implementation, implementation, minify, validate_utf8)  # noqa: F401
+from .implementation import (dom_parser_implementation, get_active_implementation, implementation, lib, minify, validate_utf8)  # noqa: F401
 
 __version__ = "0.1.0"

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsjb200.so")
+LIB_PATH = os.environ.get("SJB200_LIB") or os.path.join(_HERE, "libsjb200.so")  # SJB200_LIB: build variants for tuning
 
 # every symbol include/sjb200.h declares (checked by tests/test_abi.py)
 EXPORTS = [

@@ -60,6 +60,17 @@ SJ_HD uint32_t shl_in(uint32_t prev, uint32_t cur, int n) {
 #endif
 }
 
+// (a & m) | (b & ~m) -- one LOP3 (the compiler otherwise splits the two constant masks into two)
+SJ_HD uint32_t bitsel(uint32_t m, uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "r"(m));
+  return d;
+#else
+  return (a & m) | (b & ~m);
+#endif
+}
+
 // ------------------------------------------------------------- transpose
 // w[i] (i=0..7) holds input bytes 4i..4i+3 little-endian.  On return p[k] bit n
 // = bit k of byte n (n = 0..31).
@@ -75,11 +86,11 @@ SJ_HD void transpose32(const uint32_t w[8], uint32_t p[8]) {
   t2 = byte_perm(w[5], w[7], 0x5140); t3 = byte_perm(w[5], w[7], 0x7362);
   uint32_t a4 = byte_perm(t0, t2, 0x5410), a5 = byte_perm(t0, t2, 0x7632);
   uint32_t a6 = byte_perm(t1, t3, 0x5410), a7 = byte_perm(t1, t3, 0x7632);
-#define SJ_DSWAP(lo, hi, d, m)                                  \
-  {                                                             \
-    uint32_t nl = ((lo) & (m)) | (((hi) << (d)) & ~(m));        \
-    uint32_t nh = (((lo) >> (d)) & (m)) | ((hi) & ~(m));        \
-    lo = nl; hi = nh;                                           \
+#define SJ_DSWAP(lo, hi, d, m)                      \
+  {                                                 \
+    const uint32_t nl = bitsel(m, lo, (hi) << (d)); \
+    const uint32_t nh = bitsel(m, (lo) >> (d), hi); \
+    lo = nl; hi = nh;                               \
   }
   SJ_DSWAP(a0, a1, 1, 0x55555555u) SJ_DSWAP(a2, a3, 1, 0x55555555u)
   SJ_DSWAP(a4, a5, 1, 0x55555555u) SJ_DSWAP(a6, a7, 1, 0x55555555u)

@@ -23,6 +23,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+constexpr int kCarrySlots = 1024;
 constexpr size_t kMaxBytes = 0xFFFFFFFFull;  // SIMDJSON_MAXSIZE_BYTES (include/simdjson/base.h L23)
 
 struct PendingCall {
@@ -45,12 +46,13 @@ struct sjb200_ctx {
   size_t capacity = 0;
   cudaStream_t stream = nullptr;      // compute
   cudaStream_t copy_stream = nullptr; // H2D of the chunked host path
+  cudaStream_t out_stream = nullptr;  // D2H of finished chunks' output
   std::vector<cudaEvent_t> chunk_events;
   // scratch
   uint8_t *d_in = nullptr;    size_t d_in_bytes = 0;
   uint32_t *d_idx = nullptr;  size_t d_idx_words = 0;
   uint8_t *d_out = nullptr;   size_t d_out_bytes = 0;
-  Carry *d_carry = nullptr;   // [2] ping-pong
+  Carry *d_carry = nullptr;   // [kCarrySlots] one per chunk boundary of the chunked host pipeline
   uint32_t *d_flags = nullptr;
   uint32_t *d_ticket = nullptr;
   uint32_t *d_state_desc = nullptr;
@@ -58,14 +60,14 @@ struct sjb200_ctx {
   size_t desc_tiles = 0;
   uint8_t *d_chars = nullptr; size_t d_chars_bytes = 0;
   // pinned host mirrors
-  Carry *h_carry = nullptr;     // [2]
+  Carry *h_carry = nullptr;     // [kCarrySlots]
   uint32_t *h_flags = nullptr;
   uint8_t *h_small = nullptr;   // 64 B scratch
   uint8_t *h_chars = nullptr;   size_t h_chars_bytes = 0;
   uint32_t *h_window = nullptr; size_t h_window_words = 0;
   uint32_t epoch = 0;
   int grid[3] = {0, 0, 0};
-  long opt_use_tma = 1, opt_grid = 0, opt_chunk_bytes = 16 << 20, opt_time_kernel = 0;
+  long opt_use_tma = 1, opt_grid = 0, opt_chunk_bytes = 4 << 20, opt_time_kernel = 0;
   cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // around the scan kernel when opt_time_kernel is set
   bool ev_valid = false;
   unsigned long long launches = 0;               // kernels of ours launched by this context
@@ -186,7 +188,8 @@ int grid_for(sjb200_ctx *c, int kind, uint32_t ntiles) {
 // Enqueue the scan of document tiles [tile_begin, tile_begin+ntiles) of (d_buf,len).
 bool enqueue_scan(sjb200_ctx *c, int kind, const CUtensorMap *map, bool tma, const uint8_t *d_buf, size_t len, uint32_t tile_begin,
                   uint32_t ntiles, bool has_last_tile, uint32_t prev_word, uint32_t *d_idx, uint8_t *d_dst, int carry_in_slot,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, int carry_out_slot = -1) {
+  if (carry_out_slot < 0) carry_out_slot = carry_in_slot ^ 1;
   ScanParams p;
   memset(&p, 0, sizeof(p));
   p.buf = d_buf;
@@ -202,7 +205,7 @@ bool enqueue_scan(sjb200_ctx *c, int kind, const CUtensorMap *map, bool tma, con
   p.idx_out = d_idx;
   p.dst = d_dst;
   p.carry_in = c->d_carry + carry_in_slot;
-  p.carry_out = c->d_carry + (carry_in_slot ^ 1);
+  p.carry_out = c->d_carry + carry_out_slot;
   p.flags = c->d_flags;
   p.state_desc = c->d_state_desc;
   p.count_desc = c->d_count_desc;
@@ -326,11 +329,12 @@ extern "C" int sjb200_create(int device, size_t capacity, sjb200_ctx **out) {
   DeviceGuard g(device);
   bool good = ok(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "stream") &&
               ok(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "stream") &&
-              dev_alloc(c, &c->d_carry, 2, "cudaMalloc(carry)") && dev_alloc(c, &c->d_flags, 1, "cudaMalloc(flags)") &&
+              ok(c, cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking), "stream") &&
+              dev_alloc(c, &c->d_carry, kCarrySlots, "cudaMalloc(carry)") && dev_alloc(c, &c->d_flags, 1, "cudaMalloc(flags)") &&
               dev_alloc(c, &c->d_ticket, 2, "cudaMalloc(ticket)") &&
               ok(c, cudaMemset(c->d_ticket, 0, 2 * sizeof(uint32_t)), "memset ticket");
   void *hp = nullptr;
-  good = good && ok(c, cudaMallocHost(&hp, 2 * sizeof(Carry)), "cudaMallocHost");
+  good = good && ok(c, cudaMallocHost(&hp, kCarrySlots * sizeof(Carry)), "cudaMallocHost");
   c->h_carry = static_cast<Carry *>(hp);
   good = good && ok(c, cudaMallocHost(&hp, sizeof(uint32_t)), "cudaMallocHost");
   c->h_flags = static_cast<uint32_t *>(hp);
@@ -373,6 +377,7 @@ extern "C" void sjb200_destroy(sjb200_ctx *c) {
   for (auto e : c->chunk_events) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->out_stream) cudaStreamDestroy(c->out_stream);
   delete c;
 }
 
@@ -609,12 +614,18 @@ bool ensure_output(sjb200_ctx *c, size_t len) {
   return true;
 }
 
-// Copy the document to the device chunk by chunk and chain one scan launch per chunk behind its copy:
-// the scan of chunk k overlaps the H2D copy of chunk k+1.  Returns the carry slot with the final state.
-bool scan_host_document(sjb200_ctx *c, int kind, const uint8_t *buf, size_t len, uint32_t *d_idx, uint8_t *d_dst, int *final_slot) {
-  const size_t chunk = size_t(c->opt_chunk_bytes);
+// The host-pointer pipeline.  The document goes to the device chunk by chunk; one scan launch per chunk is
+// chained behind its copy (scanner state and output offset travel through d_carry[k] -> d_carry[k+1]); and as
+// soon as a chunk's launch has finished, the output it produced (indexes / minified bytes) starts its way
+// back while later chunks are still being copied in and scanned:  H2D(k+1) | scan(k) | D2H(k-1).
+// elt = bytes per output element (4 for indexes, 1 for minify, 0 = no output to bring back).
+bool scan_host_document(sjb200_ctx *c, int kind, const uint8_t *buf, size_t len, uint32_t *d_idx, uint8_t *d_dst, void *host_out,
+                        size_t elt, int *final_slot) {
+  size_t chunk = size_t(c->opt_chunk_bytes);
+  const size_t min_chunk = ((len / (kCarrySlots - 2)) / kTileBytes + 1) * kTileBytes;  // at most kCarrySlots-1 chunks
+  if (chunk < min_chunk) chunk = min_chunk;
   const size_t nchunks = (len + chunk - 1) / chunk;
-  while (c->chunk_events.size() < nchunks) {
+  while (c->chunk_events.size() < 2 * nchunks) {
     cudaEvent_t e;
     if (!ok(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event")) return false;
     c->chunk_events.push_back(e);
@@ -622,23 +633,41 @@ bool scan_host_document(sjb200_ctx *c, int kind, const uint8_t *buf, size_t len,
   CUtensorMap map;
   bool tma = false;
   make_tensor_map(c, &map, c->d_in, len, &tma);
-  if (!reset_document_state(c, c->stream)) return false;
-  // the copy stream must not overwrite d_in while an earlier call's kernels still read it: calls are synchronous, so it is idle
-  int slot = 0;
+  if (!ok(c, cudaMemsetAsync(c->d_flags, 0, sizeof(uint32_t), c->stream), "memset flags") ||
+      !ok(c, cudaMemsetAsync(c->d_carry, 0, sizeof(Carry), c->stream), "memset carry"))
+    return false;
+  // calls are synchronous, so no earlier kernel still reads d_in when the first copy lands
   for (size_t k = 0; k < nchunks; k++) {
     const size_t off = k * chunk;
     const size_t bytes = std::min(chunk, len - off);
-    if (!ok(c, cudaMemcpyAsync(c->d_in + off, buf + off, bytes, cudaMemcpyHostToDevice, c->copy_stream), "H2D chunk")) return false;
-    if (!ok(c, cudaEventRecord(c->chunk_events[k], c->copy_stream), "event record")) return false;
-    if (!ok(c, cudaStreamWaitEvent(c->stream, c->chunk_events[k], 0), "wait event")) return false;
-    const uint32_t tile_begin = uint32_t(off / kTileBytes);
-    const uint32_t ntiles = tiles_of(bytes);
+    cudaEvent_t copied = c->chunk_events[2 * k], scanned = c->chunk_events[2 * k + 1];
+    if (!ok(c, cudaMemcpyAsync(c->d_in + off, buf + off, bytes, cudaMemcpyHostToDevice, c->copy_stream), "H2D chunk") ||
+        !ok(c, cudaEventRecord(copied, c->copy_stream), "event record") || !ok(c, cudaStreamWaitEvent(c->stream, copied, 0), "wait event"))
+      return false;
     const bool last = (k + 1 == nchunks);
-    if (!enqueue_scan(c, kind, &map, tma, c->d_in, len, tile_begin, ntiles, last, 0x20202020u, d_idx, d_dst, slot, c->stream)) return false;
-    slot ^= 1;
+    if (!enqueue_scan(c, kind, &map, tma, c->d_in, len, uint32_t(off / kTileBytes), tiles_of(bytes), last, 0x20202020u, d_idx, d_dst, int(k),
+                      c->stream, int(k + 1)))
+      return false;
+    if (!ok(c, cudaMemcpyAsync(c->h_carry + k + 1, c->d_carry + k + 1, sizeof(Carry), cudaMemcpyDeviceToHost, c->stream), "D2H carry") ||
+        !ok(c, cudaEventRecord(scanned, c->stream), "event record"))
+      return false;
   }
-  *final_slot = slot;
-  return fetch_result(c, c->stream);
+  if (!ok(c, cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream), "D2H flags")) return false;
+  // drain: bring each chunk's output back as soon as that chunk is done
+  uint64_t have = 0;
+  for (size_t k = 0; k < nchunks; k++) {
+    if (!ok(c, cudaEventSynchronize(c->chunk_events[2 * k + 1]), "event sync")) return false;
+    const uint64_t upto = c->h_carry[k + 1].count;
+    if (elt && host_out && upto > have) {
+      const uint8_t *src = (kind == kIndex) ? reinterpret_cast<const uint8_t *>(d_idx) : d_dst;
+      if (!ok(c, cudaMemcpyAsync(static_cast<uint8_t *>(host_out) + have * elt, src + have * elt, size_t(upto - have) * elt,
+                                 cudaMemcpyDeviceToHost, c->out_stream), "D2H output"))
+        return false;
+      have = upto;
+    }
+  }
+  *final_slot = int(nchunks);
+  return ok(c, cudaStreamSynchronize(c->stream), "sync") && ok(c, cudaStreamSynchronize(c->out_stream), "sync");
 }
 
 }  // namespace
@@ -656,21 +685,12 @@ extern "C" int sjb200_stage1(sjb200_ctx *c, const uint8_t *buf, size_t len, int 
   DeviceGuard g(c->device);
   if (!ensure_input(c, len) || !ensure_index(c, len) || !ensure_desc(c, len)) return SJB200_MEMALLOC;
   int slot = 0;
-  if (!scan_host_document(c, kIndex, buf, len, c->d_idx, nullptr, &slot)) return SJB200_UNEXPECTED_ERROR;
-  if (!ok(c, cudaStreamSynchronize(c->stream), "sync")) return SJB200_UNEXPECTED_ERROR;
+  if (!scan_host_document(c, kIndex, buf, len, c->d_idx, nullptr, idx_out, sizeof(uint32_t), &slot)) return SJB200_UNEXPECTED_ERROR;
   FinishInput in;
   in.mode = mode; in.len = len;
   in.count = c->h_carry[slot].count;
   in.state = c->h_carry[slot].state;
   in.flags = *c->h_flags;
-  const bool unclosed = (in.state >> 1) & 1u;
-  const bool early = (in.flags & kFlagInternal) || (mode == SJB200_REGULAR && unclosed) || (in.flags & kFlagCtl);
-  if (!early && in.count > 0) {
-    // pageable destination: a plain synchronous copy of exactly the n indexes found
-    if (!ok(c, cudaMemcpyAsync(idx_out, c->d_idx, size_t(in.count) * 4, cudaMemcpyDeviceToHost, c->stream), "D2H idx") ||
-        !ok(c, cudaStreamSynchronize(c->stream), "sync"))
-      return SJB200_UNEXPECTED_ERROR;
-  }
   HostStructuralReader reader(buf, idx_out);
   HostIndexWriter writer(idx_out);
   bool dirty = false;
@@ -685,17 +705,11 @@ extern "C" int sjb200_minify(sjb200_ctx *c, const uint8_t *buf, size_t len, uint
   DeviceGuard g(c->device);
   if (!ensure_input(c, len) || !ensure_output(c, len) || !ensure_desc(c, len)) return SJB200_MEMALLOC;
   int slot = 0;
-  if (!scan_host_document(c, kMinify, buf, len, nullptr, c->d_out, &slot)) return SJB200_UNEXPECTED_ERROR;
-  if (!ok(c, cudaStreamSynchronize(c->stream), "sync")) return SJB200_UNEXPECTED_ERROR;
+  // the padded tail is never output, so at most len bytes are written to dst (json_minifier.h L79-95)
+  if (!scan_host_document(c, kMinify, buf, len, nullptr, c->d_out, dst, 1, &slot)) return SJB200_UNEXPECTED_ERROR;
   if (*c->h_flags & kFlagInternal) return SJB200_UNEXPECTED_ERROR;
   if ((c->h_carry[slot].state >> 1) & 1u) return SJB200_UNCLOSED_STRING;
-  const size_t kept = size_t(c->h_carry[slot].count);
-  if (kept > 0) {
-    if (!ok(c, cudaMemcpyAsync(dst, c->d_out, kept, cudaMemcpyDeviceToHost, c->stream), "D2H out") ||
-        !ok(c, cudaStreamSynchronize(c->stream), "sync"))
-      return SJB200_UNEXPECTED_ERROR;
-  }
-  *dst_len = kept;
+  *dst_len = size_t(c->h_carry[slot].count);
   return SJB200_SUCCESS;
 }
 
@@ -706,8 +720,7 @@ extern "C" int sjb200_validate_utf8(sjb200_ctx *c, const uint8_t *buf, size_t le
   DeviceGuard g(c->device);
   if (!ensure_input(c, len)) return 0;
   int slot = 0;
-  if (!scan_host_document(c, kUtf8, buf, len, nullptr, nullptr, &slot)) return 0;
-  if (!ok(c, cudaStreamSynchronize(c->stream), "sync")) return 0;
+  if (!scan_host_document(c, kUtf8, buf, len, nullptr, nullptr, nullptr, 0, &slot)) return 0;
   if (*c->h_flags & kFlagInternal) return 0;
   return (*c->h_flags & kFlagUtf8) ? 0 : 1;
 }

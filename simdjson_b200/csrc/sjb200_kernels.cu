@@ -104,6 +104,11 @@ __device__ __forceinline__ unsigned long long pack_count_desc(uint32_t epoch, ui
   return ((unsigned long long)epoch << 34) | ((unsigned long long)status << 32) | v;
 }
 
+// Both look-backs read kLook x 32 descriptors per round trip (kLook independent loads per lane):
+// with a few hundred tiles in flight the walk back to the nearest inclusive prefix is 1-3 round
+// trips instead of ~10.
+constexpr int kLook = 4;
+
 // Composition of the transducers of tiles [0, tile) (tile >= 1), by decoupled look-back.
 // Called by one full warp.
 __device__ uint32_t lookback_transducer(const ScanParams &p, uint32_t tile, int lane) {
@@ -111,42 +116,64 @@ __device__ uint32_t lookback_transducer(const ScanParams &p, uint32_t tile, int 
   bool haveF = false;
   int pos = int(tile) - 1;  // newest tile not yet folded in
   for (;;) {
-    const int j = pos - lane;
-    uint32_t status = kNone, T = 0;
-    if (j >= 0) {
-      uint32_t spins = 0;
-      for (;;) {
-        const uint32_t d = ld_relaxed_u32(p.state_desc + j);
-        if ((d >> 8) == p.epoch && (d & 3u) != kNone) {
-          status = d & 3u;
-          T = (d >> 2) & 63u;
-          break;
+    uint32_t status[kLook], T[kLook];
+    uint32_t pending = 0;
+#pragma unroll
+    for (int k = 0; k < kLook; k++) {
+      status[k] = kNone;
+      T[k] = 0;
+      if (pos - lane - 32 * k >= 0) pending |= 1u << k;
+    }
+    uint32_t spins = 0;
+    while (pending) {
+#pragma unroll
+      for (int k = 0; k < kLook; k++) {
+        if (pending & (1u << k)) {
+          const uint32_t d = ld_relaxed_u32(p.state_desc + (pos - lane - 32 * k));
+          if ((d >> 8) == p.epoch && (d & 3u) != kNone) {
+            status[k] = d & 3u;
+            T[k] = (d >> 2) & 63u;
+            pending &= ~(1u << k);
+          }
         }
+      }
+      if (pending) {
         if (++spins > kSpinLimit) {
           atomicOr(p.flags, kFlagInternal);
-          status = kInc;
-          break;
+#pragma unroll
+          for (int k = 0; k < kLook; k++)
+            if (pending & (1u << k)) status[k] = kInc;
+          pending = 0;
+        } else {
+          __nanosleep(20);
         }
-        __nanosleep(32);
       }
     }
-    const uint32_t incmask = __ballot_sync(kFull, status == kInc);
-    const int nvalid = min(32, pos + 1);
-    const int last = incmask ? (__ffs(incmask) - 1) : (nvalid - 1);  // oldest lane that takes part
-    // ordered reduction, lane 0 = newest:  R = T[0] o T[1] o ... o T[last]
-    uint32_t val = T;
-    bool valid = lane <= last;
+    bool found = false;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t oval = __shfl_down_sync(kFull, val, d);
-      const bool ovalid = __shfl_down_sync(kFull, valid ? 1 : 0, d) != 0 && (lane + d < 32);
-      if (valid && ovalid) val = tt_compose(val, oval);
+    for (int k = 0; k < kLook; k++) {
+      if (found) continue;                       // groups older than the inclusive prefix do not take part
+      const int gpos = pos - 32 * k;             // newest tile of this group of 32
+      if (gpos < 0) continue;
+      const uint32_t incmask = __ballot_sync(kFull, status[k] == kInc);
+      const int nvalid = min(32, gpos + 1);
+      const int last = incmask ? (__ffs(incmask) - 1) : (nvalid - 1);  // oldest lane that takes part
+      // ordered reduction, lane 0 = newest:  R = T[0] o T[1] o ... o T[last]
+      uint32_t val = T[k];
+      const bool valid = lane <= last;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t oval = __shfl_down_sync(kFull, val, d);
+        const bool ovalid = (lane + d <= last);
+        if (valid && ovalid) val = tt_compose(val, oval);
+      }
+      const uint32_t R = __shfl_sync(kFull, val, 0);
+      F = haveF ? tt_compose(F, R) : R;
+      haveF = true;
+      if (incmask || gpos - 31 <= 0) found = true;
     }
-    const uint32_t R = __shfl_sync(kFull, val, 0);
-    F = haveF ? tt_compose(F, R) : R;
-    haveF = true;
-    if (incmask || pos - 31 <= 0) break;
-    pos -= 32;
+    if (found) break;
+    pos -= 32 * kLook;
   }
   return F;
 }
@@ -156,34 +183,57 @@ __device__ uint32_t lookback_count(const ScanParams &p, uint32_t tile, int lane)
   uint32_t total = 0;
   int pos = int(tile) - 1;
   for (;;) {
-    const int j = pos - lane;
-    uint32_t status = kNone, v = 0;
-    if (j >= 0) {
-      uint32_t spins = 0;
-      for (;;) {
-        const unsigned long long d = ld_relaxed_u64(p.count_desc + j);
-        if (uint32_t(d >> 34) == p.epoch && (uint32_t(d >> 32) & 3u) != kNone) {
-          status = uint32_t(d >> 32) & 3u;
-          v = uint32_t(d);
-          break;
+    uint32_t status[kLook], v[kLook];
+    uint32_t pending = 0;
+#pragma unroll
+    for (int k = 0; k < kLook; k++) {
+      status[k] = kNone;
+      v[k] = 0;
+      if (pos - lane - 32 * k >= 0) pending |= 1u << k;
+    }
+    uint32_t spins = 0;
+    while (pending) {
+#pragma unroll
+      for (int k = 0; k < kLook; k++) {
+        if (pending & (1u << k)) {
+          const unsigned long long d = ld_relaxed_u64(p.count_desc + (pos - lane - 32 * k));
+          if (uint32_t(d >> 34) == p.epoch && (uint32_t(d >> 32) & 3u) != kNone) {
+            status[k] = uint32_t(d >> 32) & 3u;
+            v[k] = uint32_t(d);
+            pending &= ~(1u << k);
+          }
         }
+      }
+      if (pending) {
         if (++spins > kSpinLimit) {
           atomicOr(p.flags, kFlagInternal);
-          status = kInc;
-          break;
+#pragma unroll
+          for (int k = 0; k < kLook; k++)
+            if (pending & (1u << k)) status[k] = kInc;
+          pending = 0;
+        } else {
+          __nanosleep(20);
         }
-        __nanosleep(32);
       }
     }
-    const uint32_t incmask = __ballot_sync(kFull, status == kInc);
-    const int nvalid = min(32, pos + 1);
-    const int last = incmask ? (__ffs(incmask) - 1) : (nvalid - 1);
-    uint32_t x = (lane <= last) ? v : 0u;
+    bool found = false;
+    uint32_t x = 0;
+#pragma unroll
+    for (int k = 0; k < kLook; k++) {
+      if (found) continue;
+      const int gpos = pos - 32 * k;
+      if (gpos < 0) continue;
+      const uint32_t incmask = __ballot_sync(kFull, status[k] == kInc);
+      const int nvalid = min(32, gpos + 1);
+      const int last = incmask ? (__ffs(incmask) - 1) : (nvalid - 1);
+      if (lane <= last) x += v[k];
+      if (incmask || gpos - 31 <= 0) found = true;
+    }
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) x += __shfl_xor_sync(kFull, x, d);
     total += x;
-    if (incmask || pos - 31 <= 0) break;
-    pos -= 32;
+    if (found) break;
+    pos -= 32 * kLook;
   }
   return total;
 }
@@ -234,7 +284,10 @@ __device__ void refill_stage(uint8_t *tiles, Control *ctl, const CUtensorMap *tm
   uint32_t pw = p.prev_word;
   if (t > 0) {
     const uint8_t *q = p.buf + uint64_t(t) * kTileBytes - 4;
-    pw = uint32_t(q[0]) | (uint32_t(q[1]) << 8) | (uint32_t(q[2]) << 16) | (uint32_t(q[3]) << 24);
+    if ((reinterpret_cast<uintptr_t>(q) & 3u) == 0)
+      pw = __ldg(reinterpret_cast<const uint32_t *>(q));
+    else
+      pw = uint32_t(q[0]) | (uint32_t(q[1]) << 8) | (uint32_t(q[2]) << 16) | (uint32_t(q[3]) << 24);
   }
   ctl->stage_prev[s] = pw;
   if (p.use_tma && t < p.full_tiles) {
@@ -254,7 +307,7 @@ __device__ __forceinline__ void toggle_first_nonbackslash_quote(const uint32_t q
 
 // ------------------------------------------------------------------ the kernel
 template <int KIND>
-__global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
+__global__ void __launch_bounds__(kThreads, kMinCtasPerSm) scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   Control *ctl = reinterpret_cast<Control *>(tiles + kStages * kTileBytes);
@@ -504,15 +557,17 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
 
     // ============================ emit ============================
     if (KIND == kIndex) {
+      // one loop over the lane's 128 mask bits (not one per 32-bit word: the warp runs max-over-lanes iterations)
       uint32_t *dst = p.idx_out + (cin.count + base);
-      const uint32_t pos0 = p.pos_base + dtile * uint32_t(kTileBytes) + lane_off;
-#pragma unroll
-      for (int u = 0; u < W; u++) {
-        uint32_t m = out[u];
-        while (m) {
-          *dst++ = pos0 + 32 * u + (__ffs(m) - 1);
-          m &= m - 1;
+      uint32_t pos = p.pos_base + dtile * uint32_t(kTileBytes) + lane_off;
+      uint32_t m = out[0], m1 = out[1], m2 = out[2], m3 = out[3];
+      for (uint32_t left = cnt; left != 0; --left) {
+        while (m == 0) {  // at most three times per lane
+          m = m1; m1 = m2; m2 = m3; m3 = 0;
+          pos += 32;
         }
+        *dst++ = pos + (__ffs(m) - 1);
+        m &= m - 1;
       }
     } else {
       uint8_t *dst = p.dst + (cin.count + base);

@@ -120,6 +120,8 @@ class dom_parser_implementation:
     # -- stage 1, input already in HBM (torch uint8 CUDA tensor); indexes stay on the device
     def device_index_buffer(self, nbytes=None):
         import torch
+        if nbytes is None and self._d_idx is not None:
+            return self._d_idx  # the buffer the last device-resident call wrote
         words = lib().sjb200_index_words(self._capacity if nbytes is None else nbytes)
         if self._d_idx is None or self._d_idx.numel() < words:
             self._d_idx = torch.empty(words, dtype=torch.int32, device=f"cuda:{self._device}")

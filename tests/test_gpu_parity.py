@@ -268,7 +268,7 @@ def test_chunked_host_pipeline_carries(port):
 def test_sharded_scan_matches_single_scan(port):
     """section 8(e): byte-range shards + a fold of 6-bit transducers == one scan of the whole buffer"""
     import torch
-    L = sj.implementation.lib()
+    L = sj.lib()
     rng = random.Random(4242)
     rc, p = sj.get_active_implementation().create_dom_parser_implementation(4 << 20)
     assert rc == 0

@@ -1,4 +1,5 @@
-"""First-contact GPU probe: correctness spot checks + kernel timings (diagnostic, not the bench)."""
+"""GPU probe: kernel timings of the three scans on the 64 MiB bench document (diagnostic, not the bench).
+SJB200_LIB selects a build variant; PROBE_BYTES the size; PROBE_TMA=0 the plain-load path."""
 import json
 import os
 import sys
@@ -14,56 +15,48 @@ import oracle_lib as O  # noqa: E402
 import simdjson_b200 as sj  # noqa: E402
 from simdjson_b200 import corpus  # noqa: E402
 
-out = {}
+tag = os.path.basename(os.environ.get("SJB200_LIB", "default"))
 port = O.Port()
 impl = sj.get_active_implementation()
 size = int(os.environ.get("PROBE_BYTES", 64 << 20))
-doc = corpus.random_json(size)
+doc = corpus.random_json(size).copy()
 want = port.stage1(doc, 0)
 rc, p = impl.create_dom_parser_implementation(len(doc))
 assert rc == 0, rc
 p.set_option("time_kernel", 1)
+p.set_option("use_tma", int(os.environ.get("PROBE_TMA", 1)))
+if os.environ.get("PROBE_GRID"):
+    p.set_option("grid", int(os.environ["PROBE_GRID"]))
 d = torch.from_numpy(doc).cuda()
 dst = torch.empty(len(doc), dtype=torch.uint8, device="cuda")
-for tma in (1, 0):
-    p.set_option("use_tma", tma)
-    t0 = time.time()
-    rc = p.stage1_device(d, 0)
-    dt = time.time() - t0
-    got = p.device_index_buffer().cpu().numpy().view(np.uint32)
-    okk = rc == want.err and p.n_structural_indexes == want.n and np.array_equal(got[: want.n + 3], want.words())
-    print(f"stage1 tma={tma}: rc={rc} n={p.n_structural_indexes} want={want.n} parity={okk} first_call={dt*1e3:.2f} ms err='{p.last_cuda_error()}'", flush=True)
-    best = {}
-    for kind in ("stage1", "minify", "utf8"):
-        ts = []
-        for it in range(8):
-            if kind == "stage1":
-                rc = p.stage1_device(d, 0)
-            elif kind == "minify":
-                rc, dl = p.minify_device(d, dst)
-            else:
-                rc = p.validate_utf8_device(d)
-            ts.append(p.get_stat("kernel_ms"))
-        best[kind] = min(ts[2:])
-        print(f"  {kind:7s} tma={tma} kernel_ms best={best[kind]:.4f} median={sorted(ts)[len(ts)//2]:.4f}  -> {len(doc)/best[kind]/1e6:.1f} GB/s in (rc={rc})", flush=True)
-    out[f"tma{tma}"] = best
-werr, wout = port.minify(doc)
-rc, dl = p.minify_device(d, dst)
-print("minify parity:", rc == werr and bytes(dst[:dl].cpu().numpy()) == wout)
-print("utf8:", p.validate_utf8_device(d), port.validate_utf8(doc))
-u = corpus.random_utf8(size)
-du = torch.from_numpy(u).cuda()
+rc = p.stage1_device(d, 0)
+got = p.device_index_buffer().cpu().numpy().view(np.uint32)
+okk = rc == want.err and p.n_structural_indexes == want.n and np.array_equal(got[: want.n + 3], want.words())
+res = {"tag": tag, "parity": bool(okk), "grid": p.get_stat("grid_index")}
+for kind in ("stage1", "minify", "utf8"):
+    ts = []
+    for it in range(10):
+        if kind == "stage1":
+            rc = p.stage1_device(d, 0)
+        elif kind == "minify":
+            rc, dl = p.minify_device(d, dst)
+        else:
+            rc = p.validate_utf8_device(d)
+        ts.append(p.get_stat("kernel_ms"))
+    res[kind] = {"best_ms": min(ts[2:]), "median_ms": sorted(ts[2:])[len(ts[2:]) // 2], "gbs": len(doc) / min(ts[2:]) / 1e6}
+u = torch.from_numpy(corpus.random_utf8(size)).cuda()
 ts = []
 for it in range(6):
-    r = p.validate_utf8_device(du)
+    r = p.validate_utf8_device(u)
     ts.append(p.get_stat("kernel_ms"))
-print(f"utf8 (53% non-ascii) valid={r} kernel_ms best={min(ts[1:]):.4f} -> {len(u)/min(ts[1:])/1e6:.1f} GB/s")
-# host path
+res["utf8_dense"] = {"best_ms": min(ts[1:]), "gbs": size / min(ts[1:]) / 1e6}
 pin = torch.from_numpy(doc).pin_memory()
 hb = pin.numpy()
-for it in range(3):
-    t0 = time.time(); rc = p.stage1(hb, 0); dt = time.time() - t0
-    print(f"host-path stage1: rc={rc} n={p.n_structural_indexes} {dt*1e3:.2f} ms -> {len(doc)/dt/1e9:.2f} GB/s e2e")
-print("grid:", p.get_stat("grid_index"), "sms:", p.get_stat("sm_count"))
+hs = []
+for it in range(4):
+    t0 = time.time(); rc = p.stage1(hb, 0); hs.append(time.time() - t0)
+res["host_path_gbs"] = len(doc) / min(hs) / 1e9
+print(json.dumps(res), flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(out, open(os.path.join(ROOT, "gpurun_out", "probe.json"), "w"))
+with open(os.path.join(ROOT, "gpurun_out", "probe.jsonl"), "a") as f:
+    f.write(json.dumps(res) + "\n")
