@@ -173,7 +173,8 @@ def run_ours(args, rank, world):
         p.set_option("time_kernel", 1)
         p.device_index_buffer(DOC_BYTES)
         parsers.append(p)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)  # one explicit stream for both parser contexts: their launches serialise
+    torch.cuda.set_stream(stream)
     gather_in = torch.zeros(4, dtype=torch.int64, device=dev)
     gather_out = torch.zeros(4 * world, dtype=torch.int64, device=dev) if world > 1 else None
 

@@ -87,6 +87,11 @@ SJB200_API int sjb200_set_option(sjb200_ctx *ctx, const char *key, long value);
  * "grid_index", "sm_count"; negative when unavailable */
 SJB200_API double sjb200_get_stat(sjb200_ctx *ctx, const char *key);
 
+/* page-lock / unlock caller-owned host memory (e.g. the parser's `new uint32_t[]` index array, whose deleter the
+ * reference fixes: internal/dom_parser_implementation.h L175) so copies to it run at full PCIe speed; best effort */
+SJB200_API int sjb200_pin_host_memory(sjb200_ctx *ctx, void *ptr, size_t bytes);
+SJB200_API int sjb200_unpin_host_memory(sjb200_ctx *ctx, void *ptr);
+
 /* ---- host-pointer entry points (copy in, scan, copy out).
  * idx_out: at least sjb200_index_words(capacity) words; on success and on UTF8_ERROR / EMPTY(after scan)
  * it holds n indexes followed by the reference's three sentinel words.  *n_inout is the parser's

@@ -270,6 +270,38 @@ SJ_HD uint32_t tt_compose(uint32_t newer, uint32_t older) {
 // a chunk whose outgoing state is the constant `state` (used to seed look-back with an inclusive prefix)
 SJ_HD uint32_t tt_const(uint32_t state) { return (state & 7) | ((state & 7) << 3); }
 
+// ------------------------------------------------ boundary state from the bytes before a tile
+// Two of the three scanner-state bits entering a tile can be read off the bytes just before it:
+//   e = the tile's first byte is escaped      <=> an odd-length backslash run ends at byte -1
+//   c = byte -1 is a "non-quote scalar"       (json_scanner.h L148-149: scalar and not an unescaped quote)
+// p16[0..3] are the 16 bytes before the tile, little-endian words (byte -1 is the top byte of p16[3]).
+// Returns bit0 e, bit2 c (same positions as the scanner state) and bit3 = UNKNOWN when the backslash
+// run reaches the start of the 16 bytes (then only the look-back chain knows; the caller handles it).
+// Only the third bit, in_string, genuinely needs the whole prefix.
+SJ_HD uint32_t boundary_state_from_prev16(const uint32_t p16[4]) {
+  auto byte_at = [&](int back) -> uint32_t {  // back = 1..16 : byte -back
+    const int i = 16 - back;
+    return (p16[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+  };
+  const uint32_t last = byte_at(1);
+  int run_from = (last == '"') ? 2 : 1;  // a quote's own status depends on the run before it
+  int run = 0;
+  while (run_from + run <= 16 && byte_at(run_from + run) == '\\') run++;
+  const bool unknown = (run_from + run > 16);
+  const uint32_t odd = run & 1;
+  uint32_t e, c;
+  if (last == '"') {
+    e = 0;        // a quote never escapes what follows
+    c = odd;      // escaped quote = scalar byte; real quote = not
+  } else {
+    e = odd;      // run ending at byte -1 (run == 0 when byte -1 is not a backslash)
+    const bool ws = last == 0x20 || last == 0x09 || last == 0x0A || last == 0x0D;
+    const bool op = last == 0x2C || last == 0x3A || last == 0x5B || last == 0x5D || last == 0x7B || last == 0x7D || last == 0x0C || last == 0x1A;
+    c = (ws || op) ? 0u : 1u;
+  }
+  return e | (c << 2) | (unknown ? 8u : 0u);
+}
+
 // Resolve the escape carries of 32 consecutive lane chunks at once.
 //   G bit i: lane i ends with an unescaped backslash (evaluated with carry-in 0)
 //   P bit i: lane i is all backslashes (its carry-out equals its carry-in)

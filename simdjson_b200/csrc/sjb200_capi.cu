@@ -398,6 +398,17 @@ extern "C" size_t sjb200_capacity(const sjb200_ctx *c) { return c ? c->capacity 
 extern "C" int sjb200_device(const sjb200_ctx *c) { return c ? c->device : -1; }
 extern "C" const char *sjb200_last_cuda_error(const sjb200_ctx *c) { return c ? c->last_error.c_str() : ""; }
 
+extern "C" int sjb200_pin_host_memory(sjb200_ctx *c, void *ptr, size_t bytes) {
+  if (!c || !ptr || bytes == 0) return SJB200_UNEXPECTED_ERROR;
+  DeviceGuard g(c->device);
+  return ok(c, cudaHostRegister(ptr, bytes, cudaHostRegisterPortable), "cudaHostRegister") ? SJB200_SUCCESS : SJB200_MEMALLOC;
+}
+extern "C" int sjb200_unpin_host_memory(sjb200_ctx *c, void *ptr) {
+  if (!c || !ptr) return SJB200_UNEXPECTED_ERROR;
+  DeviceGuard g(c->device);
+  return ok(c, cudaHostUnregister(ptr), "cudaHostUnregister") ? SJB200_SUCCESS : SJB200_UNEXPECTED_ERROR;
+}
+
 extern "C" double sjb200_get_stat(sjb200_ctx *c, const char *key) {
   if (!c || !key) return -1.0;
   if (!strcmp(key, "kernel_ms")) {  // duration of the last scan kernel (needs option time_kernel=1 and a finished call)

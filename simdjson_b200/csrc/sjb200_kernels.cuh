@@ -17,10 +17,10 @@ constexpr int kThreads = 32 * kWarps;
 constexpr int kTileBytes = kWarps * kWarpBytes;      // 32 KiB
 constexpr int kTileRows = kTileBytes / 128;          // 256 rows of 128 B (max TMA box dim)
 #ifndef SJB200_STAGES
-#define SJB200_STAGES 1
+#define SJB200_STAGES 2
 #endif
 #ifndef SJB200_MIN_CTAS
-#define SJB200_MIN_CTAS 4
+#define SJB200_MIN_CTAS 3
 #endif
 constexpr int kStages = SJB200_STAGES;      // shared-memory tile buffers per CTA
 constexpr int kMinCtasPerSm = SJB200_MIN_CTAS;  // __launch_bounds__ occupancy target

@@ -70,8 +70,14 @@ class dom_parser_implementation:
 
     def close(self):
         if self._ctx:
+            self._unpin()
             lib().sjb200_destroy(self._ctx)
             self._ctx = C.c_void_p()
+
+    def _unpin(self):
+        if getattr(self, "_pinned", False) and self.structural_indexes is not None:
+            lib().sjb200_unpin_host_memory(self._ctx, self.structural_indexes.ctypes.data)
+        self._pinned = False
 
     def __del__(self):
         try:
@@ -81,9 +87,12 @@ class dom_parser_implementation:
 
     def _after_capacity(self, capacity):
         self._capacity = capacity
+        self._unpin()
         words = lib().sjb200_index_words(capacity)
         self.structural_indexes = np.zeros(words, dtype=np.uint32)
         self.structural_indexes[0] = 0
+        # page-lock the index array like the C++ plug-in does, so the D2H of the indexes runs at PCIe speed
+        self._pinned = lib().sjb200_pin_host_memory(self._ctx, self.structural_indexes.ctypes.data, words * 4) == SUCCESS
         self.n_structural_indexes = 0
         self._d_idx = None
 

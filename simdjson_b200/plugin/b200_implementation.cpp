@@ -64,6 +64,7 @@ const implementation *get_implementation(int device) noexcept {
 
 // ---------------------------------------------------------------- dom_parser_implementation
 dom_parser_implementation::~dom_parser_implementation() {
+  if (ctx_ && pinned_) sjb200_unpin_host_memory(ctx_, pinned_);
   if (ctx_) sjb200_destroy(ctx_);
 }
 
@@ -76,11 +77,15 @@ error_code dom_parser_implementation::set_capacity(size_t capacity) noexcept {
   // same contract as generic/dom_parser_implementation.h L66-82
   if (capacity > SIMDJSON_MAXSIZE_BYTES) return CAPACITY;
   const size_t words = SIMDJSON_ROUNDUP_N(capacity, 64) + 9;
+  if (ctx_ && pinned_) { sjb200_unpin_host_memory(ctx_, pinned_); pinned_ = nullptr; }
   structural_indexes.reset(new (std::nothrow) uint32_t[words]);
   if (!structural_indexes) { _capacity = 0; return MEMALLOC; }
   structural_indexes[0] = 0;
   n_structural_indexes = 0;
   if (auto err = ensure_context(capacity)) { _capacity = 0; return err; }
+  // the array must stay a plain new[] block (callers own it through unique_ptr<uint32_t[]>); page-lock it in place so
+  // the index copy-back runs at PCIe speed (best effort: a failure only costs bandwidth)
+  if (sjb200_pin_host_memory(ctx_, structural_indexes.get(), words * sizeof(uint32_t)) == SJB200_SUCCESS) pinned_ = structural_indexes.get();
   _capacity = capacity;
   return SUCCESS;
 }

@@ -72,6 +72,7 @@ class dom_parser_implementation final : public internal::dom_parser_implementati
   const uint8_t *buf_{nullptr};
   size_t len_{0};
   uint64_t gpu_calls_{0};
+  void *pinned_{nullptr};  // the index array while it is page-locked
 };
 
 // the singleton to assign to simdjson::get_active_implementation()

@@ -19,7 +19,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <random>
+#include <type_traits>
 #include <vector>
 
 extern "C" {
@@ -182,12 +184,226 @@ struct Emul {
   }
 };
 
+// ---------------------------------------------------------------------------------------------------
+// v2 data flow: ONE look-back chain.  The tile's e / c state bits come from the 16 bytes before it
+// (boundary_state_from_prev16), masks and counts are produced for BOTH in-string polarities before the
+// chain is consulted, and the chain element is {T, cnt[0], cnt[1]}.  A tile whose boundary state is
+// unknown (>= 16 backslashes right before it) publishes no aggregate, waits for exact state and redoes
+// its final-mask phase.  `window` controls how many predecessors are presented as un-finished
+// (aggregate only) to the look-back, like tiles in flight on the GPU.
 template <int W, int NWARPS>
+struct Emul2 {
+  static constexpr int LANE_BYTES = 32 * W;
+  static constexpr int WARP_BYTES = 32 * LANE_BYTES;
+  static constexpr int TILE_BYTES = NWARPS * WARP_BYTES;
+  struct Lane {
+    uint32_t bs[W], qu[W], op[W], sc[W], ctl[W];
+    uint32_t qr[W], pm[W], x0[W], in0[W];
+    int nlead; bool allbs;
+  };
+  struct Desc { bool has_agg = false, inc = false; uint32_t T = 0, cnt[2] = {0, 0}; uint32_t Tp = 0; uint64_t C = 0; bool first = false; };
+
+  const uint8_t *buf; size_t len;
+  uint32_t state0 = 0;  // scanner state entering the buffer
+  int window = 0;
+  std::vector<uint32_t> idx;
+  std::vector<uint8_t> minified;
+  bool utf8_err = false, ctl_err = false, unclosed = false;
+  int redo_count = 0;
+  std::mt19937_64 rng{12345};
+
+  uint8_t byte_at(long pos) const { return (pos >= 0 && size_t(pos) < len) ? buf[pos] : 0x20; }
+  uint32_t word_at(long pos) const {
+    return uint32_t(byte_at(pos)) | (uint32_t(byte_at(pos + 1)) << 8) | (uint32_t(byte_at(pos + 2)) << 16) | (uint32_t(byte_at(pos + 3)) << 24);
+  }
+  static void toggle(Lane &L) {
+    if (L.allbs) return;
+    const int k = L.nlead;
+    L.qr[k >> 5] ^= L.qu[k >> 5] & (1u << (k & 31));
+  }
+
+  void run() {
+    const size_t ntiles = (len + TILE_BYTES - 1) / TILE_BYTES;
+    std::vector<Desc> desc(ntiles);
+    std::vector<Lane> lanes(NWARPS * 32);
+    for (size_t t = 0; t < ntiles; t++) {
+      const long tile_start = long(t) * TILE_BYTES;
+      uint32_t warpT[NWARPS], Pmask[NWARPS];
+      // ---- phases 1+2 (as v1)
+      for (int w = 0; w < NWARPS; w++) {
+        uint32_t planes[32][W][8];
+        utf8_carry uc[32];
+        for (int l = 0; l < 32; l++) {
+          const long base = tile_start + long(w) * WARP_BYTES + long(l) * LANE_BYTES;
+          Lane &L = lanes[w * 32 + l];
+          for (int u = 0; u < W; u++) {
+            uint32_t words[8];
+            for (int i = 0; i < 8; i++) words[i] = word_at(base + 32 * u + 4 * i);
+            transpose32(words, planes[l][u]);
+            unit_classes c = classify(planes[l][u]);
+            L.bs[u] = c.bs; L.qu[u] = c.qu; L.op[u] = c.op; L.sc[u] = c.sc; L.ctl[u] = c.ctl;
+          }
+          uc[l] = utf8_carry_from_prev_word(word_at(base - 4));
+        }
+        for (int u = 0; u < W; u++) {
+          bool any = false;
+          for (int l = 0; l < 32; l++) any |= (planes[l][u][7] != 0) || utf8_carry_pending(uc[l]);
+          for (int l = 0; l < 32; l++) {
+            if (any) { if (utf8_check_unit(planes[l][u], uc[l])) utf8_err = true; } else uc[l] = utf8_carry_zero();
+          }
+        }
+        uint32_t G = 0, P = 0;
+        for (int l = 0; l < 32; l++) {
+          Lane &L = lanes[w * 32 + l];
+          uint32_t escaped[W];
+          uint32_t eo = escape_scan<W>(L.bs, escaped);
+          L.nlead = leading_backslashes<W>(L.bs);
+          L.allbs = (L.nlead == 32 * W);
+          for (int u = 0; u < W; u++) L.qr[u] = L.qu[u] & ~escaped[u];
+          G |= (eo & 1u) << l; P |= uint32_t(L.allbs) << l;
+        }
+        uint32_t cout0;
+        const uint32_t carries = escape_carries(G, P, 0, &cout0);
+        uint32_t par0 = 0;
+        for (int l = 0; l < 32; l++) {
+          Lane &L = lanes[w * 32 + l];
+          if ((carries >> l) & 1) toggle(L);
+          for (int u = 0; u < W; u++) par0 ^= popc32(L.qr[u]) & 1;
+        }
+        const bool warp_allbs = (P == 0xFFFFFFFFu);
+        uint32_t qx = 0, x_is_last = 0;
+        if (!warp_allbs) {
+          const int m = ctz32(~P);
+          const Lane &L = lanes[w * 32 + m];
+          qx = (L.qu[L.nlead >> 5] >> (L.nlead & 31)) & 1;
+          x_is_last = (m == 31 && L.nlead == 32 * W - 1);
+        }
+        const Lane &LL = lanes[w * 32 + 31];
+        const uint32_t scal0 = ((LL.sc[W - 1] & ~LL.qr[W - 1]) >> 31) & 1;
+        warpT[w] = tt_make(cout0, par0, scal0, warp_allbs ? 1u : cout0, par0 ^ qx, scal0 ^ (qx & x_is_last));
+        Pmask[w] = P;
+      }
+      uint32_t Ttile = warpT[0];
+      for (int w = 1; w < NWARPS; w++) Ttile = tt_compose(warpT[w], Ttile);
+
+      // ---- boundary state of the tile from the 16 bytes before it (tile 0: the carry-in state is exact)
+      uint32_t guess;
+      bool known;
+      if (t == 0) { guess = state0 & 5u; known = true; }
+      else {
+        uint32_t p16[4];
+        for (int i = 0; i < 4; i++) p16[i] = word_at(tile_start - 16 + 4 * i);
+        const uint32_t b = boundary_state_from_prev16(p16);
+        guess = b & 5u; known = !(b & 8u);
+      }
+      uint32_t cnt[2] = {0, 0};
+      bool err_pol[2] = {false, false};
+      uint32_t toggled_lane[NWARPS];
+      auto phase3 = [&](uint32_t et, uint32_t ct) {
+        cnt[0] = cnt[1] = 0; err_pol[0] = err_pol[1] = false;
+        uint32_t s = et | (ct << 2);  // tile-relative: in_string bit = 0
+        for (int w = 0; w < NWARPS; w++) {
+          const uint32_t e_w = s & 1, s_w = (s >> 1) & 1, c_w = (s >> 2) & 1;
+          s = tt_apply(warpT[w], s);
+          toggled_lane[w] = 0xFFFFFFFFu;
+          if (e_w && Pmask[w] != 0xFFFFFFFFu) { toggled_lane[w] = ctz32(~Pmask[w]); toggle(lanes[w * 32 + toggled_lane[w]]); }
+          uint32_t instr = s_w, scal = c_w;
+          for (int l = 0; l < 32; l++) {
+            Lane &L = lanes[w * 32 + l];
+            const long base = tile_start + long(w) * WARP_BYTES + long(l) * LANE_BYTES;
+            uint32_t prev_nq = scal << 31;
+            for (int u = 0; u < W; u++) {
+              const uint32_t in_string = prefix_xor32(L.qr[u]) ^ (instr ? 0xFFFFFFFFu : 0u);
+              instr = in_string >> 31;
+              const uint32_t nq = L.sc[u] & ~L.qr[u];
+              const uint32_t follows = shl_in(prev_nq, nq, 1);
+              prev_nq = nq;
+              L.pm[u] = L.op[u] | (L.sc[u] & ~follows);
+              L.x0[u] = in_string ^ L.qr[u];
+              L.in0[u] = in_string;
+              cnt[0] += popc32(L.pm[u] & ~L.x0[u]);
+              cnt[1] += popc32(L.pm[u] & L.x0[u]);
+              if (L.ctl[u] & in_string) err_pol[0] = true;
+              if (L.ctl[u] & ~in_string) err_pol[1] = true;
+              (void)base;
+            }
+            scal = prev_nq >> 31;
+          }
+        }
+      };
+      auto undo_toggles = [&]() {
+        for (int w = 0; w < NWARPS; w++) if (toggled_lane[w] != 0xFFFFFFFFu) toggle(lanes[w * 32 + toggled_lane[w]]);
+      };
+      phase3(guess & 1, (guess >> 2) & 1);
+      Desc &D = desc[t];
+      D.T = Ttile;
+      if (known) { D.has_agg = true; D.cnt[0] = cnt[0]; D.cnt[1] = cnt[1]; }
+      // ---- the look-back: nearest predecessor presented as inclusive, then a forward fold
+      long i = long(t) - 1;
+      {
+        const long oldest_unfinished = std::max<long>(0, long(t) - long(window ? rng() % (window + 1) : 0));
+        while (i >= 0 && i >= oldest_unfinished && desc[i].has_agg) i--;  // these are seen as aggregates
+      }
+      uint32_t S = (i < 0) ? state0 : tt_apply(desc[i].Tp, state0);
+      uint64_t C = (i < 0) ? 0 : desc[i].C;
+      uint32_t Tp = (i < 0) ? 0 : desc[i].Tp;
+      bool haveTp = i >= 0;
+      for (long j = i + 1; j < long(t); j++) {
+        C += desc[j].cnt[(S >> 1) & 1];
+        S = tt_apply(desc[j].T, S);
+        Tp = haveTp ? tt_compose(desc[j].T, Tp) : desc[j].T;
+        haveTp = true;
+      }
+      if ((S & 5u) != guess) {
+        if (known) { fprintf(stderr, "BUG: boundary state mismatch at tile %zu (guess %u exact %u)\n", t, guess, S & 5u); exit(2); }
+        undo_toggles();
+        phase3(S & 1, (S >> 2) & 1);
+        redo_count++;
+      }
+      const uint32_t pol = (S >> 1) & 1;
+      D.Tp = haveTp ? tt_compose(Ttile, Tp) : Ttile;
+      D.C = C + cnt[pol];
+      D.inc = true;
+      if (err_pol[pol]) ctl_err = true;
+      // ---- emit
+      for (int w = 0; w < NWARPS; w++)
+        for (int l = 0; l < 32; l++) {
+          Lane &L = lanes[w * 32 + l];
+          const long base = tile_start + long(w) * WARP_BYTES + long(l) * LANE_BYTES;
+          for (int u = 0; u < W; u++) {
+            const long ubase = base + 32 * u;
+            uint32_t valid = 0xFFFFFFFFu;
+            if (ubase + 32 > long(len)) valid = (ubase >= long(len)) ? 0u : ((1u << (long(len) - ubase)) - 1u);
+            const uint32_t st = pol ? (L.pm[u] & L.x0[u]) : (L.pm[u] & ~L.x0[u]);
+            const uint32_t ws = ~(L.op[u] | L.sc[u]);
+            const uint32_t ins = pol ? ~L.in0[u] : L.in0[u];
+            const uint32_t keep = ~(ws & ~ins) & valid;
+            for (uint32_t mk = st; mk; mk &= mk - 1) idx.push_back(uint32_t(ubase + ctz32(mk)));
+            for (uint32_t mk = keep; mk; mk &= mk - 1) minified.push_back(buf[ubase + ctz32(mk)]);
+          }
+        }
+      if (idx.size() != D.C) { fprintf(stderr, "BUG: count chain %zu vs %llu at tile %zu\n", idx.size(), (unsigned long long)D.C, t); exit(2); }
+      if (t + 1 == ntiles) unclosed = (tt_apply(D.Tp, state0) >> 1) & 1;
+    }
+    if (ntiles == 0) unclosed = (state0 >> 1) & 1;
+    if (len > 0) {
+      uint32_t pw = 0;
+      for (int d = 1; d <= 4; d++) pw |= uint32_t(long(len) - d >= 0 ? buf[len - d] : 0x20) << (8 * (4 - d));
+      if (utf8_carry_pending(utf8_carry_from_prev_word(pw))) utf8_err = true;
+    }
+  }
+};
+
+static long g_redos = 0;
+
+template <int W, int NWARPS, int V2 = 0>
 static int check(const std::vector<uint8_t> &in, const char *what) {
-  Emul<W, NWARPS> e;
+  typename std::conditional<V2 != 0, Emul2<W, NWARPS>, Emul<W, NWARPS>>::type e;
   e.buf = in.data();
   e.len = in.size();
+  if constexpr (V2 != 0) e.window = (V2 == 1) ? 0 : 7;
   e.run();
+  if constexpr (V2 != 0) g_redos += e.redo_count;
   // oracle, raw pieces
   std::vector<uint32_t> oidx(sjo_index_capacity(in.size()) + 16);
   uint32_t on = 0xDEADBEEF;
@@ -338,6 +554,9 @@ int main(int argc, char **argv) {
     fails += check<2, 1>(in, "W2x1") != 0;
     if (it % 8 == 0) fails += check<4, 8>(in, "W4x8") != 0;
     if (it % 8 == 1) fails += check<1, 3>(in, "W1x3") != 0;
+    fails += check<1, 1, 2>(in, "v2 W1x1 windowed") != 0;   // 1 KiB tiles: many tile boundaries, aggregates in the chain
+    fails += check<2, 1, 1>(in, "v2 W2x1") != 0;
+    if (it % 4 == 0) fails += check<4, 2, 2>(in, "v2 W4x2 windowed") != 0;
   }
   // exact tile multiples (no padding anywhere) incl. a truncated sequence at the very end
   for (int rep = 0; rep < 50 && fails < 5; rep++) {
@@ -348,6 +567,8 @@ int main(int argc, char **argv) {
     memcpy(in.data() + in.size() - strlen(t), t, strlen(t));
     fails += check<4, 2>(in, "exact") != 0;
     fails += check<2, 1>(in, "exact") != 0;
+    fails += check<1, 1, 2>(in, "v2 exact") != 0;
+    fails += check<4, 2, 2>(in, "v2 exact") != 0;
   }
   // all seven stage1 modes through the product's finish logic
   for (int it = 0; it < iters && fails < 5; it++) {
@@ -365,6 +586,6 @@ int main(int argc, char **argv) {
     fails += check_modes(in, mode) != 0;
   }
   if (fails) { printf("FAILED\n"); return 1; }
-  printf("host emulation OK (%d cases)\n", iters);
+  printf("host emulation OK (%d cases, %ld v2 redo tiles)\n", iters, g_redos);
   return 0;
 }
