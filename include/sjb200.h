@@ -87,6 +87,9 @@ SJB200_API int sjb200_set_option(sjb200_ctx *ctx, const char *key, long value);
  * "grid_index", "sm_count"; negative when unavailable */
 SJB200_API double sjb200_get_stat(sjb200_ctx *ctx, const char *key);
 
+/* tuning aid (option "debug_timeline"=1): per-tile phase timestamps of the last launch, 8 x uint64 per tile */
+SJB200_API long sjb200_get_debug_timeline(sjb200_ctx *ctx, unsigned long long *out, size_t max_tiles);
+
 /* page-lock / unlock caller-owned host memory (e.g. the parser's `new uint32_t[]` index array, whose deleter the
  * reference fixes: internal/dom_parser_implementation.h L175) so copies to it run at full PCIe speed; best effort */
 SJB200_API int sjb200_pin_host_memory(sjb200_ctx *ctx, void *ptr, size_t bytes);

@@ -55,7 +55,6 @@ struct sjb200_ctx {
   Carry *d_carry = nullptr;   // [kCarrySlots] one per chunk boundary of the chunked host pipeline
   uint32_t *d_flags = nullptr;
   uint32_t *d_ticket = nullptr;
-  uint32_t *d_state_desc = nullptr;
   unsigned long long *d_count_desc = nullptr;
   size_t desc_tiles = 0;
   uint8_t *d_chars = nullptr; size_t d_chars_bytes = 0;
@@ -67,9 +66,11 @@ struct sjb200_ctx {
   uint32_t *h_window = nullptr; size_t h_window_words = 0;
   uint32_t epoch = 0;
   int grid[3] = {0, 0, 0};
-  long opt_use_tma = 1, opt_grid = 0, opt_chunk_bytes = 4 << 20, opt_time_kernel = 0;
+  long opt_sub_per_super = 0, opt_use_tma = 1, opt_grid = 0, opt_chunk_bytes = 4 << 20, opt_time_kernel = 0;
   cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // around the scan kernel when opt_time_kernel is set
   bool ev_valid = false;
+  long opt_debug_timeline = 0;
+  unsigned long long *d_debug = nullptr; size_t debug_tiles = 0; uint32_t debug_last_tiles = 0;
   unsigned long long launches = 0;               // kernels of ours launched by this context
   PFN_encodeTiled encode = nullptr;
   PendingCall pending;
@@ -113,7 +114,6 @@ void free_sized(sjb200_ctx *c) {
   cudaFree(c->d_in); c->d_in = nullptr; c->d_in_bytes = 0;
   cudaFree(c->d_idx); c->d_idx = nullptr; c->d_idx_words = 0;
   cudaFree(c->d_out); c->d_out = nullptr; c->d_out_bytes = 0;
-  cudaFree(c->d_state_desc); c->d_state_desc = nullptr;
   cudaFree(c->d_count_desc); c->d_count_desc = nullptr;
   c->desc_tiles = 0;
 }
@@ -122,13 +122,10 @@ void free_sized(sjb200_ctx *c) {
 bool ensure_desc(sjb200_ctx *c, size_t len) {
   const size_t need = std::max<size_t>(tiles_of(len), 1);
   if (need <= c->desc_tiles) return true;
-  cudaFree(c->d_state_desc); c->d_state_desc = nullptr;
   cudaFree(c->d_count_desc); c->d_count_desc = nullptr;
   c->desc_tiles = 0;
   const size_t n = std::max(need, size_t(tiles_of(c->capacity)) + 1);
-  if (!dev_alloc(c, &c->d_state_desc, n, "cudaMalloc(state_desc)")) return false;
   if (!dev_alloc(c, &c->d_count_desc, n, "cudaMalloc(count_desc)")) return false;
-  if (!ok(c, cudaMemsetAsync(c->d_state_desc, 0, n * sizeof(uint32_t), c->stream), "memset desc")) return false;
   if (!ok(c, cudaMemsetAsync(c->d_count_desc, 0, n * sizeof(unsigned long long), c->stream), "memset desc")) return false;
   if (!ok(c, cudaStreamSynchronize(c->stream), "sync")) return false;
   c->desc_tiles = n;
@@ -138,8 +135,7 @@ bool ensure_desc(sjb200_ctx *c, size_t len) {
 
 uint32_t next_epoch(sjb200_ctx *c) {
   c->epoch++;
-  if (c->epoch >= (1u << 24)) {  // 24-bit tag wrapped: wipe the descriptors once
-    cudaMemsetAsync(c->d_state_desc, 0, c->desc_tiles * sizeof(uint32_t), c->stream);
+  if (c->epoch >= (1u << 18)) {  // 18-bit tag wrapped: wipe the descriptors once
     cudaMemsetAsync(c->d_count_desc, 0, c->desc_tiles * sizeof(unsigned long long), c->stream);
     cudaStreamSynchronize(c->stream);
     c->epoch = 1;
@@ -179,10 +175,12 @@ bool make_tensor_map(sjb200_ctx *c, CUtensorMap *map, const uint8_t *d_buf, size
   return true;
 }
 
-int grid_for(sjb200_ctx *c, int kind, uint32_t ntiles) {
+int grid_cap(sjb200_ctx *c, int kind) {
   if (c->grid[kind] == 0) c->grid[kind] = scan_max_ctas_per_sm(kind) * c->sm_count;
-  int g = c->opt_grid > 0 ? int(c->opt_grid) : c->grid[kind];
-  return int(std::max<uint32_t>(1, std::min<uint32_t>(uint32_t(g), ntiles)));
+  return c->opt_grid > 0 ? int(c->opt_grid) : c->grid[kind];
+}
+int grid_for(sjb200_ctx *c, int kind, uint32_t nelements) {
+  return int(std::max<uint32_t>(1, std::min<uint32_t>(uint32_t(grid_cap(c, kind)), nelements)));
 }
 
 // Enqueue the scan of document tiles [tile_begin, tile_begin+ntiles) of (d_buf,len).
@@ -200,6 +198,14 @@ bool enqueue_scan(sjb200_ctx *c, int kind, const CUtensorMap *map, bool tma, con
   p.use_tma = tma ? 1u : 0u;
   p.tile_begin = tile_begin;
   p.ntiles = ntiles;
+  // super-tiles: enough consecutive tiles per CTA that one wave of CTAs covers the launch (up to kMaxSub), so the
+  // look-back chain is consulted once per CTA instead of once per 32 KiB
+  const int cap = grid_cap(c, kind);
+  uint32_t R = 1;
+  if (kind == kIndex) R = std::min<uint32_t>(kMaxSub, std::max<uint32_t>(1, (ntiles + uint32_t(cap) - 1) / uint32_t(cap)));
+  if (c->opt_sub_per_super > 0 && kind == kIndex) R = std::min<uint32_t>(kMaxSub, uint32_t(c->opt_sub_per_super));
+  p.sub_per_super = R;
+  p.nsuper = (ntiles + R - 1) / R;
   p.full_tiles = uint32_t((len / 128) / kTileRows);
   p.epoch = next_epoch(c);
   p.idx_out = d_idx;
@@ -207,14 +213,21 @@ bool enqueue_scan(sjb200_ctx *c, int kind, const CUtensorMap *map, bool tma, con
   p.carry_in = c->d_carry + carry_in_slot;
   p.carry_out = c->d_carry + carry_out_slot;
   p.flags = c->d_flags;
-  p.state_desc = c->d_state_desc;
   p.count_desc = c->d_count_desc;
   p.ticket = c->d_ticket;
+  p.debug = nullptr;
+  if (c->opt_debug_timeline) {
+    if (c->debug_tiles < ntiles) {
+      cudaFree(c->d_debug); c->d_debug = nullptr; c->debug_tiles = 0;
+      if (dev_alloc(c, &c->d_debug, size_t(ntiles) * 8, "cudaMalloc(debug)")) c->debug_tiles = ntiles;
+    }
+    if (c->d_debug) { cudaMemsetAsync(c->d_debug, 0, size_t(ntiles) * 64, stream); p.debug = c->d_debug; c->debug_last_tiles = ntiles; }
+  }
   if (c->opt_time_kernel) {
     if (!c->ev_k0) { cudaEventCreate(&c->ev_k0); cudaEventCreate(&c->ev_k1); }
     cudaEventRecord(c->ev_k0, stream);
   }
-  const bool launched = ok(c, launch_scan(kind, map, p, grid_for(c, kind, ntiles), stream), "launch scan");
+  const bool launched = ok(c, launch_scan(kind, map, p, grid_for(c, kind, p.nsuper), stream), "launch scan");
   if (c->opt_time_kernel) { cudaEventRecord(c->ev_k1, stream); c->ev_valid = launched; }
   c->launches += launched ? 1 : 0;
   return launched;
@@ -367,7 +380,7 @@ extern "C" void sjb200_destroy(sjb200_ctx *c) {
   DeviceGuard g(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   free_sized(c);
-  cudaFree(c->d_carry); cudaFree(c->d_flags); cudaFree(c->d_ticket); cudaFree(c->d_chars);
+  cudaFree(c->d_carry); cudaFree(c->d_flags); cudaFree(c->d_ticket); cudaFree(c->d_chars); cudaFree(c->d_debug);
   if (c->h_carry) cudaFreeHost(c->h_carry);
   if (c->h_flags) cudaFreeHost(c->h_flags);
   if (c->h_small) cudaFreeHost(c->h_small);
@@ -397,6 +410,16 @@ extern "C" int sjb200_set_capacity(sjb200_ctx *c, size_t capacity) {
 extern "C" size_t sjb200_capacity(const sjb200_ctx *c) { return c ? c->capacity : 0; }
 extern "C" int sjb200_device(const sjb200_ctx *c) { return c ? c->device : -1; }
 extern "C" const char *sjb200_last_cuda_error(const sjb200_ctx *c) { return c ? c->last_error.c_str() : ""; }
+
+// tuning aid: copy the per-tile timeline of the last launch (8 x uint64 per tile) to host memory; returns tiles copied
+extern "C" long sjb200_get_debug_timeline(sjb200_ctx *c, unsigned long long *out, size_t max_tiles) {
+  if (!c || !c->d_debug || !out) return 0;
+  DeviceGuard g(c->device);
+  const size_t n = std::min<size_t>(max_tiles, c->debug_last_tiles);
+  cudaDeviceSynchronize();
+  if (cudaMemcpy(out, c->d_debug, n * 64, cudaMemcpyDeviceToHost) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+  return long(n);
+}
 
 extern "C" int sjb200_pin_host_memory(sjb200_ctx *c, void *ptr, size_t bytes) {
   if (!c || !ptr || bytes == 0) return SJB200_UNEXPECTED_ERROR;
@@ -428,7 +451,9 @@ extern "C" int sjb200_set_option(sjb200_ctx *c, const char *key, long value) {
   if (!c || !key) return SJB200_UNEXPECTED_ERROR;
   if (!strcmp(key, "use_tma")) c->opt_use_tma = value;
   else if (!strcmp(key, "grid")) c->opt_grid = value;
+  else if (!strcmp(key, "sub_per_super")) c->opt_sub_per_super = value;
   else if (!strcmp(key, "time_kernel")) c->opt_time_kernel = value;
+  else if (!strcmp(key, "debug_timeline")) c->opt_debug_timeline = value;
   else if (!strcmp(key, "chunk_bytes")) c->opt_chunk_bytes = std::max<long>(kTileBytes, (value / kTileBytes) * kTileBytes);
   else return SJB200_UNEXPECTED_ERROR;
   return SJB200_SUCCESS;

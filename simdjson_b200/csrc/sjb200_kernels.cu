@@ -39,18 +39,21 @@ enum : uint32_t { kNone = 0, kAgg = 1, kInc = 2 };
 
 struct Control {
   unsigned long long full_bar[kStages];
-  uint32_t stage_tile[kStages];
+  uint32_t stage_super[kStages];      // super-tile (ticket) the stage's tile belongs to
+  uint32_t stage_r[kStages];          // ... and its position inside the super-tile
   uint32_t stage_prev16[kStages][4];  // the 16 bytes before the tile (UTF-8 halo + boundary state)
+  uint32_t next_super, next_r, next_n;  // loader state: which tile to fetch next
+  uint32_t bstate_exact;
   uint32_t warpT[kWarps];
-  uint32_t warpCnt[2][kWarps];        // per in-string polarity of the tile
-  // look-back scratch, one slot per warp = per 128-tile segment of the window
-  uint32_t segHas[kWarps];            // the segment contains an inclusive prefix (or reaches tile 0)
-  uint32_t segF[kWarps];              // composed transducer of the segment's relevant tiles | 0x100 if any
-  uint32_t segIncT[kWarps];           // inclusive transducer prefix found in the segment | 0x100 if real
+  uint32_t cntw[kMaxSub][2][kWarps];  // outputs per tile of the super-tile, per in-string polarity, per warp
+  // look-back scratch, one slot per warp = per 128-element segment of the window
+  uint32_t segHas[kWarps];            // the segment contains an inclusive prefix (or reaches element 0)
+  uint32_t segF[kWarps];              // composed transducer of the segment's relevant elements | kValidBit
+  uint32_t segIncT[kWarps];           // inclusive transducer prefix found in the segment | kValidBit if real
   uint32_t segIncC[kWarps];
   uint32_t segCount[kWarps];
 };
-static_assert(sizeof(Control) <= 512, "control block");
+static_assert(sizeof(Control) <= kCtlBytes, "control block");
 
 // ------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -65,7 +68,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(unsigned long long *bar, uint3
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x4000;\n"
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
@@ -88,28 +91,48 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned l
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define SJ_TRACE(slot)                                                                       \
+  do {                                                                                       \
+    if (p.debug != nullptr && tid == 0) p.debug[uint64_t(tile) * 8 + (slot)] = globaltimer_ns(); \
+  } while (0)
+
 // byte offset inside a tile -> offset in the 128B-swizzled shared-memory image
 // (TMA SWIZZLE_128B: 16-byte chunk index bits [4,7) ^= row bits [7,10))
 __device__ __forceinline__ uint32_t swz(uint32_t off) { return off ^ ((off >> 3) & 0x70u); }
 
 // ------------------------------------------------------------- the look-back chain
-// One 64-bit descriptor per tile:  [63:40] epoch  [39:38] status  [37:32] transducer  [31:0] payload
-//   kAgg: transducer = T of the tile; payload = cnt[1]<<16 | cnt[0]: outputs of the tile for either
-//         in-string polarity at its start (the e / c bits of its incoming state are already baked in,
-//         they were read off the bytes before the tile)
-//   kInc: transducer = composition of tiles [0, tile]; payload = outputs of tiles [0, tile]
-__device__ __forceinline__ unsigned long long pack_desc(uint32_t epoch, uint32_t status, uint32_t T, uint32_t payload) {
-  return ((unsigned long long)epoch << 40) | ((unsigned long long)status << 38) | ((unsigned long long)(T & 63u) << 32) | payload;
+// One 64-bit descriptor per chain element (= super-tile):  [63:46] epoch  [45:44] status  [43:38] transducer  [37:0] payload
+//   kAgg: transducer = T of the element; payload = cnt[1]<<19 | cnt[0]: its outputs for either in-string polarity
+//         at its start (the e / c bits of its incoming state are already baked in: they were read off the bytes
+//         before it)
+//   kInc: transducer = composition of elements [0, i]; payload = outputs of elements [0, i]
+__device__ __forceinline__ unsigned long long pack_agg(uint32_t epoch, uint32_t T, uint32_t c0, uint32_t c1) {
+  return ((unsigned long long)epoch << 46) | ((unsigned long long)kAgg << 44) | ((unsigned long long)(T & 63u) << 38) |
+         ((unsigned long long)c1 << 19) | c0;
+}
+__device__ __forceinline__ unsigned long long pack_inc(uint32_t epoch, uint32_t T, uint32_t count) {
+  return ((unsigned long long)epoch << 46) | ((unsigned long long)kInc << 44) | ((unsigned long long)(T & 63u) << 38) | count;
 }
 
+#ifndef SJB200_SPIN_NS
+#define SJB200_SPIN_NS 100
+#endif
 constexpr int kLook = 4;                      // descriptors per lane: a warp covers 128 tiles of the window
 constexpr int kSegTiles = 32 * kLook;
 constexpr uint32_t kValidBit = 0x100u;        // marks "this composed transducer exists"
 
-__device__ __forceinline__ uint32_t compose_opt(uint32_t newer, uint32_t older) {  // either may be absent (no kValidBit)
+__device__ __forceinline__ uint32_t lut_compose(const uint8_t *lut, uint32_t newer, uint32_t older) {
+  return lut[((newer & 63u) << 6) | (older & 63u)];
+}
+__device__ __forceinline__ uint32_t compose_opt(const uint8_t *lut, uint32_t newer, uint32_t older) {  // either may be absent (no kValidBit)
   if (!(newer & kValidBit)) return older;
   if (!(older & kValidBit)) return newer;
-  return tt_compose(newer & 63u, older & 63u) | kValidBit;
+  return lut_compose(lut, newer, older) | kValidBit;
 }
 __device__ __forceinline__ uint32_t apply_opt(uint32_t F, uint32_t state) { return (F & kValidBit) ? tt_apply(F & 63u, state) : state; }
 
@@ -119,16 +142,16 @@ __device__ __forceinline__ uint32_t apply_opt(uint32_t F, uint32_t state) { retu
 // The walk stops at the nearest tile that already published an inclusive prefix; everything newer only
 // has an aggregate, and because an aggregate's count depends on the in-string polarity at its tile, the
 // states are folded forwards (oldest to newest) with parallel suffix scans.
-__device__ void resolve_tile(const ScanParams &p, Control *ctl, uint32_t tile, uint32_t S0, int warp, int lane, uint32_t &state_in,
-                             uint32_t &base, uint32_t &Tprefix /* | kValidBit */) {
+__device__ void resolve_tile(const ScanParams &p, Control *ctl, const uint8_t *lut, uint32_t tile, uint32_t S0, int warp, int lane,
+                             uint32_t &state_in, uint32_t &base, uint32_t &Tprefix /* | kValidBit */) {
   for (;;) {
     // ---- A: every warp fetches its segment and looks for an inclusive prefix
     const int seg_newest = int(tile) - 1 - kSegTiles * warp;  // newest tile of my segment (may be < 0: empty segment)
-    uint32_t status[kLook], T[kLook], pay[kLook];
+    uint32_t status[kLook], T[kLook], pa[kLook], pb[kLook];  // pa: cnt[0] (or the inclusive count), pb: cnt[1]
     uint32_t pending = 0;
 #pragma unroll
     for (int k = 0; k < kLook; k++) {
-      status[k] = kNone; T[k] = 0; pay[k] = 0;
+      status[k] = kNone; T[k] = 0; pa[k] = 0; pb[k] = 0;
       if (seg_newest - 32 * k - lane >= 0) pending |= 1u << k;
     }
     uint32_t spins = 0;
@@ -137,9 +160,11 @@ __device__ void resolve_tile(const ScanParams &p, Control *ctl, uint32_t tile, u
       for (int k = 0; k < kLook; k++) {
         if (pending & (1u << k)) {
           const unsigned long long d = ld_relaxed_u64(p.count_desc + (seg_newest - 32 * k - lane));
-          const uint32_t st = uint32_t(d >> 38) & 3u;
-          if (uint32_t(d >> 40) == p.epoch && st != kNone) {
-            status[k] = st; T[k] = uint32_t(d >> 32) & 63u; pay[k] = uint32_t(d);
+          const uint32_t st = uint32_t(d >> 44) & 3u;
+          if (uint32_t(d >> 46) == p.epoch && st != kNone) {
+            status[k] = st; T[k] = uint32_t(d >> 38) & 63u;
+            if (st == kInc) { pa[k] = uint32_t(d); pb[k] = 0; }
+            else { pa[k] = uint32_t(d) & 0x7FFFFu; pb[k] = uint32_t(d >> 19) & 0x7FFFFu; }
             pending &= ~(1u << k);
           }
         }
@@ -149,13 +174,14 @@ __device__ void resolve_tile(const ScanParams &p, Control *ctl, uint32_t tile, u
           atomicOr(p.flags, kFlagInternal);
 #pragma unroll
           for (int k = 0; k < kLook; k++)
-            if (pending & (1u << k)) { status[k] = kInc; T[k] = 0; pay[k] = 0; }
+            if (pending & (1u << k)) { status[k] = kInc; T[k] = 0; pa[k] = 0; pb[k] = 0; }
           pending = 0;
         } else {
-          __nanosleep(20);
+          __nanosleep(SJB200_SPIN_NS);
         }
       }
     }
+    if (p.debug != nullptr && threadIdx.x == 0) p.debug[uint64_t(tile) * 8 + 6] = globaltimer_ns();  // tile = chain element
     // nearest inclusive prefix in my segment: group kinc, lane linc (groups / lanes are ordered newest first)
     int kinc = kLook, linc = 32;
 #pragma unroll
@@ -195,13 +221,13 @@ __device__ void resolve_tile(const ScanParams &p, Control *ctl, uint32_t tile, u
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
           const uint32_t o = __shfl_down_sync(kFull, val, d);
-          if (lane + d <= lst) val = tt_compose(val, o);   // val covers [lane, lane+d), o covers [lane+d, lane+2d)
+          if (lane + d <= lst) val = lut_compose(lut, val, o);   // val covers [lane, lane+d), o covers [lane+d, lane+2d)
         }
         I[k] = val | kValidBit;
         G[k] = (lst >= 0) ? (__shfl_sync(kFull, val, 0) | kValidBit) : 0u;
       }
 #pragma unroll
-      for (int k = kLook - 1; k >= 0; k--) F = compose_opt(G[k], F);   // oldest group first
+      for (int k = kLook - 1; k >= 0; k--) F = compose_opt(lut, G[k], F);   // oldest group first
       if (lane == 0) ctl->segF[warp] = F;
       if (warp == wstar) {
         // the inclusive prefix itself: the lane that holds it publishes it (or lane 0 the virtual one before tile 0)
@@ -212,7 +238,7 @@ __device__ void resolve_tile(const ScanParams &p, Control *ctl, uint32_t tile, u
           for (int k = 0; k < kLook; k++)
             if (k == kinc && lane == linc) {
               ctl->segIncT[warp] = T[k] | kValidBit;
-              ctl->segIncC[warp] = pay[k];
+              ctl->segIncC[warp] = pa[k];
             }
         }
       }
@@ -234,7 +260,7 @@ __device__ void resolve_tile(const ScanParams &p, Control *ctl, uint32_t tile, u
         if (last[k] < 0) continue;
         const uint32_t Hn = __shfl_down_sync(kFull, I[k], 1);                 // composition of the tiles older than mine
         const uint32_t S = (lane + 1 <= last[k]) ? tt_apply(Hn & 63u, Eg) : Eg;  // state entering my tile
-        if (lane <= last[k]) cnt += ((S >> 1) & 1u) ? (pay[k] >> 16) : (pay[k] & 0xFFFFu);
+        if (lane <= last[k]) cnt += ((S >> 1) & 1u) ? pb[k] : pa[k];
         Eg = tt_apply(G[k] & 63u, Eg);
       }
 #pragma unroll
@@ -246,7 +272,7 @@ __device__ void resolve_tile(const ScanParams &p, Control *ctl, uint32_t tile, u
     uint32_t Tp = incT;
     for (int w = wstar; w >= 0; w--) {
       total += ctl->segCount[w];
-      Tp = compose_opt(ctl->segF[w], Tp);
+      Tp = compose_opt(lut, ctl->segF[w], Tp);
     }
     base = total;
     Tprefix = Tp;
@@ -291,12 +317,21 @@ __device__ __forceinline__ void load_unit(const uint8_t *T, uint32_t off, uint32
   w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
 }
 
-// One thread: take the next ticket for stage s and start its load.
+// One thread: fetch the next tile into stage s.  Tiles of a super-tile are fetched in order; when the
+// current super-tile is exhausted the next ticket is taken.  For the UTF-8 scan every tile is its own element.
 __device__ void refill_stage(uint8_t *tiles, Control *ctl, const CUtensorMap *tmap, const ScanParams &p, int s) {
-  const uint32_t k = atomicAdd(p.ticket, 1u);
-  ctl->stage_tile[s] = k;
-  if (k >= p.ntiles) return;
-  const uint32_t t = p.tile_begin + k;  // document tile
+  if (ctl->next_r >= ctl->next_n) {
+    const uint32_t k = atomicAdd(p.ticket, 1u);
+    ctl->next_super = k;
+    ctl->next_r = 0;
+    ctl->next_n = (k < p.nsuper) ? min(p.sub_per_super, p.ntiles - k * p.sub_per_super) : 1u;
+  }
+  const uint32_t k = ctl->next_super, r = ctl->next_r;
+  ctl->next_r = r + 1;
+  ctl->stage_super[s] = k;
+  ctl->stage_r[s] = r;
+  if (k >= p.nsuper) return;
+  const uint32_t t = p.tile_begin + k * p.sub_per_super + r;  // document tile
   uint32_t w0 = 0x20202020u, w1 = 0x20202020u, w2 = 0x20202020u, w3 = p.prev_word;
   if (t > 0) {
     const uint8_t *q = p.buf + uint64_t(t) * kTileBytes - 16;
@@ -327,13 +362,20 @@ __device__ __forceinline__ void toggle_first_nonbackslash_quote(const uint32_t q
 
 // ------------------------------------------------------------------ the kernel
 template <int KIND>
-__global__ void __launch_bounds__(kThreads, kMinCtasPerSm) scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
+__global__ void __launch_bounds__(kThreads, (KIND == kUtf8) ? 4 : kMinCtasPerSm)
+    scan_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1 KiB alignment for the 128B swizzle, computed on the shared-space address so the pointer keeps its address
+  // space (a round trip through uintptr_t makes every access a generic LD/ST instead of LDS/STS)
+  uint8_t *tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   Control *ctl = reinterpret_cast<Control *>(tiles + kStages * kTileBytes);
+  uint8_t *lut = reinterpret_cast<uint8_t *>(ctl) + kCtlBytes;                  // composed-transducer table
+  uint32_t *emit_scratch = reinterpret_cast<uint32_t *>(lut + kLutBytes);       // [kWarps][256]
+  uint4 *mask_slots = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(emit_scratch) + kEmitBytes);  // [kMaxSub][2][kThreads]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t lanemask_lt = (1u << lane) - 1u;
   const int kRefillThread = 32;
+  const uint32_t R = p.sub_per_super;
 
   Carry cin;
   cin.count = 0; cin.state = 0; cin.ttable = 0;
@@ -343,6 +385,10 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) scan_kernel(const __g
 #pragma unroll
     for (int s = 0; s < kStages; s++) mbar_init(&ctl->full_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    ctl->next_super = 0; ctl->next_r = 0; ctl->next_n = 0;
+  }
+  if (KIND != kUtf8) {
+    for (int i = tid; i < kLutBytes; i += kThreads) lut[i] = uint8_t(tt_compose(uint32_t(i) >> 6, uint32_t(i) & 63u));
   }
   __syncthreads();
   if (tid == kRefillThread) {
@@ -350,13 +396,26 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) scan_kernel(const __g
   }
   __syncthreads();
 
+  // state of the super-tile being scanned (identical in every thread)
+  uint32_t bstate = 0;       // e / c bits of the state entering the super-tile (bit0, bit2)
+  uint32_t srel = 0;         // scanner state entering the current tile, relative to super-tile polarity 0
+  uint32_t Tsuper = 0;       // composed transducer of the tiles scanned so far (| kValidBit)
+  bool err0 = false, err1 = false;  // unescaped control character inside a string, per super-tile polarity
+
   uint32_t phase_bits = 0;
   for (uint32_t it = 0;; it++) {
     const int s = it % kStages;
-    const uint32_t tile = ctl->stage_tile[s];  // index inside this launch (the look-back chain uses it)
-    if (tile >= p.ntiles) break;
-    const uint32_t dtile = p.tile_begin + tile;  // document tile (addresses, positions)
+    const uint32_t super = ctl->stage_super[s];  // chain element (index inside this launch)
+    const uint32_t r = ctl->stage_r[s];
+    if (super >= p.nsuper) break;
+    const uint32_t tile = super * R + r;          // tile index inside this launch
+    const uint32_t dtile = p.tile_begin + tile;   // document tile (addresses, positions)
+    const uint32_t nsub = min(R, p.ntiles - super * R);
     uint8_t *T = tiles + s * kTileBytes;
+    if (p.debug != nullptr && tid == 0 && r == 0) {
+      p.debug[uint64_t(super) * 8 + 0] = globaltimer_ns();
+      p.debug[uint64_t(super) * 8 + 7] = (uint64_t(blockIdx.x) << 32) | it;
+    }
     const bool via_tma = p.use_tma && dtile < p.full_tiles;
     if (via_tma) {
       const uint32_t parity = (phase_bits >> s) & 1u;
@@ -408,181 +467,190 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) scan_kernel(const __g
       continue;
     }
 
-    // ---- the e / c bits of the state entering this tile, from the bytes before it (exact unless a run of
-    //      >= 16 backslashes ends right at the boundary: then `known` is false and the chain decides)
-    uint32_t bstate;  // bit0 e, bit2 c
-    bool known = true;
-    if (tile == 0) {
-      bstate = cin.state & 5u;  // the launch's carry-in is exact
-    } else {
-      const uint32_t b = boundary_state_from_prev16(ctl->stage_prev16[s]);
-      bstate = b & 5u;
-      known = (b & 8u) == 0;
-    }
-
-    uint32_t m0[W], m1[W];  // kIndex: pseudo-structurals, string tail (polarity 0).  kMinify: whitespace, in_string (polarity 0)
-    uint32_t c0 = 0, c1 = 0;     // this lane's outputs for tile polarity 0 / 1
-    bool err0 = false, err1 = false;
-    uint32_t Ttile = 0, state_in = 0, base = 0, Tprefix = 0;
-
-    for (int attempt = 0; attempt < 2; attempt++) {
-      // ============================ phase 1: planes, classes, UTF-8 ============================
-      uint32_t bs[W], qu[W], op[W], sc[W], cl[W];
-      uint32_t uerr = 0;
-      {
-        const uint32_t pw = (lane_off == 0) ? ctl->stage_prev16[s][3] : *reinterpret_cast<const uint32_t *>(T + swz(lane_off - 4));
-        utf8_carry uc = utf8_carry_from_prev_word(pw);
-#pragma unroll
-        for (int u = 0; u < W; u++) {
-          uint32_t w8[8], pl[8];
-          load_unit(T, lane_off + 32 * u, w8);
-          transpose32(w8, pl);
-          const unit_classes c = classify(pl);
-          bs[u] = c.bs; qu[u] = c.qu; op[u] = c.op; sc[u] = c.sc; cl[u] = c.ctl;
-          if (__any_sync(kFull, pl[7] != 0 || utf8_carry_pending(uc))) {
-            uerr |= utf8_check_unit(pl, uc);
-          } else {
-            uc = utf8_carry_zero();
-          }
-        }
-      }
-      if (KIND != kMinify) {  // minify does not validate (json_minifier.h: "does not parse or validate")
-        if (__any_sync(kFull, uerr != 0) && lane == 0) atomicOr(p.flags, kFlagUtf8);
-      }
-
-      // ============================ phase 2: escapes, quotes, warp transducer ============================
-      uint32_t qr[W];
-      uint32_t Pmask = 0, warp_cout0 = 0;
-      int nlead = 0;
-      {
-        const uint32_t bsany = bs[0] | bs[1] | bs[2] | bs[3];
-        if (__any_sync(kFull, bsany != 0)) {
-          uint32_t escaped[W];
-          const uint32_t esc_out0 = escape_scan<W>(bs, escaped);
-#pragma unroll
-          for (int u = 0; u < W; u++) qr[u] = qu[u] & ~escaped[u];
-          nlead = leading_backslashes<W>(bs);
-          const uint32_t G = __ballot_sync(kFull, esc_out0 != 0);
-          Pmask = __ballot_sync(kFull, nlead == 32 * W);
-          const uint32_t carries = escape_carries(G, Pmask, 0u, &warp_cout0);
-          if (((carries >> lane) & 1u) && nlead != 32 * W) toggle_first_nonbackslash_quote(qu, qr, nlead);
-        } else {
-#pragma unroll
-          for (int u = 0; u < W; u++) qr[u] = qu[u];
-        }
-      }
-      const bool warp_allbs = (Pmask == kFull);
-      const int mlane = warp_allbs ? 0 : (__ffs(~Pmask) - 1);  // lane holding the first non-backslash byte
-      {
-        const uint32_t lp = (__popc(qr[0]) + __popc(qr[1]) + __popc(qr[2]) + __popc(qr[3])) & 1u;
-        const uint32_t par0 = __popc(__ballot_sync(kFull, lp != 0)) & 1u;
-        uint32_t myq = 0;
-#pragma unroll
-        for (int u = 0; u < W; u++)
-          if ((nlead >> 5) == u) myq = (qu[u] >> (nlead & 31)) & 1u;
-        uint32_t qx = __shfl_sync(kFull, myq, mlane);
-        uint32_t x_is_last = __shfl_sync(kFull, uint32_t(nlead == 32 * W - 1), 31);
-        if (warp_allbs) qx = 0;
-        if (mlane != 31) x_is_last = 0;
-        const uint32_t scal0 = __shfl_sync(kFull, (sc[W - 1] & ~qr[W - 1]) >> 31, 31);
-        const uint32_t Tw = tt_make(warp_cout0, par0, scal0, warp_allbs ? 1u : warp_cout0, par0 ^ qx, scal0 ^ (qx & x_is_last));
-        if (lane == 0) ctl->warpT[warp] = Tw;
-      }
-      __syncthreads();  // S1: all warp transducers visible
-
-      // state entering this warp, relative to the tile (tile polarity 0): compose the warps before it
-      uint32_t win = bstate;
-      for (int w = 0; w < warp; w++) win = tt_apply(ctl->warpT[w], win);
-      const uint32_t e_w = win & 1u, s_w = (win >> 1) & 1u, c_w = (win >> 2) & 1u;
-      if (attempt == 0) {
-        Ttile = ctl->warpT[0];
-#pragma unroll
-        for (int w = 1; w < kWarps; w++) Ttile = tt_compose(ctl->warpT[w], Ttile);
-      }
-
-      // ============================ phase 3: final masks, for both polarities ============================
-      if (e_w && !warp_allbs && lane == mlane) toggle_first_nonbackslash_quote(qu, qr, nlead);
-      {
-        const uint32_t lp = (__popc(qr[0]) + __popc(qr[1]) + __popc(qr[2]) + __popc(qr[3])) & 1u;
-        const uint32_t pb = __ballot_sync(kFull, lp != 0);
-        uint32_t instr = (s_w ^ uint32_t(__popc(pb & lanemask_lt))) & 1u;
-        uint32_t scal_prev = __shfl_up_sync(kFull, (sc[W - 1] & ~qr[W - 1]) >> 31, 1);
-        if (lane == 0) scal_prev = c_w;
-        uint32_t prev_nq = scal_prev << 31;
-        uint32_t hit0 = 0, hit1 = 0;
-        c0 = 0; c1 = 0;
-#pragma unroll
-        for (int u = 0; u < W; u++) {
-          const uint32_t in_string = prefix_xor32(qr[u]) ^ (0u - instr);
-          instr = in_string >> 31;
-          if (KIND == kIndex) {
-            const uint32_t nq = sc[u] & ~qr[u];
-            const uint32_t follows = shl_in(prev_nq, nq, 1);
-            prev_nq = nq;
-            const uint32_t pm = op[u] | (sc[u] & ~follows);
-            const uint32_t x0 = in_string ^ qr[u];
-            m0[u] = pm; m1[u] = x0;
-            c0 += __popc(pm & ~x0);
-            c1 += __popc(pm & x0);
-            hit0 |= cl[u] & in_string;
-            hit1 |= cl[u] & ~in_string;
-          } else {
-            uint32_t ws = ~(op[u] | sc[u]);
-            uint32_t valid = kFull;
-            if (last_tile) {  // the 0x20 padding past len is never output (json_minifier.h L79-95)
-              const uint64_t ubase = uint64_t(dtile) * kTileBytes + lane_off + 32 * u;
-              if (ubase + 32 > p.len) valid = (ubase >= p.len) ? 0u : ((1u << uint32_t(p.len - ubase)) - 1u);
+    if (r == 0) {
+      // ---- the e / c bits of the state entering this super-tile, from the bytes before it.  Exact unless a run of
+      //      >= 16 backslashes ends right at the boundary; then (rare) wait for the predecessor's inclusive prefix.
+      if (super == 0) {
+        bstate = cin.state & 5u;  // the launch's carry-in is exact
+      } else {
+        const uint32_t b = boundary_state_from_prev16(ctl->stage_prev16[s]);
+        bstate = b & 5u;
+        if (b & 8u) {
+          if (tid == 0) {
+            uint32_t spins = 0, st_exact = 0;
+            for (;;) {
+              const unsigned long long d = ld_relaxed_u64(p.count_desc + (super - 1));
+              if (uint32_t(d >> 46) == p.epoch && (uint32_t(d >> 44) & 3u) == kInc) {
+                st_exact = tt_apply(uint32_t(d >> 38) & 63u, cin.state);
+                break;
+              }
+              if (++spins > kSpinLimit) { atomicOr(p.flags, kFlagInternal); break; }
+              __nanosleep(200);
             }
-            m0[u] = ws; m1[u] = in_string;
-            c0 += __popc(valid & ~(ws & ~in_string));
-            c1 += __popc(valid & ~(ws & in_string));
+            ctl->bstate_exact = st_exact & 5u;
           }
+          __syncthreads();
+          bstate = ctl->bstate_exact;
         }
-        err0 = __any_sync(kFull, hit0 != 0);
-        err1 = __any_sync(kFull, hit1 != 0);
       }
-      {
-        uint32_t t0 = c0, t1 = c1;
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) {
-          t0 += __shfl_xor_sync(kFull, t0, d);
-          t1 += __shfl_xor_sync(kFull, t1, d);
-        }
-        if (lane == 0) { ctl->warpCnt[0][warp] = t0; ctl->warpCnt[1][warp] = t1; }
-      }
-      __syncthreads();  // S2: per-warp counts visible
-
-      if (attempt == 1) break;
-      uint32_t tc0 = 0, tc1 = 0;
-#pragma unroll
-      for (int w = 0; w < kWarps; w++) { tc0 += ctl->warpCnt[0][w]; tc1 += ctl->warpCnt[1][w]; }
-      if (tile == 0) {
-        state_in = cin.state; base = 0; Tprefix = 0;
-        break;  // bstate is exact
-      }
-      if (known && tid == 0) st_relaxed_u64(p.count_desc + tile, pack_desc(p.epoch, kAgg, Ttile, (tc1 << 16) | tc0));
-      resolve_tile(p, ctl, tile, cin.state, warp, lane, state_in, base, Tprefix);
-      if ((state_in & 5u) == bstate) break;
-      // only possible when the boundary state could not be read off the preceding bytes: redo with the exact one
-      if (known) atomicOr(p.flags, kFlagInternal);
-      bstate = state_in & 5u;
-      __syncthreads();
+      srel = bstate;
+      Tsuper = 0;
+      err0 = false; err1 = false;
     }
 
-    const uint32_t pol = (state_in >> 1) & 1u;  // in_string entering the tile
-    uint32_t tile_total = 0, warp_base = 0;
+    // ============================ phase 1: planes, classes, UTF-8 ============================
+    uint32_t bs[W], qu[W], op[W], sc[W], cl[W];
+    uint32_t uerr = 0;
+    {
+      const uint32_t pw = (lane_off == 0) ? ctl->stage_prev16[s][3] : *reinterpret_cast<const uint32_t *>(T + swz(lane_off - 4));
+      utf8_carry uc = utf8_carry_from_prev_word(pw);
 #pragma unroll
-    for (int w = 0; w < kWarps; w++) {
-      const uint32_t c = ctl->warpCnt[pol][w];
-      if (w < warp) warp_base += c;
-      tile_total += c;
+      for (int u = 0; u < W; u++) {
+        uint32_t w8[8], pl[8];
+        load_unit(T, lane_off + 32 * u, w8);
+        transpose32(w8, pl);
+        const unit_classes c = classify(pl);
+        bs[u] = c.bs; qu[u] = c.qu; op[u] = c.op; sc[u] = c.sc; cl[u] = c.ctl;
+        if (__any_sync(kFull, pl[7] != 0 || utf8_carry_pending(uc))) {
+          uerr |= utf8_check_unit(pl, uc);
+        } else {
+          uc = utf8_carry_zero();
+        }
+      }
     }
-    const uint32_t Tincl = (Tprefix & kValidBit) ? tt_compose(Ttile, Tprefix & 63u) : Ttile;
+    if (KIND != kMinify) {  // minify does not validate (json_minifier.h: "does not parse or validate")
+      if (__any_sync(kFull, uerr != 0) && lane == 0) atomicOr(p.flags, kFlagUtf8);
+    }
+
+    // ============================ phase 2: escapes, quotes, warp transducer ============================
+    uint32_t qr[W];
+    uint32_t Pmask = 0, warp_cout0 = 0;
+    int nlead = 0;
+    {
+      const uint32_t bsany = bs[0] | bs[1] | bs[2] | bs[3];
+      if (__any_sync(kFull, bsany != 0)) {
+        uint32_t escaped[W];
+        const uint32_t esc_out0 = escape_scan<W>(bs, escaped);
+#pragma unroll
+        for (int u = 0; u < W; u++) qr[u] = qu[u] & ~escaped[u];
+        nlead = leading_backslashes<W>(bs);
+        const uint32_t G = __ballot_sync(kFull, esc_out0 != 0);
+        Pmask = __ballot_sync(kFull, nlead == 32 * W);
+        const uint32_t carries = escape_carries(G, Pmask, 0u, &warp_cout0);
+        if (((carries >> lane) & 1u) && nlead != 32 * W) toggle_first_nonbackslash_quote(qu, qr, nlead);
+      } else {
+#pragma unroll
+        for (int u = 0; u < W; u++) qr[u] = qu[u];
+      }
+    }
+    const bool warp_allbs = (Pmask == kFull);
+    const int mlane = warp_allbs ? 0 : (__ffs(~Pmask) - 1);  // lane holding the first non-backslash byte
+    {
+      const uint32_t lp = (__popc(qr[0]) + __popc(qr[1]) + __popc(qr[2]) + __popc(qr[3])) & 1u;
+      const uint32_t par0 = __popc(__ballot_sync(kFull, lp != 0)) & 1u;
+      uint32_t myq = 0;
+#pragma unroll
+      for (int u = 0; u < W; u++)
+        if ((nlead >> 5) == u) myq = (qu[u] >> (nlead & 31)) & 1u;
+      uint32_t qx = __shfl_sync(kFull, myq, mlane);
+      uint32_t x_is_last = __shfl_sync(kFull, uint32_t(nlead == 32 * W - 1), 31);
+      if (warp_allbs) qx = 0;
+      if (mlane != 31) x_is_last = 0;
+      const uint32_t scal0 = __shfl_sync(kFull, (sc[W - 1] & ~qr[W - 1]) >> 31, 31);
+      const uint32_t Tw = tt_make(warp_cout0, par0, scal0, warp_allbs ? 1u : warp_cout0, par0 ^ qx, scal0 ^ (qx & x_is_last));
+      if (lane == 0) ctl->warpT[warp] = Tw;
+    }
+    __syncthreads();  // S1: all warp transducers visible; every lane holds its input in registers
+    // stage s is free: fetch the next tile of this super-tile (after the last one the buffer serves as emit staging)
+    if (KIND == kIndex && r + 1 < nsub && tid == kRefillThread) refill_stage(tiles, ctl, &tmap, p, s);
+
+    // state entering this warp (relative to super-tile polarity 0): compose the warps before it
+    uint32_t win = srel;
+    for (int w = 0; w < warp; w++) win = tt_apply(ctl->warpT[w], win);
+    const uint32_t e_w = win & 1u, s_w = (win >> 1) & 1u, c_w = (win >> 2) & 1u;
+    uint32_t Ttile = ctl->warpT[0];
+#pragma unroll
+    for (int w = 1; w < kWarps; w++) Ttile = lut_compose(lut, ctl->warpT[w], Ttile);
+    srel = tt_apply(Ttile, srel);
+    Tsuper = (Tsuper & kValidBit) ? (lut_compose(lut, Ttile, Tsuper) | kValidBit) : (Ttile | kValidBit);
+
+    // ============================ phase 3: final masks, for both polarities ============================
+    if (e_w && !warp_allbs && lane == mlane) toggle_first_nonbackslash_quote(qu, qr, nlead);
+    {
+      uint32_t m0[W], m1[W];  // kIndex: pseudo-structurals, string tail (polarity 0).  kMinify: whitespace, in_string (polarity 0)
+      uint32_t c0 = 0, c1 = 0;
+      const uint32_t lp = (__popc(qr[0]) + __popc(qr[1]) + __popc(qr[2]) + __popc(qr[3])) & 1u;
+      const uint32_t pb = __ballot_sync(kFull, lp != 0);
+      uint32_t instr = (s_w ^ uint32_t(__popc(pb & lanemask_lt))) & 1u;
+      uint32_t scal_prev = __shfl_up_sync(kFull, (sc[W - 1] & ~qr[W - 1]) >> 31, 1);
+      if (lane == 0) scal_prev = c_w;
+      uint32_t prev_nq = scal_prev << 31;
+      uint32_t hit0 = 0, hit1 = 0;
+#pragma unroll
+      for (int u = 0; u < W; u++) {
+        const uint32_t in_string = prefix_xor32(qr[u]) ^ (0u - instr);
+        instr = in_string >> 31;
+        if (KIND == kIndex) {
+          const uint32_t nq = sc[u] & ~qr[u];
+          const uint32_t follows = shl_in(prev_nq, nq, 1);
+          prev_nq = nq;
+          const uint32_t pm = op[u] | (sc[u] & ~follows);
+          const uint32_t x0 = in_string ^ qr[u];
+          m0[u] = pm; m1[u] = x0;
+          c0 += __popc(pm & ~x0);
+          c1 += __popc(pm & x0);
+          hit0 |= cl[u] & in_string;
+          hit1 |= cl[u] & ~in_string;
+        } else {
+          const uint32_t ws = ~(op[u] | sc[u]);
+          uint32_t valid = kFull;
+          if (last_tile) {  // the 0x20 padding past len is never output (json_minifier.h L79-95)
+            const uint64_t ubase = uint64_t(dtile) * kTileBytes + lane_off + 32 * u;
+            if (ubase + 32 > p.len) valid = (ubase >= p.len) ? 0u : ((1u << uint32_t(p.len - ubase)) - 1u);
+          }
+          m0[u] = ws; m1[u] = in_string;
+          c0 += __popc(valid & ~(ws & ~in_string));
+          c1 += __popc(valid & ~(ws & in_string));
+        }
+      }
+      const bool h0 = __any_sync(kFull, hit0 != 0), h1 = __any_sync(kFull, hit1 != 0);
+      err0 = err0 || h0;
+      err1 = err1 || h1;
+      // park the masks until the incoming polarity is known
+      mask_slots[(r * 2 + 0) * kThreads + tid] = make_uint4(m0[0], m0[1], m0[2], m0[3]);
+      mask_slots[(r * 2 + 1) * kThreads + tid] = make_uint4(m1[0], m1[1], m1[2], m1[3]);
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) {
+        c0 += __shfl_xor_sync(kFull, c0, d);
+        c1 += __shfl_xor_sync(kFull, c1, d);
+      }
+      if (lane == 0) { ctl->cntw[r][0][warp] = c0; ctl->cntw[r][1][warp] = c1; }
+    }
+    __syncthreads();  // S2: per-warp counts visible; warpT may be reused
+    if (r + 1 < nsub) continue;
+
+    // =============================================== end of the super-tile ===============================================
+    if (p.debug != nullptr && tid == 0) p.debug[uint64_t(super) * 8 + 3] = globaltimer_ns();
+    uint32_t tc0 = 0, tc1 = 0;
+    for (uint32_t q = 0; q < nsub; q++) {
+#pragma unroll
+      for (int w = 0; w < kWarps; w++) { tc0 += ctl->cntw[q][0][w]; tc1 += ctl->cntw[q][1][w]; }
+    }
+    uint32_t state_in = cin.state, base = 0, Tprefix = 0;
+    if (super > 0) {
+      if (tid == 0) st_relaxed_u64(p.count_desc + super, pack_agg(p.epoch, Tsuper & 63u, tc0, tc1));
+      resolve_tile(p, ctl, lut, super, cin.state, warp, lane, state_in, base, Tprefix);
+      if ((state_in & 5u) != bstate) atomicOr(p.flags, kFlagInternal);  // cannot happen: bstate was exact
+    }
+    if (p.debug != nullptr && tid == 0) p.debug[uint64_t(super) * 8 + 4] = globaltimer_ns();
+    const uint32_t pol = (state_in >> 1) & 1u;  // in_string entering the super-tile
+    const uint32_t super_total = pol ? tc1 : tc0;
+    const uint32_t Tincl = (Tprefix & kValidBit) ? lut_compose(lut, Tsuper, Tprefix) : (Tsuper & 63u);
     if (tid == 0) {
-      st_relaxed_u64(p.count_desc + tile, pack_desc(p.epoch, kInc, Tincl, base + tile_total));
-      if (last_tile) {
+      st_relaxed_u64(p.count_desc + super, pack_inc(p.epoch, Tincl, base + super_total));
+      if (super == p.nsuper - 1) {
         Carry co;
-        co.count = cin.count + base + tile_total;
+        co.count = cin.count + base + super_total;
         co.state = tt_apply(Tincl, cin.state);
         co.ttable = Tincl;
         *p.carry_out = co;
@@ -598,63 +666,130 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) scan_kernel(const __g
     }
     if (KIND == kIndex && lane == 0 && (pol ? err1 : err0)) atomicOr(p.flags, kFlagCtl);
 
-    // exclusive offsets inside the warp for the polarity that turned out to be real
-    const uint32_t cnt = pol ? c1 : c0;
-    uint32_t incl = cnt;
+    // ============================ emit every tile of the super-tile ============================
+    uint32_t run_base = base;  // outputs before the tile being emitted
+    for (uint32_t q = 0; q < nsub; q++) {
+      uint32_t warp_base = 0, tile_total = 0;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t t = __shfl_up_sync(kFull, incl, d);
-      if (lane >= d) incl += t;
-    }
-    const uint64_t out_base = cin.count + base + warp_base + (incl - cnt);
-
-    // ============================ emit ============================
-    if (KIND == kIndex) {
-      // one loop over the lane's 128 mask bits (not one per 32-bit word: the warp runs max-over-lanes iterations)
-      uint32_t *dst = p.idx_out + out_base;
-      uint32_t pos = p.pos_base + dtile * uint32_t(kTileBytes) + lane_off;
-      const uint32_t flip = pol ? 0u : kFull;
-      uint32_t m = m0[0] & (m1[0] ^ flip), n1 = m0[1] & (m1[1] ^ flip), n2 = m0[2] & (m1[2] ^ flip), n3 = m0[3] & (m1[3] ^ flip);
-      for (uint32_t left = cnt; left != 0; --left) {
-        while (m == 0) {  // at most three times per lane
-          m = n1; n1 = n2; n2 = n3; n3 = 0;
-          pos += 32;
-        }
-        *dst++ = pos + (__ffs(m) - 1);
-        m &= m - 1;
+      for (int w = 0; w < kWarps; w++) {
+        const uint32_t c = ctl->cntw[q][pol][w];
+        if (w < warp) warp_base += c;
+        tile_total += c;
       }
-      __syncthreads();  // all warps are done with the control block
-      if (tid == kRefillThread) refill_stage(tiles, ctl, &tmap, p, s);
-    } else {
-      uint8_t *dst = p.dst + out_base;
-      const uint32_t flip = pol ? kFull : 0u;
+      const uint4 a0 = mask_slots[(q * 2 + 0) * kThreads + tid];
+      const uint4 a1 = mask_slots[(q * 2 + 1) * kThreads + tid];
+      if (KIND == kIndex) {
+        const uint32_t flip = pol ? 0u : kFull;
+        const uint32_t e0 = a0.x & (a1.x ^ flip), e1 = a0.y & (a1.y ^ flip), e2 = a0.z & (a1.z ^ flip), e3 = a0.w & (a1.w ^ flip);
+        const uint32_t cnt = __popc(e0) + __popc(e1) + __popc(e2) + __popc(e3);
+        uint32_t incl = cnt;
 #pragma unroll
-      for (int u = 0; u < W; u++) {
-        uint32_t w8[8];
-        load_unit(T, lane_off + 32 * u, w8);
-        uint32_t keep = ~(m0[u] & ~(m1[u] ^ flip));
-        if (last_tile) {
-          const uint64_t ubase = uint64_t(dtile) * kTileBytes + lane_off + 32 * u;
-          if (ubase + 32 > p.len) keep &= (ubase >= p.len) ? 0u : ((1u << uint32_t(p.len - ubase)) - 1u);
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t t = __shfl_up_sync(kFull, incl, d);
+          if (lane >= d) incl += t;
         }
+        // Balanced emit.  Structurals cluster (a lane inside a numeric array holds 10x more than a lane inside a long
+        // string), so a loop over the lane's own bits leaves most lanes idle.  Instead the warp's 128 mask words and
+        // their exclusive bit counts go to shared memory and lane L takes the contiguous run of words that holds
+        // outputs [L*k, (L+1)*k), k = ceil(total/32), found by binary search.  Word w of the warp covers bytes 32w..32w+31.
+        uint32_t *wmask = emit_scratch + warp * 256;
+        uint32_t *wpre = wmask + 128;
+        const uint32_t r0 = incl - cnt, r1 = r0 + __popc(e0), r2 = r1 + __popc(e1), r3 = r2 + __popc(e2);
+        reinterpret_cast<uint4 *>(wmask)[lane] = make_uint4(e0, e1, e2, e3);
+        reinterpret_cast<uint4 *>(wpre)[lane] = make_uint4(r0, r1, r2, r3);
+        const uint32_t wtotal = __shfl_sync(kFull, incl, 31);
+        __syncwarp();
+        if (wtotal != 0) {
+          const uint32_t k = (wtotal + 31u) >> 5;
+          const uint32_t target = uint32_t(lane) * k;  // first word whose exclusive count is >= lane*k (128 if none)
+          uint32_t lo = 0;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-          const uint32_t nib = (keep >> (4 * i)) & 15u;
-          const uint32_t word = w8[i];
-          if (nib == 15u && (reinterpret_cast<uintptr_t>(dst) & 3u) == 0) {
-            *reinterpret_cast<uint32_t *>(dst) = word;
-            dst += 4;
-          } else {
+          for (int step = 64; step >= 1; step >>= 1)
+            if (wpre[lo + step - 1] < target) lo += step;  // invariant: every word before lo has count < target
+          if (wpre[lo] < target && lo == 127) lo = 128;
+          uint32_t wend = __shfl_down_sync(kFull, lo, 1);
+          if (lane == 31) wend = 128;
+          // every lane walks its run of words with the SAME trip count (the warp maximum of words + bits) and a
+          // branch-light body, so the warp stays converged: one iteration emits one index or steps to the next word.
+          // Indexes go to a shared-memory staging area (this warp's 4 KiB of the idle tile buffer) and leave the SM with
+          // coalesced stores: scattered 4-byte global stores cost one L1 wavefront each and were the emit bottleneck.
+          const uint32_t nwords = wend > lo ? wend - lo : 0u;
+          const uint32_t lim = (wend < 128u) ? wpre[wend] : wtotal;
+          const uint32_t first = nwords ? wpre[lo] : 0u;
+          const uint32_t nbits = nwords ? lim - first : 0u;
+          const uint32_t steps = __reduce_max_sync(kFull, nwords + nbits);
+          uint32_t *out = p.idx_out + (cin.count + run_base + warp_base);
+          const bool staged = wtotal <= uint32_t(kWarpBytes / 4);
+          uint32_t *stg = reinterpret_cast<uint32_t *>(T + uint32_t(warp) * kWarpBytes);
+          uint32_t *dst = (staged ? stg : out) + first;
+          uint32_t w = lo;
+          uint32_t wbase = p.pos_base + (p.tile_begin + super * R + q) * uint32_t(kTileBytes) + uint32_t(warp) * kWarpBytes + 32 * lo;
+          uint32_t m = nwords ? wmask[lo] : 0u;
+          uint32_t left = nwords;  // words of the run not yet finished (including the current one)
+          for (uint32_t i = 0; i < steps; i++) {
+            if (m != 0) {
+              *dst++ = wbase + (__ffs(m) - 1);
+              m &= m - 1;
+            } else if (left > 1) {
+              --left;
+              ++w;
+              wbase += 32;
+              m = wmask[w];
+            }
+          }
+          if (staged) {
+            __syncwarp();
+            for (uint32_t i = lane; i < wtotal; i += 32) out[i] = stg[i];
+          }
+        }
+        __syncwarp();  // the scratch is rewritten for the next tile
+      } else {
+        // kMinify (one tile per super-tile): the tile's bytes are still in stage s
+        const uint32_t flip = pol ? kFull : 0u;
+        const uint32_t k0 = ~(a0.x & ~(a1.x ^ flip)), k1 = ~(a0.y & ~(a1.y ^ flip)), k2 = ~(a0.z & ~(a1.z ^ flip)), k3 = ~(a0.w & ~(a1.w ^ flip));
+        uint32_t keepm[W] = {k0, k1, k2, k3};
+        uint32_t cnt = 0;
 #pragma unroll
-            for (int b = 0; b < 4; b++)
-              if ((nib >> b) & 1u) *dst++ = uint8_t(word >> (8 * b));
+        for (int u = 0; u < W; u++) {
+          if (last_tile) {
+            const uint64_t ubase = uint64_t(dtile) * kTileBytes + lane_off + 32 * u;
+            if (ubase + 32 > p.len) keepm[u] &= (ubase >= p.len) ? 0u : ((1u << uint32_t(p.len - ubase)) - 1u);
+          }
+          cnt += __popc(keepm[u]);
+        }
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t t = __shfl_up_sync(kFull, incl, d);
+          if (lane >= d) incl += t;
+        }
+        uint8_t *dst = p.dst + (cin.count + run_base + warp_base + (incl - cnt));
+#pragma unroll
+        for (int u = 0; u < W; u++) {
+          uint32_t w8[8];
+          load_unit(T, lane_off + 32 * u, w8);
+          const uint32_t keep = keepm[u];
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const uint32_t nib = (keep >> (4 * i)) & 15u;
+            const uint32_t word = w8[i];
+            if (nib == 15u && (reinterpret_cast<uintptr_t>(dst) & 3u) == 0) {
+              *reinterpret_cast<uint32_t *>(dst) = word;
+              dst += 4;
+            } else {
+#pragma unroll
+              for (int b = 0; b < 4; b++)
+                if ((nib >> b) & 1u) *dst++ = uint8_t(word >> (8 * b));
+            }
           }
         }
       }
-      __syncthreads();  // every warp is done with stage s
-      if (tid == kRefillThread) refill_stage(tiles, ctl, &tmap, p, s);
+      run_base += tile_total;
     }
-    __syncthreads();  // stage_tile[s] / warpCnt are reused by the next iteration
+    if (p.debug != nullptr && tid == 0) p.debug[uint64_t(super) * 8 + 5] = globaltimer_ns();
+    __syncthreads();  // every warp is done with stage s (input bytes / emit staging), the mask slots and the counts
+    if (tid == kRefillThread) refill_stage(tiles, ctl, &tmap, p, s);
+    __syncthreads();
   }
 
   // last CTA out resets the ticket for the next launch on this context
@@ -688,11 +823,11 @@ static cudaError_t launch_kind(const CUtensorMap *tmap, const ScanParams &p, int
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(scan_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(scan_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(KIND));
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  scan_kernel<KIND><<<grid, kThreads, kSmemBytes, stream>>>(*tmap, p);
+  scan_kernel<KIND><<<grid, kThreads, smem_bytes_for(KIND), stream>>>(*tmap, p);
   return cudaGetLastError();
 }
 
@@ -709,16 +844,16 @@ int scan_max_ctas_per_sm(int kind) {
   cudaError_t e;
   switch (kind) {
     case kIndex:
-      cudaFuncSetAttribute(scan_kernel<kIndex>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, scan_kernel<kIndex>, kThreads, kSmemBytes);
+      cudaFuncSetAttribute(scan_kernel<kIndex>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(kIndex));
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, scan_kernel<kIndex>, kThreads, smem_bytes_for(kIndex));
       break;
     case kMinify:
-      cudaFuncSetAttribute(scan_kernel<kMinify>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, scan_kernel<kMinify>, kThreads, kSmemBytes);
+      cudaFuncSetAttribute(scan_kernel<kMinify>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(kMinify));
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, scan_kernel<kMinify>, kThreads, smem_bytes_for(kMinify));
       break;
     default:
-      cudaFuncSetAttribute(scan_kernel<kUtf8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, scan_kernel<kUtf8>, kThreads, kSmemBytes);
+      cudaFuncSetAttribute(scan_kernel<kUtf8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(kUtf8));
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, scan_kernel<kUtf8>, kThreads, smem_bytes_for(kUtf8));
       break;
   }
   return (e == cudaSuccess && n > 0) ? n : 1;

@@ -17,14 +17,23 @@ constexpr int kThreads = 32 * kWarps;
 constexpr int kTileBytes = kWarps * kWarpBytes;      // 32 KiB
 constexpr int kTileRows = kTileBytes / 128;          // 256 rows of 128 B (max TMA box dim)
 #ifndef SJB200_STAGES
-#define SJB200_STAGES 2
+#define SJB200_STAGES 1
 #endif
 #ifndef SJB200_MIN_CTAS
-#define SJB200_MIN_CTAS 3
+#define SJB200_MIN_CTAS 2
 #endif
 constexpr int kStages = SJB200_STAGES;      // shared-memory tile buffers per CTA
 constexpr int kMinCtasPerSm = SJB200_MIN_CTAS;  // __launch_bounds__ occupancy target
-constexpr int kSmemBytes = kStages * kTileBytes + 1024 /*alignment slack*/ + 512 /*control block*/;
+// A CTA scans a "super-tile" of up to kMaxSub consecutive tiles before it consults the look-back chain once:
+// the masks of every tile wait in shared memory (8 words per lane per tile) until the incoming state is known.
+constexpr int kMaxSub = 8;
+constexpr int kCtlBytes = 1024;                       // control block
+constexpr int kLutBytes = 64 * 64;                    // composed-transducer table
+constexpr int kEmitBytes = kWarps * 1024;             // per-warp emit scratch (128 mask words + 128 counts)
+constexpr int kMaskSlotBytes = kThreads * 8 * 4;      // one tile's masks
+constexpr int kSmemBytesScan = kStages * kTileBytes + 1024 /*alignment slack*/ + kCtlBytes + kLutBytes + kEmitBytes + kMaxSub * kMaskSlotBytes;
+constexpr int kSmemBytesUtf8 = kStages * kTileBytes + 1024 + kCtlBytes;
+constexpr int smem_bytes_for(int kind) { return kind == 2 ? kSmemBytesUtf8 : kSmemBytesScan; }
 
 // ---- scan kinds
 enum : int { kIndex = 0, kMinify = 1, kUtf8 = 2 };
@@ -46,6 +55,8 @@ struct ScanParams {
   uint32_t use_tma;         // 1: full tiles arrive by cp.async.bulk.tensor (buf 16 B aligned)
   uint32_t tile_begin;      // first document tile of this launch (chunked streaming)
   uint32_t ntiles;          // tiles in this launch: document tiles [tile_begin, tile_begin+ntiles)
+  uint32_t sub_per_super;   // R: tiles per super-tile (1..kMaxSub); the look-back chain has one element per super-tile
+  uint32_t nsuper;          // ceil(ntiles / R)
   uint32_t full_tiles;      // document tiles that lie entirely inside floor(len/128) rows
   uint32_t epoch;           // tags look-back descriptors so they need no per-launch reset
   uint32_t *idx_out;        // kIndex: device index array
@@ -53,9 +64,9 @@ struct ScanParams {
   const Carry *carry_in;
   Carry *carry_out;
   uint32_t *flags;          // accumulated with atomicOr
-  uint32_t *state_desc;     // [ntiles]  look-back chain 1 (transducer)
-  unsigned long long *count_desc;  // [ntiles] look-back chain 2 (output offsets)
+  unsigned long long *count_desc;  // [nsuper] the look-back chain
   uint32_t *ticket;         // [0] next tile, [1] CTAs finished
+  unsigned long long *debug;  // optional [ntiles][8] timeline (globaltimer ns) for tuning; null in production
 };
 
 // launchers (defined in sjb200_kernels.cu)

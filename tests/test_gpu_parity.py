@@ -150,11 +150,13 @@ def _big_adversarial(rng, nbytes):
     return bytes(out[:nbytes])
 
 
-@pytest.mark.parametrize("use_tma", [1, 0])
-def test_fuzz_multi_tile(parser, port, use_tma):
+@pytest.mark.parametrize("use_tma,sub_per_super", [(1, 0), (0, 0), (1, 3), (1, 8)])
+def test_fuzz_multi_tile(parser, port, use_tma, sub_per_super):
+    """sub_per_super forces the number of tiles a CTA scans before it consults the look-back chain (0 = automatic)"""
     parser.set_option("use_tma", use_tma)
+    parser.set_option("sub_per_super", sub_per_super)
     try:
-        rng = random.Random(corpus.SEED ^ 0x77 ^ use_tma)
+        rng = random.Random(corpus.SEED ^ 0x77 ^ use_tma ^ (sub_per_super << 4))
         impl = sj.get_active_implementation()
         sizes = [TILE - 1, TILE, TILE + 1, 2 * TILE, 3 * TILE + 17, 5 * TILE - 128, 9 * TILE + 4095, 40 * TILE + 1, 64 * TILE]
         for n in sizes:
@@ -168,6 +170,7 @@ def test_fuzz_multi_tile(parser, port, use_tma):
                 assert impl.validate_utf8(b) == port.validate_utf8(b), (n, rep)
     finally:
         parser.set_option("use_tma", 1)
+        parser.set_option("sub_per_super", 0)
 
 
 def test_valid_documents_and_streams(parser, port):
