@@ -717,29 +717,54 @@ __global__ void __launch_bounds__(kThreads, (KIND == kUtf8) ? 4 : kMinCtasPerSm)
           const uint32_t lim = (wend < 128u) ? wpre[wend] : wtotal;
           const uint32_t first = nwords ? wpre[lo] : 0u;
           const uint32_t nbits = nwords ? lim - first : 0u;
-          const uint32_t steps = __reduce_max_sync(kFull, nwords + nbits);
           uint32_t *out = p.idx_out + (cin.count + run_base + warp_base);
-          const bool staged = wtotal <= uint32_t(kWarpBytes / 4);
-          uint32_t *stg = reinterpret_cast<uint32_t *>(T + uint32_t(warp) * kWarpBytes);
-          uint32_t *dst = (staged ? stg : out) + first;
           uint32_t w = lo;
           uint32_t wbase = p.pos_base + (p.tile_begin + super * R + q) * uint32_t(kTileBytes) + uint32_t(warp) * kWarpBytes + 32 * lo;
           uint32_t m = nwords ? wmask[lo] : 0u;
           uint32_t left = nwords;  // words of the run not yet finished (including the current one)
-          for (uint32_t i = 0; i < steps; i++) {
-            if (m != 0) {
-              *dst++ = wbase + (__ffs(m) - 1);
-              m &= m - 1;
-            } else if (left > 1) {
-              --left;
-              ++w;
-              wbase += 32;
-              m = wmask[w];
+          if (wtotal <= uint32_t(kWarpBytes / 4)) {
+            // Indexes go to a shared-memory staging area (this warp's 4 KiB of the idle tile buffer) and leave the SM
+            // with coalesced stores (scattered 4-byte global stores cost one L1 wavefront each).  The loop body is
+            // branch-free and retires up to two indexes per iteration; every lane runs the same trip count, the warp
+            // maximum of sum over its words of max(1, ceil(bits/2)) <= words + bits/2.
+            uint32_t *stg = reinterpret_cast<uint32_t *>(T + uint32_t(warp) * kWarpBytes);
+            uint32_t off = first;
+            const uint32_t steps = __reduce_max_sync(kFull, nwords + ((nbits + 1u) >> 1));
+            for (uint32_t i = 0; i < steps; i++) {
+              const uint32_t b1 = __ffs(m) - 1;
+              const bool h1 = m != 0;
+              const uint32_t m1 = m & (m - 1);
+              const uint32_t b2 = __ffs(m1) - 1;
+              const bool h2 = m1 != 0;
+              const uint32_t m2 = m1 & (m1 - 1);
+              if (h1) stg[off] = wbase + b1;
+              if (h2) stg[off + 1] = wbase + b2;
+              off += uint32_t(h1) + uint32_t(h2);
+              const bool adv = (m2 == 0) && (left > 1);
+              left -= uint32_t(adv);
+              w += uint32_t(adv);
+              wbase += adv ? 32u : 0u;
+              const uint32_t nm = wmask[w & 127u];
+              m = (m2 != 0) ? m2 : (adv ? nm : 0u);
             }
-          }
-          if (staged) {
             __syncwarp();
+#pragma unroll 4
             for (uint32_t i = lane; i < wtotal; i += 32) out[i] = stg[i];
+          } else {
+            // very dense chunk (> 1 structural per 4 bytes over 4 KiB): straight to global memory
+            uint32_t *dst = out + first;
+            const uint32_t steps = __reduce_max_sync(kFull, nwords + nbits);
+            for (uint32_t i = 0; i < steps; i++) {
+              if (m != 0) {
+                *dst++ = wbase + (__ffs(m) - 1);
+                m &= m - 1;
+              } else if (left > 1) {
+                --left;
+                ++w;
+                wbase += 32;
+                m = wmask[w];
+              }
+            }
           }
         }
         __syncwarp();  // the scratch is rewritten for the next tile

@@ -26,6 +26,8 @@ constexpr int kStages = SJB200_STAGES;      // shared-memory tile buffers per CT
 constexpr int kMinCtasPerSm = SJB200_MIN_CTAS;  // __launch_bounds__ occupancy target
 // A CTA scans a "super-tile" of up to kMaxSub consecutive tiles before it consults the look-back chain once:
 // the masks of every tile wait in shared memory (8 words per lane per tile) until the incoming state is known.
+// (Parking them in an L2-resident global scratch instead, to fit 4 CTAs per SM, was measured slower: the SM is
+// issue-bound, not latency-bound.)
 constexpr int kMaxSub = 8;
 constexpr int kCtlBytes = 1024;                       // control block
 constexpr int kLutBytes = 64 * 64;                    // composed-transducer table
