@@ -54,45 +54,56 @@ def peaks():
 
 
 class ClockSampler:
-    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+    """samples SM clocks / throttle reasons through NVML while the timed region runs (every ~1 ms; the timed region
+    of a 64 MiB stage-1 pass is milliseconds long, far shorter than one `nvidia-smi` invocation)"""
 
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.index, self.rows, self.stop, self.th = index, [], threading.Event(), None
+        self.index, self.rows, self.stop, self.th, self.h = index, [], threading.Event(), None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv, self.h, self.max_sm = None, None, None
 
     def _run(self):
         while not self.stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                sm = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+                try:
+                    rs = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    rs = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((sm, rs))
             except Exception:  # noqa: BLE001
                 pass
-            self.stop.wait(0.1)
+            self.stop.wait(0.001)
 
     def __enter__(self):
-        self.th = threading.Thread(target=self._run, daemon=True)
-        self.th.start()
+        if self.h is not None:
+            self.th = threading.Thread(target=self._run, daemon=True)
+            self.th.start()
         return self
 
     def __exit__(self, *a):
         self.stop.set()
-        self.th.join(timeout=6)
+        if self.th:
+            self.th.join(timeout=2)
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": ["nvml unavailable"], "samples": 0}
+        sm = sorted(r[0] for r in self.rows)
         reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            for k, nm in enumerate(names):
-                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+        for _, rs in self.rows:
+            for bit, nm in self.REASONS.items():
+                if rs & bit:
                     reasons.add(nm)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(self.rows)}
+        return {"sm_mhz": float(sm[len(sm) // 2]), "sm_max_mhz": float(self.max_sm), "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
 def make_doc(seed_offset):
@@ -165,40 +176,24 @@ def run_ours(args, rank, world):
     # (N>1: rank r's document is shard r of the stream doc_0 doc_1 ... doc_{N-1}; every shard is a complete document)
     d_docs = [torch.from_numpy(d.copy()).to(dev) for d in docs]
     pinned = [torch.from_numpy(d.copy()).pin_memory() for d in docs]
-    parsers = []
-    for _ in range(2):  # two parser contexts so one call is always queued behind the other (no idle GPU between steps)
-        rc, p = impl.create_dom_parser_implementation(DOC_BYTES)
-        if rc != sj.SUCCESS:
-            raise RuntimeError("create_dom_parser_implementation failed: " + capi.ERROR_NAMES.get(rc, str(rc)))
-        p.set_option("time_kernel", 1)
-        p.device_index_buffer(DOC_BYTES)
-        parsers.append(p)
-    stream = torch.cuda.Stream(device=dev)  # one explicit stream for both parser contexts: their launches serialise
+    rc, parser = impl.create_dom_parser_implementation(DOC_BYTES)
+    if rc != sj.SUCCESS:
+        raise RuntimeError("create_dom_parser_implementation failed: " + capi.ERROR_NAMES.get(rc, str(rc)))
+    parser.set_option("time_kernel", 1)
+    parsers = [parser]
+    stream = torch.cuda.Stream(device=dev)  # the stream every scan of the timed region is launched on
     torch.cuda.set_stream(stream)
+    words = L.sjb200_index_words(DOC_BYTES)
+    d_idxs = [torch.empty(words, dtype=torch.int32, device=dev) for _ in range(2)]
     gather_in = torch.zeros(4, dtype=torch.int64, device=dev)
     gather_out = torch.zeros(4 * world, dtype=torch.int64, device=dev) if world > 1 else None
 
     kernel_ms, n_struct = [], []
 
-    def step_enqueue(i):
-        p = parsers[i % 2]
-        if world == 1:
-            rc = p.stage1_device_enqueue(d_docs[i % ROTATE], sj.REGULAR, stream=stream)
-            assert rc == 0
-        return p
-
-    def step_finish(i, p):
-        if world == 1:
-            rc = p.stage1_device_finish()
-            if rc != sj.SUCCESS:
-                raise RuntimeError("stage1 failed: " + capi.ERROR_NAMES.get(rc, str(rc)) + " " + p.last_cuda_error())
-            return p.n_structural_indexes
-        return None
-
     def sharded_step(i):
         """one sharded pass: scan with speculated state 0, exchange, re-scan if the speculation was wrong"""
-        p = parsers[i % 2]
-        rc, res = p.stage1_shard_device(d_docs[i % ROTATE], 0, rank == world - 1, stream=stream)
+        p = parser
+        rc, res = p.stage1_shard_device(d_docs[i % ROTATE], 0, rank == world - 1, d_idx=d_idxs[i % 2], stream=stream)
         if rc != 0:
             raise RuntimeError("shard scan failed")
         gather_in[0], gather_in[1], gather_in[2] = int(res.ttable), int(res.count), int(res.flags)
@@ -207,7 +202,7 @@ def run_ours(args, rank, world):
         tts = (C.c_uint32 * world)(*[int(x) for x in g[:, 0]])
         state_in = L.sjb200_fold_state(tts, rank)
         if state_in != 0:  # wrong speculation: scan again with the true state, then publish the corrected count
-            rc, res = p.stage1_shard_device(d_docs[i % ROTATE], state_in, rank == world - 1, stream=stream)
+            rc, res = p.stage1_shard_device(d_docs[i % ROTATE], state_in, rank == world - 1, d_idx=d_idxs[i % 2], stream=stream)
             gather_in[1] = int(res.count)
         if np.any([L.sjb200_fold_state(tts, r) != 0 for r in range(world)]):
             dist.all_gather_into_tensor(gather_out, gather_in)
@@ -217,29 +212,30 @@ def run_ours(args, rank, world):
 
     def run_steps(k, record):
         t_ev0, t_ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        parser.get_stat("kernel_ms_mean")  # reset the per-launch event log
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t_ev0.record(stream)
         if world == 1:
-            inflight = step_enqueue(0)
-            for i in range(k):
-                nxt = step_enqueue(i + 1) if i + 1 < k else None
-                n = step_finish(i, inflight)
+            # K steps = K documents through the batch entry point: every scan is queued back to back on `stream`
+            res = parser.stage1_device_batch([d_docs[i % ROTATE] for i in range(k)], [d_idxs[i % 2] for i in range(k)], sj.REGULAR, stream=stream)
+            for err, n in res:
+                if err != sj.SUCCESS:
+                    raise RuntimeError("stage1 failed: " + capi.ERROR_NAMES.get(err, str(err)) + " " + parser.last_cuda_error())
                 if record:
-                    kernel_ms.append(inflight.get_stat("kernel_ms"))
                     n_struct.append(n)
-                inflight = nxt
         else:
             for i in range(k):
                 n, _base = sharded_step(i)
                 if record:
-                    kernel_ms.append(parsers[i % 2].get_stat("kernel_ms"))
                     n_struct.append(n)
         t_ev1.record(stream)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+        if record:
+            kernel_ms.append(parser.get_stat("kernel_ms_mean"))
         return t_ev0.elapsed_time(t_ev1)
 
     launches0 = sum(p.get_stat("launches") for p in parsers)
@@ -291,7 +287,7 @@ def run_ours(args, rank, world):
                        f"{world} x 64 MiB shards of one random-structure JSON stream, stage1 sharded by byte range + NCCL carry/offset all-gather",
                        "bytes_per_gpu_per_step": DOC_BYTES, "mode": "regular" if world == 1 else "shard", "structurals_per_step": int(nmean),
                        "l2": f"{ROTATE} distinct inputs used round-robin ({ROTATE * DOC_BYTES >> 20} MiB > 126 MB L2)",
-                       "pipelining": "two parser contexts, the next call is enqueued before the previous one is finished"},
+                       "api": "sjb200_stage1_dev_batch: the K documents of the timed region are queued back to back on one stream" if world == 1 else "sjb200_stage1_shard_dev + all_gather"},
             "clocks": clocks.summary(),
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": DOC_BYTES, "d2h_bytes_per_step": int(4 * e2e_n + 24), "steps": e2e_steps},
             "gpu_launches": int(launches2 - launches1),
@@ -328,7 +324,7 @@ def cpu_baseline(doc):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()

@@ -114,6 +114,17 @@ SJB200_API int sjb200_stage1_dev(sjb200_ctx *ctx, const uint8_t *d_buf, size_t l
 SJB200_API int sjb200_minify_dev(sjb200_ctx *ctx, const uint8_t *d_buf, size_t len, uint8_t *d_dst, size_t *dst_len, void *stream);
 SJB200_API int sjb200_validate_utf8_dev(sjb200_ctx *ctx, const uint8_t *d_buf, size_t len, void *stream);
 
+/* many documents per call: all scans are queued back to back, one host wait, then each document's finish().
+ * (what a caller with a corpus / NDJSON rows resident in HBM uses instead of a loop of sjb200_stage1_dev) */
+typedef struct {
+  const uint8_t *d_buf;          /* in: device pointer */
+  size_t len;                    /* in */
+  uint32_t *d_idx;               /* in: device index buffer, sjb200_index_words(len) words */
+  uint32_t n_structural_indexes; /* in/out, like sjb200_stage1_dev's n_inout */
+  int error;                     /* out: simdjson::error_code */
+} sjb200_doc;
+SJB200_API int sjb200_stage1_dev_batch(sjb200_ctx *ctx, sjb200_doc *docs, int ndocs, int mode, void *stream);
+
 /* split form of the same calls for pipelining / timing: enqueue returns as soon as the work is on the
  * stream, finish waits for it and completes the reference's finish() logic. */
 SJB200_API int sjb200_stage1_dev_enqueue(sjb200_ctx *ctx, const uint8_t *d_buf, size_t len, int mode, uint32_t *d_idx, void *stream);

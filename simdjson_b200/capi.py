@@ -14,7 +14,7 @@ EXPORTS = [
     "sjb200_create", "sjb200_destroy", "sjb200_set_capacity", "sjb200_capacity", "sjb200_index_words", "sjb200_device",
     "sjb200_last_cuda_error", "sjb200_set_option", "sjb200_get_stat", "sjb200_pin_host_memory", "sjb200_unpin_host_memory", "sjb200_get_debug_timeline",
     "sjb200_stage1", "sjb200_minify", "sjb200_validate_utf8",
-    "sjb200_stage1_dev", "sjb200_minify_dev", "sjb200_validate_utf8_dev",
+    "sjb200_stage1_dev", "sjb200_minify_dev", "sjb200_validate_utf8_dev", "sjb200_stage1_dev_batch",
     "sjb200_stage1_dev_enqueue", "sjb200_stage1_dev_finish", "sjb200_minify_dev_enqueue", "sjb200_minify_dev_finish",
     "sjb200_validate_utf8_dev_enqueue", "sjb200_validate_utf8_dev_finish",
     "sjb200_stage1_shard_dev", "sjb200_fold_state", "sjb200_shard_cut",
@@ -27,6 +27,10 @@ ERROR_NAMES = {0: "SUCCESS", 1: "CAPACITY", 2: "MEMALLOC", 11: "UTF8_ERROR", 13:
 
 # simdjson::stage1_mode (include/simdjson/internal/dom_parser_implementation.h L22-27)
 REGULAR, STREAMING_PARTIAL, STREAMING_FINAL, JSON_SEQUENCE_PARTIAL, JSON_SEQUENCE_FINAL, COMMA_DELIMITED_PARTIAL, COMMA_DELIMITED_FINAL = range(7)
+
+
+class Doc(C.Structure):
+    _fields_ = [("d_buf", C.c_void_p), ("len", C.c_size_t), ("d_idx", C.c_void_p), ("n_structural_indexes", C.c_uint32), ("error", C.c_int)]
 
 
 class ShardResult(C.Structure):
@@ -59,6 +63,7 @@ def load():
         "sjb200_stage1_dev": (C.c_int, [vp, vp, sz, C.c_int, vp, u32p, vp]),
         "sjb200_minify_dev": (C.c_int, [vp, vp, sz, vp, C.POINTER(sz), vp]),
         "sjb200_validate_utf8_dev": (C.c_int, [vp, vp, sz, vp]),
+        "sjb200_stage1_dev_batch": (C.c_int, [vp, C.POINTER(Doc), C.c_int, C.c_int, vp]),
         "sjb200_stage1_dev_enqueue": (C.c_int, [vp, vp, sz, C.c_int, vp, vp]),
         "sjb200_stage1_dev_finish": (C.c_int, [vp, u32p]),
         "sjb200_minify_dev_enqueue": (C.c_int, [vp, vp, sz, vp, vp]),

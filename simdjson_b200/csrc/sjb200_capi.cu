@@ -67,8 +67,10 @@ struct sjb200_ctx {
   uint32_t epoch = 0;
   int grid[3] = {0, 0, 0};
   long opt_sub_per_super = 0, opt_use_tma = 1, opt_grid = 0, opt_chunk_bytes = 4 << 20, opt_time_kernel = 0;
-  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // around the scan kernel when opt_time_kernel is set
+  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // around the last scan kernel when opt_time_kernel is set
   bool ev_valid = false;
+  std::vector<cudaEvent_t> ev_pool;              // [2i], [2i+1] around launch i since the last kernel_ms_mean query
+  size_t ev_used = 0;
   long opt_debug_timeline = 0;
   unsigned long long *d_debug = nullptr; size_t debug_tiles = 0; uint32_t debug_last_tiles = 0;
   unsigned long long launches = 0;               // kernels of ours launched by this context
@@ -186,8 +188,9 @@ int grid_for(sjb200_ctx *c, int kind, uint32_t nelements) {
 // Enqueue the scan of document tiles [tile_begin, tile_begin+ntiles) of (d_buf,len).
 bool enqueue_scan(sjb200_ctx *c, int kind, const CUtensorMap *map, bool tma, const uint8_t *d_buf, size_t len, uint32_t tile_begin,
                   uint32_t ntiles, bool has_last_tile, uint32_t prev_word, uint32_t *d_idx, uint8_t *d_dst, int carry_in_slot,
-                  cudaStream_t stream, int carry_out_slot = -1) {
-  if (carry_out_slot < 0) carry_out_slot = carry_in_slot ^ 1;
+                  cudaStream_t stream, int carry_out_slot = -1, bool write_sentinels = false) {
+  // carry_in_slot < 0: the launch starts a document (zero state, zero count)
+  if (carry_out_slot < 0) carry_out_slot = (carry_in_slot < 0) ? 1 : (carry_in_slot ^ 1);
   ScanParams p;
   memset(&p, 0, sizeof(p));
   p.buf = d_buf;
@@ -210,7 +213,8 @@ bool enqueue_scan(sjb200_ctx *c, int kind, const CUtensorMap *map, bool tma, con
   p.epoch = next_epoch(c);
   p.idx_out = d_idx;
   p.dst = d_dst;
-  p.carry_in = c->d_carry + carry_in_slot;
+  p.carry_in = (carry_in_slot < 0) ? nullptr : c->d_carry + carry_in_slot;
+  p.write_sentinels = write_sentinels ? 1u : 0u;
   p.carry_out = c->d_carry + carry_out_slot;
   p.flags = c->d_flags;
   p.count_desc = c->d_count_desc;
@@ -223,12 +227,18 @@ bool enqueue_scan(sjb200_ctx *c, int kind, const CUtensorMap *map, bool tma, con
     }
     if (c->d_debug) { cudaMemsetAsync(c->d_debug, 0, size_t(ntiles) * 64, stream); p.debug = c->d_debug; c->debug_last_tiles = ntiles; }
   }
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (c->opt_time_kernel) {
-    if (!c->ev_k0) { cudaEventCreate(&c->ev_k0); cudaEventCreate(&c->ev_k1); }
-    cudaEventRecord(c->ev_k0, stream);
+    if (c->ev_used + 2 > c->ev_pool.size() && c->ev_pool.size() < 4096) {
+      cudaEvent_t a, b;
+      cudaEventCreate(&a); cudaEventCreate(&b);
+      c->ev_pool.push_back(a); c->ev_pool.push_back(b);
+    }
+    if (c->ev_used + 2 <= c->ev_pool.size()) { e0 = c->ev_pool[c->ev_used]; e1 = c->ev_pool[c->ev_used + 1]; c->ev_used += 2; }
+    if (e0) cudaEventRecord(e0, stream);
   }
   const bool launched = ok(c, launch_scan(kind, map, p, grid_for(c, kind, p.nsuper), stream), "launch scan");
-  if (c->opt_time_kernel) { cudaEventRecord(c->ev_k1, stream); c->ev_valid = launched; }
+  if (e1) { cudaEventRecord(e1, stream); c->ev_k0 = e0; c->ev_k1 = e1; c->ev_valid = launched; }
   c->launches += launched ? 1 : 0;
   return launched;
 }
@@ -307,14 +317,9 @@ class DeviceIndexWriter final : public IndexWriter {
 
 bool is_filter_mode(int mode) { return mode >= SJB200_JSON_SEQUENCE_PARTIAL; }
 
-bool reset_document_state(sjb200_ctx *c, cudaStream_t s) {
-  return ok(c, cudaMemsetAsync(c->d_flags, 0, sizeof(uint32_t), s), "memset flags") &&
-         ok(c, cudaMemsetAsync(c->d_carry, 0, 2 * sizeof(Carry), s), "memset carry");
-}
-
+// one small copy brings back everything a launch reports: {count, state, transducer, flags} of slot 1
 bool fetch_result(sjb200_ctx *c, cudaStream_t s) {
-  return ok(c, cudaMemcpyAsync(c->h_carry, c->d_carry, 2 * sizeof(Carry), cudaMemcpyDeviceToHost, s), "D2H carry") &&
-         ok(c, cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, s), "D2H flags");
+  return ok(c, cudaMemcpyAsync(c->h_carry + 1, c->d_carry + 1, sizeof(Carry), cudaMemcpyDeviceToHost, s), "D2H result");
 }
 
 }  // namespace
@@ -345,7 +350,8 @@ extern "C" int sjb200_create(int device, size_t capacity, sjb200_ctx **out) {
               ok(c, cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking), "stream") &&
               dev_alloc(c, &c->d_carry, kCarrySlots, "cudaMalloc(carry)") && dev_alloc(c, &c->d_flags, 1, "cudaMalloc(flags)") &&
               dev_alloc(c, &c->d_ticket, 2, "cudaMalloc(ticket)") &&
-              ok(c, cudaMemset(c->d_ticket, 0, 2 * sizeof(uint32_t)), "memset ticket");
+              ok(c, cudaMemset(c->d_ticket, 0, 2 * sizeof(uint32_t)), "memset ticket") &&
+              ok(c, cudaMemset(c->d_flags, 0, sizeof(uint32_t)), "memset flags");
   void *hp = nullptr;
   good = good && ok(c, cudaMallocHost(&hp, kCarrySlots * sizeof(Carry)), "cudaMallocHost");
   c->h_carry = static_cast<Carry *>(hp);
@@ -386,7 +392,7 @@ extern "C" void sjb200_destroy(sjb200_ctx *c) {
   if (c->h_small) cudaFreeHost(c->h_small);
   if (c->h_chars) cudaFreeHost(c->h_chars);
   if (c->h_window) cudaFreeHost(c->h_window);
-  if (c->ev_k0) { cudaEventDestroy(c->ev_k0); cudaEventDestroy(c->ev_k1); }
+  for (auto e : c->ev_pool) cudaEventDestroy(e);
   for (auto e : c->chunk_events) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -441,6 +447,18 @@ extern "C" double sjb200_get_stat(sjb200_ctx *c, const char *key) {
     if (cudaEventElapsedTime(&ms, c->ev_k0, c->ev_k1) != cudaSuccess) { (void)cudaGetLastError(); return -1.0; }
     return double(ms);
   }
+  if (!strcmp(key, "kernel_ms_mean")) {  // mean duration of the scan kernels launched since the previous query
+    DeviceGuard g(c->device);
+    double sum = 0;
+    size_t n = 0;
+    for (size_t i = 0; i + 1 < c->ev_used; i += 2) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, c->ev_pool[i], c->ev_pool[i + 1]) == cudaSuccess) { sum += ms; n++; } else (void)cudaGetLastError();
+    }
+    c->ev_used = 0;
+    c->ev_valid = false;
+    return n ? sum / double(n) : -1.0;
+  }
   if (!strcmp(key, "launches")) return double(c->launches);
   if (!strcmp(key, "grid_index")) return double(grid_for(c, kIndex, 0xFFFFFFFFu));
   if (!strcmp(key, "sm_count")) return double(c->sm_count);
@@ -460,49 +478,42 @@ extern "C" int sjb200_set_option(sjb200_ctx *c, const char *key, long value) {
 }
 
 // =============================================================================== device-resident
-extern "C" int sjb200_stage1_dev_enqueue(sjb200_ctx *c, const uint8_t *d_buf, size_t len, int mode, uint32_t *d_idx, void *stream) {
-  if (!c) return SJB200_UNEXPECTED_ERROR;
-  DeviceGuard g(c->device);
-  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
-  PendingCall &pc = c->pending;
+namespace {
+// enqueue one device-resident stage-1 scan; its {count,state,flags} come back in h_carry[slot]
+void stage1_enqueue_into(sjb200_ctx *c, PendingCall &pc, const uint8_t *d_buf, size_t len, int mode, uint32_t *d_idx, cudaStream_t s,
+                         int slot) {
   pc = PendingCall();
-  pc.kind = kIndex; pc.mode = mode; pc.d_buf = d_buf; pc.d_idx = d_idx; pc.stream = s; pc.len = len;
-  if (mode < SJB200_REGULAR || mode > SJB200_COMMA_DELIMITED_FINAL) { pc.early_error = SJB200_UNEXPECTED_ERROR; return SJB200_SUCCESS; }
-  if (len > c->capacity) { pc.early_error = SJB200_CAPACITY; return SJB200_SUCCESS; }   // json_structural_indexer.h L195
-  if (len == 0) { pc.early_error = SJB200_EMPTY; return SJB200_SUCCESS; }                // L197
-  if (mode != SJB200_REGULAR) {                                                           // L198-204
+  pc.kind = kIndex; pc.mode = mode; pc.d_buf = d_buf; pc.d_idx = d_idx; pc.stream = s; pc.len = len; pc.carry_slot = slot;
+  if (mode < SJB200_REGULAR || mode > SJB200_COMMA_DELIMITED_FINAL) { pc.early_error = SJB200_UNEXPECTED_ERROR; return; }
+  if (len > c->capacity) { pc.early_error = SJB200_CAPACITY; return; }   // json_structural_indexer.h L195
+  if (len == 0) { pc.early_error = SJB200_EMPTY; return; }                // L197
+  if (mode != SJB200_REGULAR) {                                           // L198-204
     const size_t k = std::min<size_t>(3, len);
     if (!ok(c, cudaMemcpyAsync(c->h_small, d_buf + len - k, k, cudaMemcpyDeviceToHost, s), "D2H tail") ||
         !ok(c, cudaStreamSynchronize(s), "sync"))
-      { pc.early_error = SJB200_UNEXPECTED_ERROR; return SJB200_SUCCESS; }
+      { pc.early_error = SJB200_UNEXPECTED_ERROR; return; }
     len = trim_partial_utf8_tail(c->h_small, k, len);
     pc.len = len;
-    if (len == 0) { pc.early_error = SJB200_UTF8_ERROR; return SJB200_SUCCESS; }
+    if (len == 0) { pc.early_error = SJB200_UTF8_ERROR; return; }
   }
-  if (!ensure_desc(c, len)) { pc.early_error = SJB200_MEMALLOC; return SJB200_SUCCESS; }
+  if (!ensure_desc(c, len)) { pc.early_error = SJB200_MEMALLOC; return; }
   CUtensorMap map;
   bool tma = false;
   make_tensor_map(c, &map, d_buf, len, &tma);
-  if (!reset_document_state(c, s) ||
-      !enqueue_scan(c, kIndex, &map, tma, d_buf, len, 0, tiles_of(len), true, 0x20202020u, d_idx, nullptr, 0, s) ||
-      !fetch_result(c, s))
+  if (!enqueue_scan(c, kIndex, &map, tma, d_buf, len, 0, tiles_of(len), true, 0x20202020u, d_idx, nullptr, -1, s, slot, true) ||
+      !ok(c, cudaMemcpyAsync(c->h_carry + slot, c->d_carry + slot, sizeof(Carry), cudaMemcpyDeviceToHost, s), "D2H result"))
     pc.early_error = SJB200_UNEXPECTED_ERROR;
-  pc.carry_slot = 1;
-  return SJB200_SUCCESS;
 }
 
-extern "C" int sjb200_stage1_dev_finish(sjb200_ctx *c, uint32_t *n_inout) {
-  if (!c || c->pending.kind != kIndex) return SJB200_UNEXPECTED_ERROR;
-  DeviceGuard g(c->device);
-  PendingCall pc = c->pending;
-  c->pending.kind = -1;
+// complete one enqueued scan (the stream has been synchronised by the caller)
+int stage1_finish_from(sjb200_ctx *c, const PendingCall &pc, uint32_t *n_inout) {
   if (pc.early_error >= 0) return pc.early_error;
-  if (!ok(c, cudaStreamSynchronize(pc.stream), "sync")) return SJB200_UNEXPECTED_ERROR;
   FinishInput in;
   in.mode = pc.mode; in.len = pc.len;
   in.count = c->h_carry[pc.carry_slot].count;
   in.state = c->h_carry[pc.carry_slot].state;
-  in.flags = *c->h_flags;
+  in.flags = c->h_carry[pc.carry_slot].flags;
+  in.sentinels_written = true;
   DeviceIndexWriter writer(c, pc.d_idx, pc.stream);
   int rc;
   uint32_t n_local = n_inout ? *n_inout : 0;
@@ -517,6 +528,7 @@ extern "C" int sjb200_stage1_dev_finish(sjb200_ctx *c, uint32_t *n_inout) {
       return SJB200_UNEXPECTED_ERROR;
     HostStructuralReader reader(hbuf.data(), hidx.data());
     HostIndexWriter hw(hidx.data());
+    in.sentinels_written = false;  // the host copy holds only the n indexes
     bool dirty = false;
     rc = finish_stage1(in, reader, hw, &n_local, hbuf.data(), hidx.data(), &dirty);
     const bool wrote = !(rc == SJB200_UNCLOSED_STRING && pc.mode == SJB200_REGULAR) && rc != SJB200_UNESCAPED_CHARS && rc != SJB200_UNEXPECTED_ERROR;
@@ -534,6 +546,49 @@ extern "C" int sjb200_stage1_dev_finish(sjb200_ctx *c, uint32_t *n_inout) {
   }
   if (n_inout) *n_inout = n_local;
   return rc;
+}
+
+}  // namespace
+
+extern "C" int sjb200_stage1_dev_enqueue(sjb200_ctx *c, const uint8_t *d_buf, size_t len, int mode, uint32_t *d_idx, void *stream) {
+  if (!c) return SJB200_UNEXPECTED_ERROR;
+  DeviceGuard g(c->device);
+  stage1_enqueue_into(c, c->pending, d_buf, len, mode, d_idx, stream ? static_cast<cudaStream_t>(stream) : c->stream, 1);
+  return SJB200_SUCCESS;
+}
+
+extern "C" int sjb200_stage1_dev_finish(sjb200_ctx *c, uint32_t *n_inout) {
+  if (!c || c->pending.kind != kIndex) return SJB200_UNEXPECTED_ERROR;
+  DeviceGuard g(c->device);
+  PendingCall pc = c->pending;
+  c->pending.kind = -1;
+  if (pc.early_error < 0 && !ok(c, cudaStreamSynchronize(pc.stream), "sync")) return SJB200_UNEXPECTED_ERROR;
+  return stage1_finish_from(c, pc, n_inout);
+}
+
+// Many documents in one call (NDJSON rows, a corpus): every scan is queued back to back on the stream, the host
+// waits once, then completes each document's finish() logic.  docs[i].error receives the error_code.
+extern "C" int sjb200_stage1_dev_batch(sjb200_ctx *c, sjb200_doc *docs, int ndocs, int mode, void *stream) {
+  if (!c || (!docs && ndocs > 0) || ndocs < 0) return SJB200_UNEXPECTED_ERROR;
+  DeviceGuard g(c->device);
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+  std::vector<PendingCall> calls;
+  int done = 0;
+  while (done < ndocs) {
+    const int group = std::min(ndocs - done, kCarrySlots - 2);  // one result slot per document in flight
+    calls.assign(size_t(group), PendingCall());
+    for (int i = 0; i < group; i++) {
+      sjb200_doc &d = docs[done + i];
+      stage1_enqueue_into(c, calls[size_t(i)], d.d_buf, d.len, mode, d.d_idx, s, 1 + i);
+    }
+    if (!ok(c, cudaStreamSynchronize(s), "sync")) return SJB200_UNEXPECTED_ERROR;
+    for (int i = 0; i < group; i++) {
+      sjb200_doc &d = docs[done + i];
+      d.error = stage1_finish_from(c, calls[size_t(i)], &d.n_structural_indexes);
+    }
+    done += group;
+  }
+  return SJB200_SUCCESS;
 }
 
 extern "C" int sjb200_stage1_dev(sjb200_ctx *c, const uint8_t *d_buf, size_t len, int mode, uint32_t *d_idx, uint32_t *n_inout,
@@ -556,8 +611,7 @@ extern "C" int sjb200_minify_dev_enqueue(sjb200_ctx *c, const uint8_t *d_buf, si
   CUtensorMap map;
   bool tma = false;
   make_tensor_map(c, &map, d_buf, len, &tma);
-  if (!reset_document_state(c, s) ||
-      !enqueue_scan(c, kMinify, &map, tma, d_buf, len, 0, tiles_of(len), true, 0x20202020u, nullptr, d_dst, 0, s) ||
+  if (!enqueue_scan(c, kMinify, &map, tma, d_buf, len, 0, tiles_of(len), true, 0x20202020u, nullptr, d_dst, -1, s, 1) ||
       !fetch_result(c, s))
     pc.early_error = SJB200_UNEXPECTED_ERROR;
   pc.carry_slot = 1;
@@ -572,7 +626,7 @@ extern "C" int sjb200_minify_dev_finish(sjb200_ctx *c, size_t *dst_len) {
   if (dst_len) *dst_len = 0;
   if (pc.early_error >= 0) return pc.early_error;
   if (!ok(c, cudaStreamSynchronize(pc.stream), "sync")) return SJB200_UNEXPECTED_ERROR;
-  if (*c->h_flags & kFlagInternal) return SJB200_UNEXPECTED_ERROR;
+  if (c->h_carry[pc.carry_slot].flags & kFlagInternal) return SJB200_UNEXPECTED_ERROR;
   if ((c->h_carry[pc.carry_slot].state >> 1) & 1u) return SJB200_UNCLOSED_STRING;  // json_minifier.h L42-47
   if (dst_len) *dst_len = size_t(c->h_carry[pc.carry_slot].count);
   return SJB200_SUCCESS;
@@ -596,8 +650,7 @@ extern "C" int sjb200_validate_utf8_dev_enqueue(sjb200_ctx *c, const uint8_t *d_
   CUtensorMap map;
   bool tma = false;
   make_tensor_map(c, &map, d_buf, len, &tma);
-  if (!reset_document_state(c, s) ||
-      !enqueue_scan(c, kUtf8, &map, tma, d_buf, len, 0, tiles_of(len), true, 0x20202020u, nullptr, nullptr, 0, s) ||
+  if (!enqueue_scan(c, kUtf8, &map, tma, d_buf, len, 0, tiles_of(len), true, 0x20202020u, nullptr, nullptr, -1, s, 1) ||
       !fetch_result(c, s))
     pc.early_error = SJB200_UNEXPECTED_ERROR;
   return SJB200_SUCCESS;
@@ -612,8 +665,8 @@ extern "C" int sjb200_validate_utf8_dev_finish(sjb200_ctx *c) {
   if (pc.early_error == SJB200_SUCCESS) return 1;
   if (pc.early_error > 0) return -1;
   if (!ok(c, cudaStreamSynchronize(pc.stream), "sync")) return -1;
-  if (*c->h_flags & kFlagInternal) return -1;
-  return (*c->h_flags & kFlagUtf8) ? 0 : 1;
+  if (c->h_carry[1].flags & kFlagInternal) return -1;
+  return (c->h_carry[1].flags & kFlagUtf8) ? 0 : 1;
 }
 
 extern "C" int sjb200_validate_utf8_dev(sjb200_ctx *c, const uint8_t *d_buf, size_t len, void *stream) {
@@ -669,9 +722,6 @@ bool scan_host_document(sjb200_ctx *c, int kind, const uint8_t *buf, size_t len,
   CUtensorMap map;
   bool tma = false;
   make_tensor_map(c, &map, c->d_in, len, &tma);
-  if (!ok(c, cudaMemsetAsync(c->d_flags, 0, sizeof(uint32_t), c->stream), "memset flags") ||
-      !ok(c, cudaMemsetAsync(c->d_carry, 0, sizeof(Carry), c->stream), "memset carry"))
-    return false;
   // calls are synchronous, so no earlier kernel still reads d_in when the first copy lands
   for (size_t k = 0; k < nchunks; k++) {
     const size_t off = k * chunk;
@@ -681,14 +731,13 @@ bool scan_host_document(sjb200_ctx *c, int kind, const uint8_t *buf, size_t len,
         !ok(c, cudaEventRecord(copied, c->copy_stream), "event record") || !ok(c, cudaStreamWaitEvent(c->stream, copied, 0), "wait event"))
       return false;
     const bool last = (k + 1 == nchunks);
-    if (!enqueue_scan(c, kind, &map, tma, c->d_in, len, uint32_t(off / kTileBytes), tiles_of(bytes), last, 0x20202020u, d_idx, d_dst, int(k),
-                      c->stream, int(k + 1)))
+    if (!enqueue_scan(c, kind, &map, tma, c->d_in, len, uint32_t(off / kTileBytes), tiles_of(bytes), last, 0x20202020u, d_idx, d_dst,
+                      k == 0 ? -1 : int(k), c->stream, int(k + 1)))
       return false;
     if (!ok(c, cudaMemcpyAsync(c->h_carry + k + 1, c->d_carry + k + 1, sizeof(Carry), cudaMemcpyDeviceToHost, c->stream), "D2H carry") ||
         !ok(c, cudaEventRecord(scanned, c->stream), "event record"))
       return false;
   }
-  if (!ok(c, cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream), "D2H flags")) return false;
   // drain: bring each chunk's output back as soon as that chunk is done
   uint64_t have = 0;
   for (size_t k = 0; k < nchunks; k++) {
@@ -702,6 +751,10 @@ bool scan_host_document(sjb200_ctx *c, int kind, const uint8_t *buf, size_t len,
       have = upto;
     }
   }
+  // every launch reports (and clears) its own flags: the document's flags are their union
+  uint32_t flags = 0;
+  for (size_t k = 0; k < nchunks; k++) flags |= c->h_carry[k + 1].flags;
+  *c->h_flags = flags;
   *final_slot = int(nchunks);
   return ok(c, cudaStreamSynchronize(c->stream), "sync") && ok(c, cudaStreamSynchronize(c->out_stream), "sync");
 }
@@ -727,6 +780,7 @@ extern "C" int sjb200_stage1(sjb200_ctx *c, const uint8_t *buf, size_t len, int 
   in.count = c->h_carry[slot].count;
   in.state = c->h_carry[slot].state;
   in.flags = *c->h_flags;
+  in.sentinels_written = false;
   HostStructuralReader reader(buf, idx_out);
   HostIndexWriter writer(idx_out);
   bool dirty = false;
@@ -775,14 +829,14 @@ extern "C" int sjb200_stage1_shard_dev(sjb200_ctx *c, const uint8_t *d_buf, size
   make_tensor_map(c, &map, d_buf, len, &tma);
   c->h_carry[0].count = 0; c->h_carry[0].state = state_in & 7u; c->h_carry[0].ttable = 0;
   (void)last_shard;  // every shard checks its own end: cuts are at character boundaries (sjb200_shard_cut)
-  if (!ok(c, cudaMemsetAsync(c->d_flags, 0, sizeof(uint32_t), s), "memset flags") ||
-      !ok(c, cudaMemcpyAsync(c->d_carry, c->h_carry, sizeof(Carry), cudaMemcpyHostToDevice, s), "H2D carry") ||
+  c->h_carry[0].flags = 0; c->h_carry[0].reserved = 0;
+  if (!ok(c, cudaMemcpyAsync(c->d_carry, c->h_carry, sizeof(Carry), cudaMemcpyHostToDevice, s), "H2D carry") ||
       !enqueue_scan(c, kIndex, &map, tma, d_buf, len, 0, tiles_of(len), true, 0x20202020u, d_idx, nullptr, 0, s) ||
       !fetch_result(c, s) || !ok(c, cudaStreamSynchronize(s), "sync"))
     return SJB200_UNEXPECTED_ERROR;
   out->ttable = c->h_carry[1].ttable;
   out->state_out = c->h_carry[1].state;
-  out->flags = *c->h_flags;
+  out->flags = c->h_carry[1].flags;
   out->count = c->h_carry[1].count;
   return (out->flags & kFlagInternal) ? SJB200_UNEXPECTED_ERROR : SJB200_SUCCESS;
 }

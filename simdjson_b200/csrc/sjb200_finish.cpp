@@ -141,7 +141,7 @@ int finish_stage1(const FinishInput &in, StructuralReader &reader, IndexWriter &
   uint32_t n = uint32_t(in.count);
   const uint32_t len32 = uint32_t(in.len);
   *n_inout = n;
-  if (!writer.set3(n, len32, len32, 0)) return kUnexpectedError;       // L284-286
+  if (!in.sentinels_written && !writer.set3(n, len32, len32, 0)) return kUnexpectedError;  // L284-286
   if (n == 0) return kEmpty;                                             // L289-291
   switch (in.mode) {
     case kStreamingPartial: {                                            // L295-317

@@ -76,6 +76,7 @@ struct FinishInput {
   uint64_t count;      // structurals found
   uint32_t state;      // final scanner state (bit1: inside a string)
   uint32_t flags;
+  bool sentinels_written;  // the scan kernel already stored idx[n..n+2] (device-resident calls)
 };
 
 int finish_stage1(const FinishInput &in, StructuralReader &reader, IndexWriter &writer, uint32_t *n_inout,

@@ -378,8 +378,8 @@ __global__ void __launch_bounds__(kThreads, (KIND == kUtf8) ? 4 : kMinCtasPerSm)
   const uint32_t R = p.sub_per_super;
 
   Carry cin;
-  cin.count = 0; cin.state = 0; cin.ttable = 0;
-  if (KIND != kUtf8) cin = *p.carry_in;
+  cin.count = 0; cin.state = 0; cin.ttable = 0; cin.flags = 0; cin.reserved = 0;
+  if (KIND != kUtf8 && p.carry_in != nullptr) cin = *p.carry_in;
 
   if (tid == 0) {
 #pragma unroll
@@ -649,11 +649,16 @@ __global__ void __launch_bounds__(kThreads, (KIND == kUtf8) ? 4 : kMinCtasPerSm)
     if (tid == 0) {
       st_relaxed_u64(p.count_desc + super, pack_inc(p.epoch, Tincl, base + super_total));
       if (super == p.nsuper - 1) {
-        Carry co;
-        co.count = cin.count + base + super_total;
-        co.state = tt_apply(Tincl, cin.state);
-        co.ttable = Tincl;
-        *p.carry_out = co;
+        // (carry_out->flags is stored by the last CTA to leave the kernel)
+        p.carry_out->count = cin.count + base + super_total;
+        p.carry_out->state = tt_apply(Tincl, cin.state);
+        p.carry_out->ttable = Tincl;
+        if (KIND == kIndex && p.write_sentinels) {  // json_structural_indexer.h L284-286
+          uint32_t *tail = p.idx_out + (cin.count + base + super_total);
+          tail[0] = uint32_t(p.len);
+          tail[1] = uint32_t(p.len);
+          tail[2] = 0;
+        }
         if (KIND == kIndex && p.check_eof) {
           uint32_t tw = 0;
           for (int d = 1; d <= 4; d++) {
@@ -825,6 +830,7 @@ __global__ void __launch_bounds__(kThreads, (KIND == kUtf8) ? 4 : kMinCtasPerSm)
     if (done == gridDim.x - 1) {
       p.ticket[0] = 0;
       p.ticket[1] = 0;
+      p.carry_out->flags = atomicExch(p.flags, 0u);  // every CTA is done raising flags; hand them over and re-arm
       __threadfence();
     }
   }

@@ -46,6 +46,8 @@ struct Carry {
   uint64_t count;     // structurals (kIndex) or kept bytes (kMinify) emitted so far
   uint32_t state;
   uint32_t ttable;    // out only: the 6-bit transducer T(e) of everything this launch scanned
+  uint32_t flags;     // out only: kFlag* bits raised by this launch (the launch also clears ScanParams::flags again)
+  uint32_t reserved;
 };
 
 struct ScanParams {
@@ -63,9 +65,10 @@ struct ScanParams {
   uint32_t epoch;           // tags look-back descriptors so they need no per-launch reset
   uint32_t *idx_out;        // kIndex: device index array
   uint8_t *dst;             // kMinify: device output
-  const Carry *carry_in;
+  uint32_t write_sentinels; // kIndex: the launch that scans the last tile also stores idx[n]=idx[n+1]=len, idx[n+2]=0
+  const Carry *carry_in;    // null: zero state, zero count
   Carry *carry_out;
-  uint32_t *flags;          // accumulated with atomicOr
+  uint32_t *flags;          // accumulated with atomicOr; zero between launches (the last CTA moves it to carry_out->flags)
   unsigned long long *count_desc;  // [nsuper] the look-back chain
   uint32_t *ticket;         // [0] next tile, [1] CTAs finished
   unsigned long long *debug;  // optional [ntiles][8] timeline (globaltimer ns) for tuning; null in production

@@ -144,6 +144,20 @@ class dom_parser_implementation:
         self.n_structural_indexes = n.value
         return rc
 
+    def stage1_device_batch(self, d_bufs, d_idxs, mode=REGULAR, stream=None):
+        """many device-resident documents in one call -> list of (error_code, n_structural_indexes)"""
+        n = len(d_bufs)
+        docs = (capi.Doc * n)()
+        for i in range(n):
+            docs[i].d_buf = d_bufs[i].data_ptr()
+            docs[i].len = d_bufs[i].numel()
+            docs[i].d_idx = d_idxs[i].data_ptr()
+            docs[i].n_structural_indexes = 0
+        rc = lib().sjb200_stage1_dev_batch(self._ctx, docs, n, mode, _stream_ptr(stream))
+        if rc != SUCCESS:
+            raise RuntimeError("sjb200_stage1_dev_batch failed: " + self.last_cuda_error())
+        return [(docs[i].error, docs[i].n_structural_indexes) for i in range(n)]
+
     def stage1_device_enqueue(self, d_buf, mode=REGULAR, d_idx=None, stream=None):
         if d_idx is None:
             d_idx = self.device_index_buffer(d_buf.numel())

@@ -471,6 +471,7 @@ static int check_modes(const std::vector<uint8_t> &in, int mode) {
     fi.mode = mode; fi.len = len; fi.count = e.idx.size();
     fi.state = e.unclosed ? 2u : 0u;
     fi.flags = (e.utf8_err ? kFlagUtf8 : 0u) | (e.ctl_err ? kFlagCtl : 0u);
+    fi.sentinels_written = false;
     const bool early = (mode == kRegular && e.unclosed) || e.ctl_err;
     if (!early) memcpy(pidx.data(), e.idx.data(), e.idx.size() * 4);
     HostStructuralReader reader(in.data(), pidx.data());

@@ -235,6 +235,23 @@ def test_device_resident_matches_host_path(parser, port):
         assert parser.validate_utf8_device(d) == int(port.validate_utf8(b))
 
 
+def test_batch_entry_point(parser, port):
+    """sjb200_stage1_dev_batch == a loop of sjb200_stage1_dev"""
+    import torch
+    rng = random.Random(77)
+    docs = [_big_adversarial(rng, n) for n in (100, TILE + 3, 5 * TILE, 17, 9 * TILE + 4000)] + [b'{"a":1} [1,2', b"", b'"open']
+    for mode in (0, 1, 2):
+        d_bufs = [torch.from_numpy(np.frombuffer(b, dtype=np.uint8).copy()).cuda() if len(b) else torch.empty(0, dtype=torch.uint8, device="cuda") for b in docs]
+        d_idxs = [torch.zeros(sj.lib().sjb200_index_words(max(len(b), 1)), dtype=torch.int32, device="cuda") for b in docs]
+        res = parser.stage1_device_batch(d_bufs, d_idxs, mode)
+        for b, (err, n), di in zip(docs, res, d_idxs):
+            want = port.stage1(b, mode)
+            assert err == want.err, (len(b), mode, err, want.err)
+            if want.wrote:
+                assert n == want.n
+                assert np.array_equal(di.cpu().numpy().view(np.uint32)[: n + 3], want.words()), (len(b), mode)
+
+
 def test_unaligned_device_pointer(parser, port):
     """a device buffer that is not 16-byte aligned cannot use TMA; the plain-load path must agree"""
     import torch
