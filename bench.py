@@ -191,24 +191,23 @@ def run_ours(args, rank, world):
     kernel_ms, n_struct = [], []
 
     def sharded_step(i):
-        """one sharded pass: scan with speculated state 0, exchange, re-scan if the speculation was wrong"""
-        p = parser
-        rc, res = p.stage1_shard_device(d_docs[i % ROTATE], 0, rank == world - 1, d_idx=d_idxs[i % 2], stream=stream)
-        if rc != 0:
-            raise RuntimeError("shard scan failed")
-        gather_in[0], gather_in[1], gather_in[2] = int(res.ttable), int(res.count), int(res.flags)
-        dist.all_gather_into_tensor(gather_out, gather_in)
-        g = gather_out.view(world, 4).cpu().numpy()
-        tts = (C.c_uint32 * world)(*[int(x) for x in g[:, 0]])
-        state_in = L.sjb200_fold_state(tts, rank)
-        if state_in != 0:  # wrong speculation: scan again with the true state, then publish the corrected count
-            rc, res = p.stage1_shard_device(d_docs[i % ROTATE], state_in, rank == world - 1, d_idx=d_idxs[i % 2], stream=stream)
-            gather_in[1] = int(res.count)
-        if np.any([L.sjb200_fold_state(tts, r) != 0 for r in range(world)]):
+        """one sharded pass (simdjson_b200/sharding.py): scan with speculated state 0, all-gather {transducer,count,flags},
+        fold, re-scan if the speculation was wrong"""
+        from simdjson_b200 import sharding
+
+        def scan(state_in):
+            rc, res = parser.stage1_shard_device(d_docs[i % ROTATE], state_in, rank == world - 1, d_idx=d_idxs[i % 2], stream=stream)
+            if rc != 0:
+                raise RuntimeError("shard scan failed: " + parser.last_cuda_error())
+            return int(res.ttable), int(res.count), int(res.flags)
+
+        def all_gather(v):
+            gather_in.copy_(torch.from_numpy(v))
             dist.all_gather_into_tensor(gather_out, gather_in)
-            g = gather_out.view(world, 4).cpu().numpy()
-        base = int(g[:rank, 1].sum())  # global index base of this shard (indexes stay shard-relative + base)
-        return int(res.count), base
+            return gather_out.view(world, 4).cpu().numpy()
+
+        r = sharding.exchange(scan, rank, world, all_gather)
+        return r["count"], r["base"]
 
     def run_steps(k, record):
         t_ev0, t_ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

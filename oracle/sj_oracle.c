@@ -303,3 +303,27 @@ int sjo_minify(const uint8_t *buf, size_t len, uint8_t *dst, size_t *dst_len) {
   *dst_len = out;
   return SJO_SUCCESS;
 }
+
+/* ------------------------------------------------- helpers for the sharding tests */
+/* raw scan of a shard with a given incoming scanner state (bit0 escape, bit1 in_string, bit2 prev_scalar):
+ * number of structurals and the outgoing state; indexes (shard-relative) are stored when idx != NULL */
+uint64_t sjo_scan_shard(const uint8_t *buf, size_t len, uint32_t state_in, uint32_t *idx, uint32_t *state_out) {
+  scan_state s = {(int)(state_in & 1), (int)((state_in >> 1) & 1), (int)((state_in >> 2) & 1), 0};
+  uint64_t n = 0;
+  for (size_t i = 0; i < len; i++)
+    if (scan_byte(&s, buf[i]).structural) { if (idx) idx[n] = (uint32_t)i; n++; }
+  if (state_out) *state_out = (uint32_t)s.esc | ((uint32_t)s.instr << 1) | ((uint32_t)s.prev_nq << 2);
+  return n;
+}
+
+/* the shard's carry transducer T(e) = (esc_out, quote parity, last byte is a non-quote scalar) for e = 0, 1,
+ * packed like sjb200_shard_result.ttable */
+uint32_t sjo_transducer(const uint8_t *buf, size_t len) {
+  uint32_t T = 0;
+  for (uint32_t e = 0; e < 2; e++) {
+    uint32_t out = 0;
+    sjo_scan_shard(buf, len, e, NULL, &out); /* in_string 0 in: bit1 of out is the parity */
+    T |= (out & 7u) << (3 * e);
+  }
+  return T;
+}

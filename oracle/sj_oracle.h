@@ -73,6 +73,8 @@ int sjo_minify(const uint8_t *buf, size_t len, uint8_t *dst, size_t *dst_len);
 int sjo_validate_utf8(const uint8_t *buf, size_t len);
 
 /* helpers exposed for unit tests */
+uint64_t sjo_scan_shard(const uint8_t *buf, size_t len, uint32_t state_in, uint32_t *idx, uint32_t *state_out);
+uint32_t sjo_transducer(const uint8_t *buf, size_t len);
 size_t sjo_trim_partial_utf8(const uint8_t *buf, size_t len);
 uint32_t sjo_find_next_document_index(const uint8_t *buf, const uint32_t *idx, uint32_t n);
 
