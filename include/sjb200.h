@@ -149,6 +149,11 @@ typedef struct {
 } sjb200_shard_result;
 SJB200_API int sjb200_stage1_shard_dev(sjb200_ctx *ctx, const uint8_t *d_buf, size_t len, uint32_t state_in, int last_shard,
                             uint32_t *d_idx, sjb200_shard_result *out, void *stream);
+/* the speculative pass (incoming state 0) without host synchronisation: d_result is DEVICE memory, 24 bytes
+ * {uint64 count; uint32 state_out; uint32 ttable; uint32 flags; uint32 reserved}, e.g. the send buffer of an
+ * all-gather enqueued behind the scan on the same stream */
+SJB200_API int sjb200_stage1_shard_dev_enqueue(sjb200_ctx *ctx, const uint8_t *d_buf, size_t len, uint32_t *d_idx, void *d_result,
+                                    void *stream);
 /* fold: state entering shard r given the ttables of shards 0..r-1 and the document's initial state 0 */
 SJB200_API uint32_t sjb200_fold_state(const uint32_t *ttables, int nshards_before);
 /* largest cut <= nominal such that buf[cut] is not a UTF-8 continuation byte (host pointer) */

@@ -17,7 +17,7 @@ EXPORTS = [
     "sjb200_stage1_dev", "sjb200_minify_dev", "sjb200_validate_utf8_dev", "sjb200_stage1_dev_batch",
     "sjb200_stage1_dev_enqueue", "sjb200_stage1_dev_finish", "sjb200_minify_dev_enqueue", "sjb200_minify_dev_finish",
     "sjb200_validate_utf8_dev_enqueue", "sjb200_validate_utf8_dev_finish",
-    "sjb200_stage1_shard_dev", "sjb200_fold_state", "sjb200_shard_cut",
+    "sjb200_stage1_shard_dev", "sjb200_stage1_shard_dev_enqueue", "sjb200_fold_state", "sjb200_shard_cut",
 ]
 
 # simdjson::error_code values of this path (include/simdjson/error.h L19-54)
@@ -71,6 +71,7 @@ def load():
         "sjb200_validate_utf8_dev_enqueue": (C.c_int, [vp, vp, sz, vp]),
         "sjb200_validate_utf8_dev_finish": (C.c_int, [vp]),
         "sjb200_stage1_shard_dev": (C.c_int, [vp, vp, sz, C.c_uint32, C.c_int, vp, C.POINTER(ShardResult), vp]),
+        "sjb200_stage1_shard_dev_enqueue": (C.c_int, [vp, vp, sz, vp, vp, vp]),
         "sjb200_fold_state": (C.c_uint32, [u32p, C.c_int]),
         "sjb200_shard_cut": (sz, [vp, sz, sz]),
     }

@@ -188,7 +188,7 @@ int grid_for(sjb200_ctx *c, int kind, uint32_t nelements) {
 // Enqueue the scan of document tiles [tile_begin, tile_begin+ntiles) of (d_buf,len).
 bool enqueue_scan(sjb200_ctx *c, int kind, const CUtensorMap *map, bool tma, const uint8_t *d_buf, size_t len, uint32_t tile_begin,
                   uint32_t ntiles, bool has_last_tile, uint32_t prev_word, uint32_t *d_idx, uint8_t *d_dst, int carry_in_slot,
-                  cudaStream_t stream, int carry_out_slot = -1, bool write_sentinels = false) {
+                  cudaStream_t stream, int carry_out_slot = -1, bool write_sentinels = false, Carry *external_out = nullptr) {
   // carry_in_slot < 0: the launch starts a document (zero state, zero count)
   if (carry_out_slot < 0) carry_out_slot = (carry_in_slot < 0) ? 1 : (carry_in_slot ^ 1);
   ScanParams p;
@@ -215,7 +215,7 @@ bool enqueue_scan(sjb200_ctx *c, int kind, const CUtensorMap *map, bool tma, con
   p.dst = d_dst;
   p.carry_in = (carry_in_slot < 0) ? nullptr : c->d_carry + carry_in_slot;
   p.write_sentinels = write_sentinels ? 1u : 0u;
-  p.carry_out = c->d_carry + carry_out_slot;
+  p.carry_out = external_out ? external_out : c->d_carry + carry_out_slot;
   p.flags = c->d_flags;
   p.count_desc = c->d_count_desc;
   p.ticket = c->d_ticket;
@@ -839,6 +839,24 @@ extern "C" int sjb200_stage1_shard_dev(sjb200_ctx *c, const uint8_t *d_buf, size
   out->flags = c->h_carry[1].flags;
   out->count = c->h_carry[1].count;
   return (out->flags & kFlagInternal) ? SJB200_UNEXPECTED_ERROR : SJB200_SUCCESS;
+}
+
+// Speculative pass of a shard (incoming state 0) without any host synchronisation: the 24-byte result
+// {count, state_out, ttable, flags} is written to caller-provided DEVICE memory, ready to be the send buffer of an
+// all-gather enqueued behind it on the same stream.
+extern "C" int sjb200_stage1_shard_dev_enqueue(sjb200_ctx *c, const uint8_t *d_buf, size_t len, uint32_t *d_idx, void *d_result,
+                                               void *stream) {
+  if (!c || !d_result || len == 0 || len > kMaxBytes) return SJB200_UNEXPECTED_ERROR;
+  DeviceGuard g(c->device);
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+  if (!ensure_desc(c, len)) return SJB200_MEMALLOC;
+  CUtensorMap map;
+  bool tma = false;
+  make_tensor_map(c, &map, d_buf, len, &tma);
+  if (!enqueue_scan(c, kIndex, &map, tma, d_buf, len, 0, tiles_of(len), true, 0x20202020u, d_idx, nullptr, -1, s, 1, false,
+                    static_cast<Carry *>(d_result)))
+    return SJB200_UNEXPECTED_ERROR;
+  return SJB200_SUCCESS;
 }
 
 extern "C" uint32_t sjb200_fold_state(const uint32_t *ttables, int nshards_before) {

@@ -178,6 +178,13 @@ class dom_parser_implementation:
                                            C.byref(res), _stream_ptr(stream))
         return rc, res
 
+    def stage1_shard_device_enqueue(self, d_buf, d_result, d_idx=None, stream=None):
+        """speculative shard pass, no host sync: d_result = 3 x int64 device tensor {count, state|ttable<<32, flags}"""
+        if d_idx is None:
+            d_idx = self.device_index_buffer(d_buf.numel())
+        return lib().sjb200_stage1_shard_dev_enqueue(self._ctx, d_buf.data_ptr(), d_buf.numel(), d_idx.data_ptr(), d_result.data_ptr(),
+                                                     _stream_ptr(stream))
+
     # -- minify / utf8 on this parser's context (the reference routes them through `implementation`)
     def _minify_host(self, buf):
         a = _host_u8(buf)

@@ -50,3 +50,17 @@ def exchange(scan, rank, world, all_gather):
         g = all_gather(np.array([tt, count, flags, 0], dtype=np.int64))
     return {"state_in": states[rank], "base": int(g[:rank, 1].sum()), "count": int(count), "flags": int(np.bitwise_or.reduce(g[:, 2])),
             "rescanned": rescanned, "ttables": [int(x) for x in g[:, 0]], "total": int(g[:, 1].sum())}
+
+
+def unpack_result(row):
+    """int64[3] written by sjb200_stage1_shard_dev_enqueue -> (ttable, count, flags, state_out)"""
+    count, st_tt, fl = int(row[0]), int(row[1]), int(row[2])
+    return (st_tt >> 32) & 0xFFFFFFFF, count, fl & 0xFFFFFFFF, st_tt & 0xFFFFFFFF
+
+
+def verify_speculation(gathered, rank):
+    """gathered: int64[world][3] from the all-gather of one speculative pass.  Returns (ok_for_everyone, my_state_in, my_base)."""
+    rows = [unpack_result(r) for r in gathered]
+    states = fold_states([r[0] for r in rows])
+    base = sum(r[1] for r in rows[:rank])
+    return all(s == 0 for s in states), states[rank], base
