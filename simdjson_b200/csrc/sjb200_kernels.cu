@@ -793,7 +793,15 @@ __global__ void __launch_bounds__(kThreads, (KIND == kUtf8) ? 4 : kMinCtasPerSm)
           const uint32_t t = __shfl_up_sync(kFull, incl, d);
           if (lane >= d) incl += t;
         }
-        uint8_t *dst = p.dst + (cin.count + run_base + warp_base + (incl - cnt));
+        // Kept bytes are compacted into shared memory first (byte stores there are cheap) and leave the SM as aligned
+        // 16-byte vectors: scattered byte stores to global memory cost one L1 wavefront each and were ~90 % of the
+        // kernel time.  The staging area (the mask slots 1..7, unused when a super-tile is one tile) starts at the
+        // same offset modulo 16 as the destination, so interior 16-byte groups line up.
+        const uint32_t wtotal = __shfl_sync(kFull, incl, 31);
+        uint8_t *gdst = p.dst + (cin.count + run_base + warp_base);
+        const uint32_t a = uint32_t(reinterpret_cast<uintptr_t>(gdst) & 15u);
+        uint8_t *stg = reinterpret_cast<uint8_t *>(mask_slots) + kMaskSlotBytes + uint32_t(warp) * 6144u;
+        uint8_t *sp = stg + a + (incl - cnt);
 #pragma unroll
         for (int u = 0; u < W; u++) {
           uint32_t w8[8];
@@ -803,16 +811,32 @@ __global__ void __launch_bounds__(kThreads, (KIND == kUtf8) ? 4 : kMinCtasPerSm)
           for (int i = 0; i < 8; i++) {
             const uint32_t nib = (keep >> (4 * i)) & 15u;
             const uint32_t word = w8[i];
-            if (nib == 15u && (reinterpret_cast<uintptr_t>(dst) & 3u) == 0) {
-              *reinterpret_cast<uint32_t *>(dst) = word;
-              dst += 4;
+            if (nib == 15u) {
+              if ((smem_u32(sp) & 3u) == 0) {
+                *reinterpret_cast<uint32_t *>(sp) = word;
+              } else {
+                sp[0] = uint8_t(word); sp[1] = uint8_t(word >> 8); sp[2] = uint8_t(word >> 16); sp[3] = uint8_t(word >> 24);
+              }
+              sp += 4;
             } else {
 #pragma unroll
               for (int b = 0; b < 4; b++)
-                if ((nib >> b) & 1u) *dst++ = uint8_t(word >> (8 * b));
+                if ((nib >> b) & 1u) *sp++ = uint8_t(word >> (8 * b));
             }
           }
         }
+        __syncwarp();
+        {
+          const uint32_t head = min(wtotal, (16u - a) & 15u);           // bytes before the first aligned 16-byte group
+          const uint32_t nvec = (wtotal - head) >> 4;
+          const uint32_t tail = wtotal - head - (nvec << 4);
+          if (uint32_t(lane) < head) gdst[lane] = stg[a + lane];
+          const uint4 *sv = reinterpret_cast<const uint4 *>(stg + a + head);  // (a + head) % 16 == 0
+          uint4 *gv = reinterpret_cast<uint4 *>(gdst + head);
+          for (uint32_t i = lane; i < nvec; i += 32) gv[i] = sv[i];
+          if (uint32_t(lane) < tail) gdst[head + (nvec << 4) + lane] = stg[a + head + (nvec << 4) + lane];
+        }
+        __syncwarp();
       }
       run_base += tile_total;
     }

@@ -28,7 +28,10 @@ constexpr int kMinCtasPerSm = SJB200_MIN_CTAS;  // __launch_bounds__ occupancy t
 // the masks of every tile wait in shared memory (8 words per lane per tile) until the incoming state is known.
 // (Parking them in an L2-resident global scratch instead, to fit 4 CTAs per SM, was measured slower: the SM is
 // issue-bound, not latency-bound.)
-constexpr int kMaxSub = 8;
+#ifndef SJB200_MAX_SUB
+#define SJB200_MAX_SUB 8
+#endif
+constexpr int kMaxSub = SJB200_MAX_SUB;
 constexpr int kCtlBytes = 1024;                       // control block
 constexpr int kLutBytes = 64 * 64;                    // composed-transducer table
 constexpr int kEmitBytes = kWarps * 1024;             // per-warp emit scratch (128 mask words + 128 counts)

@@ -33,7 +33,8 @@ rc = p.stage1_device(d, 0)
 got = p.device_index_buffer().cpu().numpy().view(np.uint32)
 okk = rc == want.err and p.n_structural_indexes == want.n and np.array_equal(got[: want.n + 3], want.words())
 res = {"tag": tag, "parity": bool(okk), "grid": p.get_stat("grid_index")}
-for kind in ("stage1", "minify", "utf8"):
+kinds = os.environ.get("PROBE_KINDS", "stage1,minify,utf8").split(",")
+for kind in kinds:
     ts = []
     for it in range(10):
         if kind == "stage1":
