@@ -66,6 +66,8 @@ struct sjb200_ctx {
   uint32_t *h_window = nullptr; size_t h_window_words = 0;
   uint32_t epoch = 0;
   int grid[3] = {0, 0, 0};
+  long opt_kernel = 4;  // stage-1 kernel generation: 4 = scan4 (sjb200_scan4.cuh), 3 = the tile-synchronous scan_kernel<kIndex>
+  int grid4 = 0;
   long opt_sub_per_super = 0, opt_use_tma = 1, opt_grid = 0, opt_chunk_bytes = 4 << 20, opt_time_kernel = 0;
   cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // around the last scan kernel when opt_time_kernel is set
   bool ev_valid = false;
@@ -156,7 +158,7 @@ bool ensure_host_scratch(sjb200_ctx *c, uint8_t **p, size_t *have, size_t need) 
   return true;
 }
 
-bool make_tensor_map(sjb200_ctx *c, CUtensorMap *map, const uint8_t *d_buf, size_t len, bool *usable) {
+bool make_tensor_map(sjb200_ctx *c, CUtensorMap *map, const uint8_t *d_buf, size_t len, bool *usable, int box_rows = kTileRows) {
   memset(map, 0, sizeof(*map));
   *usable = false;
   const uint64_t rows = len / 128;
@@ -164,7 +166,7 @@ bool make_tensor_map(sjb200_ctx *c, CUtensorMap *map, const uint8_t *d_buf, size
   if ((reinterpret_cast<uintptr_t>(d_buf) & 15u) != 0) return true;  // TMA needs a 16-byte aligned base
   cuuint64_t dims[2] = {128, rows};
   cuuint64_t strides[1] = {128};
-  cuuint32_t box[2] = {128, (cuuint32_t)kTileRows};
+  cuuint32_t box[2] = {128, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = c->encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t *>(d_buf), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -177,7 +179,12 @@ bool make_tensor_map(sjb200_ctx *c, CUtensorMap *map, const uint8_t *d_buf, size
   return true;
 }
 
+bool use_scan4(const sjb200_ctx *c, int kind) { return kind == kIndex && c->opt_kernel == 4; }
 int grid_cap(sjb200_ctx *c, int kind) {
+  if (use_scan4(c, kind)) {
+    if (c->grid4 == 0) c->grid4 = scan4_max_ctas_per_sm() * c->sm_count;
+    return c->opt_grid > 0 ? int(c->opt_grid) : c->grid4;
+  }
   if (c->grid[kind] == 0) c->grid[kind] = scan_max_ctas_per_sm(kind) * c->sm_count;
   return c->opt_grid > 0 ? int(c->opt_grid) : c->grid[kind];
 }
@@ -237,7 +244,17 @@ bool enqueue_scan(sjb200_ctx *c, int kind, const CUtensorMap *map, bool tma, con
     if (c->ev_used + 2 <= c->ev_pool.size()) { e0 = c->ev_pool[c->ev_used]; e1 = c->ev_pool[c->ev_used + 1]; c->ev_used += 2; }
     if (e0) cudaEventRecord(e0, stream);
   }
-  const bool launched = ok(c, launch_scan(kind, map, p, grid_for(c, kind, p.nsuper), stream), "launch scan");
+  bool launched;
+  if (use_scan4(c, kind)) {
+    // scan4 reads 4 KiB boxes: its own tensor map over the same bytes (an element of its chain is one tile)
+    CUtensorMap map4;
+    bool tma4 = false;
+    make_tensor_map(c, &map4, d_buf, len, &tma4, kScan4BoxRows);
+    p.use_tma = (tma && tma4) ? 1u : 0u;
+    launched = ok(c, launch_scan4(&map4, p, grid_for(c, kind, ntiles), stream), "launch scan4");
+  } else {
+    launched = ok(c, launch_scan(kind, map, p, grid_for(c, kind, p.nsuper), stream), "launch scan");
+  }
   if (e1) { cudaEventRecord(e1, stream); c->ev_k0 = e0; c->ev_k1 = e1; c->ev_valid = launched; }
   c->launches += launched ? 1 : 0;
   return launched;
@@ -470,6 +487,7 @@ extern "C" int sjb200_set_option(sjb200_ctx *c, const char *key, long value) {
   if (!strcmp(key, "use_tma")) c->opt_use_tma = value;
   else if (!strcmp(key, "grid")) c->opt_grid = value;
   else if (!strcmp(key, "sub_per_super")) c->opt_sub_per_super = value;
+  else if (!strcmp(key, "kernel")) c->opt_kernel = (value == 3) ? 3 : 4;
   else if (!strcmp(key, "time_kernel")) c->opt_time_kernel = value;
   else if (!strcmp(key, "debug_timeline")) c->opt_debug_timeline = value;
   else if (!strcmp(key, "chunk_bytes")) c->opt_chunk_bytes = std::max<long>(kTileBytes, (value / kTileBytes) * kTileBytes);

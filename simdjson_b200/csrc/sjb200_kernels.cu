@@ -27,6 +27,7 @@
 #include "sjb200_kernels.cuh"
 
 #include "sjb200_bits.cuh"
+#include "sjb200_scan4.cuh"
 
 namespace sjb200 {
 
@@ -860,6 +861,13 @@ __global__ void __launch_bounds__(kThreads, (KIND == kUtf8) ? 4 : kMinCtasPerSm)
   }
 }
 
+// ------------------------------------------------------------------ scan4 (stage 1; see sjb200_scan4.cuh)
+__global__ void __launch_bounds__(scan4::kThreads4, SJB200_SCAN4_MIN_CTAS)
+    scan4_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
+  extern __shared__ uint8_t smem_raw4[];
+  scan4::scan4_body(&tmap, p, smem_raw4, sj_smem_u32(smem_raw4));
+}
+
 // ------------------------------------------------------------------ small helpers
 __global__ void gather_chars_kernel(const uint8_t *buf, const uint32_t *idx, uint32_t first, uint32_t count, uint8_t *out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -884,6 +892,26 @@ static cudaError_t launch_kind(const CUtensorMap *tmap, const ScanParams &p, int
   }
   scan_kernel<KIND><<<grid, kThreads, smem_bytes_for(KIND), stream>>>(*tmap, p);
   return cudaGetLastError();
+}
+
+cudaError_t launch_scan4(const CUtensorMap *tmap, const ScanParams &p, int grid, cudaStream_t stream) {
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(scan4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, scan4::kSmemBytes4);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  scan4_kernel<<<grid, scan4::kThreads4, scan4::kSmemBytes4, stream>>>(*tmap, p);
+  return cudaGetLastError();
+}
+
+int scan4_max_ctas_per_sm() {
+  int n = 0;
+  cudaFuncSetAttribute(scan4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, scan4::kSmemBytes4);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, scan4_kernel, scan4::kThreads4, scan4::kSmemBytes4);
+  return (e == cudaSuccess && n > 0) ? n : 1;
 }
 
 cudaError_t launch_scan(int kind, const CUtensorMap *tmap, const ScanParams &p, int grid, cudaStream_t stream) {

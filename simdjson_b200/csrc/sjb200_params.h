@@ -1,0 +1,82 @@
+// sjb200_params.h -- geometry, scan kinds and the launch parameter block shared by the kernels, the C-ABI host
+// code and the host SIMT emulation of the scan4 kernel (tests/simt_emul.cpp).  No CUDA types.
+#pragma once
+#include <stdint.h>
+
+#include "sjb200_common.h"
+
+namespace sjb200 {
+
+// ---- geometry (one "tile" is what one CTA scans per loop iteration)
+constexpr int kUnitsPerLane = 4;                     // 32-byte transposition units per lane
+constexpr int kLaneBytes = 32 * kUnitsPerLane;       // 128 B = one TMA 128B-swizzle row
+constexpr int kWarpBytes = 32 * kLaneBytes;          // 4 KiB
+constexpr int kWarps = 8;
+constexpr int kThreads = 32 * kWarps;
+constexpr int kTileBytes = kWarps * kWarpBytes;      // 32 KiB
+constexpr int kTileRows = kTileBytes / 128;          // 256 rows of 128 B (max TMA box dim)
+#ifndef SJB200_STAGES
+#define SJB200_STAGES 1
+#endif
+#ifndef SJB200_MIN_CTAS
+#define SJB200_MIN_CTAS 2
+#endif
+constexpr int kStages = SJB200_STAGES;      // shared-memory tile buffers per CTA
+constexpr int kMinCtasPerSm = SJB200_MIN_CTAS;  // __launch_bounds__ occupancy target
+// A CTA scans a "super-tile" of up to kMaxSub consecutive tiles before it consults the look-back chain once:
+// the masks of every tile wait in shared memory (8 words per lane per tile) until the incoming state is known.
+// (Parking them in an L2-resident global scratch instead, to fit 4 CTAs per SM, was measured slower: the SM is
+// issue-bound, not latency-bound.)
+#ifndef SJB200_SCAN4_MIN_CTAS
+#define SJB200_SCAN4_MIN_CTAS 2
+#endif
+#ifndef SJB200_MAX_SUB
+#define SJB200_MAX_SUB 8
+#endif
+constexpr int kMaxSub = SJB200_MAX_SUB;
+constexpr int kCtlBytes = 1024;                       // control block
+constexpr int kLutBytes = 64 * 64;                    // composed-transducer table
+constexpr int kEmitBytes = kWarps * 1024;             // per-warp emit scratch (128 mask words + 128 counts)
+constexpr int kMaskSlotBytes = kThreads * 8 * 4;      // one tile's masks
+constexpr int kSmemBytesScan = kStages * kTileBytes + 1024 /*alignment slack*/ + kCtlBytes + kLutBytes + kEmitBytes + kMaxSub * kMaskSlotBytes;
+constexpr int kSmemBytesUtf8 = kStages * kTileBytes + 1024 + kCtlBytes;
+constexpr int smem_bytes_for(int kind) { return kind == 2 ? kSmemBytesUtf8 : kSmemBytesScan; }
+
+// ---- scan kinds
+enum : int { kIndex = 0, kMinify = 1, kUtf8 = 2 };
+
+// Scanner state between consecutive launches of one document (chunked streaming,
+// multi-GPU shards).  state: bit0 escape, bit1 in_string, bit2 prev_scalar.
+struct Carry {
+  uint64_t count;     // structurals (kIndex) or kept bytes (kMinify) emitted so far
+  uint32_t state;
+  uint32_t ttable;    // out only: the 6-bit transducer T(e) of everything this launch scanned
+  uint32_t flags;     // out only: kFlag* bits raised by this launch (the launch also clears ScanParams::flags again)
+  uint32_t reserved;
+};
+
+struct ScanParams {
+  const uint8_t *buf;       // device pointer to byte 0 of the document (or shard)
+  uint64_t len;             // document length in bytes (<= 4 GiB - 1); bytes past it read as 0x20
+  uint32_t pos_base;        // added to every emitted index (0: positions relative to buf)
+  uint32_t prev_word;       // the 4 bytes that precede buf[0] (0x20202020 at start of document)
+  uint32_t check_eof;       // 1: this launch scans the last tile -> flag a truncated UTF-8 sequence
+  uint32_t use_tma;         // 1: full tiles arrive by cp.async.bulk.tensor (buf 16 B aligned)
+  uint32_t tile_begin;      // first document tile of this launch (chunked streaming)
+  uint32_t ntiles;          // tiles in this launch: document tiles [tile_begin, tile_begin+ntiles)
+  uint32_t sub_per_super;   // R: tiles per super-tile (1..kMaxSub); the look-back chain has one element per super-tile
+  uint32_t nsuper;          // ceil(ntiles / R)
+  uint32_t full_tiles;      // document tiles that lie entirely inside floor(len/128) rows
+  uint32_t epoch;           // tags look-back descriptors so they need no per-launch reset
+  uint32_t *idx_out;        // kIndex: device index array
+  uint8_t *dst;             // kMinify: device output
+  uint32_t write_sentinels; // kIndex: the launch that scans the last tile also stores idx[n]=idx[n+1]=len, idx[n+2]=0
+  const Carry *carry_in;    // null: zero state, zero count
+  Carry *carry_out;
+  uint32_t *flags;          // accumulated with atomicOr; zero between launches (the last CTA moves it to carry_out->flags)
+  unsigned long long *count_desc;  // [nsuper] the look-back chain
+  uint32_t *ticket;         // [0] next tile, [1] CTAs finished
+  unsigned long long *debug;  // optional [ntiles][8] timeline (globaltimer ns) for tuning; null in production
+};
+
+}  // namespace sjb200

@@ -1,0 +1,698 @@
+// sjb200_scan4.cuh -- the stage-1 structural indexer, fourth generation ("scan4").
+//
+// What it replaces in the reference (CPU, 64-byte SIMD blocks, strictly serial carries):
+//   json_structural_indexer::index<128> / step / next   src/generic/stage1/json_structural_indexer.h L193-247
+//   json_scanner::next, json_string_scanner::next, json_escape_scanner::next
+//                                                        json_scanner.h L134-157, json_string_scanner.h L62-85,
+//                                                        json_escape_scanner.h L50-71
+//   bit_indexer::write                                   json_structural_indexer.h L93-122 (src/icelake.cpp L129-160)
+//   utf8_checker                                         utf8_lookup4_algorithm.h L145-202
+//
+// Design (B200-first; nothing here resembles the reference's block loop):
+//   * The document is cut into 4 KiB *blocks* (one TMA box of 32 rows x 128 B, 128B-swizzled, so lane L owns row L and
+//     reads it with conflict-free LDS.128) and 32 KiB *elements* (8 consecutive blocks, one per scan warp).
+//   * A CTA is 8 independent *scan warps* + 1 *chain warp*, persistent, pulling elements from an atomic ticket.
+//     Scan warps never synchronise with each other: every block is scanned on its own.  Two of the three scanner
+//     state bits entering a block (next-byte-is-escaped, previous-byte-is-a-scalar) are read off the bytes before it;
+//     the third (in-string) needs the whole prefix, so a block is finished for BOTH polarities: two candidate
+//     structural masks, two counts, one quote parity.  The masks wait in shared memory.
+//   * The chain warp owns everything serial: it hands out tickets, composes the 8 block summaries of an element,
+//     publishes the element's aggregate {parity, count0, count1} in a decoupled look-back chain (one 64-bit
+//     descriptor per element), walks back 256 descriptors per round trip to the nearest inclusive prefix, and posts
+//     every block's polarity and output offset back to the scan warps through an mbarrier.
+//   * Software pipeline: a scan warp scans element j+1 while the chain warp resolves element j, then emits element j
+//     (per-lane bit loops into a shared-memory staging area -- the block buffer it has just consumed -- and coalesced
+//     stores).  The TMA load of its next block is always in flight.
+//   * All arithmetic is the bit-plane algebra of sjb200_bits.cuh: 32 bytes per LOP3, no per-byte code.
+//
+// The same source compiles for the host SIMT emulation (SJB200_HOST_EMU, tests/simt_emul.cpp), which runs it with one
+// OS thread per CUDA thread against the oracle on machines without a GPU.
+#pragma once
+#include "sjb200_bits.cuh"
+#include "sjb200_params.h"
+#include "sjb200_simt.cuh"
+
+namespace sjb200 {
+namespace scan4 {
+
+constexpr int kScanWarps = 8;
+constexpr int kBlockBytes = 4096;
+constexpr int kBlockRows = kBlockBytes / 128;
+constexpr int kThreads4 = 32 * (kScanWarps + 1);
+constexpr int kNS = 4;           // ring of element slots (tickets, summaries, resolutions)
+constexpr int kLookK = 8;        // descriptors per lane and look-back round trip (window of 256 elements)
+constexpr uint32_t kSpinLimit4 = 1u << 21;  // bounded waits: a stuck protocol becomes kFlagInternal, never a hang
+constexpr uint32_t kStageWords = kBlockBytes / 4;
+static_assert(kScanWarps * kBlockBytes == kTileBytes, "an element is one tile of the launch parameter block");
+
+enum : uint32_t { kDescNone = 0, kDescAgg = 1, kDescInc = 2 };
+
+struct Smem {
+  uint8_t ring[kScanWarps][2][kBlockBytes];   // per scan warp: two block buffers (TMA destination / emit staging)
+  sj_u4 park[2][2][kScanWarps * 32];          // [pipeline buffer][polarity][thread]: candidate structural masks
+  uint32_t parkpre[2][kScanWarps * 32];       // exclusive prefix of the lane's counts inside its block, both polarities packed
+  uint32_t ticket[kNS];
+  uint32_t summary[kNS][kScanWarps];          // c0 | c1<<16 | parity<<29 | ctl-hit0<<30 | ctl-hit1<<31
+  uint32_t res_pol[kNS][kScanWarps];          // in-string polarity entering the block
+  uint32_t res_base[kNS][kScanWarps];         // outputs of this launch before the block
+  sj_mbar_t full[kScanWarps][2];
+  sj_mbar_t ticket_ready[kNS];
+  sj_mbar_t scanned[kNS];
+  sj_mbar_t resolved[kNS];
+};
+constexpr int kSmemBytes4 = int(sizeof(Smem)) + 1024;
+
+// byte offset inside a block -> offset in the 128B-swizzled shared-memory image
+SJ_DEV uint32_t swz(uint32_t off) { return off ^ ((off >> 3) & 0x70u); }
+
+// ------------------------------------------------------------------------------------------------ descriptors
+// [63:46] epoch  [45:44] status  [43:0] payload
+//   aggregate: [38] quote parity of the element, [37:19] outputs if it is entered inside a string, [18:0] ... outside
+//   inclusive: [32] in-string after the element, [31:0] outputs of elements [0, i]
+SJ_DEV unsigned long long pack_agg(uint32_t epoch, uint32_t par, uint32_t c0, uint32_t c1) {
+  return ((unsigned long long)epoch << 46) | ((unsigned long long)kDescAgg << 44) | ((unsigned long long)(par & 1u) << 38) |
+         ((unsigned long long)c1 << 19) | c0;
+}
+SJ_DEV unsigned long long pack_inc(uint32_t epoch, uint32_t s_out, uint32_t count) {
+  return ((unsigned long long)epoch << 46) | ((unsigned long long)kDescInc << 44) | ((unsigned long long)(s_out & 1u) << 32) | count;
+}
+
+// The effect of a run of elements on (in-string, outputs): p = quote parity, a / b = outputs when entered outside /
+// inside a string.  compose(older, newer) is associative; identity = (0,0,0).
+struct Eff {
+  uint32_t p, a, b;
+};
+SJ_DEV Eff compose(const Eff &o, const Eff &n) {
+  Eff r;
+  r.p = o.p ^ n.p;
+  r.a = o.a + (o.p ? n.b : n.a);
+  r.b = o.b + (o.p ? n.a : n.b);
+  return r;
+}
+
+SJ_DEV bool wait_bar(sj_mbar_t *bar, uint32_t parity, const ScanParams &p) {
+  uint32_t spins = 0;
+  while (!sj_mbar_try_wait(bar, parity)) {
+    if (++spins > kSpinLimit4) {
+      sj_atomic_or(p.flags, kFlagInternal);
+      return false;
+    }
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------ byte helpers
+SJ_DEV bool byte_is_scalar(uint32_t b) {
+  const bool ws = b == 0x20u || b == 0x09u || b == 0x0Au || b == 0x0Du;
+  const bool op = b == 0x2Cu || b == 0x3Au || b == 0x5Bu || b == 0x5Du || b == 0x7Bu || b == 0x7Du || b == 0x0Cu || b == 0x1Au;
+  return !(ws || op);
+}
+
+// Length of the run of backslashes that ends just before `end` (exclusive), not looking below `floor`.
+// *hit_floor: the run reaches `floor`.  Called by a whole warp; the result is uniform.  Rare path (the byte before a
+// block is a backslash or a quote): 32 bytes per step, 512 when the run is long and the address allows vector loads.
+SJ_DEV uint64_t run_back(const uint8_t *buf, uint64_t end, uint64_t floor, unsigned lane, bool *hit_floor) {
+  uint64_t cur = end, total = 0;
+  *hit_floor = false;
+  uint32_t steps = 0;
+  for (;;) {
+    if (cur == floor) {
+      *hit_floor = true;
+      return total;
+    }
+    if (steps >= 4 && cur - floor >= 512 && ((reinterpret_cast<uintptr_t>(buf) + cur) & 15u) == 0) {
+      const sj_u4 v = sj_ldg_u4(buf + cur - 16 * (uint64_t(lane) + 1));
+      const bool allbs = (v.x == 0x5C5C5C5Cu) && (v.y == 0x5C5C5C5Cu) && (v.z == 0x5C5C5C5Cu) && (v.w == 0x5C5C5C5Cu);
+      const uint32_t m = sj_ballot(!allbs);
+      if (m == 0) {
+        total += 512;
+        cur -= 512;
+        continue;
+      }
+      const uint32_t f = uint32_t(sj_ffs(m) - 1);
+      total += 16ull * f;
+      cur -= 16ull * f;  // the chunk that stops the run is finished byte by byte below
+    }
+    const uint64_t avail64 = cur - floor;
+    const uint32_t avail = avail64 < 32 ? uint32_t(avail64) : 32u;
+    const bool isbs = lane < avail && sj_ldg_u8(buf + cur - 1 - lane) == 0x5Cu;
+    const uint32_t m = sj_ballot(!isbs);
+    if (m != 0) {
+      const uint32_t f = uint32_t(sj_ffs(m) - 1);
+      total += f;
+      if (f == avail && avail < 32) *hit_floor = true;
+      if (f == avail && avail == 32) { /* cannot happen: m != 0 means some lane < 32 stopped */ }
+      return total;
+    }
+    total += 32;
+    cur -= 32;
+    steps++;
+  }
+}
+// ... and the run that starts at `begin`, not looking at or beyond `limit`
+SJ_DEV uint64_t run_forward(const uint8_t *buf, uint64_t begin, uint64_t limit, unsigned lane) {
+  uint64_t cur = begin, total = 0;
+  uint32_t steps = 0;
+  for (;;) {
+    if (cur >= limit) return total;
+    if (steps >= 4 && limit - cur >= 512 && ((reinterpret_cast<uintptr_t>(buf) + cur) & 15u) == 0) {
+      const sj_u4 v = sj_ldg_u4(buf + cur + 16 * uint64_t(lane));
+      const bool allbs = (v.x == 0x5C5C5C5Cu) && (v.y == 0x5C5C5C5Cu) && (v.z == 0x5C5C5C5Cu) && (v.w == 0x5C5C5C5Cu);
+      const uint32_t m = sj_ballot(!allbs);
+      if (m == 0) {
+        total += 512;
+        cur += 512;
+        continue;
+      }
+      const uint32_t f = uint32_t(sj_ffs(m) - 1);
+      total += 16ull * f;
+      cur += 16ull * f;
+    }
+    const uint64_t avail64 = limit - cur;
+    const uint32_t avail = avail64 < 32 ? uint32_t(avail64) : 32u;
+    const bool isbs = lane < avail && sj_ldg_u8(buf + cur + lane) == 0x5Cu;
+    const uint32_t m = sj_ballot(!isbs);
+    if (m != 0) return total + uint32_t(sj_ffs(m) - 1);
+    total += 32;
+    cur += 32;
+    steps++;
+  }
+}
+
+// Scanner state entering byte `pos` of the document: bit0 = the byte is escaped (an odd-length backslash run ends at
+// pos-1), bit2 = byte pos-1 is a "non-quote scalar" (json_scanner.h L148-149).  Exact for any input: the run is
+// followed back as far as it goes, at most to the first byte of this launch, where the launch's carry-in takes over.
+// `b1` = byte pos-1.  Warp-uniform.
+SJ_DEV uint32_t boundary_state(const ScanParams &p, uint64_t pos, uint64_t launch_start, uint32_t cin_state, uint32_t b1, unsigned lane) {
+  if (pos == launch_start) return cin_state & 5u;
+  if (b1 != 0x5Cu && b1 != 0x22u) return byte_is_scalar(b1) ? 4u : 0u;  // the common case: one byte decides
+  const uint64_t end = (b1 == 0x22u) ? pos - 1 : pos;  // a quote's own status depends on the run before it
+  bool hit = false;
+  const uint64_t run = run_back(p.buf, end, launch_start, lane, &hit);
+  const uint32_t odd = uint32_t(run + ((hit && (cin_state & 1u)) ? 1u : 0u)) & 1u;
+  if (b1 == 0x22u) return odd << 2;  // escaped quote = scalar byte; a real quote is not; neither escapes what follows
+  return odd | 4u;                   // a backslash is a scalar byte
+}
+
+// the 4 bytes before document offset `pos` as a little-endian word (byte pos-1 on top)
+SJ_DEV uint32_t word_before(const ScanParams &p, uint64_t pos) {
+  if (pos == 0) return p.prev_word;
+  if (pos >= 4 && ((reinterpret_cast<uintptr_t>(p.buf) + pos) & 3u) == 0) return sj_ldg_u32(p.buf + pos - 4);
+  uint32_t w = 0;
+  for (int d = 1; d <= 4; d++) {
+    const uint32_t b = (pos >= uint64_t(d)) ? sj_ldg_u8(p.buf + pos - d) : ((p.prev_word >> (8 * (4 - d + int(pos)))) & 0xFFu);
+    w |= b << (8 * (4 - d));
+  }
+  return w;
+}
+
+// ------------------------------------------------------------------------------------------------ block I/O
+// A warp copies one block global -> shared in the swizzled layout, padding with 0x20 past len.  Used for the last
+// (partial) block and for buffers TMA cannot address (stage 1 never reads past len: buf_block_reader.h L98-104).
+SJ_DEV void fill_block_guarded(uint8_t *T, const ScanParams &p, uint64_t bstart, unsigned lane) {
+  const bool aligned = (reinterpret_cast<uintptr_t>(p.buf) & 15u) == 0;
+  for (uint32_t c = lane; c < uint32_t(kBlockBytes / 16); c += 32) {
+    const uint64_t g = bstart + uint64_t(c) * 16;
+    sj_u4 v;
+    if (aligned && g + 16 <= p.len) {
+      v = sj_ldg_u4(p.buf + g);
+    } else {
+      uint32_t w[4];
+      for (int k = 0; k < 4; k++) {
+        uint32_t x = 0;
+        for (int b = 0; b < 4; b++) {
+          const uint64_t q = g + 4 * k + b;
+          const uint32_t byte = (q < p.len) ? sj_ldg_u8(p.buf + q) : 0x20u;
+          x |= byte << (8 * b);
+        }
+        w[k] = x;
+      }
+      v = sj_make_u4(w[0], w[1], w[2], w[3]);
+    }
+    *reinterpret_cast<sj_u4 *>(T + swz(c * 16)) = v;
+  }
+}
+
+SJ_DEV void load_unit(const uint8_t *T, uint32_t off, uint32_t w[8]) {
+  const sj_u4 a = *reinterpret_cast<const sj_u4 *>(T + swz(off));
+  const sj_u4 b = *reinterpret_cast<const sj_u4 *>(T + swz(off + 16));
+  w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+  w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+}
+
+// an incoming escape flips the "escaped" status of the first byte that is not a backslash; it only matters when
+// that byte is a quote (carry state)
+SJ_DEV void toggle_quote_at(const uint32_t qu[4], uint32_t qr[4], int k) {
+#pragma unroll
+  for (int u = 0; u < 4; u++)
+    if ((k >> 5) == u) qr[u] ^= qu[u] & (1u << (k & 31));
+}
+
+// ------------------------------------------------------------------------------------------------ scan one block
+// T: the block in shared memory.  pw0: the 4 bytes before the block (only lane 0's copy is used).  e_in / c_in: the two
+// locally known state bits entering the block.  Parks the two candidate masks and the lane's exclusive output prefix,
+// returns the block summary word (uniform).
+SJ_DEV uint32_t scan_block(const uint8_t *T, uint32_t pw0, uint32_t e_in, uint32_t c_in, unsigned lane, const ScanParams &p, sj_u4 *park0,
+                           sj_u4 *park1, uint32_t *parkpre) {
+  const uint32_t lane_off = lane * 128u;
+  uint32_t bs[4], qu[4], op[4], sc[4], cl[4];
+  uint32_t uerr = 0;
+  {
+    const uint32_t pw = (lane == 0) ? pw0 : *reinterpret_cast<const uint32_t *>(T + swz(lane_off - 4));
+    utf8_carry uc = utf8_carry_from_prev_word(pw);
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      uint32_t w8[8], pl[8];
+      load_unit(T, lane_off + 32u * u, w8);
+      transpose32(w8, pl);
+      const unit_classes c = classify(pl);
+      bs[u] = c.bs; qu[u] = c.qu; op[u] = c.op; sc[u] = c.sc; cl[u] = c.ctl;
+      if (sj_any(pl[7] != 0 || utf8_carry_pending(uc))) {
+        uerr |= utf8_check_unit(pl, uc);
+      } else {
+        uc = utf8_carry_zero();
+      }
+    }
+  }
+  if (sj_any(uerr != 0) && lane == 0) sj_atomic_or(p.flags, kFlagUtf8);
+
+  // ---- escapes: which quotes are real (json_escape_scanner.h L96-143, resolved across lanes with one addition)
+  uint32_t qr[4];
+  {
+    const uint32_t bsany = bs[0] | bs[1] | bs[2] | bs[3];
+    if (sj_any(bsany != 0)) {
+      uint32_t escaped[4];
+      const uint32_t esc_out0 = escape_scan<4>(bs, escaped);
+#pragma unroll
+      for (int u = 0; u < 4; u++) qr[u] = qu[u] & ~escaped[u];
+      const int nlead = leading_backslashes<4>(bs);
+      const uint32_t G = sj_ballot(esc_out0 != 0);
+      const uint32_t P = sj_ballot(nlead == 128);
+      uint32_t cout_unused;
+      const uint32_t carries = escape_carries(G, P, e_in & 1u, &cout_unused);
+      if (((carries >> lane) & 1u) && nlead != 128) toggle_quote_at(qu, qr, nlead);
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; u++) qr[u] = qu[u];
+      if ((e_in & 1u) && lane == 0) qr[0] ^= qu[0] & 1u;
+    }
+  }
+
+  // ---- strings and pseudo-structurals, for both in-string polarities at the start of the block
+  const uint32_t lp = uint32_t(sj_popc(qr[0] ^ qr[1] ^ qr[2] ^ qr[3])) & 1u;
+  const uint32_t pb = sj_ballot(lp != 0);
+  uint32_t instr = uint32_t(sj_popc(pb & ((1u << lane) - 1u))) & 1u;
+  const uint32_t par = uint32_t(sj_popc(pb)) & 1u;
+  uint32_t scal_prev = sj_shfl_up((sc[3] & ~qr[3]) >> 31, 1);
+  if (lane == 0) scal_prev = c_in & 1u;
+  uint32_t prev_nq = scal_prev << 31;
+  uint32_t e0[4], e1[4];
+  uint32_t hit0 = 0, hit1 = 0, cnt = 0;
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    const uint32_t in_string = prefix_xor32(qr[u]) ^ (0u - instr);  // json_string_scanner.h L73
+    instr = in_string >> 31;
+    const uint32_t nq = sc[u] & ~qr[u];                              // json_scanner.h L148
+    const uint32_t follows = shl_in(prev_nq, nq, 1);                 // L149
+    prev_nq = nq;
+    const uint32_t pm = op[u] | (sc[u] & ~follows);                  // L68-79
+    const uint32_t tail0 = in_string ^ qr[u];                        // string tail if the block starts outside a string
+    e0[u] = pm & ~tail0;
+    e1[u] = pm & tail0;
+    hit0 |= cl[u] & in_string;                                       // json_structural_indexer.h L246
+    hit1 |= cl[u] & ~in_string;
+    cnt += uint32_t(sj_popc(e0[u])) | (uint32_t(sj_popc(e1[u])) << 16);
+  }
+  uint32_t incl = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = sj_shfl_up(incl, d);
+    if (int(lane) >= d) incl += t;
+  }
+  const uint32_t total = sj_shfl(incl, 31);
+  const unsigned tid = sj_tid();
+  park0[tid] = sj_make_u4(e0[0], e0[1], e0[2], e0[3]);
+  park1[tid] = sj_make_u4(e1[0], e1[1], e1[2], e1[3]);
+  parkpre[tid] = incl - cnt;
+  const uint32_t h0 = sj_any(hit0 != 0) ? 1u : 0u, h1 = sj_any(hit1 != 0) ? 1u : 0u;
+  return total | (par << 29) | (h0 << 30) | (h1 << 31);
+}
+
+// ------------------------------------------------------------------------------------------------ emit one block
+template <bool kStaged>
+SJ_DEV void emit_columns(const sj_u4 ev, uint32_t off, uint32_t pos_lane, uint32_t *dst) {
+  const uint32_t m4[4] = {ev.x, ev.y, ev.z, ev.w};
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    uint32_t m = m4[u];
+    const uint32_t pb = pos_lane + 32u * u;
+    const uint32_t n = sj_reduce_max(uint32_t(sj_popc(m)));  // uniform trip count: the fullest word of this column
+    for (uint32_t k = 0; k < n; k++) {
+      if (m != 0) {
+        dst[off] = pb + uint32_t(sj_ffs(m) - 1);
+        off++;
+        m &= m - 1;
+      }
+    }
+  }
+}
+
+SJ_DEV void emit_block(Smem *S, const ScanParams &p, uint64_t out_base, uint32_t elem, unsigned warp, unsigned lane, int ns, int pbuf,
+                       uint32_t *stg) {
+  const uint32_t sum = S->summary[ns][warp];
+  const uint32_t pol = S->res_pol[ns][warp] & 1u;
+  const uint32_t total = pol ? ((sum >> 16) & 0x1FFFu) : (sum & 0xFFFFu);
+  if (total == 0) return;
+  const unsigned tid = warp * 32 + lane;
+  const sj_u4 ev = S->park[pbuf][pol][tid];
+  const uint32_t off = (S->parkpre[pbuf][tid] >> (16 * pol)) & 0xFFFFu;
+  const uint32_t pos_lane = p.pos_base + (p.tile_begin + elem) * uint32_t(kTileBytes) + warp * uint32_t(kBlockBytes) + lane * 128u;
+  uint32_t *out = p.idx_out + (out_base + S->res_base[ns][warp]);
+  if (total <= kStageWords) {
+    // positions go to shared memory (scattered 4-byte global stores cost one L1 wavefront each) and leave coalesced
+    sj_syncwarp();
+    emit_columns<true>(ev, off, pos_lane, stg);
+    sj_syncwarp();
+    for (uint32_t i = lane; i < total; i += 32) out[i] = stg[i];
+    sj_syncwarp();
+  } else {
+    emit_columns<false>(ev, off, pos_lane, out);  // > 1 structural per 4 bytes over 4 KiB: straight to global memory
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ scan warps
+SJ_DEV uint32_t wait_ticket(Smem *S, uint32_t j, const ScanParams &p) {
+  if (!wait_bar(&S->ticket_ready[j % kNS], (j / kNS) & 1u, p)) return 0xFFFFFFFFu;
+  return S->ticket[j % kNS];
+}
+
+// start the load of block `warp` of element `elem` into ring slot r; returns true when it arrives by TMA
+SJ_DEV bool issue_load(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, uint32_t elem, unsigned warp, unsigned lane, int r,
+                       uint32_t *pw_out) {
+  const uint64_t bstart = (uint64_t(p.tile_begin) + elem) * kTileBytes + uint64_t(warp) * kBlockBytes;
+  const uint64_t row = bstart / 128;
+  const bool full = p.use_tma && (row + kBlockRows <= p.len / 128);
+  sj_syncwarp();  // every lane is done with the slot (previous block, emit staging)
+  if (lane == 0) {
+    *pw_out = (bstart < p.len) ? word_before(p, bstart) : 0x20202020u;
+    if (full) {
+      sj_fence_proxy_async();
+      sj_mbar_arrive_expect_tx(&S->full[warp][r], kBlockBytes);
+      sj_tma_load_rows(S->ring[warp][r], tmap, &S->full[warp][r], uint32_t(row));
+    }
+  }
+  return full;
+}
+
+SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, const Carry &cin, unsigned warp, unsigned lane) {
+  const uint32_t nelem = p.ntiles;
+  const uint64_t launch_start = uint64_t(p.tile_begin) * kTileBytes;
+  const uint64_t out_base = cin.count;
+  uint32_t full_phase = 0;
+  uint32_t pw_cur = 0x20202020u, pw_next = 0x20202020u;
+  bool tma_cur = false, tma_next = false;
+  uint32_t t = wait_ticket(S, 0, p);
+  if (t < nelem) tma_cur = issue_load(S, tmap, p, t, warp, lane, 0, &pw_cur);
+  uint32_t t_prev = 0;
+  uint32_t j = 0;
+  for (;; j++) {
+    if (t >= nelem) break;
+    const int r = int(j & 1u);
+    const uint32_t tn = wait_ticket(S, j + 1, p);
+    if (tn < nelem) tma_next = issue_load(S, tmap, p, tn, warp, lane, r ^ 1, &pw_next);
+    uint8_t *T = S->ring[warp][r];
+    const uint64_t bstart = (uint64_t(p.tile_begin) + t) * kTileBytes + uint64_t(warp) * kBlockBytes;
+    if (p.debug != nullptr && warp == 0 && lane == 0) {
+      p.debug[uint64_t(t) * 8 + 0] = sj_globaltimer();
+      p.debug[uint64_t(t) * 8 + 7] = ((unsigned long long)sj_cta() << 32) | j;
+    }
+    uint32_t summary = 0;
+    if (bstart < p.len) {
+      if (tma_cur) {
+        wait_bar(&S->full[warp][r], (full_phase >> r) & 1u, p);
+        full_phase ^= 1u << r;
+      } else {
+        fill_block_guarded(T, p, bstart, lane);
+        sj_syncwarp();
+      }
+      const uint32_t pw0 = sj_shfl(pw_cur, 0);
+      const uint32_t st = boundary_state(p, bstart, launch_start, cin.state, pw0 >> 24, lane);
+      summary = scan_block(T, pw0, st & 1u, (st >> 2) & 1u, lane, p, S->park[r][0], S->park[r][1], S->parkpre[r]);
+    }
+    if (lane == 0) {
+      S->summary[j % kNS][warp] = summary;
+      sj_mbar_arrive(&S->scanned[j % kNS]);
+    }
+    if (j > 0) {
+      wait_bar(&S->resolved[(j - 1) % kNS], ((j - 1) / kNS) & 1u, p);
+      emit_block(S, p, out_base, t_prev, warp, lane, int((j - 1) % kNS), r ^ 1, reinterpret_cast<uint32_t *>(T));
+      if (p.debug != nullptr && warp == 0 && lane == 0) p.debug[uint64_t(t_prev) * 8 + 5] = sj_globaltimer();
+    }
+    t_prev = t;
+    t = tn;
+    tma_cur = tma_next;
+    pw_cur = pw_next;
+  }
+  if (j > 0) {  // drain the pipeline: the last element this CTA scanned
+    wait_bar(&S->resolved[(j - 1) % kNS], ((j - 1) / kNS) & 1u, p);
+    emit_block(S, p, out_base, t_prev, warp, lane, int((j - 1) % kNS), int((j - 1) & 1u), reinterpret_cast<uint32_t *>(S->ring[warp][j & 1u]));
+    if (p.debug != nullptr && warp == 0 && lane == 0) p.debug[uint64_t(t_prev) * 8 + 5] = sj_globaltimer();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ chain warp
+SJ_DEV void acquire_ticket(Smem *S, uint32_t j, const ScanParams &p, unsigned lane) {
+  if (lane == 0) {
+    S->ticket[j % kNS] = sj_atomic_add(p.ticket, 1u);
+    sj_mbar_arrive(&S->ticket_ready[j % kNS]);
+  }
+  sj_syncwarp();
+}
+
+// Decoupled look-back: in-string state and output count entering element t (t >= 1).
+SJ_DEV void look_back(const ScanParams &p, uint32_t t, unsigned lane, uint32_t *s_in, uint32_t *base) {
+  Eff acc;
+  acc.p = 0; acc.a = 0; acc.b = 0;
+  int64_t newest = int64_t(t) - 1;
+  for (;;) {
+    uint32_t st[kLookK], P[kLookK], A[kLookK], B[kLookK];
+    uint32_t want = 0, have = 0;
+#pragma unroll
+    for (int k = 0; k < kLookK; k++) {
+      st[k] = kDescNone; P[k] = 0; A[k] = 0; B[k] = 0;
+      if (newest - int64_t(lane * kLookK + k) >= 0) want |= 1u << k;
+    }
+    int inc_lane = 32, inc_k = kLookK;
+    uint32_t spins = 0;
+    for (;;) {
+#pragma unroll
+      for (int k = 0; k < kLookK; k++) {
+        if ((want & ~have) & (1u << k)) {
+          const unsigned long long d = sj_ld_relaxed_u64(p.count_desc + (newest - int64_t(lane * kLookK + k)));
+          const uint32_t s = uint32_t(d >> 44) & 3u;
+          if (uint32_t(d >> 46) == p.epoch && s != kDescNone) {
+            st[k] = s;
+            if (s == kDescInc) { P[k] = uint32_t(d >> 32) & 1u; A[k] = uint32_t(d); B[k] = 0; }
+            else { P[k] = uint32_t(d >> 38) & 1u; A[k] = uint32_t(d) & 0x7FFFFu; B[k] = uint32_t(d >> 19) & 0x7FFFFu; }
+            have |= 1u << k;
+          }
+        }
+      }
+      // nearest inclusive prefix among what has arrived (lanes and k are ordered newest first)
+      int my_inc = kLookK;
+#pragma unroll
+      for (int k = kLookK - 1; k >= 0; k--)
+        if (st[k] == kDescInc) my_inc = k;
+      const uint32_t m = sj_ballot(my_inc < kLookK);
+      if (m != 0) {
+        inc_lane = sj_ffs(m) - 1;
+        inc_k = int(sj_shfl(uint32_t(my_inc), inc_lane));
+      } else {
+        inc_lane = 32;
+        inc_k = kLookK;
+      }
+      // everything newer than it must have arrived
+      uint32_t needed = 0;
+      if (int(lane) < inc_lane) needed = (1u << kLookK) - 1u;
+      else if (int(lane) == inc_lane) needed = (1u << inc_k) - 1u;
+      const uint32_t missing = want & needed & ~have;
+      if (!sj_any(missing != 0)) break;
+      if (++spins > kSpinLimit4) {  // never expected: report, and let the caller finish with what there is
+        sj_atomic_or(p.flags, kFlagInternal);
+        break;
+      }
+      sj_nanosleep(100);
+    }
+    // ordered product of the aggregates newer than the inclusive prefix: oldest first inside the lane ...
+    Eff w;
+    w.p = 0; w.a = 0; w.b = 0;
+#pragma unroll
+    for (int k = kLookK - 1; k >= 0; k--) {
+      const bool use = ((want & have) & (1u << k)) && (int(lane) < inc_lane || (int(lane) == inc_lane && k < inc_k));
+      if (use) {
+        Eff n;
+        n.p = P[k]; n.a = A[k]; n.b = B[k];
+        w = compose(w, n);
+      }
+    }
+    // ... then across lanes (higher lanes hold older elements)
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      Eff o;
+      o.p = sj_shfl_down(w.p, d);
+      o.a = sj_shfl_down(w.a, d);
+      o.b = sj_shfl_down(w.b, d);
+      if (int(lane) + d < 32) w = compose(o, w);
+    }
+    Eff win;
+    win.p = sj_shfl(w.p, 0);
+    win.a = sj_shfl(w.a, 0);
+    win.b = sj_shfl(w.b, 0);
+    acc = compose(win, acc);
+    if (inc_lane < 32) {
+      uint32_t sk = 0, ck = 0;
+#pragma unroll
+      for (int k = 0; k < kLookK; k++)
+        if (k == inc_k) { sk = P[k]; ck = A[k]; }
+      sk = sj_shfl(sk, inc_lane);
+      ck = sj_shfl(ck, inc_lane);
+      *s_in = sk ^ acc.p;
+      *base = ck + (sk ? acc.b : acc.a);
+      return;
+    }
+    newest -= 32 * kLookK;
+    if (newest < 0) {  // cannot happen (element 0 always publishes an inclusive prefix); never loop forever
+      sj_atomic_or(p.flags, kFlagInternal);
+      *s_in = acc.p;
+      *base = acc.a;
+      return;
+    }
+  }
+}
+
+// The launch is over: total count, outgoing scanner state, the 6-bit carry transducer of everything it scanned
+// (multi-GPU shards fold these: SURVEY.md 8e), sentinels, end-of-input UTF-8 rule.
+SJ_DEV void finalize_launch(const ScanParams &p, const Carry &cin, uint32_t s_out, uint64_t count_total, unsigned lane) {
+  const uint64_t launch_start = uint64_t(p.tile_begin) * kTileBytes;
+  const uint64_t end_scanned = launch_start + uint64_t(p.ntiles) * kTileBytes;
+  const uint64_t end_real = p.len < end_scanned ? p.len : end_scanned;
+  // state after the last real byte, for the carry-in this launch actually had
+  const uint32_t b1 = (end_real > launch_start) ? sj_ldg_u8(p.buf + end_real - 1) : 0x20u;
+  const uint32_t st = boundary_state(p, end_real, launch_start, cin.state, b1, lane);
+  const uint32_t e_a = st & 1u, c_a = (st >> 2) & 1u, par_a = (s_out ^ (cin.state >> 1)) & 1u;
+  // ... and for the opposite incoming escape: it can only toggle the first byte that is not a backslash
+  const uint64_t nlead = run_forward(p.buf, launch_start, end_real, lane);
+  uint32_t e_o = e_a, c_o = c_a, par_o = par_a;
+  if (launch_start + nlead >= end_real) {
+    e_o ^= 1u;  // nothing but backslashes: the carry goes straight through
+  } else if (sj_ldg_u8(p.buf + launch_start + nlead) == 0x22u) {
+    par_o ^= 1u;
+    if (launch_start + nlead == end_real - 1) c_o ^= 1u;
+  }
+  const uint32_t ein = cin.state & 1u;
+  const uint32_t T0 = ein ? (e_o | (par_o << 1) | (c_o << 2)) : (e_a | (par_a << 1) | (c_a << 2));
+  const uint32_t T1 = ein ? (e_a | (par_a << 1) | (c_a << 2)) : (e_o | (par_o << 1) | (c_o << 2));
+  if (lane == 0) {
+    p.carry_out->count = count_total;
+    p.carry_out->state = e_a | (s_out << 1) | (c_a << 2);
+    p.carry_out->ttable = T0 | (T1 << 3);
+    if (p.write_sentinels) {  // json_structural_indexer.h L284-286
+      uint32_t *tail = p.idx_out + count_total;
+      tail[0] = uint32_t(p.len);
+      tail[1] = uint32_t(p.len);
+      tail[2] = 0;
+    }
+    if (p.check_eof) {  // utf8_checker::check_eof (utf8_lookup4_algorithm.h L167-171)
+      const uint32_t tw = word_before(p, p.len);
+      if (utf8_carry_pending(utf8_carry_from_prev_word(tw))) sj_atomic_or(p.flags, kFlagUtf8);
+    }
+  }
+}
+
+SJ_DEV void chain_role(Smem *S, const ScanParams &p, const Carry &cin, unsigned lane) {
+  const uint32_t nelem = p.ntiles;
+  acquire_ticket(S, 0, p, lane);
+  acquire_ticket(S, 1, p, lane);
+  for (uint32_t j = 0;; j++) {
+    const int ns = int(j % kNS);
+    const uint32_t t = S->ticket[ns];
+    if (t >= nelem) break;
+    acquire_ticket(S, j + 2, p, lane);
+    wait_bar(&S->scanned[ns], (j / kNS) & 1u, p);
+    if (p.debug != nullptr && lane == 0) p.debug[uint64_t(t) * 8 + 3] = sj_globaltimer();
+    // compose the 8 block summaries, for either polarity at the start of the element
+    const uint32_t mine = (lane < uint32_t(kScanWarps)) ? S->summary[ns][lane] : 0u;
+    uint32_t s0 = 0, s1 = 1, b0 = 0, b1 = 0, hit0 = 0, hit1 = 0;
+    uint32_t my_pol0 = 0, my_pol1 = 1, my_b0 = 0, my_b1 = 0;
+#pragma unroll
+    for (int w = 0; w < kScanWarps; w++) {
+      const uint32_t r = sj_shfl(mine, w);
+      const uint32_t c0 = r & 0xFFFFu, c1 = (r >> 16) & 0x1FFFu, par = (r >> 29) & 1u, h0 = (r >> 30) & 1u, h1 = r >> 31;
+      if (int(lane) == w) { my_pol0 = s0; my_pol1 = s1; my_b0 = b0; my_b1 = b1; }
+      b0 += s0 ? c1 : c0;
+      hit0 |= s0 ? h1 : h0;
+      s0 ^= par;
+      b1 += s1 ? c1 : c0;
+      hit1 |= s1 ? h1 : h0;
+      s1 ^= par;
+    }
+    const uint32_t par = s0;  // quote parity of the element; b0 / b1 = its outputs entered outside / inside a string
+    uint32_t s_in = (cin.state >> 1) & 1u, base = 0;
+    if (t > 0) {
+      if (lane == 0) sj_st_relaxed_u64(p.count_desc + t, pack_agg(p.epoch, par, b0, b1));
+      look_back(p, t, lane, &s_in, &base);
+    }
+    const uint32_t mine_total = s_in ? b1 : b0;
+    const uint32_t s_out = s_in ^ par;
+    if (lane == 0) sj_st_relaxed_u64(p.count_desc + t, pack_inc(p.epoch, s_out, base + mine_total));
+    if (lane < uint32_t(kScanWarps)) {
+      S->res_pol[ns][lane] = s_in ? my_pol1 : my_pol0;
+      S->res_base[ns][lane] = base + (s_in ? my_b1 : my_b0);
+    }
+    if (lane == 0 && (s_in ? hit1 : hit0)) sj_atomic_or(p.flags, kFlagCtl);
+    sj_syncwarp();
+    if (lane == 0) sj_mbar_arrive(&S->resolved[ns]);
+    if (p.debug != nullptr && lane == 0) p.debug[uint64_t(t) * 8 + 4] = sj_globaltimer();
+    if (t == nelem - 1) finalize_launch(p, cin, s_out, cin.count + base + mine_total, lane);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel body
+SJ_DEV void scan4_body(const sj_tensor_map *tmap, const ScanParams &p, uint8_t *smem_raw, uint32_t smem_raw_addr) {
+  // 1 KiB alignment for the 128B swizzle, computed on the shared-space address so the pointer keeps its address space
+  Smem *S = reinterpret_cast<Smem *>(smem_raw + ((1024u - (smem_raw_addr & 1023u)) & 1023u));
+  const unsigned tid = sj_tid(), lane = tid & 31u, warp = tid >> 5;
+  Carry cin;
+  cin.count = 0; cin.state = 0; cin.ttable = 0; cin.flags = 0; cin.reserved = 0;
+  if (p.carry_in != nullptr) cin = *p.carry_in;
+  if (tid == 0) {
+    for (int w = 0; w < kScanWarps; w++) {
+      sj_mbar_init(&S->full[w][0], 1);
+      sj_mbar_init(&S->full[w][1], 1);
+    }
+    for (int i = 0; i < kNS; i++) {
+      sj_mbar_init(&S->ticket_ready[i], 1);
+      sj_mbar_init(&S->scanned[i], kScanWarps);
+      sj_mbar_init(&S->resolved[i], 1);
+    }
+    sj_fence_mbar_init();
+  }
+  sj_syncthreads();
+  if (warp < unsigned(kScanWarps)) scan_role(S, tmap, p, cin, warp, lane);
+  else chain_role(S, p, cin, lane);
+  // last CTA out resets the ticket for the next launch on this context and hands the flags over
+  sj_syncthreads();
+  if (tid == 0) {
+    sj_threadfence();
+    const uint32_t done = sj_atomic_add(p.ticket + 1, 1u);
+    if (done == sj_nctas() - 1) {
+      p.ticket[0] = 0;
+      p.ticket[1] = 0;
+      p.carry_out->flags = sj_atomic_exch(p.flags, 0u);
+      sj_threadfence();
+    }
+  }
+}
+
+}  // namespace scan4
+}  // namespace sjb200
