@@ -141,7 +141,6 @@ SJ_DEV uint64_t run_back(const uint8_t *buf, uint64_t end, uint64_t floor, unsig
       const uint32_t f = uint32_t(sj_ffs(m) - 1);
       total += f;
       if (f == avail && avail < 32) *hit_floor = true;
-      if (f == avail && avail == 32) { /* cannot happen: m != 0 means some lane < 32 stopped */ }
       return total;
     }
     total += 32;
@@ -240,14 +239,6 @@ SJ_DEV void load_unit(const uint8_t *T, uint32_t off, uint32_t w[8]) {
   w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
 }
 
-// an incoming escape flips the "escaped" status of the first byte that is not a backslash; it only matters when
-// that byte is a quote (carry state)
-SJ_DEV void toggle_quote_at(const uint32_t qu[4], uint32_t qr[4], int k) {
-#pragma unroll
-  for (int u = 0; u < 4; u++)
-    if ((k >> 5) == u) qr[u] ^= qu[u] & (1u << (k & 31));
-}
-
 // ------------------------------------------------------------------------------------------------ scan one block
 // T: the block in shared memory.  pw0: the 4 bytes before the block (only lane 0's copy is used).  e_in / c_in: the two
 // locally known state bits entering the block.  Parks the two candidate masks and the lane's exclusive output prefix,
@@ -260,6 +251,7 @@ SJ_DEV uint32_t scan_block(const uint8_t *T, uint32_t pw0, uint32_t e_in, uint32
   {
     const uint32_t pw = (lane == 0) ? pw0 : *reinterpret_cast<const uint32_t *>(T + swz(lane_off - 4));
     utf8_carry uc = utf8_carry_from_prev_word(pw);
+    uint32_t pend = utf8_carry_pending(uc) ? 1u : 0u;  // the previous unit ended inside a multi-byte sequence
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       uint32_t w8[8], pl[8];
@@ -267,8 +259,9 @@ SJ_DEV uint32_t scan_block(const uint8_t *T, uint32_t pw0, uint32_t e_in, uint32
       transpose32(w8, pl);
       const unit_classes c = classify(pl);
       bs[u] = c.bs; qu[u] = c.qu; op[u] = c.op; sc[u] = c.sc; cl[u] = c.ctl;
-      if (sj_any(pl[7] != 0 || utf8_carry_pending(uc))) {
+      if (sj_any((pl[7] | pend) != 0)) {  // all-ASCII units of a warp (and nothing pending) need no check
         uerr |= utf8_check_unit(pl, uc);
+        pend = (uc.n1 >> 31) | (uc.n2 >> 30) | (uc.n3 >> 29);
       } else {
         uc = utf8_carry_zero();
       }
@@ -285,12 +278,17 @@ SJ_DEV uint32_t scan_block(const uint8_t *T, uint32_t pw0, uint32_t e_in, uint32
       const uint32_t esc_out0 = escape_scan<4>(bs, escaped);
 #pragma unroll
       for (int u = 0; u < 4; u++) qr[u] = qu[u] & ~escaped[u];
-      const int nlead = leading_backslashes<4>(bs);
+      const bool allbs = (bs[0] & bs[1] & bs[2] & bs[3]) == 0xFFFFFFFFu;
       const uint32_t G = sj_ballot(esc_out0 != 0);
-      const uint32_t P = sj_ballot(nlead == 128);
+      const uint32_t P = sj_ballot(allbs);
       uint32_t cout_unused;
-      const uint32_t carries = escape_carries(G, P, e_in & 1u, &cout_unused);
-      if (((carries >> lane) & 1u) && nlead != 128) toggle_quote_at(qu, qr, nlead);
+      const uint32_t carries = escape_carries(G, P, e_in & 1u, &cout_unused) & ~P;
+      if (carries != 0) {  // rare: some lane starts right after an unescaped backslash
+        const int nlead = leading_backslashes<4>(bs);
+        const uint32_t bit = ((carries >> lane) & 1u) ? (1u << (nlead & 31)) : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; u++) qr[u] ^= qu[u] & (((nlead >> 5) == u) ? bit : 0u);
+      }
     } else {
 #pragma unroll
       for (int u = 0; u < 4; u++) qr[u] = qu[u];
@@ -339,20 +337,25 @@ SJ_DEV uint32_t scan_block(const uint8_t *T, uint32_t pw0, uint32_t e_in, uint32
 }
 
 // ------------------------------------------------------------------------------------------------ emit one block
-template <bool kStaged>
+// Each lane walks its own four mask words, column by column: every lane runs the trip count of the fullest word of the
+// column (uniform), pulls the highest set bit per iteration (one FLO) and stores its position -- descending, so the
+// store offset is an immediate of the unrolled loop.
 SJ_DEV void emit_columns(const sj_u4 ev, uint32_t off, uint32_t pos_lane, uint32_t *dst) {
   const uint32_t m4[4] = {ev.x, ev.y, ev.z, ev.w};
 #pragma unroll
   for (int u = 0; u < 4; u++) {
     uint32_t m = m4[u];
+    const uint32_t c = uint32_t(sj_popc(m));
+    const uint32_t n = sj_reduce_max(c);
     const uint32_t pb = pos_lane + 32u * u;
-    const uint32_t n = sj_reduce_max(uint32_t(sj_popc(m)));  // uniform trip count: the fullest word of this column
-    for (uint32_t k = 0; k < n; k++) {
-      if (m != 0) {
-        dst[off] = pb + uint32_t(sj_ffs(m) - 1);
-        off++;
-        m &= m - 1;
-      }
+    uint32_t *q = dst + (off + c);  // one past the word's last output
+    off += c;
+#pragma unroll 4
+    for (uint32_t k = 1; k <= n; k++) {
+      const bool has = m != 0;
+      const uint32_t h = sj_bfind(m);
+      if (has) q[-int(k)] = pb + h;
+      m &= ~(1u << (h & 31u));
     }
   }
 }
@@ -371,12 +374,12 @@ SJ_DEV void emit_block(Smem *S, const ScanParams &p, uint64_t out_base, uint32_t
   if (total <= kStageWords) {
     // positions go to shared memory (scattered 4-byte global stores cost one L1 wavefront each) and leave coalesced
     sj_syncwarp();
-    emit_columns<true>(ev, off, pos_lane, stg);
+    emit_columns(ev, off, pos_lane, stg);
     sj_syncwarp();
     for (uint32_t i = lane; i < total; i += 32) out[i] = stg[i];
     sj_syncwarp();
   } else {
-    emit_columns<false>(ev, off, pos_lane, out);  // > 1 structural per 4 bytes over 4 KiB: straight to global memory
+    emit_columns(ev, off, pos_lane, out);  // > 1 structural per 4 bytes over 4 KiB: straight to global memory
   }
 }
 

@@ -105,6 +105,7 @@ SJ_DEV void sj_syncthreads() { pthread_barrier_wait(&simt::tctx.ctas->bar); }
 
 SJ_DEV int sj_popc(uint32_t x) { return __builtin_popcount(x); }
 SJ_DEV int sj_ffs(uint32_t x) { return __builtin_ffs(int(x)); }
+SJ_DEV uint32_t sj_bfind(uint32_t x) { return x ? uint32_t(31 - __builtin_clz(x)) : 0xFFFFFFFFu; }
 SJ_DEV uint32_t sj_funnel_l(uint32_t lo, uint32_t hi, int n) { return n ? ((hi << n) | (lo >> (32 - n))) : hi; }
 
 SJ_DEV uint32_t sj_atomic_add(uint32_t *p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
@@ -228,6 +229,11 @@ SJ_DEV void sj_syncwarp() { __syncwarp(); }
 SJ_DEV void sj_syncthreads() { __syncthreads(); }
 SJ_DEV int sj_popc(uint32_t x) { return __popc(x); }
 SJ_DEV int sj_ffs(uint32_t x) { return __ffs(int(x)); }
+SJ_DEV uint32_t sj_bfind(uint32_t x) {  // index of the highest set bit (0xFFFFFFFF for 0): one FLO
+  uint32_t r;
+  asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+  return r;
+}
 SJ_DEV uint32_t sj_funnel_l(uint32_t lo, uint32_t hi, int n) { return __funnelshift_l(lo, hi, n); }
 
 SJ_DEV uint32_t sj_atomic_add(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }

@@ -17,6 +17,8 @@ doc = corpus.random_json(size).copy()
 rc, p = sj.get_active_implementation().create_dom_parser_implementation(len(doc))
 p.set_option("debug_timeline", 1)
 p.set_option("time_kernel", 1)
+if os.environ.get("PROBE_KERNEL"):
+    p.set_option("kernel", int(os.environ["PROBE_KERNEL"]))
 if os.environ.get("PROBE_R"):
     p.set_option("sub_per_super", int(os.environ["PROBE_R"]))
 d = torch.from_numpy(doc).cuda()
@@ -31,6 +33,10 @@ t = t[t[:, 0] > 0]
 n = len(t)
 t0 = t[:, 0].min()
 print("elements", n, "span_us", (t[:, 5].max() - t0) / 1e3)
+ctas = t[:, 7] >> 32
+print("ctas", len(np.unique(ctas)), "elements per cta: max", np.bincount(ctas.astype(np.int64)).max())
+print("resolve lag (resolved - scanned)  mean %.2f p90 %.2f max %.2f us" % (((t[:, 4] - t[:, 3]) / 1e3).mean(), np.percentile((t[:, 4] - t[:, 3]) / 1e3, 90), ((t[:, 4] - t[:, 3]) / 1e3).max()))
+print("emit done after resolved          mean %.2f p90 %.2f max %.2f us" % (((t[:, 5] - t[:, 4]) / 1e3).mean(), np.percentile((t[:, 5] - t[:, 4]) / 1e3, 90), ((t[:, 5] - t[:, 4]) / 1e3).max()))
 front = (t[:, 3] - t[:, 0]) / 1e3
 v6 = t[:, 6] > 0
 wait = (t[v6, 6] - t[v6, 3]) / 1e3
