@@ -38,9 +38,22 @@ namespace scan4 {
 constexpr int kScanWarps = 8;
 constexpr int kBlockBytes = 4096;
 constexpr int kBlockRows = kBlockBytes / 128;
-constexpr int kThreads4 = 32 * (kScanWarps + 1);
-constexpr int kNS = 4;           // ring of element slots (tickets, summaries, resolutions)
-constexpr int kLookK = 8;        // descriptors per lane and look-back round trip (window of 256 elements)
+#ifndef SJB200_SCAN4_CHAIN
+#define SJB200_SCAN4_CHAIN 1
+#endif
+constexpr int kChainWarps = SJB200_SCAN4_CHAIN;  // chain warp c resolves this CTA's elements j = c, c + kChainWarps, ...
+constexpr int kThreads4 = 32 * (kScanWarps + kChainWarps);
+#ifndef SJB200_SCAN4_PARK
+#define SJB200_SCAN4_PARK 3
+#endif
+constexpr int kPark = SJB200_SCAN4_PARK;  // elements whose masks wait in shared memory: a scan warp emits element j-kLag after scanning j
+constexpr int kLag = kPark - 1;
+constexpr int kNS = 8;           // ring of element slots (tickets, summaries, resolutions); >= kLag + 4
+constexpr int kLookK = 10;       // descriptors per lane and look-back round trip (window of 320 elements >= one wave of CTAs)
+static_assert(kLag >= 1 && kLag <= 5 && (kNS & (kNS - 1)) == 0, "slot ring");
+#ifndef SJB200_SCAN4_SLEEP
+#define SJB200_SCAN4_SLEEP 1
+#endif
 constexpr uint32_t kSpinLimit4 = 1u << 21;  // bounded waits: a stuck protocol becomes kFlagInternal, never a hang
 constexpr uint32_t kStageWords = kBlockBytes / 4;
 static_assert(kScanWarps * kBlockBytes == kTileBytes, "an element is one tile of the launch parameter block");
@@ -49,10 +62,13 @@ enum : uint32_t { kDescNone = 0, kDescAgg = 1, kDescInc = 2 };
 
 struct Smem {
   uint8_t ring[kScanWarps][2][kBlockBytes];   // per scan warp: two block buffers (TMA destination / emit staging)
-  sj_u4 park[2][2][kScanWarps * 32];          // [pipeline buffer][polarity][thread]: candidate structural masks
-  uint32_t parkpre[2][kScanWarps * 32];       // exclusive prefix of the lane's counts inside its block, both polarities packed
+  sj_u4 park[kPark][2][kScanWarps * 32];          // [pipeline buffer][polarity][thread]: candidate structural masks
+  uint32_t parkpre[kPark][kScanWarps * 32];       // exclusive prefix of the lane's counts inside its block, both polarities packed
   uint32_t ticket[kNS];
   uint32_t summary[kNS][kScanWarps];          // c0 | c1<<16 | parity<<29 | ctl-hit0<<30 | ctl-hit1<<31
+  uint32_t arrived[kNS];                      // scan warps done with the element (the last one composes and publishes)
+  uint32_t elem[kNS][4];                      // composed element: quote parity, outputs entered outside / inside a string, ctl hits (bit0/1)
+  uint32_t pre[kNS][2][kScanWarps];           // per block, for either polarity at the start of the element: polarity<<31 | outputs before it
   uint32_t res_pol[kNS][kScanWarps];          // in-string polarity entering the block
   uint32_t res_base[kNS][kScanWarps];         // outputs of this launch before the block
   sj_mbar_t full[kScanWarps][2];
@@ -90,13 +106,18 @@ SJ_DEV Eff compose(const Eff &o, const Eff &n) {
   return r;
 }
 
-SJ_DEV bool wait_bar(sj_mbar_t *bar, uint32_t parity, const ScanParams &p) {
+// A waiting warp must not spin at full speed: mbarrier.try_wait returns at once, and a busy loop takes issue slots
+// from the warps that do the work (measured: 20 % of all issued instructions).  `ns` = back-off between polls.
+SJ_DEV bool wait_bar(sj_mbar_t *bar, uint32_t parity, const ScanParams &p, unsigned ns) {
   uint32_t spins = 0;
   while (!sj_mbar_try_wait(bar, parity)) {
     if (++spins > kSpinLimit4) {
       sj_atomic_or(p.flags, kFlagInternal);
       return false;
     }
+#if SJB200_SCAN4_SLEEP
+    sj_nanosleep(ns);
+#endif
   }
   return true;
 }
@@ -182,15 +203,37 @@ SJ_DEV uint64_t run_forward(const uint8_t *buf, uint64_t begin, uint64_t limit, 
 // pos-1), bit2 = byte pos-1 is a "non-quote scalar" (json_scanner.h L148-149).  Exact for any input: the run is
 // followed back as far as it goes, at most to the first byte of this launch, where the launch's carry-in takes over.
 // `b1` = byte pos-1.  Warp-uniform.
-SJ_DEV uint32_t boundary_state(const ScanParams &p, uint64_t pos, uint64_t launch_start, uint32_t cin_state, uint32_t b1, unsigned lane) {
+SJ_DEV uint32_t boundary_state(const ScanParams &p, uint64_t pos, uint64_t launch_start, uint32_t cin_state, uint32_t pw, unsigned lane) {
   if (pos == launch_start) return cin_state & 5u;
+  const uint32_t b1 = pw >> 24;
   if (b1 != 0x5Cu && b1 != 0x22u) return byte_is_scalar(b1) ? 4u : 0u;  // the common case: one byte decides
-  const uint64_t end = (b1 == 0x22u) ? pos - 1 : pos;  // a quote's own status depends on the run before it
-  bool hit = false;
-  const uint64_t run = run_back(p.buf, end, launch_start, lane, &hit);
-  const uint32_t odd = uint32_t(run + ((hit && (cin_state & 1u)) ? 1u : 0u)) & 1u;
-  if (b1 == 0x22u) return odd << 2;  // escaped quote = scalar byte; a real quote is not; neither escapes what follows
-  return odd | 4u;                   // a backslash is a scalar byte
+  // a quote's own status depends on the run before it.  Short runs are decided from the four bytes at hand (a quote
+  // right before a block boundary is common; going back to global memory for it would cost the warp a round trip to L2)
+  const uint32_t b2 = (pw >> 16) & 0xFFu, b3 = (pw >> 8) & 0xFFu, b4 = pw & 0xFFu;
+  const bool isq = (b1 == 0x22u);
+  uint32_t run = 0xFFFFFFFFu;  // backslashes ending at byte -1 (or at byte -2 when byte -1 is a quote); unknown yet
+  if (pos - launch_start >= 4) {
+    if (isq) {
+      if (b2 != 0x5Cu) run = 0;
+      else if (b3 != 0x5Cu) run = 1;
+      else if (b4 != 0x5Cu) run = 2;
+    } else {
+      if (b2 != 0x5Cu) run = 1;
+      else if (b3 != 0x5Cu) run = 2;
+      else if (b4 != 0x5Cu) run = 3;
+    }
+  }
+  uint32_t odd;
+  if (run != 0xFFFFFFFFu) {
+    odd = run & 1u;
+  } else {
+    const uint64_t end = isq ? pos - 1 : pos;
+    bool hit = false;
+    const uint64_t r = run_back(p.buf, end, launch_start, lane, &hit);
+    odd = uint32_t(r + ((hit && (cin_state & 1u)) ? 1u : 0u)) & 1u;
+  }
+  if (isq) return odd << 2;  // escaped quote = scalar byte; a real quote is not; neither escapes what follows
+  return odd | 4u;           // a backslash is a scalar byte
 }
 
 // the 4 bytes before document offset `pos` as a little-endian word (byte pos-1 on top)
@@ -383,9 +426,51 @@ SJ_DEV void emit_block(Smem *S, const ScanParams &p, uint64_t out_base, uint32_t
   }
 }
 
+// ------------------------------------------------------------------------------------------------ element summary
+// Run by the LAST scan warp to finish an element (so the aggregate is out as early as possible, independent of how far
+// the chain warp is with older elements): compose the 8 block summaries for either polarity at the start of the
+// element, publish the aggregate in the look-back chain, leave the per-block prefixes for the chain warp.
+SJ_DEV void compose_element(Smem *S, const ScanParams &p, int ns, uint32_t t, unsigned lane) {
+  const uint32_t mine = (lane < uint32_t(kScanWarps)) ? S->summary[ns][lane] : 0u;
+  uint32_t s0 = 0, s1 = 1, b0 = 0, b1 = 0, hit0 = 0, hit1 = 0;
+  uint32_t my0 = 0, my1 = 0;
+#pragma unroll
+  for (int w = 0; w < kScanWarps; w++) {
+    const uint32_t r = sj_shfl(mine, w);
+    const uint32_t c0 = r & 0xFFFFu, c1 = (r >> 16) & 0x1FFFu, par = (r >> 29) & 1u, h0 = (r >> 30) & 1u, h1 = r >> 31;
+    if (int(lane) == w) { my0 = (s0 << 31) | b0; my1 = (s1 << 31) | b1; }
+    b0 += s0 ? c1 : c0;
+    hit0 |= s0 ? h1 : h0;
+    s0 ^= par;
+    b1 += s1 ? c1 : c0;
+    hit1 |= s1 ? h1 : h0;
+    s1 ^= par;
+  }
+  if (lane < uint32_t(kScanWarps)) {
+    S->pre[ns][0][lane] = my0;
+    S->pre[ns][1][lane] = my1;
+  }
+  if (lane == 0) {
+    S->elem[ns][0] = s0;  // quote parity of the element
+    S->elem[ns][1] = b0;
+    S->elem[ns][2] = b1;
+    S->elem[ns][3] = hit0 | (hit1 << 1);
+    if (t > 0) sj_st_relaxed_u64(p.count_desc + t, pack_agg(p.epoch, s0, b0, b1));  // element 0 goes straight to inclusive
+  }
+  sj_syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------ scan warps
+SJ_DEV void publish_ticket(Smem *S, uint32_t j, uint32_t value, unsigned lane) {
+  if (lane == 0) {
+    S->ticket[j % kNS] = value;
+    sj_mbar_arrive(&S->ticket_ready[j % kNS]);
+  }
+  sj_syncwarp();
+}
+
 SJ_DEV uint32_t wait_ticket(Smem *S, uint32_t j, const ScanParams &p) {
-  if (!wait_bar(&S->ticket_ready[j % kNS], (j / kNS) & 1u, p)) return 0xFFFFFFFFu;
+  if (!wait_bar(&S->ticket_ready[j % kNS], (j / kNS) & 1u, p, 100)) return 0xFFFFFFFFu;
   return S->ticket[j % kNS];
 }
 
@@ -414,151 +499,186 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
   uint32_t full_phase = 0;
   uint32_t pw_cur = 0x20202020u, pw_next = 0x20202020u;
   bool tma_cur = false, tma_next = false;
+  // Warp 0 is the ticket master.  Tickets must not depend on the chain warp's progress (it may sit in a look-back
+  // while the scan warps run ahead), and a ticket is taken one iteration before it is published, so nobody ever
+  // waits for the atomic's round trip to L2.
+  if (warp == 0) {
+    uint32_t a0 = 0, a1 = 0;
+    if (lane == 0) {
+      a0 = sj_atomic_add(p.ticket, 1u);
+      a1 = sj_atomic_add(p.ticket, 1u);
+    }
+    publish_ticket(S, 0, a0, lane);
+    publish_ticket(S, 1, a1, lane);
+  }
   uint32_t t = wait_ticket(S, 0, p);
+  uint32_t th[kLag];  // th[0] = ticket of element j - kLag at the emit of iteration j
+#pragma unroll
+  for (int i = 0; i < kLag; i++) th[i] = t;
   if (t < nelem) tma_cur = issue_load(S, tmap, p, t, warp, lane, 0, &pw_cur);
-  uint32_t t_prev = 0;
   uint32_t j = 0;
   for (;; j++) {
     if (t >= nelem) break;
     const int r = int(j & 1u);
+    uint32_t t_acq = 0;
+    if (warp == 0 && lane == 0) t_acq = sj_atomic_add(p.ticket, 1u);  // element j+2 of this CTA
     const uint32_t tn = wait_ticket(S, j + 1, p);
     if (tn < nelem) tma_next = issue_load(S, tmap, p, tn, warp, lane, r ^ 1, &pw_next);
     uint8_t *T = S->ring[warp][r];
     const uint64_t bstart = (uint64_t(p.tile_begin) + t) * kTileBytes + uint64_t(warp) * kBlockBytes;
     if (p.debug != nullptr && warp == 0 && lane == 0) {
       p.debug[uint64_t(t) * 8 + 0] = sj_globaltimer();
-      p.debug[uint64_t(t) * 8 + 7] = ((unsigned long long)sj_cta() << 32) | j;
+      p.debug[uint64_t(t) * 8 + 7] = ((unsigned long long)sj_smid() << 48) | ((unsigned long long)sj_cta() << 32) | j;
     }
     uint32_t summary = 0;
     if (bstart < p.len) {
       if (tma_cur) {
-        wait_bar(&S->full[warp][r], (full_phase >> r) & 1u, p);
+        wait_bar(&S->full[warp][r], (full_phase >> r) & 1u, p, 32);
         full_phase ^= 1u << r;
       } else {
         fill_block_guarded(T, p, bstart, lane);
         sj_syncwarp();
       }
       const uint32_t pw0 = sj_shfl(pw_cur, 0);
-      const uint32_t st = boundary_state(p, bstart, launch_start, cin.state, pw0 >> 24, lane);
-      summary = scan_block(T, pw0, st & 1u, (st >> 2) & 1u, lane, p, S->park[r][0], S->park[r][1], S->parkpre[r]);
+      const uint32_t st = boundary_state(p, bstart, launch_start, cin.state, pw0, lane);
+      summary = scan_block(T, pw0, st & 1u, (st >> 2) & 1u, lane, p, S->park[j % kPark][0], S->park[j % kPark][1], S->parkpre[j % kPark]);
     }
-    if (lane == 0) {
-      S->summary[j % kNS][warp] = summary;
-      sj_mbar_arrive(&S->scanned[j % kNS]);
+    {
+      const int ns = int(j % kNS);
+      uint32_t last = 0;
+      if (lane == 0) {
+        S->summary[ns][warp] = summary;
+        sj_fence_block();
+        last = (sj_atomic_add(&S->arrived[ns], 1u) == uint32_t(kScanWarps - 1)) ? 1u : 0u;
+      }
+      if (sj_shfl(last, 0)) {
+        sj_fence_block();
+        if (p.debug != nullptr && lane == 0) p.debug[uint64_t(t) * 8 + 3] = sj_globaltimer();
+        compose_element(S, p, ns, t, lane);
+        if (lane == 0) {
+          S->arrived[ns] = 0;
+          sj_mbar_arrive(&S->scanned[ns]);
+        }
+      }
     }
-    if (j > 0) {
-      wait_bar(&S->resolved[(j - 1) % kNS], ((j - 1) / kNS) & 1u, p);
-      emit_block(S, p, out_base, t_prev, warp, lane, int((j - 1) % kNS), r ^ 1, reinterpret_cast<uint32_t *>(T));
-      if (p.debug != nullptr && warp == 0 && lane == 0) p.debug[uint64_t(t_prev) * 8 + 5] = sj_globaltimer();
+    if (warp == 0) publish_ticket(S, j + 2, t_acq, lane);
+    if (j >= uint32_t(kLag)) {  // the chain warp has had kLag scans' time to resolve this one
+      const uint32_t e = j - uint32_t(kLag);
+      wait_bar(&S->resolved[e % kNS], (e / kNS) & 1u, p, 64);
+      const uint32_t te = th[0];
+      emit_block(S, p, out_base, te, warp, lane, int(e % kNS), int(e % kPark), reinterpret_cast<uint32_t *>(T));
+      if (p.debug != nullptr && warp == 0 && lane == 0) p.debug[uint64_t(te) * 8 + 5] = sj_globaltimer();
     }
-    t_prev = t;
+#pragma unroll
+    for (int i = 0; i + 1 < kLag; i++) th[i] = th[i + 1];  // tickets of the elements still waiting to be emitted
+    th[kLag - 1] = t;
     t = tn;
     tma_cur = tma_next;
     pw_cur = pw_next;
   }
-  if (j > 0) {  // drain the pipeline: the last element this CTA scanned
-    wait_bar(&S->resolved[(j - 1) % kNS], ((j - 1) / kNS) & 1u, p);
-    emit_block(S, p, out_base, t_prev, warp, lane, int((j - 1) % kNS), int((j - 1) & 1u), reinterpret_cast<uint32_t *>(S->ring[warp][j & 1u]));
-    if (p.debug != nullptr && warp == 0 && lane == 0) p.debug[uint64_t(t_prev) * 8 + 5] = sj_globaltimer();
+  // every chain warp must meet an invalid ticket at its next index: j and j+1 are out already
+  if (warp == 0)
+    for (uint32_t x = j + 2; x < j + uint32_t(kChainWarps); x++) publish_ticket(S, x, 0xFFFFFFFFu, lane);
+  // drain the pipeline: the last kLag elements this CTA scanned (no load is in flight: both ring slots are free)
+#pragma unroll
+  for (int i = 0; i < kLag; i++) {
+    if (j + uint32_t(i) < uint32_t(kLag)) continue;  // fewer than kLag elements were scanned
+    const uint32_t e = j + uint32_t(i) - uint32_t(kLag);
+    wait_bar(&S->resolved[e % kNS], (e / kNS) & 1u, p, 64);
+    const uint32_t te = th[i];
+    emit_block(S, p, out_base, te, warp, lane, int(e % kNS), int(e % kPark), reinterpret_cast<uint32_t *>(S->ring[warp][0]));
+    if (p.debug != nullptr && warp == 0 && lane == 0) p.debug[uint64_t(te) * 8 + 5] = sj_globaltimer();
   }
 }
 
 // ------------------------------------------------------------------------------------------------ chain warp
-SJ_DEV void acquire_ticket(Smem *S, uint32_t j, const ScanParams &p, unsigned lane) {
-  if (lane == 0) {
-    S->ticket[j % kNS] = sj_atomic_add(p.ticket, 1u);
-    sj_mbar_arrive(&S->ticket_ready[j % kNS]);
-  }
-  sj_syncwarp();
-}
 
 // Decoupled look-back: in-string state and output count entering element t (t >= 1).
+// A window is 32*kLookK descriptors, laid out k-major: load k of lane L is the descriptor at distance 32k + L behind
+// t-1, so every load instruction of the warp reads 256 contiguous bytes (all CTAs poll the same few cache lines of L2:
+// with a lane-major layout every poll was ~200 line requests per warp and the chain warps queued behind one another).
+// The window is complete when everything newer than the nearest inclusive prefix has arrived.  Folding uses the fact
+// that only one bit is order-dependent: the quote parities of a group of 32 elements are one ballot word, an element's
+// polarity relative to the oldest element of the window is a popcount, and the counts are then plain sums.
 SJ_DEV void look_back(const ScanParams &p, uint32_t t, unsigned lane, uint32_t *s_in, uint32_t *base) {
   Eff acc;
   acc.p = 0; acc.a = 0; acc.b = 0;
   int64_t newest = int64_t(t) - 1;
+  const uint32_t key_agg = (p.epoch << 2) | kDescAgg;  // bits [63:44] of a descriptor of this launch: key_agg or key_agg + 1
   for (;;) {
-    uint32_t st[kLookK], P[kLookK], A[kLookK], B[kLookK];
-    uint32_t want = 0, have = 0;
+    const int64_t first = newest - int64_t(lane);  // my k-th descriptor is first - 32k
+    unsigned long long d[kLookK];
+    uint32_t pend = 0;  // bit k: wanted and not yet arrived
 #pragma unroll
     for (int k = 0; k < kLookK; k++) {
-      st[k] = kDescNone; P[k] = 0; A[k] = 0; B[k] = 0;
-      if (newest - int64_t(lane * kLookK + k) >= 0) want |= 1u << k;
+      d[k] = 0;
+      if (first - 32 * k >= 0) pend |= 1u << k;
     }
-    int inc_lane = 32, inc_k = kLookK;
+    const uint32_t want = pend;
+    uint32_t inc_dist = 0xFFFFFFFFu, needed = (1u << kLookK) - 1u;
     uint32_t spins = 0;
     for (;;) {
+      // one poll: independent predicated loads straight into d[k] (a word that has not arrived is simply loaded again
+      // by the next poll), then three independent instructions per word
+      const uint32_t todo = pend;
+#pragma unroll
+      for (int k = 0; k < kLookK; k++)
+        if (todo & (1u << k)) d[k] = sj_ld_relaxed_u64(p.count_desc + (first - 32 * k));
+      uint32_t okm = 0, incm = 0;
 #pragma unroll
       for (int k = 0; k < kLookK; k++) {
-        if ((want & ~have) & (1u << k)) {
-          const unsigned long long d = sj_ld_relaxed_u64(p.count_desc + (newest - int64_t(lane * kLookK + k)));
-          const uint32_t s = uint32_t(d >> 44) & 3u;
-          if (uint32_t(d >> 46) == p.epoch && s != kDescNone) {
-            st[k] = s;
-            if (s == kDescInc) { P[k] = uint32_t(d >> 32) & 1u; A[k] = uint32_t(d); B[k] = 0; }
-            else { P[k] = uint32_t(d >> 38) & 1u; A[k] = uint32_t(d) & 0x7FFFFu; B[k] = uint32_t(d >> 19) & 0x7FFFFu; }
-            have |= 1u << k;
-          }
-        }
+        const uint32_t rel = uint32_t(d[k] >> 44) - key_agg;  // 0: aggregate, 1: inclusive, anything else: not this launch's
+        if (rel <= 1u) okm |= 1u << k;
+        if (rel == 1u) incm |= 1u << k;
       }
-      // nearest inclusive prefix among what has arrived (lanes and k are ordered newest first)
-      int my_inc = kLookK;
-#pragma unroll
-      for (int k = kLookK - 1; k >= 0; k--)
-        if (st[k] == kDescInc) my_inc = k;
-      const uint32_t m = sj_ballot(my_inc < kLookK);
-      if (m != 0) {
-        inc_lane = sj_ffs(m) - 1;
-        inc_k = int(sj_shfl(uint32_t(my_inc), inc_lane));
-      } else {
-        inc_lane = 32;
-        inc_k = kLookK;
+      pend &= ~okm;
+      incm &= want;
+      // nearest inclusive prefix: for one lane a smaller k is nearer
+      const uint32_t my_dist = incm ? uint32_t(sj_ffs(incm) - 1) * 32u + lane : 0xFFFFFFFFu;
+      inc_dist = sj_reduce_min(my_dist);
+      if (inc_dist != 0xFFFFFFFFu) {  // needed: distance < inc_dist  <=>  k < ceil((inc_dist - lane) / 32)
+        const uint32_t nk = (inc_dist > lane) ? (inc_dist - lane + 31u) / 32u : 0u;
+        needed = (1u << nk) - 1u;
       }
-      // everything newer than it must have arrived
-      uint32_t needed = 0;
-      if (int(lane) < inc_lane) needed = (1u << kLookK) - 1u;
-      else if (int(lane) == inc_lane) needed = (1u << inc_k) - 1u;
-      const uint32_t missing = want & needed & ~have;
-      if (!sj_any(missing != 0)) break;
-      if (++spins > kSpinLimit4) {  // never expected: report, and let the caller finish with what there is
+      if (!sj_any((pend & needed) != 0)) break;
+      if (++spins > kSpinLimit4) {  // never expected: report, and finish with what there is
         sj_atomic_or(p.flags, kFlagInternal);
         break;
       }
+#if SJB200_SCAN4_SLEEP
       sj_nanosleep(100);
+#endif
     }
-    // ordered product of the aggregates newer than the inclusive prefix: oldest first inside the lane ...
-    Eff w;
-    w.p = 0; w.a = 0; w.b = 0;
+    // ---- fold the aggregates newer than the inclusive prefix
+    const uint32_t use = want & ~pend & needed;
+    uint32_t bal[kLookK];
+#pragma unroll
+    for (int k = 0; k < kLookK; k++) bal[k] = sj_ballot(((use >> k) & 1u) && ((uint32_t(d[k] >> 38) & 1u) != 0));
+    uint32_t older = 0;  // parity of everything older than group k (uniform)
+    uint32_t sa = 0, sb = 0;
 #pragma unroll
     for (int k = kLookK - 1; k >= 0; k--) {
-      const bool use = ((want & have) & (1u << k)) && (int(lane) < inc_lane || (int(lane) == inc_lane && k < inc_k));
-      if (use) {
-        Eff n;
-        n.p = P[k]; n.a = A[k]; n.b = B[k];
-        w = compose(w, n);
+      const uint32_t rel = (uint32_t(sj_popc((bal[k] >> lane) >> 1)) ^ older) & 1u;  // my element's polarity relative to the window's oldest
+      if ((use >> k) & 1u) {
+        const uint32_t a = uint32_t(d[k]) & 0x7FFFFu, b = uint32_t(d[k] >> 19) & 0x7FFFFu;
+        sa += rel ? b : a;
+        sb += rel ? a : b;
       }
-    }
-    // ... then across lanes (higher lanes hold older elements)
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      Eff o;
-      o.p = sj_shfl_down(w.p, d);
-      o.a = sj_shfl_down(w.a, d);
-      o.b = sj_shfl_down(w.b, d);
-      if (int(lane) + d < 32) w = compose(o, w);
+      older ^= uint32_t(sj_popc(bal[k])) & 1u;
     }
     Eff win;
-    win.p = sj_shfl(w.p, 0);
-    win.a = sj_shfl(w.a, 0);
-    win.b = sj_shfl(w.b, 0);
+    win.p = older;
+    win.a = sj_reduce_add(sa);
+    win.b = sj_reduce_add(sb);
     acc = compose(win, acc);
-    if (inc_lane < 32) {
+    if (inc_dist != 0xFFFFFFFFu) {
+      const uint32_t ik = inc_dist >> 5, il = inc_dist & 31u;
       uint32_t sk = 0, ck = 0;
 #pragma unroll
       for (int k = 0; k < kLookK; k++)
-        if (k == inc_k) { sk = P[k]; ck = A[k]; }
-      sk = sj_shfl(sk, inc_lane);
-      ck = sj_shfl(ck, inc_lane);
+        if (uint32_t(k) == ik) { sk = uint32_t(d[k] >> 32) & 1u; ck = uint32_t(d[k]); }
+      sk = sj_shfl(sk, int(il));
+      ck = sj_shfl(ck, int(il));
       *s_in = sk ^ acc.p;
       *base = ck + (sk ? acc.b : acc.a);
       return;
@@ -580,8 +700,7 @@ SJ_DEV void finalize_launch(const ScanParams &p, const Carry &cin, uint32_t s_ou
   const uint64_t end_scanned = launch_start + uint64_t(p.ntiles) * kTileBytes;
   const uint64_t end_real = p.len < end_scanned ? p.len : end_scanned;
   // state after the last real byte, for the carry-in this launch actually had
-  const uint32_t b1 = (end_real > launch_start) ? sj_ldg_u8(p.buf + end_real - 1) : 0x20u;
-  const uint32_t st = boundary_state(p, end_real, launch_start, cin.state, b1, lane);
+  const uint32_t st = boundary_state(p, end_real, launch_start, cin.state, word_before(p, end_real), lane);
   const uint32_t e_a = st & 1u, c_a = (st >> 2) & 1u, par_a = (s_out ^ (cin.state >> 1)) & 1u;
   // ... and for the opposite incoming escape: it can only toggle the first byte that is not a backslash
   const uint64_t nlead = run_forward(p.buf, launch_start, end_real, lane);
@@ -612,46 +731,26 @@ SJ_DEV void finalize_launch(const ScanParams &p, const Carry &cin, uint32_t s_ou
   }
 }
 
-SJ_DEV void chain_role(Smem *S, const ScanParams &p, const Carry &cin, unsigned lane) {
+SJ_DEV void chain_role(Smem *S, const ScanParams &p, const Carry &cin, unsigned lane, unsigned c) {
   const uint32_t nelem = p.ntiles;
-  acquire_ticket(S, 0, p, lane);
-  acquire_ticket(S, 1, p, lane);
-  for (uint32_t j = 0;; j++) {
+  for (uint32_t j = c;; j += uint32_t(kChainWarps)) {
     const int ns = int(j % kNS);
-    const uint32_t t = S->ticket[ns];
+    const uint32_t t = wait_ticket(S, j, p);
     if (t >= nelem) break;
-    acquire_ticket(S, j + 2, p, lane);
-    wait_bar(&S->scanned[ns], (j / kNS) & 1u, p);
-    if (p.debug != nullptr && lane == 0) p.debug[uint64_t(t) * 8 + 3] = sj_globaltimer();
-    // compose the 8 block summaries, for either polarity at the start of the element
-    const uint32_t mine = (lane < uint32_t(kScanWarps)) ? S->summary[ns][lane] : 0u;
-    uint32_t s0 = 0, s1 = 1, b0 = 0, b1 = 0, hit0 = 0, hit1 = 0;
-    uint32_t my_pol0 = 0, my_pol1 = 1, my_b0 = 0, my_b1 = 0;
-#pragma unroll
-    for (int w = 0; w < kScanWarps; w++) {
-      const uint32_t r = sj_shfl(mine, w);
-      const uint32_t c0 = r & 0xFFFFu, c1 = (r >> 16) & 0x1FFFu, par = (r >> 29) & 1u, h0 = (r >> 30) & 1u, h1 = r >> 31;
-      if (int(lane) == w) { my_pol0 = s0; my_pol1 = s1; my_b0 = b0; my_b1 = b1; }
-      b0 += s0 ? c1 : c0;
-      hit0 |= s0 ? h1 : h0;
-      s0 ^= par;
-      b1 += s1 ? c1 : c0;
-      hit1 |= s1 ? h1 : h0;
-      s1 ^= par;
-    }
-    const uint32_t par = s0;  // quote parity of the element; b0 / b1 = its outputs entered outside / inside a string
+    wait_bar(&S->scanned[ns], (j / kNS) & 1u, p, 200);
+    if (p.debug != nullptr && lane == 0) p.debug[uint64_t(t) * 8 + 6] = sj_globaltimer();
+    const uint32_t par = S->elem[ns][0], b0 = S->elem[ns][1], b1 = S->elem[ns][2], hits = S->elem[ns][3];
     uint32_t s_in = (cin.state >> 1) & 1u, base = 0;
-    if (t > 0) {
-      if (lane == 0) sj_st_relaxed_u64(p.count_desc + t, pack_agg(p.epoch, par, b0, b1));
-      look_back(p, t, lane, &s_in, &base);
-    }
+    if (t > 0) look_back(p, t, lane, &s_in, &base);
     const uint32_t mine_total = s_in ? b1 : b0;
     const uint32_t s_out = s_in ^ par;
     if (lane == 0) sj_st_relaxed_u64(p.count_desc + t, pack_inc(p.epoch, s_out, base + mine_total));
     if (lane < uint32_t(kScanWarps)) {
-      S->res_pol[ns][lane] = s_in ? my_pol1 : my_pol0;
-      S->res_base[ns][lane] = base + (s_in ? my_b1 : my_b0);
+      const uint32_t pk = S->pre[ns][s_in][lane];
+      S->res_pol[ns][lane] = pk >> 31;
+      S->res_base[ns][lane] = base + (pk & 0x7FFFFFFFu);
     }
+    const uint32_t hit0 = hits & 1u, hit1 = (hits >> 1) & 1u;
     if (lane == 0 && (s_in ? hit1 : hit0)) sj_atomic_or(p.flags, kFlagCtl);
     sj_syncwarp();
     if (lane == 0) sj_mbar_arrive(&S->resolved[ns]);
@@ -675,14 +774,15 @@ SJ_DEV void scan4_body(const sj_tensor_map *tmap, const ScanParams &p, uint8_t *
     }
     for (int i = 0; i < kNS; i++) {
       sj_mbar_init(&S->ticket_ready[i], 1);
-      sj_mbar_init(&S->scanned[i], kScanWarps);
+      sj_mbar_init(&S->scanned[i], 1);
+      S->arrived[i] = 0;
       sj_mbar_init(&S->resolved[i], 1);
     }
     sj_fence_mbar_init();
   }
   sj_syncthreads();
   if (warp < unsigned(kScanWarps)) scan_role(S, tmap, p, cin, warp, lane);
-  else chain_role(S, p, cin, lane);
+  else chain_role(S, p, cin, lane, warp - unsigned(kScanWarps));
   // last CTA out resets the ticket for the next launch on this context and hands the flags over
   sj_syncthreads();
   if (tid == 0) {

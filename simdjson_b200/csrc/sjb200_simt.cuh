@@ -97,6 +97,20 @@ SJ_DEV uint32_t sj_reduce_max(uint32_t v) {
   for (int i = 0; i < 32; i++) m = simt::tctx.warp->vals[ph][i] > m ? simt::tctx.warp->vals[ph][i] : m;
   return m;
 }
+SJ_DEV uint32_t sj_reduce_min(uint32_t v) {
+  unsigned ph;
+  simt::exchange(v, ph);
+  uint32_t m = 0xFFFFFFFFu;
+  for (int i = 0; i < 32; i++) m = simt::tctx.warp->vals[ph][i] < m ? simt::tctx.warp->vals[ph][i] : m;
+  return m;
+}
+SJ_DEV uint32_t sj_reduce_add(uint32_t v) {
+  unsigned ph;
+  simt::exchange(v, ph);
+  uint32_t m = 0;
+  for (int i = 0; i < 32; i++) m += simt::tctx.warp->vals[ph][i];
+  return m;
+}
 SJ_DEV void sj_syncwarp() {
   unsigned ph;
   simt::exchange(0, ph);
@@ -114,10 +128,12 @@ SJ_DEV uint32_t sj_atomic_exch(uint32_t *p, uint32_t v) { return __atomic_exchan
 SJ_DEV unsigned long long sj_ld_relaxed_u64(const unsigned long long *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 SJ_DEV void sj_st_relaxed_u64(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 SJ_DEV void sj_threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+SJ_DEV void sj_fence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 SJ_DEV void sj_nanosleep(unsigned) {
   struct timespec ts = {0, 20000};
   nanosleep(&ts, nullptr);
 }
+SJ_DEV unsigned sj_smid() { return simt::tctx.cta; }
 SJ_DEV unsigned long long sj_globaltimer() {
   struct timespec ts;
   clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -225,6 +241,8 @@ SJ_DEV uint32_t sj_shfl_down(uint32_t v, int d) { return __shfl_down_sync(kFullM
 SJ_DEV uint32_t sj_ballot(bool pred) { return __ballot_sync(kFullMask, pred); }
 SJ_DEV bool sj_any(bool pred) { return __any_sync(kFullMask, pred); }
 SJ_DEV uint32_t sj_reduce_max(uint32_t v) { return __reduce_max_sync(kFullMask, v); }
+SJ_DEV uint32_t sj_reduce_min(uint32_t v) { return __reduce_min_sync(kFullMask, v); }
+SJ_DEV uint32_t sj_reduce_add(uint32_t v) { return __reduce_add_sync(kFullMask, v); }
 SJ_DEV void sj_syncwarp() { __syncwarp(); }
 SJ_DEV void sj_syncthreads() { __syncthreads(); }
 SJ_DEV int sj_popc(uint32_t x) { return __popc(x); }
@@ -248,7 +266,13 @@ SJ_DEV void sj_st_relaxed_u64(unsigned long long *p, unsigned long long v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 SJ_DEV void sj_threadfence() { __threadfence(); }
+SJ_DEV void sj_fence_block() { __threadfence_block(); }
 SJ_DEV void sj_nanosleep(unsigned ns) { __nanosleep(ns); }
+SJ_DEV unsigned sj_smid() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+  return r;
+}
 SJ_DEV unsigned long long sj_globaltimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));

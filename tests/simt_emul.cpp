@@ -202,6 +202,78 @@ int check(EmuCtx &cx, const std::vector<uint8_t> &store, size_t misalign, uint32
   return bad;
 }
 
+// ---- the look-back fold on its own: one emulated warp against a scalar walk, with the nearest inclusive prefix up to
+// three windows away and stale / missing descriptors behind it (the multi-CTA runs above only reach short distances)
+struct LbArgs {
+  const ScanParams *p;
+  uint32_t t;
+  simt::WarpShared *warp;
+  simt::CtaShared *cta;
+  unsigned lane;
+  uint32_t s_in, base;
+};
+void *lb_thread(void *arg) {
+  LbArgs *a = static_cast<LbArgs *>(arg);
+  simt::tctx = simt::ThreadCtx();
+  simt::tctx.tid = a->lane;
+  simt::tctx.nctas = 1;
+  simt::tctx.warp = a->warp;
+  simt::tctx.ctas = a->cta;
+  scan4::look_back(*a->p, a->t, a->lane, &a->s_in, &a->base);
+  return nullptr;
+}
+int test_look_back(std::mt19937_64 &rng, int cases) {
+  int bad = 0;
+  for (int c = 0; c < cases && bad < 3; c++) {
+    const uint32_t t = 1 + uint32_t(rng() % 1500);
+    const uint32_t epoch = 1 + uint32_t(rng() % 1000);
+    std::vector<unsigned long long> desc(t + 1, 0ull);
+    uint32_t flags = 0;
+    // nearest inclusive prefix at `inc`; everything newer is an aggregate; older entries are junk that must not matter
+    const uint32_t maxback = std::min<uint32_t>(t, 1 + uint32_t(rng() % 1000));
+    const uint32_t inc = t - 1 - uint32_t(rng() % maxback);
+    const uint32_t s_k = uint32_t(rng() & 1), c_k = uint32_t(rng() % 100000000u);
+    for (uint32_t i = 0; i < t; i++) {
+      const uint32_t par = uint32_t(rng() & 1), c0 = uint32_t(rng() % 32769), c1 = uint32_t(rng() % 32769);
+      if (i > inc) desc[i] = scan4::pack_agg(epoch, par, c0, c1);
+      else if (i == inc) desc[i] = scan4::pack_inc(epoch, s_k, c_k);
+      else {
+        const int kind = int(rng() % 4);
+        desc[i] = kind == 0 ? 0ull : kind == 1 ? scan4::pack_agg(epoch - 1, par, c0, c1) : kind == 2 ? scan4::pack_inc(epoch, par, c0) : scan4::pack_agg(epoch, par, c0, c1);
+      }
+    }
+    desc[0] = (inc == 0) ? desc[0] : scan4::pack_inc(epoch, uint32_t(rng() & 1), 12345);  // element 0 is always inclusive
+    uint32_t s = s_k;
+    uint64_t cnt = c_k;
+    for (uint32_t i = inc + 1; i < t; i++) {
+      const unsigned long long d = desc[i];
+      cnt += s ? (uint32_t(d >> 19) & 0x7FFFFu) : (uint32_t(d) & 0x7FFFFu);
+      s ^= uint32_t(d >> 38) & 1u;
+    }
+    ScanParams p;
+    memset(&p, 0, sizeof(p));
+    p.epoch = epoch; p.count_desc = desc.data(); p.flags = &flags;
+    simt::WarpShared w;
+    simt::CtaShared cta;
+    pthread_barrier_init(&w.bar, nullptr, 32);
+    std::vector<LbArgs> args(32);
+    std::vector<pthread_t> th(32);
+    for (unsigned l = 0; l < 32; l++) {
+      args[l] = LbArgs{&p, t, &w, &cta, l, 0, 0};
+      pthread_create(&th[l], nullptr, lb_thread, &args[l]);
+    }
+    for (auto &x : th) pthread_join(x, nullptr);
+    pthread_barrier_destroy(&w.bar);
+    for (unsigned l = 0; l < 32; l++)
+      if (args[l].s_in != s || args[l].base != uint32_t(cnt) || flags != 0) {
+        fprintf(stderr, "LOOK-BACK MISMATCH t=%u inc=%u lane=%u: got (%u,%u) want (%u,%u) flags=%u\n", t, inc, l, args[l].s_in, args[l].base, s, uint32_t(cnt), flags);
+        bad++;
+        break;
+      }
+  }
+  return bad;
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -210,6 +282,7 @@ int main(int argc, char **argv) {
   const char *alphabets[] = {"\\\\\\\"\" {}[],: \n\tabc1\x01\x0c\x1a\x1e", "\\\"", "\\\\\\\\\\\\\\\"a ", "\"{}[],:0 ", " \n\r\t\"a\\", ",{}[] 1 \"a\":\n"};
   const char *utf8bits[] = {"\xc3\xa9", "\xe2\x82\xac", "\xf0\x9f\x98\x80", "\xff", "\xc3", "\xe2\x82", "\xf0\x9f\x98", "\x80", "\xed\xa0\x80", "\xc0\xaf", "\xf4\x90\x80\x80", "\xe0\x9f\xbf", "\xf0\x8f\xbf\xbf", "\xf5\x80\x80\x80", "\xed\x9f\xbf", "\xf4\x8f\xbf\xbf", "\xe0\xa0\x80", "\xf0\x90\x80\x80", "\xc2\x80", "\xdf\xbf"};
   EmuCtx cx;
+  g_fail += test_look_back(rng, 300);
   for (int it = 0; it < iters && g_fail < 5; it++) {
     std::vector<uint8_t> in;
     const int kind = int(rng() % 8);
@@ -221,8 +294,8 @@ int main(int argc, char **argv) {
       size_t pre = rng() % 3 ? (rng() % 5) * 128 + (rng() % 9) + 4096 * (rng() % 9) : rng() % 300;
       if (pre >= 4) pre -= rng() % 5;
       for (size_t i = 0; i < pre; i++) in.push_back(uint8_t(a[rng() % alen]));
-      const size_t runs[] = {1, 2, 3, 15, 16, 17, 31, 32, 33, 127, 128, 129, 4095, 4096, 4097, 8191, 8192, 8193, 33000};
-      const size_t run = runs[rng() % 19] + rng() % 2;
+      const size_t runs[] = {1, 2, 3, 15, 16, 17, 31, 32, 33, 127, 128, 129, 4095, 4096, 4097, 8191, 8192, 8193};
+      const size_t run = ((rng() % 10 == 0) ? size_t(33000) : runs[rng() % 18]) + rng() % 2;
       for (size_t i = 0; i < run; i++) in.push_back('\\');
       const size_t post = rng() % 5000;
       for (size_t i = 0; i < post; i++) in.push_back(uint8_t(a[rng() % alen]));
@@ -259,8 +332,9 @@ int main(int argc, char **argv) {
       const char *t = tails[rng() % 10];
       memcpy(in.data() + in.size() - strlen(t), t, strlen(t));
     } else if (kind == 5) {  // the document (or shard) starts inside a backslash run: launch carry-in meets boundary walks
-      const size_t runs[] = {0, 1, 2, 3, 31, 32, 33, 4095, 4096, 4097, 8192, 32767, 32768, 32769, 36864};
-      const size_t run = runs[rng() % 15];
+      const size_t runs[] = {0, 1, 2, 3, 15, 16, 17, 31, 32, 33, 127, 129, 4095, 4096, 4097, 8192};
+      const size_t long_runs[] = {32767, 32768, 32769, 36864};  // (slow under emulation: one rendezvous per 32 bytes walked)
+      const size_t run = (rng() % 8 == 0) ? long_runs[rng() % 4] : runs[rng() % 16];
       for (size_t i = 0; i < run; i++) in.push_back('\\');
       if (rng() % 2) in.push_back('"');
       const size_t post = rng() % 3 ? rng() % 6000 : 0;

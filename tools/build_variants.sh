@@ -1,0 +1,12 @@
+#!/bin/bash
+# tuning aid: builds libsjb200 variants with different -D flags into tools/variants/ (select one with SJB200_LIB=...)
+set -e
+cd "$(dirname "$0")/.."
+SRCS="simdjson_b200/csrc/sjb200_kernels.cu simdjson_b200/csrc/sjb200_capi.cu simdjson_b200/csrc/sjb200_finish.cpp"
+FLAGS="-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-fvisibility=hidden -shared"
+build() { name=$1; shift; nvcc $FLAGS "$@" -o tools/variants/lib_$name.so $SRCS & }
+build chain2 -DSJB200_SCAN4_CHAIN=2
+build chain4 -DSJB200_SCAN4_CHAIN=4
+build park4 -DSJB200_SCAN4_PARK=4
+wait
+ls -la tools/variants

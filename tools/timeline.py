@@ -33,10 +33,35 @@ t = t[t[:, 0] > 0]
 n = len(t)
 t0 = t[:, 0].min()
 print("elements", n, "span_us", (t[:, 5].max() - t0) / 1e3)
-ctas = t[:, 7] >> 32
+ctas = (t[:, 7] >> 32) & 0xFFFF
+smid = t[:, 7] >> 48
+iters = t[:, 7] & 0xFFFFFFFF
 print("ctas", len(np.unique(ctas)), "elements per cta: max", np.bincount(ctas.astype(np.int64)).max())
 print("resolve lag (resolved - scanned)  mean %.2f p90 %.2f max %.2f us" % (((t[:, 4] - t[:, 3]) / 1e3).mean(), np.percentile((t[:, 4] - t[:, 3]) / 1e3, 90), ((t[:, 4] - t[:, 3]) / 1e3).max()))
 print("emit done after resolved          mean %.2f p90 %.2f max %.2f us" % (((t[:, 5] - t[:, 4]) / 1e3).mean(), np.percentile((t[:, 5] - t[:, 4]) / 1e3, 90), ((t[:, 5] - t[:, 4]) / 1e3).max()))
+if os.environ.get("PROBE_KERNEL", "4") == "4":
+    # scan4: slots 0 scan start (warp 0), 3 all 8 blocks scanned (last scan warp; aggregate published), 6 the chain warp
+    # picks the element up, 4 resolved, 5 emitted (warp 0)
+    o = np.argsort(t[:, 0])  # tickets are handed out in order; rows are indexed by element already
+    scanned = t[:, 3].astype(np.float64)
+    ready = np.maximum.accumulate(scanned)  # every predecessor's aggregate is out
+    us = lambda a: (a.mean() / 1e3, np.median(a) / 1e3, np.percentile(a, 90) / 1e3, a.max() / 1e3)
+    for nm, a in (("scan (start -> all blocks scanned)", t[:, 3] - t[:, 0]), ("resolved - scanned", t[:, 4] - t[:, 3]), ("chain pick-up - scanned", t[:, 6] - t[:, 3]),
+                  ("resolved - (all predecessors scanned)", t[:, 4] - ready), ("emitted - resolved", t[:, 5] - t[:, 4]),
+                  ("emitted - scan start", t[:, 5] - t[:, 0])):
+        print("%-40s mean %7.2f us  p50 %7.2f  p90 %7.2f  max %7.2f" % ((nm,) + us(a.astype(np.float64))))
+    dur = (t[:, 3] - t[:, 0]) / 1e3
+    print("slowest scans (element, cta, sm, iteration, start us, duration us):")
+    for i in np.argsort(-dur)[:14]:
+        print("   #%d cta %d sm %d it %d start %.1f dur %.1f" % (i, ctas[i], smid[i], iters[i], (t[i, 0] - t0) / 1e3, dur[i]))
+    gate = np.maximum.accumulate(scanned)
+    jumps = np.argsort(-(gate[1:] - gate[:-1]))[:8] + 1
+    print("elements that gate their successors longest (element, scanned us, gate jump us):", [(int(i), round((scanned[i] - t0) / 1e3, 1), round((gate[i] - gate[i - 1]) / 1e3, 1)) for i in sorted(jumps)])
+    for c in np.unique(ctas)[:3]:
+        rows = t[ctas == c]
+        rows = rows[np.argsort(rows[:, 0])]
+        print("cta", int(c), " ".join("[#%d: %.1f %.1f %.1f %.1f %.1f]" % (int(np.where((t == r).all(axis=1))[0][0]), (r[0] - t0) / 1e3, (r[3] - t0) / 1e3, (r[6] - t0) / 1e3, (r[4] - t0) / 1e3, (r[5] - t0) / 1e3) for i, r in enumerate(rows)))
+    sys.exit(0)
 front = (t[:, 3] - t[:, 0]) / 1e3
 v6 = t[:, 6] > 0
 wait = (t[v6, 6] - t[v6, 3]) / 1e3
