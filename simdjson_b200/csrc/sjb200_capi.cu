@@ -58,6 +58,7 @@ struct sjb200_ctx {
   unsigned long long *d_count_desc = nullptr;
   size_t desc_tiles = 0;
   uint8_t *d_chars = nullptr; size_t d_chars_bytes = 0;
+  uint32_t *d_park = nullptr; size_t d_park_words = 0;  // scan4: parked masks (a per-CTA ring, independent of the input size)
   // pinned host mirrors
   Carry *h_carry = nullptr;     // [kCarrySlots]
   uint32_t *h_flags = nullptr;
@@ -251,7 +252,16 @@ bool enqueue_scan(sjb200_ctx *c, int kind, const CUtensorMap *map, bool tma, con
     bool tma4 = false;
     make_tensor_map(c, &map4, d_buf, len, &tma4, kScan4BoxRows);
     p.use_tma = (tma && tma4) ? 1u : 0u;
-    launched = ok(c, launch_scan4(&map4, p, grid_for(c, kind, ntiles), stream), "launch scan4");
+    const int grid = grid_for(c, kind, ntiles);
+    const size_t need = scan4_park_words(grid_cap(c, kind));
+    if (c->d_park_words < need) {
+      cudaStreamSynchronize(c->stream);
+      cudaFree(c->d_park); c->d_park = nullptr; c->d_park_words = 0;
+      if (!dev_alloc(c, &c->d_park, need, "cudaMalloc(park)")) return false;
+      c->d_park_words = need;
+    }
+    p.park = c->d_park;
+    launched = ok(c, launch_scan4(&map4, p, grid, stream), "launch scan4");
   } else {
     launched = ok(c, launch_scan(kind, map, p, grid_for(c, kind, p.nsuper), stream), "launch scan");
   }
@@ -403,7 +413,7 @@ extern "C" void sjb200_destroy(sjb200_ctx *c) {
   DeviceGuard g(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   free_sized(c);
-  cudaFree(c->d_carry); cudaFree(c->d_flags); cudaFree(c->d_ticket); cudaFree(c->d_chars); cudaFree(c->d_debug);
+  cudaFree(c->d_carry); cudaFree(c->d_flags); cudaFree(c->d_ticket); cudaFree(c->d_chars); cudaFree(c->d_debug); cudaFree(c->d_park);
   if (c->h_carry) cudaFreeHost(c->h_carry);
   if (c->h_flags) cudaFreeHost(c->h_flags);
   if (c->h_small) cudaFreeHost(c->h_small);

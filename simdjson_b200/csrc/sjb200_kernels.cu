@@ -907,6 +907,8 @@ cudaError_t launch_scan4(const CUtensorMap *tmap, const ScanParams &p, int grid,
   return cudaGetLastError();
 }
 
+size_t scan4_park_words(int grid) { return size_t(grid) * scan4::kPark * scan4::kScanWarps * scan4::kParkWords; }
+
 int scan4_max_ctas_per_sm() {
   int n = 0;
   cudaFuncSetAttribute(scan4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, scan4::kSmemBytes4);

@@ -44,13 +44,14 @@ constexpr int kBlockRows = kBlockBytes / 128;
 constexpr int kChainWarps = SJB200_SCAN4_CHAIN;  // chain warp c resolves this CTA's elements j = c, c + kChainWarps, ...
 constexpr int kThreads4 = 32 * (kScanWarps + kChainWarps);
 #ifndef SJB200_SCAN4_PARK
-#define SJB200_SCAN4_PARK 3
+#define SJB200_SCAN4_PARK 7
 #endif
-constexpr int kPark = SJB200_SCAN4_PARK;  // elements whose masks wait in shared memory: a scan warp emits element j-kLag after scanning j
+constexpr int kPark = SJB200_SCAN4_PARK;  // elements of a CTA whose masks may wait (in an L2-resident scratch ring) for their resolution
 constexpr int kLag = kPark - 1;
-constexpr int kNS = 8;           // ring of element slots (tickets, summaries, resolutions); >= kLag + 4
+constexpr int kNS = 16;          // ring of element slots (tickets, summaries, resolutions)
+constexpr int kParkWords = 288;  // per block: 32 x uint4 (outside), 32 x uint4 (inside), 32 x packed prefix
 constexpr int kLookK = 10;       // descriptors per lane and look-back round trip (window of 320 elements >= one wave of CTAs)
-static_assert(kLag >= 1 && kLag <= 5 && (kNS & (kNS - 1)) == 0, "slot ring");
+static_assert(kLag >= 1 && 2 * kLag + 3 <= kNS && (kNS & (kNS - 1)) == 0, "slot ring");
 #ifndef SJB200_SCAN4_SLEEP
 #define SJB200_SCAN4_SLEEP 1
 #endif
@@ -62,8 +63,6 @@ enum : uint32_t { kDescNone = 0, kDescAgg = 1, kDescInc = 2 };
 
 struct Smem {
   uint8_t ring[kScanWarps][2][kBlockBytes];   // per scan warp: two block buffers (TMA destination / emit staging)
-  sj_u4 park[kPark][2][kScanWarps * 32];          // [pipeline buffer][polarity][thread]: candidate structural masks
-  uint32_t parkpre[kPark][kScanWarps * 32];       // exclusive prefix of the lane's counts inside its block, both polarities packed
   uint32_t ticket[kNS];
   uint32_t summary[kNS][kScanWarps];          // c0 | c1<<16 | parity<<29 | ctl-hit0<<30 | ctl-hit1<<31
   uint32_t arrived[kNS];                      // scan warps done with the element (the last one composes and publishes)
@@ -286,8 +285,7 @@ SJ_DEV void load_unit(const uint8_t *T, uint32_t off, uint32_t w[8]) {
 // T: the block in shared memory.  pw0: the 4 bytes before the block (only lane 0's copy is used).  e_in / c_in: the two
 // locally known state bits entering the block.  Parks the two candidate masks and the lane's exclusive output prefix,
 // returns the block summary word (uniform).
-SJ_DEV uint32_t scan_block(const uint8_t *T, uint32_t pw0, uint32_t e_in, uint32_t c_in, unsigned lane, const ScanParams &p, sj_u4 *park0,
-                           sj_u4 *park1, uint32_t *parkpre) {
+SJ_DEV uint32_t scan_block(const uint8_t *T, uint32_t pw0, uint32_t e_in, uint32_t c_in, unsigned lane, const ScanParams &p, uint32_t *park) {
   const uint32_t lane_off = lane * 128u;
   uint32_t bs[4], qu[4], op[4], sc[4], cl[4];
   uint32_t uerr = 0;
@@ -371,10 +369,9 @@ SJ_DEV uint32_t scan_block(const uint8_t *T, uint32_t pw0, uint32_t e_in, uint32
     if (int(lane) >= d) incl += t;
   }
   const uint32_t total = sj_shfl(incl, 31);
-  const unsigned tid = sj_tid();
-  park0[tid] = sj_make_u4(e0[0], e0[1], e0[2], e0[3]);
-  park1[tid] = sj_make_u4(e1[0], e1[1], e1[2], e1[3]);
-  parkpre[tid] = incl - cnt;
+  reinterpret_cast<sj_u4 *>(park)[lane] = sj_make_u4(e0[0], e0[1], e0[2], e0[3]);
+  reinterpret_cast<sj_u4 *>(park + 128)[lane] = sj_make_u4(e1[0], e1[1], e1[2], e1[3]);
+  park[256 + lane] = incl - cnt;
   const uint32_t h0 = sj_any(hit0 != 0) ? 1u : 0u, h1 = sj_any(hit1 != 0) ? 1u : 0u;
   return total | (par << 29) | (h0 << 30) | (h1 << 31);
 }
@@ -403,15 +400,21 @@ SJ_DEV void emit_columns(const sj_u4 ev, uint32_t off, uint32_t pos_lane, uint32
   }
 }
 
-SJ_DEV void emit_block(Smem *S, const ScanParams &p, uint64_t out_base, uint32_t elem, unsigned warp, unsigned lane, int ns, int pbuf,
-                       uint32_t *stg) {
+SJ_DEV uint32_t *park_of(const ScanParams &p, uint32_t e, unsigned warp) {
+  return p.park + ((size_t(sj_cta()) * kPark + (e % uint32_t(kPark))) * kScanWarps + warp) * size_t(kParkWords);
+}
+
+// emit block `warp` of this CTA's e-th element (resolved); stg: 4 KiB of shared memory nobody else is using
+SJ_DEV void emit_block(Smem *S, const ScanParams &p, uint64_t out_base, uint32_t e, unsigned warp, unsigned lane, uint32_t *stg) {
+  const int ns = int(e % kNS);
   const uint32_t sum = S->summary[ns][warp];
   const uint32_t pol = S->res_pol[ns][warp] & 1u;
   const uint32_t total = pol ? ((sum >> 16) & 0x1FFFu) : (sum & 0xFFFFu);
   if (total == 0) return;
-  const unsigned tid = warp * 32 + lane;
-  const sj_u4 ev = S->park[pbuf][pol][tid];
-  const uint32_t off = (S->parkpre[pbuf][tid] >> (16 * pol)) & 0xFFFFu;
+  const uint32_t elem = S->ticket[ns];
+  const uint32_t *park = park_of(p, e, warp);
+  const sj_u4 ev = sj_ld_u4(park + 128 * pol + 4 * lane);
+  const uint32_t off = (sj_ld_u32(park + 256 + lane) >> (16 * pol)) & 0xFFFFu;
   const uint32_t pos_lane = p.pos_base + (p.tile_begin + elem) * uint32_t(kTileBytes) + warp * uint32_t(kBlockBytes) + lane * 128u;
   uint32_t *out = p.idx_out + (out_base + S->res_base[ns][warp]);
   if (total <= kStageWords) {
@@ -424,6 +427,7 @@ SJ_DEV void emit_block(Smem *S, const ScanParams &p, uint64_t out_base, uint32_t
   } else {
     emit_columns(ev, off, pos_lane, out);  // > 1 structural per 4 bytes over 4 KiB: straight to global memory
   }
+  if (p.debug != nullptr && warp == 0 && lane == 0) p.debug[uint64_t(elem) * 8 + 5] = sj_globaltimer();
 }
 
 // ------------------------------------------------------------------------------------------------ element summary
@@ -512,14 +516,18 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
     publish_ticket(S, 1, a1, lane);
   }
   uint32_t t = wait_ticket(S, 0, p);
-  uint32_t th[kLag];  // th[0] = ticket of element j - kLag at the emit of iteration j
-#pragma unroll
-  for (int i = 0; i < kLag; i++) th[i] = t;
+  uint32_t ne = 0;  // this CTA's next element to emit (elements are emitted in order, as soon as they are resolved)
   if (t < nelem) tma_cur = issue_load(S, tmap, p, t, warp, lane, 0, &pw_cur);
   uint32_t j = 0;
   for (;; j++) {
     if (t >= nelem) break;
     const int r = int(j & 1u);
+    // the scratch slot of element j must be free (only binds when resolution falls kPark elements behind)
+    while (ne + uint32_t(kPark) <= j) {
+      wait_bar(&S->resolved[ne % kNS], (ne / kNS) & 1u, p, 64);
+      emit_block(S, p, out_base, ne, warp, lane, reinterpret_cast<uint32_t *>(S->ring[warp][r ^ 1]));
+      ne++;
+    }
     uint32_t t_acq = 0;
     if (warp == 0 && lane == 0) t_acq = sj_atomic_add(p.ticket, 1u);  // element j+2 of this CTA
     const uint32_t tn = wait_ticket(S, j + 1, p);
@@ -541,7 +549,7 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
       }
       const uint32_t pw0 = sj_shfl(pw_cur, 0);
       const uint32_t st = boundary_state(p, bstart, launch_start, cin.state, pw0, lane);
-      summary = scan_block(T, pw0, st & 1u, (st >> 2) & 1u, lane, p, S->park[j % kPark][0], S->park[j % kPark][1], S->parkpre[j % kPark]);
+      summary = scan_block(T, pw0, st & 1u, (st >> 2) & 1u, lane, p, park_of(p, j, warp));
     }
     {
       const int ns = int(j % kNS);
@@ -562,16 +570,15 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
       }
     }
     if (warp == 0) publish_ticket(S, j + 2, t_acq, lane);
-    if (j >= uint32_t(kLag)) {  // the chain warp has had kLag scans' time to resolve this one
-      const uint32_t e = j - uint32_t(kLag);
-      wait_bar(&S->resolved[e % kNS], (e / kNS) & 1u, p, 64);
-      const uint32_t te = th[0];
-      emit_block(S, p, out_base, te, warp, lane, int(e % kNS), int(e % kPark), reinterpret_cast<uint32_t *>(T));
-      if (p.debug != nullptr && warp == 0 && lane == 0) p.debug[uint64_t(te) * 8 + 5] = sj_globaltimer();
+    // emit whatever is resolved by now (never wait here: the masks are parked, the scan goes on)
+#pragma unroll 1
+    for (int q = 0; q < 2 && ne <= j; q++) {
+      uint32_t ready = 0;
+      if (lane == 0) ready = sj_mbar_try_wait(&S->resolved[ne % kNS], (ne / kNS) & 1u) ? 1u : 0u;
+      if (!sj_shfl(ready, 0)) break;
+      emit_block(S, p, out_base, ne, warp, lane, reinterpret_cast<uint32_t *>(T));
+      ne++;
     }
-#pragma unroll
-    for (int i = 0; i + 1 < kLag; i++) th[i] = th[i + 1];  // tickets of the elements still waiting to be emitted
-    th[kLag - 1] = t;
     t = tn;
     tma_cur = tma_next;
     pw_cur = pw_next;
@@ -579,15 +586,11 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
   // every chain warp must meet an invalid ticket at its next index: j and j+1 are out already
   if (warp == 0)
     for (uint32_t x = j + 2; x < j + uint32_t(kChainWarps); x++) publish_ticket(S, x, 0xFFFFFFFFu, lane);
-  // drain the pipeline: the last kLag elements this CTA scanned (no load is in flight: both ring slots are free)
-#pragma unroll
-  for (int i = 0; i < kLag; i++) {
-    if (j + uint32_t(i) < uint32_t(kLag)) continue;  // fewer than kLag elements were scanned
-    const uint32_t e = j + uint32_t(i) - uint32_t(kLag);
-    wait_bar(&S->resolved[e % kNS], (e / kNS) & 1u, p, 64);
-    const uint32_t te = th[i];
-    emit_block(S, p, out_base, te, warp, lane, int(e % kNS), int(e % kPark), reinterpret_cast<uint32_t *>(S->ring[warp][0]));
-    if (p.debug != nullptr && warp == 0 && lane == 0) p.debug[uint64_t(te) * 8 + 5] = sj_globaltimer();
+  // drain: what this CTA scanned and has not emitted yet (no load is in flight: both ring slots are free)
+  while (ne < j) {
+    wait_bar(&S->resolved[ne % kNS], (ne / kNS) & 1u, p, 64);
+    emit_block(S, p, out_base, ne, warp, lane, reinterpret_cast<uint32_t *>(S->ring[warp][0]));
+    ne++;
   }
 }
 

@@ -59,6 +59,8 @@ SJ_DEV sj_u4 sj_make_u4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { sj_u4 
 SJ_DEV sj_u4 sj_ldg_u4(const void *p) { sj_u4 v; memcpy(&v, p, 16); return v; }
 SJ_DEV uint32_t sj_ldg_u32(const void *p) { uint32_t v; memcpy(&v, p, 4); return v; }
 SJ_DEV uint32_t sj_ldg_u8(const uint8_t *p) { return *p; }
+SJ_DEV sj_u4 sj_ld_u4(const void *p) { sj_u4 v; memcpy(&v, p, 16); return v; }
+SJ_DEV uint32_t sj_ld_u32(const void *p) { uint32_t v; memcpy(&v, p, 4); return v; }
 
 SJ_DEV unsigned sj_tid() { return simt::tctx.tid; }
 SJ_DEV unsigned sj_cta() { return simt::tctx.cta; }
@@ -230,6 +232,9 @@ SJ_DEV sj_u4 sj_make_u4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return
 SJ_DEV sj_u4 sj_ldg_u4(const void *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
 SJ_DEV uint32_t sj_ldg_u32(const void *p) { return __ldg(reinterpret_cast<const uint32_t *>(p)); }
 SJ_DEV uint32_t sj_ldg_u8(const uint8_t *p) { return __ldg(p); }
+// data written earlier by this same kernel (the parked masks): plain loads, not the read-only path
+SJ_DEV sj_u4 sj_ld_u4(const void *p) { return *reinterpret_cast<const uint4 *>(p); }
+SJ_DEV uint32_t sj_ld_u32(const void *p) { return *reinterpret_cast<const uint32_t *>(p); }
 
 SJ_DEV unsigned sj_tid() { return threadIdx.x; }
 SJ_DEV unsigned sj_cta() { return blockIdx.x; }

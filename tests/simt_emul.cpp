@@ -87,6 +87,7 @@ void emu_launch(unsigned grid, const sj_tensor_map &tmap, const ScanParams &p) {
 // what sjb200_capi.cu keeps per context
 struct EmuCtx {
   std::vector<unsigned long long> desc;
+  std::vector<uint32_t> park;
   uint32_t ticket[2] = {0, 0};
   uint32_t flags = 0;
   uint32_t epoch = 0;
@@ -130,6 +131,9 @@ Result run_scan4(EmuCtx &cx, const uint8_t *buf, size_t len, uint32_t state_in, 
     p.carry_in = &cx.carry[slot];
     p.carry_out = &cx.carry[slot + 1];
     p.flags = &cx.flags; p.count_desc = cx.desc.data(); p.ticket = cx.ticket; p.debug = nullptr;
+    const unsigned g = std::min<unsigned>(grid, nt);
+    cx.park.assign(size_t(g) * scan4::kPark * scan4::kScanWarps * scan4::kParkWords + 4, 0xDEADBEEFu);
+    p.park = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(cx.park.data()) + 15) & ~uintptr_t(15));
     cx.carry[slot + 1] = Carry();
     emu_launch(std::min<unsigned>(grid, nt), tmap, p);
     if (cx.ticket[0] != 0 || cx.ticket[1] != 0 || cx.flags != 0) { fprintf(stderr, "BUG: ticket/flags not re-armed\n"); exit(2); }

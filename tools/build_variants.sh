@@ -6,7 +6,7 @@ SRCS="simdjson_b200/csrc/sjb200_kernels.cu simdjson_b200/csrc/sjb200_capi.cu sim
 FLAGS="-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-fvisibility=hidden -shared"
 build() { name=$1; shift; nvcc $FLAGS "$@" -o tools/variants/lib_$name.so $SRCS & }
 build chain2 -DSJB200_SCAN4_CHAIN=2
-build chain4 -DSJB200_SCAN4_CHAIN=4
-build park4 -DSJB200_SCAN4_PARK=4
+build park3 -DSJB200_SCAN4_PARK=3
+build park5 -DSJB200_SCAN4_PARK=5
 wait
 ls -la tools/variants
