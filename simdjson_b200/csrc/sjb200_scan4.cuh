@@ -52,6 +52,9 @@ constexpr int kNS = 16;          // ring of element slots (tickets, summaries, r
 constexpr int kParkWords = 288;  // per block: 32 x uint4 (outside), 32 x uint4 (inside), 32 x packed prefix
 constexpr int kLookK = 10;       // descriptors per lane and look-back round trip (window of 320 elements >= one wave of CTAs)
 static_assert(kLag >= 1 && 2 * kLag + 3 <= kNS && (kNS & (kNS - 1)) == 0, "slot ring");
+#ifndef SJB200_SCAN4_HELP
+#define SJB200_SCAN4_HELP 1
+#endif
 #ifndef SJB200_SCAN4_SLEEP
 #define SJB200_SCAN4_SLEEP 1
 #endif
@@ -504,20 +507,24 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
   uint32_t pw_cur = 0x20202020u, pw_next = 0x20202020u;
   bool tma_cur = false, tma_next = false;
   // Warp 0 is the ticket master.  Tickets must not depend on the chain warp's progress (it may sit in a look-back
-  // while the scan warps run ahead), and a ticket is taken one iteration before it is published, so nobody ever
-  // waits for the atomic's round trip to L2.
+  // while the scan warps run ahead).  In the steady state the ticket of element j+2 is taken at the start of iteration
+  // j and published after the scan, so nobody waits for the atomic's round trip to L2.  Tickets should be scanned in
+  // roughly the order they were taken (every element waits for ALL lower tickets): at start-up the second ticket is
+  // therefore taken only once the first block has arrived, when every CTA of the launch has its first ticket.
   if (warp == 0) {
-    uint32_t a0 = 0, a1 = 0;
-    if (lane == 0) {
-      a0 = sj_atomic_add(p.ticket, 1u);
-      a1 = sj_atomic_add(p.ticket, 1u);
-    }
+    uint32_t a0 = 0;
+    if (lane == 0) a0 = sj_atomic_add(p.ticket, 1u);
     publish_ticket(S, 0, a0, lane);
-    publish_ticket(S, 1, a1, lane);
   }
   uint32_t t = wait_ticket(S, 0, p);
-  uint32_t ne = 0;  // this CTA's next element to emit (elements are emitted in order, as soon as they are resolved)
   if (t < nelem) tma_cur = issue_load(S, tmap, p, t, warp, lane, 0, &pw_cur);
+  if (warp == 0) {
+    if (tma_cur) wait_bar(&S->full[0][0], 0u, p, 32);
+    uint32_t a1 = 0;
+    if (lane == 0) a1 = sj_atomic_add(p.ticket, 1u);
+    publish_ticket(S, 1, a1, lane);
+  }
+  uint32_t ne = 0;  // this CTA's next element to emit (elements are emitted in order, as soon as they are resolved)
   uint32_t j = 0;
   for (;; j++) {
     if (t >= nelem) break;
@@ -684,6 +691,35 @@ SJ_DEV void look_back(const ScanParams &p, uint32_t t, unsigned lane, uint32_t *
       ck = sj_shfl(ck, int(il));
       *s_in = sk ^ acc.p;
       *base = ck + (sk ? acc.b : acc.a);
+#if SJB200_SCAN4_HELP
+      // Help: the walk has just computed what every element between the inclusive prefix and t needs, so publish THEIR
+      // inclusive prefixes too (the owners would write exactly the same words).  Other CTAs then find an inclusive
+      // prefix right behind their element instead of walking over everything in flight: a backlog of unresolved
+      // elements clears in one round instead of feeding on itself.
+      {
+        uint32_t older_p = 0;   // parity of the used elements older than group k
+        uint32_t older_c = ck;  // outputs up to and including the used elements older than group k
+#pragma unroll
+        for (int k = kLookK - 1; k >= 0; k--) {
+          const bool u = (use >> k) & 1u;
+          const uint32_t rel = (uint32_t(sj_popc((bal[k] >> lane) >> 1)) ^ older_p ^ sk) & 1u;  // in-string entering my element
+          const uint32_t a = uint32_t(d[k]) & 0x7FFFFu, b = uint32_t(d[k] >> 19) & 0x7FFFFu;
+          const uint32_t mine = u ? (rel ? b : a) : 0u;
+          uint32_t suf = mine;  // suffix sum over lanes >= mine (older elements of the group first)
+#pragma unroll
+          for (int dd = 1; dd < 32; dd <<= 1) {
+            const uint32_t o = sj_shfl_down(suf, dd);
+            if (int(lane) + dd < 32) suf += o;
+          }
+          if (u) {
+            const uint32_t s_after = rel ^ (uint32_t(d[k] >> 38) & 1u);
+            sj_st_relaxed_u64(p.count_desc + (first - 32 * k), pack_inc(p.epoch, s_after, older_c + suf));
+          }
+          older_c += sj_shfl(suf, 0);
+          older_p ^= uint32_t(sj_popc(bal[k])) & 1u;
+        }
+      }
+#endif
       return;
     }
     newest -= 32 * kLookK;

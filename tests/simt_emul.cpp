@@ -249,11 +249,14 @@ int test_look_back(std::mt19937_64 &rng, int cases) {
     desc[0] = (inc == 0) ? desc[0] : scan4::pack_inc(epoch, uint32_t(rng() & 1), 12345);  // element 0 is always inclusive
     uint32_t s = s_k;
     uint64_t cnt = c_k;
+    std::vector<unsigned long long> helped(t, 0ull);  // the inclusive prefix of every element between inc and t
     for (uint32_t i = inc + 1; i < t; i++) {
       const unsigned long long d = desc[i];
       cnt += s ? (uint32_t(d >> 19) & 0x7FFFFu) : (uint32_t(d) & 0x7FFFFu);
       s ^= uint32_t(d >> 38) & 1u;
+      helped[i] = scan4::pack_inc(epoch, s, uint32_t(cnt));
     }
+    const std::vector<unsigned long long> before(desc);
     ScanParams p;
     memset(&p, 0, sizeof(p));
     p.epoch = epoch; p.count_desc = desc.data(); p.flags = &flags;
@@ -274,6 +277,18 @@ int test_look_back(std::mt19937_64 &rng, int cases) {
         bad++;
         break;
       }
+    // helping: inside the window that held the inclusive prefix, every newer element now carries ITS inclusive prefix;
+    // nothing else was touched
+    const uint32_t win = uint32_t(32 * scan4::kLookK), D = t - 1 - inc, w0 = (D / win) * win;
+    for (uint32_t i = 0; i < t && !bad; i++) {
+      const uint32_t dist = t - 1 - i;
+      const bool expect_help = SJB200_SCAN4_HELP && dist >= w0 && dist < D;
+      const unsigned long long want = expect_help ? helped[i] : before[i];
+      if (desc[i] != want) {
+        fprintf(stderr, "HELP MISMATCH t=%u inc=%u i=%u: got %llx want %llx\n", t, inc, i, desc[i], want);
+        bad++;
+      }
+    }
   }
   return bad;
 }
