@@ -38,11 +38,7 @@ namespace scan4 {
 constexpr int kScanWarps = 8;
 constexpr int kBlockBytes = 4096;
 constexpr int kBlockRows = kBlockBytes / 128;
-#ifndef SJB200_SCAN4_CHAIN
-#define SJB200_SCAN4_CHAIN 1
-#endif
-constexpr int kChainWarps = SJB200_SCAN4_CHAIN;  // chain warp c resolves this CTA's elements j = c, c + kChainWarps, ...
-constexpr int kThreads4 = 32 * (kScanWarps + kChainWarps);
+constexpr int kThreads4 = 32 * (kScanWarps + 2);  // + the owner warp + the resolver warp (active in one CTA of the launch)
 #ifndef SJB200_SCAN4_PARK
 #define SJB200_SCAN4_PARK 7
 #endif
@@ -52,9 +48,6 @@ constexpr int kNS = 16;          // ring of element slots (tickets, summaries, r
 constexpr int kParkWords = 288;  // per block: 32 x uint4 (outside), 32 x uint4 (inside), 32 x packed prefix
 constexpr int kLookK = 10;       // descriptors per lane and look-back round trip (window of 320 elements >= one wave of CTAs)
 static_assert(kLag >= 1 && 2 * kLag + 3 <= kNS && (kNS & (kNS - 1)) == 0, "slot ring");
-#ifndef SJB200_SCAN4_HELP
-#define SJB200_SCAN4_HELP 1
-#endif
 #ifndef SJB200_SCAN4_SLEEP
 #define SJB200_SCAN4_SLEEP 1
 #endif
@@ -93,19 +86,6 @@ SJ_DEV unsigned long long pack_agg(uint32_t epoch, uint32_t par, uint32_t c0, ui
 }
 SJ_DEV unsigned long long pack_inc(uint32_t epoch, uint32_t s_out, uint32_t count) {
   return ((unsigned long long)epoch << 46) | ((unsigned long long)kDescInc << 44) | ((unsigned long long)(s_out & 1u) << 32) | count;
-}
-
-// The effect of a run of elements on (in-string, outputs): p = quote parity, a / b = outputs when entered outside /
-// inside a string.  compose(older, newer) is associative; identity = (0,0,0).
-struct Eff {
-  uint32_t p, a, b;
-};
-SJ_DEV Eff compose(const Eff &o, const Eff &n) {
-  Eff r;
-  r.p = o.p ^ n.p;
-  r.a = o.a + (o.p ? n.b : n.a);
-  r.b = o.b + (o.p ? n.a : n.b);
-  return r;
 }
 
 // A waiting warp must not spin at full speed: mbarrier.try_wait returns at once, and a busy loop takes issue slots
@@ -462,7 +442,7 @@ SJ_DEV void compose_element(Smem *S, const ScanParams &p, int ns, uint32_t t, un
     S->elem[ns][1] = b0;
     S->elem[ns][2] = b1;
     S->elem[ns][3] = hit0 | (hit1 << 1);
-    if (t > 0) sj_st_relaxed_u64(p.count_desc + t, pack_agg(p.epoch, s0, b0, b1));  // element 0 goes straight to inclusive
+    sj_st_relaxed_u64(p.count_desc + t, pack_agg(p.epoch, s0, b0, b1));
   }
   sj_syncwarp();
 }
@@ -590,9 +570,6 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
     tma_cur = tma_next;
     pw_cur = pw_next;
   }
-  // every chain warp must meet an invalid ticket at its next index: j and j+1 are out already
-  if (warp == 0)
-    for (uint32_t x = j + 2; x < j + uint32_t(kChainWarps); x++) publish_ticket(S, x, 0xFFFFFFFFu, lane);
   // drain: what this CTA scanned and has not emitted yet (no load is in flight: both ring slots are free)
   while (ne < j) {
     wait_bar(&S->resolved[ne % kNS], (ne / kNS) & 1u, p, 64);
@@ -601,134 +578,74 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
   }
 }
 
-// ------------------------------------------------------------------------------------------------ chain warp
-
-// Decoupled look-back: in-string state and output count entering element t (t >= 1).
-// A window is 32*kLookK descriptors, laid out k-major: load k of lane L is the descriptor at distance 32k + L behind
-// t-1, so every load instruction of the warp reads 256 contiguous bytes (all CTAs poll the same few cache lines of L2:
-// with a lane-major layout every poll was ~200 line requests per warp and the chain warps queued behind one another).
-// The window is complete when everything newer than the nearest inclusive prefix has arrived.  Folding uses the fact
-// that only one bit is order-dependent: the quote parities of a group of 32 elements are one ballot word, an element's
-// polarity relative to the oldest element of the window is a popcount, and the counts are then plain sums.
-SJ_DEV void look_back(const ScanParams &p, uint32_t t, unsigned lane, uint32_t *s_in, uint32_t *base) {
-  Eff acc;
-  acc.p = 0; acc.a = 0; acc.b = 0;
-  int64_t newest = int64_t(t) - 1;
-  const uint32_t key_agg = (p.epoch << 2) | kDescAgg;  // bits [63:44] of a descriptor of this launch: key_agg or key_agg + 1
-  for (;;) {
-    const int64_t first = newest - int64_t(lane);  // my k-th descriptor is first - 32k
+// ------------------------------------------------------------------------------------------------ resolver
+// ONE warp of the whole launch (in the CTA that drew ticket 0, so it is resident by construction) turns aggregates
+// into inclusive prefixes, in element order: it polls a window of 32*kLookK descriptors (k-major: every load
+// instruction of the warp reads 256 contiguous bytes), takes the longest prefix of the window that has arrived,
+// computes each element's inclusive (in-string, count) -- quote parities of 32 elements are one ballot word, an element's
+// polarity is a popcount, counts are warp prefix sums -- and stores them over the aggregates.  Every other CTA only
+// polls its own descriptor.
+// (A decoupled look-back by every CTA was measured first: ~300 warps polling the same twenty cache lines of L2 made
+// one poll take 2-10 us, resolution fell behind the scan, the backlog lengthened the walks, and it never recovered.)
+SJ_DEV void resolver_role(Smem *S, const ScanParams &p, const Carry &cin, unsigned lane) {
+  if (wait_ticket(S, 0, p) != 0u) return;  // not the CTA that drew ticket 0
+  const uint32_t nelem = p.ntiles;
+  const uint32_t key_agg = (p.epoch << 2) | kDescAgg;
+  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t s = (cin.state >> 1) & 1u;  // in-string entering element `next`
+  uint32_t base = 0;                   // outputs of the launch before element `next`
+  uint32_t next = 0;
+  uint32_t idle = 0;
+  while (next < nelem) {
     unsigned long long d[kLookK];
-    uint32_t pend = 0;  // bit k: wanted and not yet arrived
+    uint32_t want = 0;
 #pragma unroll
     for (int k = 0; k < kLookK; k++) {
       d[k] = 0;
-      if (first - 32 * k >= 0) pend |= 1u << k;
+      if (next + 32u * k + lane < nelem) {
+        want |= 1u << k;
+        d[k] = sj_ld_relaxed_u64(p.count_desc + (next + 32u * k + lane));
+      }
     }
-    const uint32_t want = pend;
-    uint32_t inc_dist = 0xFFFFFFFFu, needed = (1u << kLookK) - 1u;
-    uint32_t spins = 0;
-    for (;;) {
-      // one poll: independent predicated loads straight into d[k] (a word that has not arrived is simply loaded again
-      // by the next poll), then three independent instructions per word
-      const uint32_t todo = pend;
+    // the longest prefix of the window that has arrived
+    uint32_t bad = 0xFFFFFFFFu;  // my first element that has not
 #pragma unroll
-      for (int k = 0; k < kLookK; k++)
-        if (todo & (1u << k)) d[k] = sj_ld_relaxed_u64(p.count_desc + (first - 32 * k));
-      uint32_t okm = 0, incm = 0;
-#pragma unroll
-      for (int k = 0; k < kLookK; k++) {
-        const uint32_t rel = uint32_t(d[k] >> 44) - key_agg;  // 0: aggregate, 1: inclusive, anything else: not this launch's
-        if (rel <= 1u) okm |= 1u << k;
-        if (rel == 1u) incm |= 1u << k;
-      }
-      pend &= ~okm;
-      incm &= want;
-      // nearest inclusive prefix: for one lane a smaller k is nearer
-      const uint32_t my_dist = incm ? uint32_t(sj_ffs(incm) - 1) * 32u + lane : 0xFFFFFFFFu;
-      inc_dist = sj_reduce_min(my_dist);
-      if (inc_dist != 0xFFFFFFFFu) {  // needed: distance < inc_dist  <=>  k < ceil((inc_dist - lane) / 32)
-        const uint32_t nk = (inc_dist > lane) ? (inc_dist - lane + 31u) / 32u : 0u;
-        needed = (1u << nk) - 1u;
-      }
-      if (!sj_any((pend & needed) != 0)) break;
-      if (++spins > kSpinLimit4) {  // never expected: report, and finish with what there is
+    for (int k = kLookK - 1; k >= 0; k--)
+      if (((want >> k) & 1u) && (uint32_t(d[k] >> 44) != key_agg)) bad = 32u * k + lane;
+    uint32_t m = sj_reduce_min(bad);
+    const uint32_t left = nelem - next;
+    if (m > left) m = left;
+    if (m > 32u * kLookK) m = 32u * kLookK;
+    if (m == 0) {
+      if (++idle > kSpinLimit4) {  // never expected: give up; the owners will time out and report
         sj_atomic_or(p.flags, kFlagInternal);
-        break;
+        return;
       }
 #if SJB200_SCAN4_SLEEP
       sj_nanosleep(100);
 #endif
+      continue;
     }
-    // ---- fold the aggregates newer than the inclusive prefix
-    const uint32_t use = want & ~pend & needed;
-    uint32_t bal[kLookK];
+    idle = 0;
 #pragma unroll
-    for (int k = 0; k < kLookK; k++) bal[k] = sj_ballot(((use >> k) & 1u) && ((uint32_t(d[k] >> 38) & 1u) != 0));
-    uint32_t older = 0;  // parity of everything older than group k (uniform)
-    uint32_t sa = 0, sb = 0;
+    for (int k = 0; k < kLookK; k++) {
+      if (32u * k >= m) break;  // uniform
+      const bool use = 32u * k + lane < m;
+      const uint32_t par = use ? (uint32_t(d[k] >> 38) & 1u) : 0u;
+      const uint32_t bal = sj_ballot(par != 0);
+      const uint32_t pol = (s ^ uint32_t(sj_popc(bal & lt))) & 1u;  // in-string entering my element
+      const uint32_t a = uint32_t(d[k]) & 0x7FFFFu, b = uint32_t(d[k] >> 19) & 0x7FFFFu;
+      uint32_t incl = use ? (pol ? b : a) : 0u;
 #pragma unroll
-    for (int k = kLookK - 1; k >= 0; k--) {
-      const uint32_t rel = (uint32_t(sj_popc((bal[k] >> lane) >> 1)) ^ older) & 1u;  // my element's polarity relative to the window's oldest
-      if ((use >> k) & 1u) {
-        const uint32_t a = uint32_t(d[k]) & 0x7FFFFu, b = uint32_t(d[k] >> 19) & 0x7FFFFu;
-        sa += rel ? b : a;
-        sb += rel ? a : b;
+      for (int dd = 1; dd < 32; dd <<= 1) {
+        const uint32_t o = sj_shfl_up(incl, dd);
+        if (int(lane) >= dd) incl += o;
       }
-      older ^= uint32_t(sj_popc(bal[k])) & 1u;
+      if (use) sj_st_relaxed_u64(p.count_desc + (next + 32u * k + lane), pack_inc(p.epoch, pol ^ par, base + incl));
+      base += sj_shfl(incl, 31);
+      s ^= uint32_t(sj_popc(bal)) & 1u;
     }
-    Eff win;
-    win.p = older;
-    win.a = sj_reduce_add(sa);
-    win.b = sj_reduce_add(sb);
-    acc = compose(win, acc);
-    if (inc_dist != 0xFFFFFFFFu) {
-      const uint32_t ik = inc_dist >> 5, il = inc_dist & 31u;
-      uint32_t sk = 0, ck = 0;
-#pragma unroll
-      for (int k = 0; k < kLookK; k++)
-        if (uint32_t(k) == ik) { sk = uint32_t(d[k] >> 32) & 1u; ck = uint32_t(d[k]); }
-      sk = sj_shfl(sk, int(il));
-      ck = sj_shfl(ck, int(il));
-      *s_in = sk ^ acc.p;
-      *base = ck + (sk ? acc.b : acc.a);
-#if SJB200_SCAN4_HELP
-      // Help: the walk has just computed what every element between the inclusive prefix and t needs, so publish THEIR
-      // inclusive prefixes too (the owners would write exactly the same words).  Other CTAs then find an inclusive
-      // prefix right behind their element instead of walking over everything in flight: a backlog of unresolved
-      // elements clears in one round instead of feeding on itself.
-      {
-        uint32_t older_p = 0;   // parity of the used elements older than group k
-        uint32_t older_c = ck;  // outputs up to and including the used elements older than group k
-#pragma unroll
-        for (int k = kLookK - 1; k >= 0; k--) {
-          const bool u = (use >> k) & 1u;
-          const uint32_t rel = (uint32_t(sj_popc((bal[k] >> lane) >> 1)) ^ older_p ^ sk) & 1u;  // in-string entering my element
-          const uint32_t a = uint32_t(d[k]) & 0x7FFFFu, b = uint32_t(d[k] >> 19) & 0x7FFFFu;
-          const uint32_t mine = u ? (rel ? b : a) : 0u;
-          uint32_t suf = mine;  // suffix sum over lanes >= mine (older elements of the group first)
-#pragma unroll
-          for (int dd = 1; dd < 32; dd <<= 1) {
-            const uint32_t o = sj_shfl_down(suf, dd);
-            if (int(lane) + dd < 32) suf += o;
-          }
-          if (u) {
-            const uint32_t s_after = rel ^ (uint32_t(d[k] >> 38) & 1u);
-            sj_st_relaxed_u64(p.count_desc + (first - 32 * k), pack_inc(p.epoch, s_after, older_c + suf));
-          }
-          older_c += sj_shfl(suf, 0);
-          older_p ^= uint32_t(sj_popc(bal[k])) & 1u;
-        }
-      }
-#endif
-      return;
-    }
-    newest -= 32 * kLookK;
-    if (newest < 0) {  // cannot happen (element 0 always publishes an inclusive prefix); never loop forever
-      sj_atomic_or(p.flags, kFlagInternal);
-      *s_in = acc.p;
-      *base = acc.a;
-      return;
-    }
+    next += m;
   }
 }
 
@@ -770,31 +687,46 @@ SJ_DEV void finalize_launch(const ScanParams &p, const Carry &cin, uint32_t s_ou
   }
 }
 
-SJ_DEV void chain_role(Smem *S, const ScanParams &p, const Carry &cin, unsigned lane, unsigned c) {
+// ------------------------------------------------------------------------------------------------ owner warp
+// One per CTA: waits for each of the CTA's elements to be scanned, then for the resolver to turn its descriptor into
+// an inclusive prefix (polling ONE word, its own), and posts every block's polarity and output offset to the scan warps.
+SJ_DEV void owner_role(Smem *S, const ScanParams &p, const Carry &cin, unsigned lane) {
   const uint32_t nelem = p.ntiles;
-  for (uint32_t j = c;; j += uint32_t(kChainWarps)) {
+  const uint32_t key_inc = (p.epoch << 2) | kDescInc;
+  for (uint32_t j = 0;; j++) {
     const int ns = int(j % kNS);
     const uint32_t t = wait_ticket(S, j, p);
     if (t >= nelem) break;
     wait_bar(&S->scanned[ns], (j / kNS) & 1u, p, 200);
     if (p.debug != nullptr && lane == 0) p.debug[uint64_t(t) * 8 + 6] = sj_globaltimer();
     const uint32_t par = S->elem[ns][0], b0 = S->elem[ns][1], b1 = S->elem[ns][2], hits = S->elem[ns][3];
-    uint32_t s_in = (cin.state >> 1) & 1u, base = 0;
-    if (t > 0) look_back(p, t, lane, &s_in, &base);
+    unsigned long long d = 0;
+    uint32_t spins = 0;
+    for (;;) {
+      d = sj_ld_relaxed_u64(p.count_desc + t);  // every lane reads the same word: one request
+      if (uint32_t(d >> 44) == key_inc) break;
+      if (++spins > kSpinLimit4) {
+        sj_atomic_or(p.flags, kFlagInternal);
+        break;
+      }
+#if SJB200_SCAN4_SLEEP
+      sj_nanosleep(200);
+#endif
+    }
+    const uint32_t s_out = uint32_t(d >> 32) & 1u, through = uint32_t(d);
+    const uint32_t s_in = s_out ^ par;
     const uint32_t mine_total = s_in ? b1 : b0;
-    const uint32_t s_out = s_in ^ par;
-    if (lane == 0) sj_st_relaxed_u64(p.count_desc + t, pack_inc(p.epoch, s_out, base + mine_total));
+    const uint32_t base = through - mine_total;
     if (lane < uint32_t(kScanWarps)) {
       const uint32_t pk = S->pre[ns][s_in][lane];
       S->res_pol[ns][lane] = pk >> 31;
       S->res_base[ns][lane] = base + (pk & 0x7FFFFFFFu);
     }
-    const uint32_t hit0 = hits & 1u, hit1 = (hits >> 1) & 1u;
-    if (lane == 0 && (s_in ? hit1 : hit0)) sj_atomic_or(p.flags, kFlagCtl);
+    if (lane == 0 && ((hits >> s_in) & 1u)) sj_atomic_or(p.flags, kFlagCtl);
     sj_syncwarp();
     if (lane == 0) sj_mbar_arrive(&S->resolved[ns]);
     if (p.debug != nullptr && lane == 0) p.debug[uint64_t(t) * 8 + 4] = sj_globaltimer();
-    if (t == nelem - 1) finalize_launch(p, cin, s_out, cin.count + base + mine_total, lane);
+    if (t == nelem - 1) finalize_launch(p, cin, s_out, cin.count + through, lane);
   }
 }
 
@@ -821,7 +753,8 @@ SJ_DEV void scan4_body(const sj_tensor_map *tmap, const ScanParams &p, uint8_t *
   }
   sj_syncthreads();
   if (warp < unsigned(kScanWarps)) scan_role(S, tmap, p, cin, warp, lane);
-  else chain_role(S, p, cin, lane, warp - unsigned(kScanWarps));
+  else if (warp == unsigned(kScanWarps)) owner_role(S, p, cin, lane);
+  else resolver_role(S, p, cin, lane);
   // last CTA out resets the ticket for the next launch on this context and hands the flags over
   sj_syncthreads();
   if (tid == 0) {

@@ -206,89 +206,82 @@ int check(EmuCtx &cx, const std::vector<uint8_t> &store, size_t misalign, uint32
   return bad;
 }
 
-// ---- the look-back fold on its own: one emulated warp against a scalar walk, with the nearest inclusive prefix up to
-// three windows away and stale / missing descriptors behind it (the multi-CTA runs above only reach short distances)
-struct LbArgs {
+// ---- the resolver on its own: one emulated warp turns up to ~1500 aggregates into inclusive prefixes while a feeder
+// thread publishes them in bursts (partial windows, all ten k-groups, several windows); checked against a scalar walk
+struct RsArgs {
+  scan4::Smem *S;
   const ScanParams *p;
-  uint32_t t;
+  Carry cin;
   simt::WarpShared *warp;
   simt::CtaShared *cta;
   unsigned lane;
-  uint32_t s_in, base;
 };
-void *lb_thread(void *arg) {
-  LbArgs *a = static_cast<LbArgs *>(arg);
+void *rs_thread(void *arg) {
+  RsArgs *a = static_cast<RsArgs *>(arg);
   simt::tctx = simt::ThreadCtx();
   simt::tctx.tid = a->lane;
   simt::tctx.nctas = 1;
   simt::tctx.warp = a->warp;
   simt::tctx.ctas = a->cta;
-  scan4::look_back(*a->p, a->t, a->lane, &a->s_in, &a->base);
+  scan4::resolver_role(a->S, *a->p, a->cin, a->lane);
   return nullptr;
 }
-int test_look_back(std::mt19937_64 &rng, int cases) {
+int test_resolver(std::mt19937_64 &rng, int cases) {
   int bad = 0;
   for (int c = 0; c < cases && bad < 3; c++) {
-    const uint32_t t = 1 + uint32_t(rng() % 1500);
+    const uint32_t n = 1 + uint32_t(rng() % (c % 3 == 0 ? 1500 : 400));
     const uint32_t epoch = 1 + uint32_t(rng() % 1000);
-    std::vector<unsigned long long> desc(t + 1, 0ull);
-    uint32_t flags = 0;
-    // nearest inclusive prefix at `inc`; everything newer is an aggregate; older entries are junk that must not matter
-    const uint32_t maxback = std::min<uint32_t>(t, 1 + uint32_t(rng() % 1000));
-    const uint32_t inc = t - 1 - uint32_t(rng() % maxback);
-    const uint32_t s_k = uint32_t(rng() & 1), c_k = uint32_t(rng() % 100000000u);
-    for (uint32_t i = 0; i < t; i++) {
+    std::vector<unsigned long long> agg(n), desc(n + 1, 0ull), want(n);
+    const uint32_t s0 = uint32_t(rng() & 1);
+    uint32_t s = s0;
+    uint64_t cnt = 0;
+    for (uint32_t i = 0; i < n; i++) {
       const uint32_t par = uint32_t(rng() & 1), c0 = uint32_t(rng() % 32769), c1 = uint32_t(rng() % 32769);
-      if (i > inc) desc[i] = scan4::pack_agg(epoch, par, c0, c1);
-      else if (i == inc) desc[i] = scan4::pack_inc(epoch, s_k, c_k);
-      else {
-        const int kind = int(rng() % 4);
-        desc[i] = kind == 0 ? 0ull : kind == 1 ? scan4::pack_agg(epoch - 1, par, c0, c1) : kind == 2 ? scan4::pack_inc(epoch, par, c0) : scan4::pack_agg(epoch, par, c0, c1);
-      }
+      agg[i] = scan4::pack_agg(epoch, par, c0, c1);
+      cnt += s ? c1 : c0;
+      s ^= par;
+      want[i] = scan4::pack_inc(epoch, s, uint32_t(cnt));
+      if (rng() % 5 == 0) desc[i] = scan4::pack_agg(epoch - 1, par, c1, c0);  // stale word of an earlier launch
     }
-    desc[0] = (inc == 0) ? desc[0] : scan4::pack_inc(epoch, uint32_t(rng() & 1), 12345);  // element 0 is always inclusive
-    uint32_t s = s_k;
-    uint64_t cnt = c_k;
-    std::vector<unsigned long long> helped(t, 0ull);  // the inclusive prefix of every element between inc and t
-    for (uint32_t i = inc + 1; i < t; i++) {
-      const unsigned long long d = desc[i];
-      cnt += s ? (uint32_t(d >> 19) & 0x7FFFFu) : (uint32_t(d) & 0x7FFFFu);
-      s ^= uint32_t(d >> 38) & 1u;
-      helped[i] = scan4::pack_inc(epoch, s, uint32_t(cnt));
-    }
-    const std::vector<unsigned long long> before(desc);
+    uint32_t flags = 0;
     ScanParams p;
     memset(&p, 0, sizeof(p));
-    p.epoch = epoch; p.count_desc = desc.data(); p.flags = &flags;
+    p.epoch = epoch; p.count_desc = desc.data(); p.flags = &flags; p.ntiles = n;
+    std::vector<uint8_t> smem(sizeof(scan4::Smem) + 64);
+    scan4::Smem *S = reinterpret_cast<scan4::Smem *>((reinterpret_cast<uintptr_t>(smem.data()) + 63) & ~uintptr_t(63));
+    sj_mbar_init(&S->ticket_ready[0], 1);
+    S->ticket[0] = 0;
+    sj_mbar_arrive(&S->ticket_ready[0]);
     simt::WarpShared w;
     simt::CtaShared cta;
     pthread_barrier_init(&w.bar, nullptr, 32);
-    std::vector<LbArgs> args(32);
+    std::vector<RsArgs> args(32);
     std::vector<pthread_t> th(32);
+    Carry cin = Carry();
+    cin.state = s0 << 1;
     for (unsigned l = 0; l < 32; l++) {
-      args[l] = LbArgs{&p, t, &w, &cta, l, 0, 0};
-      pthread_create(&th[l], nullptr, lb_thread, &args[l]);
+      args[l] = RsArgs{S, &p, cin, &w, &cta, l};
+      pthread_create(&th[l], nullptr, rs_thread, &args[l]);
+    }
+    // feeder: aggregates arrive out of order inside bursts
+    std::vector<uint32_t> order(n);
+    for (uint32_t i = 0; i < n; i++) order[i] = i;
+    for (uint32_t i = 0; i < n; i++) {
+      const uint32_t span = 1 + uint32_t(rng() % 97);
+      const uint32_t jx = i + uint32_t(rng() % span);
+      if (jx < n) std::swap(order[i], order[jx]);
+    }
+    for (uint32_t i = 0; i < n; i++) {
+      __atomic_store_n(&desc[order[i]], agg[order[i]], __ATOMIC_RELEASE);
+      if (rng() % 64 == 0) { struct timespec ts = {0, 30000}; nanosleep(&ts, nullptr); }
     }
     for (auto &x : th) pthread_join(x, nullptr);
     pthread_barrier_destroy(&w.bar);
-    for (unsigned l = 0; l < 32; l++)
-      if (args[l].s_in != s || args[l].base != uint32_t(cnt) || flags != 0) {
-        fprintf(stderr, "LOOK-BACK MISMATCH t=%u inc=%u lane=%u: got (%u,%u) want (%u,%u) flags=%u\n", t, inc, l, args[l].s_in, args[l].base, s, uint32_t(cnt), flags);
-        bad++;
-        break;
-      }
-    // helping: inside the window that held the inclusive prefix, every newer element now carries ITS inclusive prefix;
-    // nothing else was touched
-    const uint32_t win = uint32_t(32 * scan4::kLookK), D = t - 1 - inc, w0 = (D / win) * win;
-    for (uint32_t i = 0; i < t && !bad; i++) {
-      const uint32_t dist = t - 1 - i;
-      const bool expect_help = SJB200_SCAN4_HELP && dist >= w0 && dist < D;
-      const unsigned long long want = expect_help ? helped[i] : before[i];
-      if (desc[i] != want) {
-        fprintf(stderr, "HELP MISMATCH t=%u inc=%u i=%u: got %llx want %llx\n", t, inc, i, desc[i], want);
+    for (uint32_t i = 0; i < n && !bad; i++)
+      if (desc[i] != want[i] || flags != 0) {
+        fprintf(stderr, "RESOLVER MISMATCH n=%u i=%u: got %llx want %llx flags=%u\n", n, i, desc[i], want[i], flags);
         bad++;
       }
-    }
   }
   return bad;
 }
@@ -301,7 +294,7 @@ int main(int argc, char **argv) {
   const char *alphabets[] = {"\\\\\\\"\" {}[],: \n\tabc1\x01\x0c\x1a\x1e", "\\\"", "\\\\\\\\\\\\\\\"a ", "\"{}[],:0 ", " \n\r\t\"a\\", ",{}[] 1 \"a\":\n"};
   const char *utf8bits[] = {"\xc3\xa9", "\xe2\x82\xac", "\xf0\x9f\x98\x80", "\xff", "\xc3", "\xe2\x82", "\xf0\x9f\x98", "\x80", "\xed\xa0\x80", "\xc0\xaf", "\xf4\x90\x80\x80", "\xe0\x9f\xbf", "\xf0\x8f\xbf\xbf", "\xf5\x80\x80\x80", "\xed\x9f\xbf", "\xf4\x8f\xbf\xbf", "\xe0\xa0\x80", "\xf0\x90\x80\x80", "\xc2\x80", "\xdf\xbf"};
   EmuCtx cx;
-  g_fail += test_look_back(rng, 300);
+  g_fail += test_resolver(rng, 120);
   for (int it = 0; it < iters && g_fail < 5; it++) {
     std::vector<uint8_t> in;
     const int kind = int(rng() % 8);
