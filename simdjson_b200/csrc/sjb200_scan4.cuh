@@ -387,28 +387,42 @@ SJ_DEV uint32_t *park_of(const ScanParams &p, uint32_t e, unsigned warp) {
   return p.park + ((size_t(sj_cta()) * kPark + (e % uint32_t(kPark))) * kScanWarps + warp) * size_t(kParkWords);
 }
 
+// the parked words of block `warp` of this CTA's e-th element (resolved): the mask of the polarity it turned out to
+// have and the lane's packed output prefix.  Separate from the emit so that the round trip to L2 can overlap a scan.
+struct Parked {
+  sj_u4 ev;
+  uint32_t pre;
+};
+SJ_DEV Parked load_parked(Smem *S, const ScanParams &p, uint32_t e, unsigned warp, unsigned lane) {
+  const uint32_t pol = S->res_pol[e % kNS][warp] & 1u;
+  const uint32_t *park = park_of(p, e, warp);
+  Parked k;
+  k.ev = sj_ld_u4(park + 128 * pol + 4 * lane);
+  k.pre = sj_ld_u32(park + 256 + lane);
+  return k;
+}
+
 // emit block `warp` of this CTA's e-th element (resolved); stg: 4 KiB of shared memory nobody else is using
-SJ_DEV void emit_block(Smem *S, const ScanParams &p, uint64_t out_base, uint32_t e, unsigned warp, unsigned lane, uint32_t *stg) {
+// (not inlined: four call sites, and the kernel already strains the instruction cache)
+SJ_DEV_NOINLINE void emit_block(Smem *S, const ScanParams &p, uint64_t out_base, uint32_t e, unsigned warp, unsigned lane, uint32_t *stg, const Parked &k) {
   const int ns = int(e % kNS);
   const uint32_t sum = S->summary[ns][warp];
   const uint32_t pol = S->res_pol[ns][warp] & 1u;
   const uint32_t total = pol ? ((sum >> 16) & 0x1FFFu) : (sum & 0xFFFFu);
   if (total == 0) return;
   const uint32_t elem = S->ticket[ns];
-  const uint32_t *park = park_of(p, e, warp);
-  const sj_u4 ev = sj_ld_u4(park + 128 * pol + 4 * lane);
-  const uint32_t off = (sj_ld_u32(park + 256 + lane) >> (16 * pol)) & 0xFFFFu;
+  const uint32_t off = (k.pre >> (16 * pol)) & 0xFFFFu;
   const uint32_t pos_lane = p.pos_base + (p.tile_begin + elem) * uint32_t(kTileBytes) + warp * uint32_t(kBlockBytes) + lane * 128u;
   uint32_t *out = p.idx_out + (out_base + S->res_base[ns][warp]);
   if (total <= kStageWords) {
     // positions go to shared memory (scattered 4-byte global stores cost one L1 wavefront each) and leave coalesced
     sj_syncwarp();
-    emit_columns(ev, off, pos_lane, stg);
+    emit_columns(k.ev, off, pos_lane, stg);
     sj_syncwarp();
     for (uint32_t i = lane; i < total; i += 32) out[i] = stg[i];
     sj_syncwarp();
   } else {
-    emit_columns(ev, off, pos_lane, out);  // > 1 structural per 4 bytes over 4 KiB: straight to global memory
+    emit_columns(k.ev, off, pos_lane, out);  // > 1 structural per 4 bytes over 4 KiB: straight to global memory
   }
   if (p.debug != nullptr && warp == 0 && lane == 0) p.debug[uint64_t(elem) * 8 + 5] = sj_globaltimer();
 }
@@ -512,8 +526,21 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
     // the scratch slot of element j must be free (only binds when resolution falls kPark elements behind)
     while (ne + uint32_t(kPark) <= j) {
       wait_bar(&S->resolved[ne % kNS], (ne / kNS) & 1u, p, 64);
-      emit_block(S, p, out_base, ne, warp, lane, reinterpret_cast<uint32_t *>(S->ring[warp][r ^ 1]));
+      emit_block(S, p, out_base, ne, warp, lane, reinterpret_cast<uint32_t *>(S->ring[warp][r ^ 1]), load_parked(S, p, ne, warp, lane));
       ne++;
+    }
+    // if the next element to emit is resolved by now, fetch its parked words: the round trip overlaps the scan below
+    bool have_pre = false;
+    Parked pre;
+    pre.ev = sj_make_u4(0, 0, 0, 0);
+    pre.pre = 0;
+    if (ne < j) {
+      uint32_t ready = 0;
+      if (lane == 0) ready = sj_mbar_try_wait(&S->resolved[ne % kNS], (ne / kNS) & 1u) ? 1u : 0u;
+      if (sj_shfl(ready, 0)) {
+        pre = load_parked(S, p, ne, warp, lane);
+        have_pre = true;
+      }
     }
     uint32_t t_acq = 0;
     if (warp == 0 && lane == 0) t_acq = sj_atomic_add(p.ticket, 1u);  // element j+2 of this CTA
@@ -557,14 +584,19 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
       }
     }
     if (warp == 0) publish_ticket(S, j + 2, t_acq, lane);
-    // emit whatever is resolved by now (never wait here: the masks are parked, the scan goes on)
-#pragma unroll 1
-    for (int q = 0; q < 2 && ne <= j; q++) {
+    // emit what was found resolved before the scan (its words are here), then whatever else is resolved by now; never
+    // wait: the masks are parked, the scan goes on
+    if (have_pre) {
+      emit_block(S, p, out_base, ne, warp, lane, reinterpret_cast<uint32_t *>(T), pre);
+      ne++;
+    }
+    if (ne <= j) {
       uint32_t ready = 0;
       if (lane == 0) ready = sj_mbar_try_wait(&S->resolved[ne % kNS], (ne / kNS) & 1u) ? 1u : 0u;
-      if (!sj_shfl(ready, 0)) break;
-      emit_block(S, p, out_base, ne, warp, lane, reinterpret_cast<uint32_t *>(T));
-      ne++;
+      if (sj_shfl(ready, 0)) {
+        emit_block(S, p, out_base, ne, warp, lane, reinterpret_cast<uint32_t *>(T), load_parked(S, p, ne, warp, lane));
+        ne++;
+      }
     }
     t = tn;
     tma_cur = tma_next;
@@ -573,7 +605,7 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
   // drain: what this CTA scanned and has not emitted yet (no load is in flight: both ring slots are free)
   while (ne < j) {
     wait_bar(&S->resolved[ne % kNS], (ne / kNS) & 1u, p, 64);
-    emit_block(S, p, out_base, ne, warp, lane, reinterpret_cast<uint32_t *>(S->ring[warp][0]));
+    emit_block(S, p, out_base, ne, warp, lane, reinterpret_cast<uint32_t *>(S->ring[warp][0]), load_parked(S, p, ne, warp, lane));
     ne++;
   }
 }

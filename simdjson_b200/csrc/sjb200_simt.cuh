@@ -22,7 +22,7 @@
 #include <new>
 
 #define SJ_DEV inline
-#define SJ_DEV_NOINLINE
+#define SJ_DEV_NOINLINE inline
 
 namespace sjb200 {
 namespace simt {

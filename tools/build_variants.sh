@@ -5,7 +5,7 @@ cd "$(dirname "$0")/.."
 SRCS="simdjson_b200/csrc/sjb200_kernels.cu simdjson_b200/csrc/sjb200_capi.cu simdjson_b200/csrc/sjb200_finish.cpp"
 FLAGS="-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-fvisibility=hidden -shared"
 build() { name=$1; shift; nvcc $FLAGS "$@" -o tools/variants/lib_$name.so $SRCS & }
-build park2 -DSJB200_SCAN4_PARK=2
+build nosleep -DSJB200_SCAN4_SLEEP=0
 build park3 -DSJB200_SCAN4_PARK=3
 build park5 -DSJB200_SCAN4_PARK=5
 wait

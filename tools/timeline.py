@@ -57,6 +57,10 @@ if os.environ.get("PROBE_KERNEL", "4") == "4":
     gate = np.maximum.accumulate(scanned)
     jumps = np.argsort(-(gate[1:] - gate[:-1]))[:8] + 1
     print("elements that gate their successors longest (element, scanned us, gate jump us):", [(int(i), round((scanned[i] - t0) / 1e3, 1), round((gate[i] - gate[i - 1]) / 1e3, 1)) for i in sorted(jumps)])
+    for i in sorted(jumps)[:6]:
+        rows = np.where(ctas == ctas[i])[0]
+        rows = rows[np.argsort(t[rows, 0])]
+        print("gate #%d: cta %d sm %d it %d | its CTA:" % (i, ctas[i], smid[i], iters[i]), " ".join("[#%d it%d: %.1f %.1f %.1f %.1f %.1f]" % (r, iters[r], (t[r, 0] - t0) / 1e3, (t[r, 3] - t0) / 1e3, (t[r, 6] - t0) / 1e3, (t[r, 4] - t0) / 1e3, (t[r, 5] - t0) / 1e3) for r in rows))
     for c in np.unique(ctas)[:3]:
         rows = t[ctas == c]
         rows = rows[np.argsort(rows[:, 0])]
