@@ -58,7 +58,8 @@ struct sjb200_ctx {
   unsigned long long *d_count_desc = nullptr;
   size_t desc_tiles = 0;
   uint8_t *d_chars = nullptr; size_t d_chars_bytes = 0;
-  uint32_t *d_park = nullptr; size_t d_park_words = 0;  // scan4: parked masks (a per-CTA ring, independent of the input size)
+  uint32_t *d_park = nullptr; size_t d_park_words = 0;  // scan4 deferred mode: parked masks (a per-CTA ring, independent of the input size)
+  long opt_deferred = 1;  // 1: launches that fit use the deferred variant of scan4; 0: never; 2: always
   // pinned host mirrors
   Carry *h_carry = nullptr;     // [kCarrySlots]
   uint32_t *h_flags = nullptr;
@@ -253,15 +254,19 @@ bool enqueue_scan(sjb200_ctx *c, int kind, const CUtensorMap *map, bool tma, con
     make_tensor_map(c, &map4, d_buf, len, &tma4, kScan4BoxRows);
     p.use_tma = (tma && tma4) ? 1u : 0u;
     const int grid = grid_for(c, kind, ntiles);
-    const size_t need = scan4_park_words(grid_cap(c, kind));
-    if (c->d_park_words < need) {
-      cudaStreamSynchronize(c->stream);
-      cudaFree(c->d_park); c->d_park = nullptr; c->d_park_words = 0;
-      if (!dev_alloc(c, &c->d_park, need, "cudaMalloc(park)")) return false;
-      c->d_park_words = need;
+    // deferred emit when every CTA can hold all the elements it will draw (small launches: one wave of CTAs)
+    bool deferred = c->opt_deferred == 2 || (c->opt_deferred == 1 && uint64_t(ntiles) * 4 <= uint64_t(grid) * uint64_t(scan4_deferred_capacity()) * 3);
+    if (deferred) {
+      const size_t need = scan4_park_words(grid_cap(c, kind));
+      if (c->d_park_words < need) {
+        cudaStreamSynchronize(c->stream);
+        cudaFree(c->d_park); c->d_park = nullptr; c->d_park_words = 0;
+        if (dev_alloc(c, &c->d_park, need, "cudaMalloc(park)")) c->d_park_words = need;
+        else deferred = false;
+      }
+      p.park = c->d_park;
     }
-    p.park = c->d_park;
-    launched = ok(c, launch_scan4(&map4, p, grid, stream), "launch scan4");
+    launched = ok(c, launch_scan4(&map4, p, grid, deferred, stream), "launch scan4");
   } else {
     launched = ok(c, launch_scan(kind, map, p, grid_for(c, kind, p.nsuper), stream), "launch scan");
   }
@@ -498,6 +503,7 @@ extern "C" int sjb200_set_option(sjb200_ctx *c, const char *key, long value) {
   else if (!strcmp(key, "grid")) c->opt_grid = value;
   else if (!strcmp(key, "sub_per_super")) c->opt_sub_per_super = value;
   else if (!strcmp(key, "kernel")) c->opt_kernel = (value == 3) ? 3 : 4;
+  else if (!strcmp(key, "deferred")) c->opt_deferred = value;
   else if (!strcmp(key, "time_kernel")) c->opt_time_kernel = value;
   else if (!strcmp(key, "debug_timeline")) c->opt_debug_timeline = value;
   else if (!strcmp(key, "chunk_bytes")) c->opt_chunk_bytes = std::max<long>(kTileBytes, (value / kTileBytes) * kTileBytes);

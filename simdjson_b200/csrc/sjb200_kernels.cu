@@ -862,10 +862,18 @@ __global__ void __launch_bounds__(kThreads, (KIND == kUtf8) ? 4 : kMinCtasPerSm)
 }
 
 // ------------------------------------------------------------------ scan4 (stage 1; see sjb200_scan4.cuh)
+// two variants of one source: pipelined (masks wait in shared memory, an element is emitted two scans after it was scanned)
+// and deferred (masks wait in an L2-resident scratch ring, everything is emitted after the CTA's last scan: launches
+// small enough that every CTA holds all its elements at once never stall on the chain)
 __global__ void __launch_bounds__(scan4::kThreads4, SJB200_SCAN4_MIN_CTAS)
     scan4_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
   extern __shared__ uint8_t smem_raw4[];
-  scan4::scan4_body(&tmap, p, smem_raw4, sj_smem_u32(smem_raw4));
+  scan4::scan4_body<false>(&tmap, p, smem_raw4, sj_smem_u32(smem_raw4));
+}
+__global__ void __launch_bounds__(scan4::kThreads4, SJB200_SCAN4_MIN_CTAS)
+    scan4_deferred_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
+  extern __shared__ uint8_t smem_raw4[];
+  scan4::scan4_body<true>(&tmap, p, smem_raw4, sj_smem_u32(smem_raw4));
 }
 
 // ------------------------------------------------------------------ small helpers
@@ -894,20 +902,23 @@ static cudaError_t launch_kind(const CUtensorMap *tmap, const ScanParams &p, int
   return cudaGetLastError();
 }
 
-cudaError_t launch_scan4(const CUtensorMap *tmap, const ScanParams &p, int grid, cudaStream_t stream) {
+cudaError_t launch_scan4(const CUtensorMap *tmap, const ScanParams &p, int grid, bool deferred, cudaStream_t stream) {
   static bool configured[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(scan4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, scan4::kSmemBytes4);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(scan4_deferred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, scan4::kSmemBytes4);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  scan4_kernel<<<grid, scan4::kThreads4, scan4::kSmemBytes4, stream>>>(*tmap, p);
+  if (deferred) scan4_deferred_kernel<<<grid, scan4::kThreads4, scan4::kSmemBytes4, stream>>>(*tmap, p);
+  else scan4_kernel<<<grid, scan4::kThreads4, scan4::kSmemBytes4, stream>>>(*tmap, p);
   return cudaGetLastError();
 }
 
-size_t scan4_park_words(int grid) { return size_t(grid) * scan4::kPark * scan4::kScanWarps * scan4::kParkWords; }
+size_t scan4_park_words(int grid) { return size_t(grid) * scan4::kParkD * scan4::kParkSlotWords; }
+int scan4_deferred_capacity() { return scan4::kParkD; }
 
 int scan4_max_ctas_per_sm() {
   int n = 0;

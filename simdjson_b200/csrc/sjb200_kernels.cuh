@@ -13,9 +13,10 @@ namespace sjb200 {
 cudaError_t launch_scan(int kind, const CUtensorMap *tmap, const ScanParams &p, int grid, cudaStream_t stream);
 int scan_max_ctas_per_sm(int kind);
 // scan4: the stage-1 indexer of sjb200_scan4.cuh (4 KiB blocks; its tensor map has a 32-row box)
-cudaError_t launch_scan4(const CUtensorMap *tmap, const ScanParams &p, int grid, cudaStream_t stream);
+cudaError_t launch_scan4(const CUtensorMap *tmap, const ScanParams &p, int grid, bool deferred, cudaStream_t stream);
+size_t scan4_park_words(int grid);   // uint32 words of ScanParams::park for a deferred launch of `grid` CTAs
+int scan4_deferred_capacity();       // elements per CTA the deferred variant can hold at once
 int scan4_max_ctas_per_sm();
-size_t scan4_park_words(int grid);  // uint32 words of ScanParams::park for a launch of `grid` CTAs
 constexpr int kScan4BoxRows = 32;
 cudaError_t launch_gather_chars(const uint8_t *buf, const uint32_t *idx, uint32_t first, uint32_t count, uint8_t *out,
                                 cudaStream_t stream);

@@ -76,7 +76,7 @@ struct ScanParams {
   uint32_t *flags;          // accumulated with atomicOr; zero between launches (the last CTA moves it to carry_out->flags)
   unsigned long long *count_desc;  // [nsuper] the look-back chain
   uint32_t *ticket;         // [0] next tile, [1] CTAs finished
-  uint32_t *park;           // scan4: scratch ring for parked masks, scan4_park_words(grid) words (stays in L2)
+  uint32_t *park;           // scan4, deferred mode: scratch ring for parked masks, scan4_park_words(grid) words (stays in L2)
   unsigned long long *debug;  // optional [ntiles][8] timeline (globaltimer ns) for tuning; null in production
 };
 

@@ -38,16 +38,24 @@ namespace scan4 {
 constexpr int kScanWarps = 8;
 constexpr int kBlockBytes = 4096;
 constexpr int kBlockRows = kBlockBytes / 128;
-constexpr int kThreads4 = 32 * (kScanWarps + 2);  // + the owner warp + the resolver warp (active in one CTA of the launch)
-#ifndef SJB200_SCAN4_PARK
-#define SJB200_SCAN4_PARK 7
+#ifndef SJB200_SCAN4_CHAIN
+#define SJB200_SCAN4_CHAIN 1
 #endif
-constexpr int kPark = SJB200_SCAN4_PARK;  // elements of a CTA whose masks may wait (in an L2-resident scratch ring) for their resolution
+constexpr int kChainWarps = SJB200_SCAN4_CHAIN;  // chain warp c resolves this CTA's elements j = c, c + kChainWarps, ...
+constexpr int kThreads4 = 32 * (kScanWarps + kChainWarps);
+#ifndef SJB200_SCAN4_PARK
+#define SJB200_SCAN4_PARK 3
+#endif
+constexpr int kPark = SJB200_SCAN4_PARK;  // elements whose masks wait in shared memory: a scan warp emits element j-kLag after scanning j
 constexpr int kLag = kPark - 1;
-constexpr int kNS = 16;          // ring of element slots (tickets, summaries, resolutions)
-constexpr int kParkWords = 288;  // per block: 32 x uint4 (outside), 32 x uint4 (inside), 32 x packed prefix
+constexpr int kNS = 32;          // ring of element slots (tickets, summaries, resolutions)
+#ifndef SJB200_SCAN4_DEFER_PARK
+#define SJB200_SCAN4_DEFER_PARK 12
+#endif
+constexpr int kParkD = SJB200_SCAN4_DEFER_PARK;  // deferred mode: elements of a CTA whose masks may wait in the L2-resident scratch ring
+constexpr int kParkSlotWords = 2 * kScanWarps * 32 * 4 + kScanWarps * 32;  // one element's parked words (both polarities + prefixes)
 constexpr int kLookK = 10;       // descriptors per lane and look-back round trip (window of 320 elements >= one wave of CTAs)
-static_assert(kLag >= 1 && 2 * kLag + 3 <= kNS && (kNS & (kNS - 1)) == 0, "slot ring");
+static_assert(kLag >= 1 && 2 * kLag + 3 <= kNS && 2 * (kParkD - 1) + 3 <= kNS && (kNS & (kNS - 1)) == 0, "slot ring");
 #ifndef SJB200_SCAN4_SLEEP
 #define SJB200_SCAN4_SLEEP 1
 #endif
@@ -59,6 +67,8 @@ enum : uint32_t { kDescNone = 0, kDescAgg = 1, kDescInc = 2 };
 
 struct Smem {
   uint8_t ring[kScanWarps][2][kBlockBytes];   // per scan warp: two block buffers (TMA destination / emit staging)
+  sj_u4 park[kPark][2][kScanWarps * 32];          // [pipeline buffer][polarity][thread]: candidate structural masks
+  uint32_t parkpre[kPark][kScanWarps * 32];       // exclusive prefix of the lane's counts inside its block, both polarities packed
   uint32_t ticket[kNS];
   uint32_t summary[kNS][kScanWarps];          // c0 | c1<<16 | parity<<29 | ctl-hit0<<30 | ctl-hit1<<31
   uint32_t arrived[kNS];                      // scan warps done with the element (the last one composes and publishes)
@@ -86,6 +96,19 @@ SJ_DEV unsigned long long pack_agg(uint32_t epoch, uint32_t par, uint32_t c0, ui
 }
 SJ_DEV unsigned long long pack_inc(uint32_t epoch, uint32_t s_out, uint32_t count) {
   return ((unsigned long long)epoch << 46) | ((unsigned long long)kDescInc << 44) | ((unsigned long long)(s_out & 1u) << 32) | count;
+}
+
+// The effect of a run of elements on (in-string, outputs): p = quote parity, a / b = outputs when entered outside /
+// inside a string.  compose(older, newer) is associative; identity = (0,0,0).
+struct Eff {
+  uint32_t p, a, b;
+};
+SJ_DEV Eff compose(const Eff &o, const Eff &n) {
+  Eff r;
+  r.p = o.p ^ n.p;
+  r.a = o.a + (o.p ? n.b : n.a);
+  r.b = o.b + (o.p ? n.a : n.b);
+  return r;
 }
 
 // A waiting warp must not spin at full speed: mbarrier.try_wait returns at once, and a busy loop takes issue slots
@@ -268,7 +291,8 @@ SJ_DEV void load_unit(const uint8_t *T, uint32_t off, uint32_t w[8]) {
 // T: the block in shared memory.  pw0: the 4 bytes before the block (only lane 0's copy is used).  e_in / c_in: the two
 // locally known state bits entering the block.  Parks the two candidate masks and the lane's exclusive output prefix,
 // returns the block summary word (uniform).
-SJ_DEV uint32_t scan_block(const uint8_t *T, uint32_t pw0, uint32_t e_in, uint32_t c_in, unsigned lane, const ScanParams &p, uint32_t *park) {
+SJ_DEV uint32_t scan_block(const uint8_t *T, uint32_t pw0, uint32_t e_in, uint32_t c_in, unsigned lane, const ScanParams &p, sj_u4 *park0,
+                           sj_u4 *park1, uint32_t *parkpre) {
   const uint32_t lane_off = lane * 128u;
   uint32_t bs[4], qu[4], op[4], sc[4], cl[4];
   uint32_t uerr = 0;
@@ -352,9 +376,10 @@ SJ_DEV uint32_t scan_block(const uint8_t *T, uint32_t pw0, uint32_t e_in, uint32
     if (int(lane) >= d) incl += t;
   }
   const uint32_t total = sj_shfl(incl, 31);
-  reinterpret_cast<sj_u4 *>(park)[lane] = sj_make_u4(e0[0], e0[1], e0[2], e0[3]);
-  reinterpret_cast<sj_u4 *>(park + 128)[lane] = sj_make_u4(e1[0], e1[1], e1[2], e1[3]);
-  park[256 + lane] = incl - cnt;
+  const unsigned tid = sj_tid();
+  park0[tid] = sj_make_u4(e0[0], e0[1], e0[2], e0[3]);
+  park1[tid] = sj_make_u4(e1[0], e1[1], e1[2], e1[3]);
+  parkpre[tid] = incl - cnt;
   const uint32_t h0 = sj_any(hit0 != 0) ? 1u : 0u, h1 = sj_any(hit1 != 0) ? 1u : 0u;
   return total | (par << 29) | (h0 << 30) | (h1 << 31);
 }
@@ -383,48 +408,53 @@ SJ_DEV void emit_columns(const sj_u4 ev, uint32_t off, uint32_t pos_lane, uint32
   }
 }
 
-SJ_DEV uint32_t *park_of(const ScanParams &p, uint32_t e, unsigned warp) {
-  return p.park + ((size_t(sj_cta()) * kPark + (e % uint32_t(kPark))) * kScanWarps + warp) * size_t(kParkWords);
-}
-
-// the parked words of block `warp` of this CTA's e-th element (resolved): the mask of the polarity it turned out to
-// have and the lane's packed output prefix.  Separate from the emit so that the round trip to L2 can overlap a scan.
-struct Parked {
-  sj_u4 ev;
-  uint32_t pre;
-};
-SJ_DEV Parked load_parked(Smem *S, const ScanParams &p, uint32_t e, unsigned warp, unsigned lane) {
-  const uint32_t pol = S->res_pol[e % kNS][warp] & 1u;
-  const uint32_t *park = park_of(p, e, warp);
-  Parked k;
-  k.ev = sj_ld_u4(park + 128 * pol + 4 * lane);
-  k.pre = sj_ld_u32(park + 256 + lane);
-  return k;
-}
-
-// emit block `warp` of this CTA's e-th element (resolved); stg: 4 KiB of shared memory nobody else is using
-// (not inlined: four call sites, and the kernel already strains the instruction cache)
-SJ_DEV_NOINLINE void emit_block(Smem *S, const ScanParams &p, uint64_t out_base, uint32_t e, unsigned warp, unsigned lane, uint32_t *stg, const Parked &k) {
+// emit block `warp` of this CTA's e-th element (resolved).  ev / prew: the lane's parked mask for the polarity the
+// block turned out to have and its packed output prefix.  stg: 4 KiB of shared memory nobody else is using.
+SJ_DEV void emit_block(Smem *S, const ScanParams &p, uint64_t out_base, uint32_t e, unsigned warp, unsigned lane, const sj_u4 ev, uint32_t prew,
+                       uint32_t *stg) {
   const int ns = int(e % kNS);
   const uint32_t sum = S->summary[ns][warp];
   const uint32_t pol = S->res_pol[ns][warp] & 1u;
   const uint32_t total = pol ? ((sum >> 16) & 0x1FFFu) : (sum & 0xFFFFu);
   if (total == 0) return;
   const uint32_t elem = S->ticket[ns];
-  const uint32_t off = (k.pre >> (16 * pol)) & 0xFFFFu;
+  const uint32_t off = (prew >> (16 * pol)) & 0xFFFFu;
   const uint32_t pos_lane = p.pos_base + (p.tile_begin + elem) * uint32_t(kTileBytes) + warp * uint32_t(kBlockBytes) + lane * 128u;
   uint32_t *out = p.idx_out + (out_base + S->res_base[ns][warp]);
   if (total <= kStageWords) {
     // positions go to shared memory (scattered 4-byte global stores cost one L1 wavefront each) and leave coalesced
     sj_syncwarp();
-    emit_columns(k.ev, off, pos_lane, stg);
+    emit_columns(ev, off, pos_lane, stg);
     sj_syncwarp();
     for (uint32_t i = lane; i < total; i += 32) out[i] = stg[i];
     sj_syncwarp();
   } else {
-    emit_columns(k.ev, off, pos_lane, out);  // > 1 structural per 4 bytes over 4 KiB: straight to global memory
+    emit_columns(ev, off, pos_lane, out);  // > 1 structural per 4 bytes over 4 KiB: straight to global memory
   }
   if (p.debug != nullptr && warp == 0 && lane == 0) p.debug[uint64_t(elem) * 8 + 5] = sj_globaltimer();
+}
+
+// pipelined mode: the masks wait in shared memory
+SJ_DEV void emit_from_smem(Smem *S, const ScanParams &p, uint64_t out_base, uint32_t e, unsigned warp, unsigned lane, uint32_t *stg) {
+  const uint32_t pol = S->res_pol[e % kNS][warp] & 1u;
+  const unsigned tid = warp * 32 + lane;
+  emit_block(S, p, out_base, e, warp, lane, S->park[e % kPark][pol][tid], S->parkpre[e % kPark][tid], stg);
+}
+
+// deferred mode: the masks wait in the scratch ring of ScanParams::park (it stays in L2)
+struct Parked {
+  sj_u4 ev;
+  uint32_t prew;
+};
+SJ_DEV uint32_t *park_slot(const ScanParams &p, uint32_t e) { return p.park + (size_t(sj_cta()) * kParkD + (e % uint32_t(kParkD))) * size_t(kParkSlotWords); }
+SJ_DEV Parked load_parked(Smem *S, const ScanParams &p, uint32_t e, unsigned warp, unsigned lane) {
+  const uint32_t pol = S->res_pol[e % kNS][warp] & 1u;
+  const uint32_t *slot = park_slot(p, e);
+  const unsigned tid = warp * 32 + lane;
+  Parked k;
+  k.ev = sj_ld_u4(slot + (pol * kScanWarps * 32 + tid) * 4);
+  k.prew = sj_ld_u32(slot + 2 * kScanWarps * 32 * 4 + tid);
+  return k;
 }
 
 // ------------------------------------------------------------------------------------------------ element summary
@@ -456,7 +486,7 @@ SJ_DEV void compose_element(Smem *S, const ScanParams &p, int ns, uint32_t t, un
     S->elem[ns][1] = b0;
     S->elem[ns][2] = b1;
     S->elem[ns][3] = hit0 | (hit1 << 1);
-    sj_st_relaxed_u64(p.count_desc + t, pack_agg(p.epoch, s0, b0, b1));
+    if (t > 0) sj_st_relaxed_u64(p.count_desc + t, pack_agg(p.epoch, s0, b0, b1));  // element 0 goes straight to inclusive
   }
   sj_syncwarp();
 }
@@ -493,6 +523,7 @@ SJ_DEV bool issue_load(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, 
   return full;
 }
 
+template <bool kDefer>
 SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, const Carry &cin, unsigned warp, unsigned lane) {
   const uint32_t nelem = p.ntiles;
   const uint64_t launch_start = uint64_t(p.tile_begin) * kTileBytes;
@@ -501,10 +532,11 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
   uint32_t pw_cur = 0x20202020u, pw_next = 0x20202020u;
   bool tma_cur = false, tma_next = false;
   // Warp 0 is the ticket master.  Tickets must not depend on the chain warp's progress (it may sit in a look-back
-  // while the scan warps run ahead).  In the steady state the ticket of element j+2 is taken at the start of iteration
-  // j and published after the scan, so nobody waits for the atomic's round trip to L2.  Tickets should be scanned in
-  // roughly the order they were taken (every element waits for ALL lower tickets): at start-up the second ticket is
-  // therefore taken only once the first block has arrived, when every CTA of the launch has its first ticket.
+  // while the scan warps run ahead), and a ticket is taken one iteration before it is published, so nobody ever
+  // waits for the atomic's round trip to L2.
+  // Tickets should be scanned in roughly the order they were taken (every element waits for ALL lower tickets): at
+  // start-up the second ticket is therefore taken only once the first block has arrived, when every CTA of the launch
+  // has drawn its first one.
   if (warp == 0) {
     uint32_t a0 = 0;
     if (lane == 0) a0 = sj_atomic_add(p.ticket, 1u);
@@ -518,32 +550,22 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
     if (lane == 0) a1 = sj_atomic_add(p.ticket, 1u);
     publish_ticket(S, 1, a1, lane);
   }
-  uint32_t ne = 0;  // this CTA's next element to emit (elements are emitted in order, as soon as they are resolved)
+  uint32_t ne = 0;  // this CTA's next element to emit (elements are emitted in order)
   uint32_t j = 0;
   for (;; j++) {
     if (t >= nelem) break;
     const int r = int(j & 1u);
-    // the scratch slot of element j must be free (only binds when resolution falls kPark elements behind)
-    while (ne + uint32_t(kPark) <= j) {
-      wait_bar(&S->resolved[ne % kNS], (ne / kNS) & 1u, p, 64);
-      emit_block(S, p, out_base, ne, warp, lane, reinterpret_cast<uint32_t *>(S->ring[warp][r ^ 1]), load_parked(S, p, ne, warp, lane));
-      ne++;
-    }
-    // if the next element to emit is resolved by now, fetch its parked words: the round trip overlaps the scan below
-    bool have_pre = false;
-    Parked pre;
-    pre.ev = sj_make_u4(0, 0, 0, 0);
-    pre.pre = 0;
-    if (ne < j) {
-      uint32_t ready = 0;
-      if (lane == 0) ready = sj_mbar_try_wait(&S->resolved[ne % kNS], (ne / kNS) & 1u) ? 1u : 0u;
-      if (sj_shfl(ready, 0)) {
-        pre = load_parked(S, p, ne, warp, lane);
-        have_pre = true;
+    if (kDefer) {
+      // the scratch slot of element j must be free (only binds when a CTA draws more than kParkD elements)
+      while (ne + uint32_t(kParkD) <= j) {
+        wait_bar(&S->resolved[ne % kNS], (ne / kNS) & 1u, p, 64);
+        const Parked k = load_parked(S, p, ne, warp, lane);
+        emit_block(S, p, out_base, ne, warp, lane, k.ev, k.prew, reinterpret_cast<uint32_t *>(S->ring[warp][r ^ 1]));
+        ne++;
       }
     }
     uint32_t t_acq = 0;
-    if (warp == 0 && lane == 0) t_acq = sj_atomic_add(p.ticket, 1u);  // element j+2 of this CTA
+    if (warp == 0 && lane == 0 && j > 0) t_acq = sj_atomic_add(p.ticket, 1u);  // element j+2 of this CTA (see below for j == 0)
     const uint32_t tn = wait_ticket(S, j + 1, p);
     if (tn < nelem) tma_next = issue_load(S, tmap, p, tn, warp, lane, r ^ 1, &pw_next);
     uint8_t *T = S->ring[warp][r];
@@ -563,7 +585,13 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
       }
       const uint32_t pw0 = sj_shfl(pw_cur, 0);
       const uint32_t st = boundary_state(p, bstart, launch_start, cin.state, pw0, lane);
-      summary = scan_block(T, pw0, st & 1u, (st >> 2) & 1u, lane, p, park_of(p, j, warp));
+      if (kDefer) {
+        uint32_t *slot = park_slot(p, j);
+        summary = scan_block(T, pw0, st & 1u, (st >> 2) & 1u, lane, p, reinterpret_cast<sj_u4 *>(slot), reinterpret_cast<sj_u4 *>(slot) + kScanWarps * 32,
+                             slot + 2 * kScanWarps * 32 * 4);
+      } else {
+        summary = scan_block(T, pw0, st & 1u, (st >> 2) & 1u, lane, p, S->park[j % kPark][0], S->park[j % kPark][1], S->parkpre[j % kPark]);
+      }
     }
     {
       const int ns = int(j % kNS);
@@ -583,101 +611,156 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
         }
       }
     }
-    if (warp == 0) publish_ticket(S, j + 2, t_acq, lane);
-    // emit what was found resolved before the scan (its words are here), then whatever else is resolved by now; never
-    // wait: the masks are parked, the scan goes on
-    if (have_pre) {
-      emit_block(S, p, out_base, ne, warp, lane, reinterpret_cast<uint32_t *>(T), pre);
-      ne++;
+    if (warp == 0) {
+      if (j == 0 && lane == 0) t_acq = sj_atomic_add(p.ticket, 1u);  // start-up: keep the third ticket behind everybody's second
+      publish_ticket(S, j + 2, t_acq, lane);
     }
-    if (ne <= j) {
-      uint32_t ready = 0;
-      if (lane == 0) ready = sj_mbar_try_wait(&S->resolved[ne % kNS], (ne / kNS) & 1u) ? 1u : 0u;
-      if (sj_shfl(ready, 0)) {
-        emit_block(S, p, out_base, ne, warp, lane, reinterpret_cast<uint32_t *>(T), load_parked(S, p, ne, warp, lane));
-        ne++;
-      }
+    if (!kDefer && j >= uint32_t(kLag)) {  // pipelined: the chain warp has had kLag scans' time to resolve this one
+      wait_bar(&S->resolved[ne % kNS], (ne / kNS) & 1u, p, 64);
+      emit_from_smem(S, p, out_base, ne, warp, lane, reinterpret_cast<uint32_t *>(T));
+      ne++;
     }
     t = tn;
     tma_cur = tma_next;
     pw_cur = pw_next;
   }
   // drain: what this CTA scanned and has not emitted yet (no load is in flight: both ring slots are free)
-  while (ne < j) {
-    wait_bar(&S->resolved[ne % kNS], (ne / kNS) & 1u, p, 64);
-    emit_block(S, p, out_base, ne, warp, lane, reinterpret_cast<uint32_t *>(S->ring[warp][0]), load_parked(S, p, ne, warp, lane));
-    ne++;
+  if (kDefer) {
+    // deferred mode emits everything here: the scan phase ran without ever waiting for the chain.  The parked words of
+    // the next element are fetched while the current one is emitted.
+    bool have = false;
+    Parked cur;
+    cur.ev = sj_make_u4(0, 0, 0, 0);
+    cur.prew = 0;
+    while (ne < j) {
+      if (!have) {
+        wait_bar(&S->resolved[ne % kNS], (ne / kNS) & 1u, p, 64);
+        cur = load_parked(S, p, ne, warp, lane);
+      }
+      have = false;
+      Parked nxt;
+      nxt.ev = sj_make_u4(0, 0, 0, 0);
+      nxt.prew = 0;
+      if (ne + 1 < j) {
+        uint32_t ready = 0;
+        if (lane == 0) ready = sj_mbar_try_wait(&S->resolved[(ne + 1) % kNS], ((ne + 1) / kNS) & 1u) ? 1u : 0u;
+        if (sj_shfl(ready, 0)) {
+          nxt = load_parked(S, p, ne + 1, warp, lane);
+          have = true;
+        }
+      }
+      emit_block(S, p, out_base, ne, warp, lane, cur.ev, cur.prew, reinterpret_cast<uint32_t *>(S->ring[warp][ne & 1u]));
+      cur = nxt;
+      ne++;
+    }
+  } else {
+    while (ne < j) {
+      wait_bar(&S->resolved[ne % kNS], (ne / kNS) & 1u, p, 64);
+      emit_from_smem(S, p, out_base, ne, warp, lane, reinterpret_cast<uint32_t *>(S->ring[warp][0]));
+      ne++;
+    }
   }
 }
 
-// ------------------------------------------------------------------------------------------------ resolver
-// ONE warp of the whole launch (in the CTA that drew ticket 0, so it is resident by construction) turns aggregates
-// into inclusive prefixes, in element order: it polls a window of 32*kLookK descriptors (k-major: every load
-// instruction of the warp reads 256 contiguous bytes), takes the longest prefix of the window that has arrived,
-// computes each element's inclusive (in-string, count) -- quote parities of 32 elements are one ballot word, an element's
-// polarity is a popcount, counts are warp prefix sums -- and stores them over the aggregates.  Every other CTA only
-// polls its own descriptor.
-// (A decoupled look-back by every CTA was measured first: ~300 warps polling the same twenty cache lines of L2 made
-// one poll take 2-10 us, resolution fell behind the scan, the backlog lengthened the walks, and it never recovered.)
-SJ_DEV void resolver_role(Smem *S, const ScanParams &p, const Carry &cin, unsigned lane) {
-  if (wait_ticket(S, 0, p) != 0u) return;  // not the CTA that drew ticket 0
-  const uint32_t nelem = p.ntiles;
-  const uint32_t key_agg = (p.epoch << 2) | kDescAgg;
-  const uint32_t lt = (1u << lane) - 1u;
-  uint32_t s = (cin.state >> 1) & 1u;  // in-string entering element `next`
-  uint32_t base = 0;                   // outputs of the launch before element `next`
-  uint32_t next = 0;
-  uint32_t idle = 0;
-  while (next < nelem) {
+// ------------------------------------------------------------------------------------------------ chain warp
+
+// Decoupled look-back: in-string state and output count entering element t (t >= 1).
+// A window is 32*kLookK descriptors, laid out k-major: load k of lane L is the descriptor at distance 32k + L behind
+// t-1, so every load instruction of the warp reads 256 contiguous bytes (all CTAs poll the same few cache lines of L2:
+// with a lane-major layout every poll was ~200 line requests per warp and the chain warps queued behind one another).
+// The window is complete when everything newer than the nearest inclusive prefix has arrived.  Folding uses the fact
+// that only one bit is order-dependent: the quote parities of a group of 32 elements are one ballot word, an element's
+// polarity relative to the oldest element of the window is a popcount, and the counts are then plain sums.
+SJ_DEV void look_back(const ScanParams &p, uint32_t t, unsigned lane, uint32_t *s_in, uint32_t *base) {
+  Eff acc;
+  acc.p = 0; acc.a = 0; acc.b = 0;
+  int64_t newest = int64_t(t) - 1;
+  const uint32_t key_agg = (p.epoch << 2) | kDescAgg;  // bits [63:44] of a descriptor of this launch: key_agg or key_agg + 1
+  for (;;) {
+    const int64_t first = newest - int64_t(lane);  // my k-th descriptor is first - 32k
     unsigned long long d[kLookK];
-    uint32_t want = 0;
+    uint32_t pend = 0;  // bit k: wanted and not yet arrived
 #pragma unroll
     for (int k = 0; k < kLookK; k++) {
       d[k] = 0;
-      if (next + 32u * k + lane < nelem) {
-        want |= 1u << k;
-        d[k] = sj_ld_relaxed_u64(p.count_desc + (next + 32u * k + lane));
-      }
+      if (first - 32 * k >= 0) pend |= 1u << k;
     }
-    // the longest prefix of the window that has arrived
-    uint32_t bad = 0xFFFFFFFFu;  // my first element that has not
+    const uint32_t want = pend;
+    uint32_t inc_dist = 0xFFFFFFFFu, needed = (1u << kLookK) - 1u;
+    uint32_t spins = 0;
+    for (;;) {
+      // one poll: independent predicated loads straight into d[k] (a word that has not arrived is simply loaded again
+      // by the next poll), then three independent instructions per word
+      const uint32_t todo = pend;
 #pragma unroll
-    for (int k = kLookK - 1; k >= 0; k--)
-      if (((want >> k) & 1u) && (uint32_t(d[k] >> 44) != key_agg)) bad = 32u * k + lane;
-    uint32_t m = sj_reduce_min(bad);
-    const uint32_t left = nelem - next;
-    if (m > left) m = left;
-    if (m > 32u * kLookK) m = 32u * kLookK;
-    if (m == 0) {
-      if (++idle > kSpinLimit4) {  // never expected: give up; the owners will time out and report
+      for (int k = 0; k < kLookK; k++)
+        if (todo & (1u << k)) d[k] = sj_ld_relaxed_u64(p.count_desc + (first - 32 * k));
+      uint32_t okm = 0, incm = 0;
+#pragma unroll
+      for (int k = 0; k < kLookK; k++) {
+        const uint32_t rel = uint32_t(d[k] >> 44) - key_agg;  // 0: aggregate, 1: inclusive, anything else: not this launch's
+        if (rel <= 1u) okm |= 1u << k;
+        if (rel == 1u) incm |= 1u << k;
+      }
+      pend &= ~okm;
+      incm &= want;
+      // nearest inclusive prefix: for one lane a smaller k is nearer
+      const uint32_t my_dist = incm ? uint32_t(sj_ffs(incm) - 1) * 32u + lane : 0xFFFFFFFFu;
+      inc_dist = sj_reduce_min(my_dist);
+      if (inc_dist != 0xFFFFFFFFu) {  // needed: distance < inc_dist  <=>  k < ceil((inc_dist - lane) / 32)
+        const uint32_t nk = (inc_dist > lane) ? (inc_dist - lane + 31u) / 32u : 0u;
+        needed = (1u << nk) - 1u;
+      }
+      if (!sj_any((pend & needed) != 0)) break;
+      if (++spins > kSpinLimit4) {  // never expected: report, and finish with what there is
         sj_atomic_or(p.flags, kFlagInternal);
-        return;
+        break;
       }
 #if SJB200_SCAN4_SLEEP
       sj_nanosleep(100);
 #endif
-      continue;
     }
-    idle = 0;
+    // ---- fold the aggregates newer than the inclusive prefix
+    const uint32_t use = want & ~pend & needed;
+    uint32_t bal[kLookK];
 #pragma unroll
-    for (int k = 0; k < kLookK; k++) {
-      if (32u * k >= m) break;  // uniform
-      const bool use = 32u * k + lane < m;
-      const uint32_t par = use ? (uint32_t(d[k] >> 38) & 1u) : 0u;
-      const uint32_t bal = sj_ballot(par != 0);
-      const uint32_t pol = (s ^ uint32_t(sj_popc(bal & lt))) & 1u;  // in-string entering my element
-      const uint32_t a = uint32_t(d[k]) & 0x7FFFFu, b = uint32_t(d[k] >> 19) & 0x7FFFFu;
-      uint32_t incl = use ? (pol ? b : a) : 0u;
+    for (int k = 0; k < kLookK; k++) bal[k] = sj_ballot(((use >> k) & 1u) && ((uint32_t(d[k] >> 38) & 1u) != 0));
+    uint32_t older = 0;  // parity of everything older than group k (uniform)
+    uint32_t sa = 0, sb = 0;
 #pragma unroll
-      for (int dd = 1; dd < 32; dd <<= 1) {
-        const uint32_t o = sj_shfl_up(incl, dd);
-        if (int(lane) >= dd) incl += o;
+    for (int k = kLookK - 1; k >= 0; k--) {
+      const uint32_t rel = (uint32_t(sj_popc((bal[k] >> lane) >> 1)) ^ older) & 1u;  // my element's polarity relative to the window's oldest
+      if ((use >> k) & 1u) {
+        const uint32_t a = uint32_t(d[k]) & 0x7FFFFu, b = uint32_t(d[k] >> 19) & 0x7FFFFu;
+        sa += rel ? b : a;
+        sb += rel ? a : b;
       }
-      if (use) sj_st_relaxed_u64(p.count_desc + (next + 32u * k + lane), pack_inc(p.epoch, pol ^ par, base + incl));
-      base += sj_shfl(incl, 31);
-      s ^= uint32_t(sj_popc(bal)) & 1u;
+      older ^= uint32_t(sj_popc(bal[k])) & 1u;
     }
-    next += m;
+    Eff win;
+    win.p = older;
+    win.a = sj_reduce_add(sa);
+    win.b = sj_reduce_add(sb);
+    acc = compose(win, acc);
+    if (inc_dist != 0xFFFFFFFFu) {
+      const uint32_t ik = inc_dist >> 5, il = inc_dist & 31u;
+      uint32_t sk = 0, ck = 0;
+#pragma unroll
+      for (int k = 0; k < kLookK; k++)
+        if (uint32_t(k) == ik) { sk = uint32_t(d[k] >> 32) & 1u; ck = uint32_t(d[k]); }
+      sk = sj_shfl(sk, int(il));
+      ck = sj_shfl(ck, int(il));
+      *s_in = sk ^ acc.p;
+      *base = ck + (sk ? acc.b : acc.a);
+      return;
+    }
+    newest -= 32 * kLookK;
+    if (newest < 0) {  // cannot happen (element 0 always publishes an inclusive prefix); never loop forever
+      sj_atomic_or(p.flags, kFlagInternal);
+      *s_in = acc.p;
+      *base = acc.a;
+      return;
+    }
   }
 }
 
@@ -719,50 +802,36 @@ SJ_DEV void finalize_launch(const ScanParams &p, const Carry &cin, uint32_t s_ou
   }
 }
 
-// ------------------------------------------------------------------------------------------------ owner warp
-// One per CTA: waits for each of the CTA's elements to be scanned, then for the resolver to turn its descriptor into
-// an inclusive prefix (polling ONE word, its own), and posts every block's polarity and output offset to the scan warps.
-SJ_DEV void owner_role(Smem *S, const ScanParams &p, const Carry &cin, unsigned lane) {
+SJ_DEV void chain_role(Smem *S, const ScanParams &p, const Carry &cin, unsigned lane, unsigned c) {
   const uint32_t nelem = p.ntiles;
-  const uint32_t key_inc = (p.epoch << 2) | kDescInc;
-  for (uint32_t j = 0;; j++) {
+  for (uint32_t j = c;; j += uint32_t(kChainWarps)) {
     const int ns = int(j % kNS);
     const uint32_t t = wait_ticket(S, j, p);
     if (t >= nelem) break;
     wait_bar(&S->scanned[ns], (j / kNS) & 1u, p, 200);
     if (p.debug != nullptr && lane == 0) p.debug[uint64_t(t) * 8 + 6] = sj_globaltimer();
     const uint32_t par = S->elem[ns][0], b0 = S->elem[ns][1], b1 = S->elem[ns][2], hits = S->elem[ns][3];
-    unsigned long long d = 0;
-    uint32_t spins = 0;
-    for (;;) {
-      d = sj_ld_relaxed_u64(p.count_desc + t);  // every lane reads the same word: one request
-      if (uint32_t(d >> 44) == key_inc) break;
-      if (++spins > kSpinLimit4) {
-        sj_atomic_or(p.flags, kFlagInternal);
-        break;
-      }
-#if SJB200_SCAN4_SLEEP
-      sj_nanosleep(200);
-#endif
-    }
-    const uint32_t s_out = uint32_t(d >> 32) & 1u, through = uint32_t(d);
-    const uint32_t s_in = s_out ^ par;
+    uint32_t s_in = (cin.state >> 1) & 1u, base = 0;
+    if (t > 0) look_back(p, t, lane, &s_in, &base);
     const uint32_t mine_total = s_in ? b1 : b0;
-    const uint32_t base = through - mine_total;
+    const uint32_t s_out = s_in ^ par;
+    if (lane == 0) sj_st_relaxed_u64(p.count_desc + t, pack_inc(p.epoch, s_out, base + mine_total));
     if (lane < uint32_t(kScanWarps)) {
       const uint32_t pk = S->pre[ns][s_in][lane];
       S->res_pol[ns][lane] = pk >> 31;
       S->res_base[ns][lane] = base + (pk & 0x7FFFFFFFu);
     }
-    if (lane == 0 && ((hits >> s_in) & 1u)) sj_atomic_or(p.flags, kFlagCtl);
+    const uint32_t hit0 = hits & 1u, hit1 = (hits >> 1) & 1u;
+    if (lane == 0 && (s_in ? hit1 : hit0)) sj_atomic_or(p.flags, kFlagCtl);
     sj_syncwarp();
     if (lane == 0) sj_mbar_arrive(&S->resolved[ns]);
     if (p.debug != nullptr && lane == 0) p.debug[uint64_t(t) * 8 + 4] = sj_globaltimer();
-    if (t == nelem - 1) finalize_launch(p, cin, s_out, cin.count + through, lane);
+    if (t == nelem - 1) finalize_launch(p, cin, s_out, cin.count + base + mine_total, lane);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel body
+template <bool kDefer>
 SJ_DEV void scan4_body(const sj_tensor_map *tmap, const ScanParams &p, uint8_t *smem_raw, uint32_t smem_raw_addr) {
   // 1 KiB alignment for the 128B swizzle, computed on the shared-space address so the pointer keeps its address space
   Smem *S = reinterpret_cast<Smem *>(smem_raw + ((1024u - (smem_raw_addr & 1023u)) & 1023u));
@@ -784,9 +853,8 @@ SJ_DEV void scan4_body(const sj_tensor_map *tmap, const ScanParams &p, uint8_t *
     sj_fence_mbar_init();
   }
   sj_syncthreads();
-  if (warp < unsigned(kScanWarps)) scan_role(S, tmap, p, cin, warp, lane);
-  else if (warp == unsigned(kScanWarps)) owner_role(S, p, cin, lane);
-  else resolver_role(S, p, cin, lane);
+  if (warp < unsigned(kScanWarps)) scan_role<kDefer>(S, tmap, p, cin, warp, lane);
+  else chain_role(S, p, cin, lane, warp - unsigned(kScanWarps));
   // last CTA out resets the ticket for the next launch on this context and hands the flags over
   sj_syncthreads();
   if (tid == 0) {

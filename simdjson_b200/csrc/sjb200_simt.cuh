@@ -22,7 +22,7 @@
 #include <new>
 
 #define SJ_DEV inline
-#define SJ_DEV_NOINLINE inline
+#define SJ_DEV_NOINLINE
 
 namespace sjb200 {
 namespace simt {

@@ -32,6 +32,7 @@ struct LaunchArgs {
   unsigned grid;
   const sj_tensor_map *tmap;
   const ScanParams *p;
+  bool deferred;
 };
 
 void *thread_main(void *arg);
@@ -49,13 +50,14 @@ void *thread_main(void *arg) {
   simt::tctx.nctas = a->la->grid;
   simt::tctx.warp = a->warp;
   simt::tctx.ctas = a->cta;
-  scan4::scan4_body(a->la->tmap, *a->la->p, a->cta->smem, uint32_t(reinterpret_cast<uintptr_t>(a->cta->smem)));
+  if (a->la->deferred) scan4::scan4_body<true>(a->la->tmap, *a->la->p, a->cta->smem, uint32_t(reinterpret_cast<uintptr_t>(a->cta->smem)));
+  else scan4::scan4_body<false>(a->la->tmap, *a->la->p, a->cta->smem, uint32_t(reinterpret_cast<uintptr_t>(a->cta->smem)));
   return nullptr;
 }
 
-void emu_launch(unsigned grid, const sj_tensor_map &tmap, const ScanParams &p) {
+void emu_launch(unsigned grid, const sj_tensor_map &tmap, const ScanParams &p, bool deferred) {
   const unsigned T = scan4::kThreads4, W = T / 32;
-  LaunchArgs la{grid, &tmap, &p};
+  LaunchArgs la{grid, &tmap, &p, deferred};
   std::vector<simt::CtaShared> ctas(grid);
   std::vector<simt::WarpShared> warps(size_t(grid) * W);
   std::vector<ThreadArg> args(size_t(grid) * T);
@@ -83,6 +85,8 @@ void emu_launch(unsigned grid, const sj_tensor_map &tmap, const ScanParams &p) {
     for (unsigned w = 0; w < W; w++) pthread_barrier_destroy(&warps[c * W + w].bar);
   }
 }
+
+bool g_deferred = false;  // which variant of the kernel the next launches run
 
 // what sjb200_capi.cu keeps per context
 struct EmuCtx {
@@ -131,11 +135,11 @@ Result run_scan4(EmuCtx &cx, const uint8_t *buf, size_t len, uint32_t state_in, 
     p.carry_in = &cx.carry[slot];
     p.carry_out = &cx.carry[slot + 1];
     p.flags = &cx.flags; p.count_desc = cx.desc.data(); p.ticket = cx.ticket; p.debug = nullptr;
-    const unsigned g = std::min<unsigned>(grid, nt);
-    cx.park.assign(size_t(g) * scan4::kPark * scan4::kScanWarps * scan4::kParkWords + 4, 0xDEADBEEFu);
-    p.park = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(cx.park.data()) + 15) & ~uintptr_t(15));
     cx.carry[slot + 1] = Carry();
-    emu_launch(std::min<unsigned>(grid, nt), tmap, p);
+    const unsigned g = std::min<unsigned>(grid, nt);
+    cx.park.assign(size_t(g) * scan4::kParkD * scan4::kParkSlotWords + 4, 0xDEADBEEFu);
+    p.park = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(cx.park.data()) + 15) & ~uintptr_t(15));
+    emu_launch(g, tmap, p, g_deferred);
     if (cx.ticket[0] != 0 || cx.ticket[1] != 0 || cx.flags != 0) { fprintf(stderr, "BUG: ticket/flags not re-armed\n"); exit(2); }
     flags |= cx.carry[slot + 1].flags;
     slot++;
@@ -206,81 +210,73 @@ int check(EmuCtx &cx, const std::vector<uint8_t> &store, size_t misalign, uint32
   return bad;
 }
 
-// ---- the resolver on its own: one emulated warp turns up to ~1500 aggregates into inclusive prefixes while a feeder
-// thread publishes them in bursts (partial windows, all ten k-groups, several windows); checked against a scalar walk
-struct RsArgs {
-  scan4::Smem *S;
+// ---- the look-back fold on its own: one emulated warp against a scalar walk, with the nearest inclusive prefix up to
+// three windows away and stale / missing descriptors behind it (the multi-CTA runs above only reach short distances)
+struct LbArgs {
   const ScanParams *p;
-  Carry cin;
+  uint32_t t;
   simt::WarpShared *warp;
   simt::CtaShared *cta;
   unsigned lane;
+  uint32_t s_in, base;
 };
-void *rs_thread(void *arg) {
-  RsArgs *a = static_cast<RsArgs *>(arg);
+void *lb_thread(void *arg) {
+  LbArgs *a = static_cast<LbArgs *>(arg);
   simt::tctx = simt::ThreadCtx();
   simt::tctx.tid = a->lane;
   simt::tctx.nctas = 1;
   simt::tctx.warp = a->warp;
   simt::tctx.ctas = a->cta;
-  scan4::resolver_role(a->S, *a->p, a->cin, a->lane);
+  scan4::look_back(*a->p, a->t, a->lane, &a->s_in, &a->base);
   return nullptr;
 }
-int test_resolver(std::mt19937_64 &rng, int cases) {
+int test_look_back(std::mt19937_64 &rng, int cases) {
   int bad = 0;
   for (int c = 0; c < cases && bad < 3; c++) {
-    const uint32_t n = 1 + uint32_t(rng() % (c % 3 == 0 ? 1500 : 400));
+    const uint32_t t = 1 + uint32_t(rng() % 1500);
     const uint32_t epoch = 1 + uint32_t(rng() % 1000);
-    std::vector<unsigned long long> agg(n), desc(n + 1, 0ull), want(n);
-    const uint32_t s0 = uint32_t(rng() & 1);
-    uint32_t s = s0;
-    uint64_t cnt = 0;
-    for (uint32_t i = 0; i < n; i++) {
-      const uint32_t par = uint32_t(rng() & 1), c0 = uint32_t(rng() % 32769), c1 = uint32_t(rng() % 32769);
-      agg[i] = scan4::pack_agg(epoch, par, c0, c1);
-      cnt += s ? c1 : c0;
-      s ^= par;
-      want[i] = scan4::pack_inc(epoch, s, uint32_t(cnt));
-      if (rng() % 5 == 0) desc[i] = scan4::pack_agg(epoch - 1, par, c1, c0);  // stale word of an earlier launch
-    }
+    std::vector<unsigned long long> desc(t + 1, 0ull);
     uint32_t flags = 0;
+    // nearest inclusive prefix at `inc`; everything newer is an aggregate; older entries are junk that must not matter
+    const uint32_t maxback = std::min<uint32_t>(t, 1 + uint32_t(rng() % 1000));
+    const uint32_t inc = t - 1 - uint32_t(rng() % maxback);
+    const uint32_t s_k = uint32_t(rng() & 1), c_k = uint32_t(rng() % 100000000u);
+    for (uint32_t i = 0; i < t; i++) {
+      const uint32_t par = uint32_t(rng() & 1), c0 = uint32_t(rng() % 32769), c1 = uint32_t(rng() % 32769);
+      if (i > inc) desc[i] = scan4::pack_agg(epoch, par, c0, c1);
+      else if (i == inc) desc[i] = scan4::pack_inc(epoch, s_k, c_k);
+      else {
+        const int kind = int(rng() % 4);
+        desc[i] = kind == 0 ? 0ull : kind == 1 ? scan4::pack_agg(epoch - 1, par, c0, c1) : kind == 2 ? scan4::pack_inc(epoch, par, c0) : scan4::pack_agg(epoch, par, c0, c1);
+      }
+    }
+    desc[0] = (inc == 0) ? desc[0] : scan4::pack_inc(epoch, uint32_t(rng() & 1), 12345);  // element 0 is always inclusive
+    uint32_t s = s_k;
+    uint64_t cnt = c_k;
+    for (uint32_t i = inc + 1; i < t; i++) {
+      const unsigned long long d = desc[i];
+      cnt += s ? (uint32_t(d >> 19) & 0x7FFFFu) : (uint32_t(d) & 0x7FFFFu);
+      s ^= uint32_t(d >> 38) & 1u;
+    }
     ScanParams p;
     memset(&p, 0, sizeof(p));
-    p.epoch = epoch; p.count_desc = desc.data(); p.flags = &flags; p.ntiles = n;
-    std::vector<uint8_t> smem(sizeof(scan4::Smem) + 64);
-    scan4::Smem *S = reinterpret_cast<scan4::Smem *>((reinterpret_cast<uintptr_t>(smem.data()) + 63) & ~uintptr_t(63));
-    sj_mbar_init(&S->ticket_ready[0], 1);
-    S->ticket[0] = 0;
-    sj_mbar_arrive(&S->ticket_ready[0]);
+    p.epoch = epoch; p.count_desc = desc.data(); p.flags = &flags;
     simt::WarpShared w;
     simt::CtaShared cta;
     pthread_barrier_init(&w.bar, nullptr, 32);
-    std::vector<RsArgs> args(32);
+    std::vector<LbArgs> args(32);
     std::vector<pthread_t> th(32);
-    Carry cin = Carry();
-    cin.state = s0 << 1;
     for (unsigned l = 0; l < 32; l++) {
-      args[l] = RsArgs{S, &p, cin, &w, &cta, l};
-      pthread_create(&th[l], nullptr, rs_thread, &args[l]);
-    }
-    // feeder: aggregates arrive out of order inside bursts
-    std::vector<uint32_t> order(n);
-    for (uint32_t i = 0; i < n; i++) order[i] = i;
-    for (uint32_t i = 0; i < n; i++) {
-      const uint32_t span = 1 + uint32_t(rng() % 97);
-      const uint32_t jx = i + uint32_t(rng() % span);
-      if (jx < n) std::swap(order[i], order[jx]);
-    }
-    for (uint32_t i = 0; i < n; i++) {
-      __atomic_store_n(&desc[order[i]], agg[order[i]], __ATOMIC_RELEASE);
-      if (rng() % 64 == 0) { struct timespec ts = {0, 30000}; nanosleep(&ts, nullptr); }
+      args[l] = LbArgs{&p, t, &w, &cta, l, 0, 0};
+      pthread_create(&th[l], nullptr, lb_thread, &args[l]);
     }
     for (auto &x : th) pthread_join(x, nullptr);
     pthread_barrier_destroy(&w.bar);
-    for (uint32_t i = 0; i < n && !bad; i++)
-      if (desc[i] != want[i] || flags != 0) {
-        fprintf(stderr, "RESOLVER MISMATCH n=%u i=%u: got %llx want %llx flags=%u\n", n, i, desc[i], want[i], flags);
+    for (unsigned l = 0; l < 32; l++)
+      if (args[l].s_in != s || args[l].base != uint32_t(cnt) || flags != 0) {
+        fprintf(stderr, "LOOK-BACK MISMATCH t=%u inc=%u lane=%u: got (%u,%u) want (%u,%u) flags=%u\n", t, inc, l, args[l].s_in, args[l].base, s, uint32_t(cnt), flags);
         bad++;
+        break;
       }
   }
   return bad;
@@ -294,7 +290,7 @@ int main(int argc, char **argv) {
   const char *alphabets[] = {"\\\\\\\"\" {}[],: \n\tabc1\x01\x0c\x1a\x1e", "\\\"", "\\\\\\\\\\\\\\\"a ", "\"{}[],:0 ", " \n\r\t\"a\\", ",{}[] 1 \"a\":\n"};
   const char *utf8bits[] = {"\xc3\xa9", "\xe2\x82\xac", "\xf0\x9f\x98\x80", "\xff", "\xc3", "\xe2\x82", "\xf0\x9f\x98", "\x80", "\xed\xa0\x80", "\xc0\xaf", "\xf4\x90\x80\x80", "\xe0\x9f\xbf", "\xf0\x8f\xbf\xbf", "\xf5\x80\x80\x80", "\xed\x9f\xbf", "\xf4\x8f\xbf\xbf", "\xe0\xa0\x80", "\xf0\x90\x80\x80", "\xc2\x80", "\xdf\xbf"};
   EmuCtx cx;
-  g_fail += test_resolver(rng, 120);
+  g_fail += test_look_back(rng, 300);
   for (int it = 0; it < iters && g_fail < 5; it++) {
     std::vector<uint8_t> in;
     const int kind = int(rng() % 8);
@@ -362,7 +358,8 @@ int main(int argc, char **argv) {
     if (reinterpret_cast<uintptr_t>(buf0.data()) & 15u) { fprintf(stderr, "unaligned vector storage\n"); return 3; }
     const unsigned grid = 1 + unsigned(rng() % 3);
     const uint32_t state_in = (force_state != 0xFFFFFFFFu) ? force_state : ((rng() % 3 == 0) ? uint32_t(rng() % 8) : 0u);
-    check(cx, buf0, 0, state_in, 0, grid, true, "tma");
+    g_deferred = (it & 1) != 0;  // alternate between the pipelined and the deferred variant
+    check(cx, buf0, 0, state_in, 0, grid, true, g_deferred ? "tma, deferred" : "tma, pipelined");
     if (it % 3 == 0) check(cx, buf0, 0, state_in, 1 + uint32_t(rng() % 3), grid, true, "chunked");
     if (it % 4 == 1) check(cx, buf0, 0, state_in, 0, grid, false, "plain loads");
     if (it % 4 == 2 && buf0.size() > 3) check(cx, buf0, 1 + rng() % 3, state_in, 0, grid, true, "misaligned");

@@ -17,6 +17,8 @@ doc = corpus.random_json(size).copy()
 rc, p = sj.get_active_implementation().create_dom_parser_implementation(len(doc))
 p.set_option("debug_timeline", 1)
 p.set_option("time_kernel", 1)
+if os.environ.get("PROBE_DEFERRED"):
+    p.set_option("deferred", int(os.environ["PROBE_DEFERRED"]))
 if os.environ.get("PROBE_KERNEL"):
     p.set_option("kernel", int(os.environ["PROBE_KERNEL"]))
 if os.environ.get("PROBE_R"):
