@@ -307,7 +307,7 @@ def run_ours(args, rank, world):
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": DOC_BYTES, "d2h_bytes_per_step": int(4 * e2e_n + 24), "steps": e2e_steps},
             "gpu_launches": int(launches2 - launches1),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
-                         "peak_source": peak_src, "kernel": "sjb200::scan_kernel<kIndex>", "kernel_ms": round(kms, 5), "algorithmic_bytes": int(algo_bytes),
+                         "peak_source": peak_src, "kernel": "sjb200::scan4_deferred_kernel / scan4_kernel (sjb200_scan4.cuh)", "kernel_ms": round(kms, 5), "algorithmic_bytes": int(algo_bytes),
                          "input_gbs_kernel_only": round(DOC_BYTES / (kms * 1e-3) / 1e9, 1)},
         }
         line["cpu_baseline"] = cpu_baseline(docs[0])

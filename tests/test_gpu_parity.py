@@ -9,6 +9,7 @@ import random
 import threading
 
 import numpy as np
+import torch
 import pytest
 
 import oracle_lib as O
@@ -171,6 +172,33 @@ def test_fuzz_multi_tile(parser, port, use_tma, sub_per_super):
     finally:
         parser.set_option("use_tma", 1)
         parser.set_option("sub_per_super", 0)
+
+
+@pytest.mark.parametrize("kernel,deferred", [(4, 0), (4, 2), (4, 1), (3, 0)])
+def test_stage1_kernel_variants(port, kernel, deferred):
+    """every stage-1 kernel the library can launch gives the oracle's answer: scan4 pipelined (deferred=0), scan4 with
+    deferred emit forced (2) or chosen by size (1), and the tile-synchronous scan_kernel<kIndex> (kernel=3); sizes from
+    one partial block to more elements than one wave of CTAs holds, so rings wrap and the deferred ring's blocking path runs"""
+    rc, parser = sj.get_active_implementation().create_dom_parser_implementation(32 << 20)
+    assert rc == sj.SUCCESS
+    parser.set_option("kernel", kernel)
+    parser.set_option("deferred", deferred)
+    try:
+        rng = random.Random(corpus.SEED ^ 0x4D ^ (kernel << 8) ^ deferred)
+        sizes = [1, 4095, 4096, 4097, TILE, TILE + 1, 7 * TILE + 4100, 300 * TILE + 77, 31 * (1 << 20) + 12345]
+        for n in sizes:
+            b = _big_adversarial(rng, n) if n < (8 << 20) else (_big_adversarial(rng, 1 << 20) * 32)[:n]
+            for mode in (0, 2):
+                assert_same(run_stage1(parser, b, mode), port.stage1(b, mode), (kernel, deferred, n, mode))
+        doc = corpus.random_json(24 << 20)
+        d = torch.from_numpy(doc.copy()).cuda()
+        want = port.stage1(doc, 0)
+        rc = parser.stage1_device(d, 0)
+        got = parser.device_index_buffer().cpu().numpy().view(np.uint32)
+        assert rc == want.err and parser.n_structural_indexes == want.n
+        assert np.array_equal(got[: want.n + 3], want.words())
+    finally:
+        parser.close()
 
 
 def test_valid_documents_and_streams(parser, port):
