@@ -59,7 +59,7 @@ struct sjb200_ctx {
   size_t desc_tiles = 0;
   uint8_t *d_chars = nullptr; size_t d_chars_bytes = 0;
   uint32_t *d_park = nullptr; size_t d_park_words = 0;  // scan4 deferred mode: parked masks (a per-CTA ring, independent of the input size)
-  long opt_deferred = 1;  // 1: launches that fit use the deferred variant of scan4; 0: never; 2: always
+  long opt_deferred = 0;  // 0: never use the deferred variant of scan4 (default until measured better); 1: for launches that fit; 2: always
   // pinned host mirrors
   Carry *h_carry = nullptr;     // [kCarrySlots]
   uint32_t *h_flags = nullptr;
@@ -197,7 +197,8 @@ int grid_for(sjb200_ctx *c, int kind, uint32_t nelements) {
 // Enqueue the scan of document tiles [tile_begin, tile_begin+ntiles) of (d_buf,len).
 bool enqueue_scan(sjb200_ctx *c, int kind, const CUtensorMap *map, bool tma, const uint8_t *d_buf, size_t len, uint32_t tile_begin,
                   uint32_t ntiles, bool has_last_tile, uint32_t prev_word, uint32_t *d_idx, uint8_t *d_dst, int carry_in_slot,
-                  cudaStream_t stream, int carry_out_slot = -1, bool write_sentinels = false, Carry *external_out = nullptr) {
+                  cudaStream_t stream, int carry_out_slot = -1, bool write_sentinels = false, Carry *external_out = nullptr,
+                  Carry *host_out = nullptr) {
   // carry_in_slot < 0: the launch starts a document (zero state, zero count)
   if (carry_out_slot < 0) carry_out_slot = (carry_in_slot < 0) ? 1 : (carry_in_slot ^ 1);
   ScanParams p;
@@ -225,6 +226,7 @@ bool enqueue_scan(sjb200_ctx *c, int kind, const CUtensorMap *map, bool tma, con
   p.carry_in = (carry_in_slot < 0) ? nullptr : c->d_carry + carry_in_slot;
   p.write_sentinels = write_sentinels ? 1u : 0u;
   p.carry_out = external_out ? external_out : c->d_carry + carry_out_slot;
+  p.carry_out_host = use_scan4(c, kind) ? host_out : nullptr;
   p.flags = c->d_flags;
   p.count_desc = c->d_count_desc;
   p.ticket = c->d_ticket;
@@ -253,9 +255,11 @@ bool enqueue_scan(sjb200_ctx *c, int kind, const CUtensorMap *map, bool tma, con
     bool tma4 = false;
     make_tensor_map(c, &map4, d_buf, len, &tma4, kScan4BoxRows);
     p.use_tma = (tma && tma4) ? 1u : 0u;
-    const int grid = grid_for(c, kind, ntiles);
+    const uint32_t tpe = uint32_t(scan4_tiles_per_element());
+    const uint32_t nelem = (ntiles + tpe - 1) / tpe;
+    const int grid = grid_for(c, kind, nelem);
     // deferred emit when every CTA can hold all the elements it will draw (small launches: one wave of CTAs)
-    bool deferred = c->opt_deferred == 2 || (c->opt_deferred == 1 && uint64_t(ntiles) * 4 <= uint64_t(grid) * uint64_t(scan4_deferred_capacity()) * 3);
+    bool deferred = c->opt_deferred == 2 || (c->opt_deferred == 1 && uint64_t(nelem) * 4 <= uint64_t(grid) * uint64_t(scan4_deferred_capacity()) * 3);
     if (deferred) {
       const size_t need = scan4_park_words(grid_cap(c, kind));
       if (c->d_park_words < need) {
@@ -534,8 +538,11 @@ void stage1_enqueue_into(sjb200_ctx *c, PendingCall &pc, const uint8_t *d_buf, s
   CUtensorMap map;
   bool tma = false;
   make_tensor_map(c, &map, d_buf, len, &tma);
-  if (!enqueue_scan(c, kIndex, &map, tma, d_buf, len, 0, tiles_of(len), true, 0x20202020u, d_idx, nullptr, -1, s, slot, true) ||
-      !ok(c, cudaMemcpyAsync(c->h_carry + slot, c->d_carry + slot, sizeof(Carry), cudaMemcpyDeviceToHost, s), "D2H result"))
+  // scan4 stores its result in the pinned host mirror itself; the older kernel needs the copy engine for it
+  if (!enqueue_scan(c, kIndex, &map, tma, d_buf, len, 0, tiles_of(len), true, 0x20202020u, d_idx, nullptr, -1, s, slot, true, nullptr,
+                    c->h_carry + slot) ||
+      (!use_scan4(c, kIndex) &&
+       !ok(c, cudaMemcpyAsync(c->h_carry + slot, c->d_carry + slot, sizeof(Carry), cudaMemcpyDeviceToHost, s), "D2H result")))
     pc.early_error = SJB200_UNEXPECTED_ERROR;
 }
 

@@ -865,12 +865,12 @@ __global__ void __launch_bounds__(kThreads, (KIND == kUtf8) ? 4 : kMinCtasPerSm)
 // two variants of one source: pipelined (masks wait in shared memory, an element is emitted two scans after it was scanned)
 // and deferred (masks wait in an L2-resident scratch ring, everything is emitted after the CTA's last scan: launches
 // small enough that every CTA holds all its elements at once never stall on the chain)
-__global__ void __launch_bounds__(scan4::kThreads4, SJB200_SCAN4_MIN_CTAS)
+__global__ void __launch_bounds__(scan4::kThreads4, (SJB200_SCAN4_WARPS > 8) ? 1 : SJB200_SCAN4_MIN_CTAS)
     scan4_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
   extern __shared__ uint8_t smem_raw4[];
   scan4::scan4_body<false>(&tmap, p, smem_raw4, sj_smem_u32(smem_raw4));
 }
-__global__ void __launch_bounds__(scan4::kThreads4, SJB200_SCAN4_MIN_CTAS)
+__global__ void __launch_bounds__(scan4::kThreads4, (SJB200_SCAN4_WARPS > 8) ? 1 : SJB200_SCAN4_MIN_CTAS)
     scan4_deferred_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
   extern __shared__ uint8_t smem_raw4[];
   scan4::scan4_body<true>(&tmap, p, smem_raw4, sj_smem_u32(smem_raw4));
@@ -919,6 +919,7 @@ cudaError_t launch_scan4(const CUtensorMap *tmap, const ScanParams &p, int grid,
 
 size_t scan4_park_words(int grid) { return size_t(grid) * scan4::kParkD * scan4::kParkSlotWords; }
 int scan4_deferred_capacity() { return scan4::kParkD; }
+int scan4_tiles_per_element() { return scan4::kElemBytes / kTileBytes; }
 
 int scan4_max_ctas_per_sm() {
   int n = 0;

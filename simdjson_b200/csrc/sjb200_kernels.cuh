@@ -15,6 +15,7 @@ int scan_max_ctas_per_sm(int kind);
 // scan4: the stage-1 indexer of sjb200_scan4.cuh (4 KiB blocks; its tensor map has a 32-row box)
 cudaError_t launch_scan4(const CUtensorMap *tmap, const ScanParams &p, int grid, bool deferred, cudaStream_t stream);
 size_t scan4_park_words(int grid);   // uint32 words of ScanParams::park for a deferred launch of `grid` CTAs
+int scan4_tiles_per_element();      // 32 KiB tiles of the launch parameter block per scan4 element
 int scan4_deferred_capacity();       // elements per CTA the deferred variant can hold at once
 int scan4_max_ctas_per_sm();
 constexpr int kScan4BoxRows = 32;

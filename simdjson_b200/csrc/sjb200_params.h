@@ -73,6 +73,7 @@ struct ScanParams {
   uint32_t write_sentinels; // kIndex: the launch that scans the last tile also stores idx[n]=idx[n+1]=len, idx[n+2]=0
   const Carry *carry_in;    // null: zero state, zero count
   Carry *carry_out;
+  Carry *carry_out_host;    // scan4: optional second copy of the result in pinned host memory (saves the copy engine a trip between launches)
   uint32_t *flags;          // accumulated with atomicOr; zero between launches (the last CTA moves it to carry_out->flags)
   unsigned long long *count_desc;  // [nsuper] the look-back chain
   uint32_t *ticket;         // [0] next tile, [1] CTAs finished

@@ -35,7 +35,10 @@
 namespace sjb200 {
 namespace scan4 {
 
-constexpr int kScanWarps = 8;
+#ifndef SJB200_SCAN4_WARPS
+#define SJB200_SCAN4_WARPS 8
+#endif
+constexpr int kScanWarps = SJB200_SCAN4_WARPS;  // scan warps per CTA = blocks per element (8: 2 CTAs per SM, 16: 1 CTA per SM)
 constexpr int kBlockBytes = 4096;
 constexpr int kBlockRows = kBlockBytes / 128;
 #ifndef SJB200_SCAN4_CHAIN
@@ -54,14 +57,19 @@ constexpr int kNS = 32;          // ring of element slots (tickets, summaries, r
 #endif
 constexpr int kParkD = SJB200_SCAN4_DEFER_PARK;  // deferred mode: elements of a CTA whose masks may wait in the L2-resident scratch ring
 constexpr int kParkSlotWords = 2 * kScanWarps * 32 * 4 + kScanWarps * 32;  // one element's parked words (both polarities + prefixes)
-constexpr int kLookK = 10;       // descriptors per lane and look-back round trip (window of 320 elements >= one wave of CTAs)
+#ifndef SJB200_SCAN4_LOOKK
+#define SJB200_SCAN4_LOOKK 10
+#endif
+constexpr int kLookK = SJB200_SCAN4_LOOKK;       // descriptors per lane and look-back round trip (window of 320 elements >= one wave of CTAs)
 static_assert(kLag >= 1 && 2 * kLag + 3 <= kNS && 2 * (kParkD - 1) + 3 <= kNS && (kNS & (kNS - 1)) == 0, "slot ring");
 #ifndef SJB200_SCAN4_SLEEP
 #define SJB200_SCAN4_SLEEP 1
 #endif
 constexpr uint32_t kSpinLimit4 = 1u << 21;  // bounded waits: a stuck protocol becomes kFlagInternal, never a hang
 constexpr uint32_t kStageWords = kBlockBytes / 4;
-static_assert(kScanWarps * kBlockBytes == kTileBytes, "an element is one tile of the launch parameter block");
+constexpr int kElemBytes = kScanWarps * kBlockBytes;  // 32 KiB or 64 KiB: what one CTA scans per ticket, one look-back descriptor
+static_assert(kElemBytes % kTileBytes == 0 && kScanWarps <= 16, "an element is a whole number of tiles of the launch parameter block");
+SJ_DEV uint32_t elements_of(const ScanParams &p) { return uint32_t((uint64_t(p.ntiles) * kTileBytes + kElemBytes - 1) / kElemBytes); }
 
 enum : uint32_t { kDescNone = 0, kDescAgg = 1, kDescInc = 2 };
 
@@ -419,7 +427,7 @@ SJ_DEV void emit_block(Smem *S, const ScanParams &p, uint64_t out_base, uint32_t
   if (total == 0) return;
   const uint32_t elem = S->ticket[ns];
   const uint32_t off = (prew >> (16 * pol)) & 0xFFFFu;
-  const uint32_t pos_lane = p.pos_base + (p.tile_begin + elem) * uint32_t(kTileBytes) + warp * uint32_t(kBlockBytes) + lane * 128u;
+  const uint32_t pos_lane = p.pos_base + p.tile_begin * uint32_t(kTileBytes) + elem * uint32_t(kElemBytes) + warp * uint32_t(kBlockBytes) + lane * 128u;
   uint32_t *out = p.idx_out + (out_base + S->res_base[ns][warp]);
   if (total <= kStageWords) {
     // positions go to shared memory (scattered 4-byte global stores cost one L1 wavefront each) and leave coalesced
@@ -507,10 +515,10 @@ SJ_DEV uint32_t wait_ticket(Smem *S, uint32_t j, const ScanParams &p) {
 
 // start the load of block `warp` of element `elem` into ring slot r; returns true when it arrives by TMA
 SJ_DEV bool issue_load(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, uint32_t elem, unsigned warp, unsigned lane, int r,
-                       uint32_t *pw_out) {
-  const uint64_t bstart = (uint64_t(p.tile_begin) + elem) * kTileBytes + uint64_t(warp) * kBlockBytes;
+                       uint32_t *pw_out, uint64_t scan_limit) {
+  const uint64_t bstart = uint64_t(p.tile_begin) * kTileBytes + uint64_t(elem) * kElemBytes + uint64_t(warp) * kBlockBytes;
   const uint64_t row = bstart / 128;
-  const bool full = p.use_tma && (row + kBlockRows <= p.len / 128);
+  const bool full = p.use_tma && bstart < scan_limit && (row + kBlockRows <= p.len / 128);
   sj_syncwarp();  // every lane is done with the slot (previous block, emit staging)
   if (lane == 0) {
     *pw_out = (bstart < p.len) ? word_before(p, bstart) : 0x20202020u;
@@ -525,8 +533,10 @@ SJ_DEV bool issue_load(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, 
 
 template <bool kDefer>
 SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, const Carry &cin, unsigned warp, unsigned lane) {
-  const uint32_t nelem = p.ntiles;
+  const uint32_t nelem = elements_of(p);
   const uint64_t launch_start = uint64_t(p.tile_begin) * kTileBytes;
+  const uint64_t launch_end = launch_start + uint64_t(p.ntiles) * kTileBytes;
+  const uint64_t scan_limit = p.len < launch_end ? p.len : launch_end;  // blocks at or beyond it are not this launch's
   const uint64_t out_base = cin.count;
   uint32_t full_phase = 0;
   uint32_t pw_cur = 0x20202020u, pw_next = 0x20202020u;
@@ -543,7 +553,7 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
     publish_ticket(S, 0, a0, lane);
   }
   uint32_t t = wait_ticket(S, 0, p);
-  if (t < nelem) tma_cur = issue_load(S, tmap, p, t, warp, lane, 0, &pw_cur);
+  if (t < nelem) tma_cur = issue_load(S, tmap, p, t, warp, lane, 0, &pw_cur, scan_limit);
   if (warp == 0) {
     if (tma_cur) wait_bar(&S->full[0][0], 0u, p, 32);
     uint32_t a1 = 0;
@@ -567,15 +577,15 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
     uint32_t t_acq = 0;
     if (warp == 0 && lane == 0 && j > 0) t_acq = sj_atomic_add(p.ticket, 1u);  // element j+2 of this CTA (see below for j == 0)
     const uint32_t tn = wait_ticket(S, j + 1, p);
-    if (tn < nelem) tma_next = issue_load(S, tmap, p, tn, warp, lane, r ^ 1, &pw_next);
+    if (tn < nelem) tma_next = issue_load(S, tmap, p, tn, warp, lane, r ^ 1, &pw_next, scan_limit);
     uint8_t *T = S->ring[warp][r];
-    const uint64_t bstart = (uint64_t(p.tile_begin) + t) * kTileBytes + uint64_t(warp) * kBlockBytes;
+    const uint64_t bstart = launch_start + uint64_t(t) * kElemBytes + uint64_t(warp) * kBlockBytes;
     if (p.debug != nullptr && warp == 0 && lane == 0) {
       p.debug[uint64_t(t) * 8 + 0] = sj_globaltimer();
       p.debug[uint64_t(t) * 8 + 7] = ((unsigned long long)sj_smid() << 48) | ((unsigned long long)sj_cta() << 32) | j;
     }
     uint32_t summary = 0;
-    if (bstart < p.len) {
+    if (bstart < scan_limit) {
       if (tma_cur) {
         wait_bar(&S->full[warp][r], (full_phase >> r) & 1u, p, 32);
         full_phase ^= 1u << r;
@@ -789,6 +799,11 @@ SJ_DEV void finalize_launch(const ScanParams &p, const Carry &cin, uint32_t s_ou
     p.carry_out->count = count_total;
     p.carry_out->state = e_a | (s_out << 1) | (c_a << 2);
     p.carry_out->ttable = T0 | (T1 << 3);
+    if (p.carry_out_host != nullptr) {
+      p.carry_out_host->count = count_total;
+      p.carry_out_host->state = e_a | (s_out << 1) | (c_a << 2);
+      p.carry_out_host->ttable = T0 | (T1 << 3);
+    }
     if (p.write_sentinels) {  // json_structural_indexer.h L284-286
       uint32_t *tail = p.idx_out + count_total;
       tail[0] = uint32_t(p.len);
@@ -803,7 +818,7 @@ SJ_DEV void finalize_launch(const ScanParams &p, const Carry &cin, uint32_t s_ou
 }
 
 SJ_DEV void chain_role(Smem *S, const ScanParams &p, const Carry &cin, unsigned lane, unsigned c) {
-  const uint32_t nelem = p.ntiles;
+  const uint32_t nelem = elements_of(p);
   for (uint32_t j = c;; j += uint32_t(kChainWarps)) {
     const int ns = int(j % kNS);
     const uint32_t t = wait_ticket(S, j, p);
@@ -863,7 +878,9 @@ SJ_DEV void scan4_body(const sj_tensor_map *tmap, const ScanParams &p, uint8_t *
     if (done == sj_nctas() - 1) {
       p.ticket[0] = 0;
       p.ticket[1] = 0;
-      p.carry_out->flags = sj_atomic_exch(p.flags, 0u);
+      const uint32_t fl = sj_atomic_exch(p.flags, 0u);
+      p.carry_out->flags = fl;
+      if (p.carry_out_host != nullptr) p.carry_out_host->flags = fl;
       sj_threadfence();
     }
   }

@@ -4,9 +4,9 @@ set -e
 cd "$(dirname "$0")/.."
 SRCS="simdjson_b200/csrc/sjb200_kernels.cu simdjson_b200/csrc/sjb200_capi.cu simdjson_b200/csrc/sjb200_finish.cpp"
 FLAGS="-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-fvisibility=hidden -shared"
+mkdir -p tools/variants
 build() { name=$1; shift; nvcc $FLAGS "$@" -o tools/variants/lib_$name.so $SRCS & }
-build nosleep -DSJB200_SCAN4_SLEEP=0
-build park3 -DSJB200_SCAN4_PARK=3
-build park5 -DSJB200_SCAN4_PARK=5
+build w16 -DSJB200_SCAN4_WARPS=16
+build w16k5 -DSJB200_SCAN4_WARPS=16 -DSJB200_SCAN4_LOOKK=5
 wait
 ls -la tools/variants
