@@ -429,12 +429,22 @@ SJ_DEV void emit_block(Smem *S, const ScanParams &p, uint64_t out_base, uint32_t
   const uint32_t off = (prew >> (16 * pol)) & 0xFFFFu;
   const uint32_t pos_lane = p.pos_base + p.tile_begin * uint32_t(kTileBytes) + elem * uint32_t(kElemBytes) + warp * uint32_t(kBlockBytes) + lane * 128u;
   uint32_t *out = p.idx_out + (out_base + S->res_base[ns][warp]);
-  if (total <= kStageWords) {
-    // positions go to shared memory (scattered 4-byte global stores cost one L1 wavefront each) and leave coalesced
+  if (total + 3 <= kStageWords) {
+    // positions go to shared memory (scattered 4-byte global stores cost one L1 wavefront each) and leave as coalesced
+    // 16-byte vectors: the staging area starts at the same offset modulo 4 words as the destination, so the aligned
+    // groups of the two line up
+    const uint32_t a = uint32_t((reinterpret_cast<uintptr_t>(out) >> 2) & 3u);  // out is 4-byte aligned
     sj_syncwarp();
-    emit_columns(ev, off, pos_lane, stg);
+    emit_columns(ev, off, pos_lane, stg + a);
     sj_syncwarp();
-    for (uint32_t i = lane; i < total; i += 32) out[i] = stg[i];
+    const uint32_t head = (total < ((4u - a) & 3u)) ? total : ((4u - a) & 3u);  // words before the first aligned group
+    const uint32_t nvec = (total - head) >> 2;
+    const uint32_t tail = total - head - (nvec << 2);
+    if (lane < head) out[lane] = stg[a + lane];
+    const sj_u4 *sv = reinterpret_cast<const sj_u4 *>(stg + a + head);  // (a + head) % 4 == 0
+    sj_u4 *gv = reinterpret_cast<sj_u4 *>(out + head);
+    for (uint32_t i = lane; i < nvec; i += 32) gv[i] = sv[i];
+    if (lane < tail) out[head + (nvec << 2) + lane] = stg[a + head + (nvec << 2) + lane];
     sj_syncwarp();
   } else {
     emit_columns(ev, off, pos_lane, out);  // > 1 structural per 4 bytes over 4 KiB: straight to global memory

@@ -1,0 +1,36 @@
+"""Summarise one `ncu --set full` report into the JSON kept under profiles/ (the .ncu-rep itself stays in gpurun_out/).
+usage: python tools/ncu_summary.py gpurun_out/scan4_full.ncu-rep profiles/NAME.json"""
+import csv
+import json
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_bytes.sum", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+    "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__cycles_active.avg",
+    "sm__cycles_elapsed.max",
+]
+
+
+def main(rep, out):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    res = []
+    for vals in rows[2:]:
+        d = {"Kernel Name": vals[hdr.index("Kernel Name")]}
+        for i, h in enumerate(hdr):
+            if h in KEYS or ("issue_stalled" in h and h.endswith("per_issue_active.ratio")):
+                d[h] = [vals[i], units[i]]
+        res.append(d)
+    json.dump(res if len(res) > 1 else res[0], open(out, "w"), indent=1)
+    print("wrote", out, "kernels:", [r["Kernel Name"][:60] for r in res])
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], sys.argv[2])
