@@ -6,7 +6,8 @@ SRCS="simdjson_b200/csrc/sjb200_kernels.cu simdjson_b200/csrc/sjb200_capi.cu sim
 FLAGS="-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-fvisibility=hidden -shared"
 mkdir -p tools/variants
 build() { name=$1; shift; nvcc $FLAGS "$@" -o tools/variants/lib_$name.so $SRCS & }
-build w16 -DSJB200_SCAN4_WARPS=16
-build w16k5 -DSJB200_SCAN4_WARPS=16 -DSJB200_SCAN4_LOOKK=5
+build park4 -DSJB200_SCAN4_PARK=4
+build park4k5 -DSJB200_SCAN4_PARK=4 -DSJB200_SCAN4_LOOKK=5
+build k5 -DSJB200_SCAN4_LOOKK=5
 wait
 ls -la tools/variants
