@@ -10,19 +10,22 @@
 //
 // Design (B200-first; nothing here resembles the reference's block loop):
 //   * The document is cut into 4 KiB *blocks* (one TMA box of 32 rows x 128 B, 128B-swizzled, so lane L owns row L and
-//     reads it with conflict-free LDS.128) and 32 KiB *elements* (8 consecutive blocks, one per scan warp).
-//   * A CTA is 8 independent *scan warps* + 1 *chain warp*, persistent, pulling elements from an atomic ticket.
-//     Scan warps never synchronise with each other: every block is scanned on its own.  Two of the three scanner
-//     state bits entering a block (next-byte-is-escaped, previous-byte-is-a-scalar) are read off the bytes before it;
-//     the third (in-string) needs the whole prefix, so a block is finished for BOTH polarities: two candidate
-//     structural masks, two counts, one quote parity.  The masks wait in shared memory.
-//   * The chain warp owns everything serial: it hands out tickets, composes the 8 block summaries of an element,
-//     publishes the element's aggregate {parity, count0, count1} in a decoupled look-back chain (one 64-bit
-//     descriptor per element), walks back 256 descriptors per round trip to the nearest inclusive prefix, and posts
-//     every block's polarity and output offset back to the scan warps through an mbarrier.
-//   * Software pipeline: a scan warp scans element j+1 while the chain warp resolves element j, then emits element j
-//     (per-lane bit loops into a shared-memory staging area -- the block buffer it has just consumed -- and coalesced
-//     stores).  The TMA load of its next block is always in flight.
+//     reads it with conflict-free LDS.128) and *elements* of kScanWarps consecutive blocks (64 KiB), one block per scan warp.
+//   * A CTA is kScanWarps (16) independent *scan warps* + 1 *chain warp*, persistent, one CTA per SM, pulling elements
+//     from an atomic ticket.  Scan warps never synchronise with each other: every block is scanned on its own.  Two of
+//     the three scanner state bits entering a block (next-byte-is-escaped, previous-byte-is-a-scalar) are read off the
+//     bytes before it; the third (in-string) needs the whole prefix, so a block is finished for BOTH polarities: two
+//     candidate structural masks, two counts, one quote parity.  The masks wait ("are parked") until the block's
+//     polarity and output offset are known.
+//   * The last scan warp to finish an element composes its block summaries and publishes the element's aggregate
+//     {parity, count0, count1} in a decoupled look-back chain (one 64-bit descriptor per element).
+//   * The chain warp walks back 320 descriptors per round trip (k-major: 256 contiguous bytes per load instruction) to
+//     the nearest inclusive prefix, folds them with ballots / popcounts / REDUX, publishes the element's inclusive
+//     prefix and posts every block's polarity and output offset to the scan warps through an mbarrier.
+//   * Software pipeline: a scan warp emits element j-2 after scanning element j (per-lane bit loops into a
+//     shared-memory staging area -- the block buffer it has just consumed -- and coalesced 16-byte stores).  The TMA
+//     load of its next block is always in flight.  A second schedule ("deferred": masks parked in an L2-resident
+//     scratch ring, all emits after the CTA's last scan) is kept as an option.
 //   * All arithmetic is the bit-plane algebra of sjb200_bits.cuh: 32 bytes per LOP3, no per-byte code.
 //
 // The same source compiles for the host SIMT emulation (SJB200_HOST_EMU, tests/simt_emul.cpp), which runs it with one
@@ -479,7 +482,7 @@ SJ_DEV Parked load_parked(Smem *S, const ScanParams &p, uint32_t e, unsigned war
 
 // ------------------------------------------------------------------------------------------------ element summary
 // Run by the LAST scan warp to finish an element (so the aggregate is out as early as possible, independent of how far
-// the chain warp is with older elements): compose the 8 block summaries for either polarity at the start of the
+// the chain warp is with older elements): compose the block summaries for either polarity at the start of the
 // element, publish the aggregate in the look-back chain, leave the per-block prefixes for the chain warp.
 SJ_DEV void compose_element(Smem *S, const ScanParams &p, int ns, uint32_t t, unsigned lane) {
   const uint32_t mine = (lane < uint32_t(kScanWarps)) ? S->summary[ns][lane] : 0u;
