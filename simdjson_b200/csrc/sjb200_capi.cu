@@ -59,6 +59,7 @@ struct sjb200_ctx {
   size_t desc_tiles = 0;
   uint8_t *d_chars = nullptr; size_t d_chars_bytes = 0;
   uint32_t *d_park = nullptr; size_t d_park_words = 0;  // scan4 deferred mode: parked masks (a per-CTA ring, independent of the input size)
+  long opt_minify_kernel = 3;  // 3: scan_kernel<kMinify>; 4: minify on the scan4 structure (not yet measured on hardware)
   long opt_deferred = 0;  // 0: never use the deferred variant of scan4 (default until measured better); 1: for launches that fit; 2: always
   // pinned host mirrors
   Carry *h_carry = nullptr;     // [kCarrySlots]
@@ -181,7 +182,7 @@ bool make_tensor_map(sjb200_ctx *c, CUtensorMap *map, const uint8_t *d_buf, size
   return true;
 }
 
-bool use_scan4(const sjb200_ctx *c, int kind) { return kind == kIndex && c->opt_kernel == 4; }
+bool use_scan4(const sjb200_ctx *c, int kind) { return (kind == kIndex && c->opt_kernel == 4) || (kind == kMinify && c->opt_minify_kernel == 4); }
 int grid_cap(sjb200_ctx *c, int kind) {
   if (use_scan4(c, kind)) {
     if (c->grid4 == 0) c->grid4 = scan4_max_ctas_per_sm() * c->sm_count;
@@ -259,7 +260,7 @@ bool enqueue_scan(sjb200_ctx *c, int kind, const CUtensorMap *map, bool tma, con
     const uint32_t nelem = (ntiles + tpe - 1) / tpe;
     const int grid = grid_for(c, kind, nelem);
     // deferred emit when every CTA can hold all the elements it will draw (small launches: one wave of CTAs)
-    bool deferred = c->opt_deferred == 2 || (c->opt_deferred == 1 && uint64_t(nelem) * 4 <= uint64_t(grid) * uint64_t(scan4_deferred_capacity()) * 3);
+    bool deferred = kind == kIndex && (c->opt_deferred == 2 || (c->opt_deferred == 1 && uint64_t(nelem) * 4 <= uint64_t(grid) * uint64_t(scan4_deferred_capacity()) * 3));
     if (deferred) {
       const size_t need = scan4_park_words(grid_cap(c, kind));
       if (c->d_park_words < need) {
@@ -270,7 +271,7 @@ bool enqueue_scan(sjb200_ctx *c, int kind, const CUtensorMap *map, bool tma, con
       }
       p.park = c->d_park;
     }
-    launched = ok(c, launch_scan4(&map4, p, grid, deferred, stream), "launch scan4");
+    launched = ok(c, launch_scan4(&map4, p, grid, kind == kMinify ? 2 : (deferred ? 1 : 0), stream), "launch scan4");
   } else {
     launched = ok(c, launch_scan(kind, map, p, grid_for(c, kind, p.nsuper), stream), "launch scan");
   }
@@ -508,6 +509,7 @@ extern "C" int sjb200_set_option(sjb200_ctx *c, const char *key, long value) {
   else if (!strcmp(key, "sub_per_super")) c->opt_sub_per_super = value;
   else if (!strcmp(key, "kernel")) c->opt_kernel = (value == 3) ? 3 : 4;
   else if (!strcmp(key, "deferred")) c->opt_deferred = value;
+  else if (!strcmp(key, "minify_kernel")) c->opt_minify_kernel = (value == 4) ? 4 : 3;
   else if (!strcmp(key, "time_kernel")) c->opt_time_kernel = value;
   else if (!strcmp(key, "debug_timeline")) c->opt_debug_timeline = value;
   else if (!strcmp(key, "chunk_bytes")) c->opt_chunk_bytes = std::max<long>(kTileBytes, (value / kTileBytes) * kTileBytes);

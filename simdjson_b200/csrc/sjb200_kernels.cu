@@ -868,12 +868,18 @@ __global__ void __launch_bounds__(kThreads, (KIND == kUtf8) ? 4 : kMinCtasPerSm)
 __global__ void __launch_bounds__(scan4::kThreads4, (SJB200_SCAN4_WARPS > 8) ? 1 : SJB200_SCAN4_MIN_CTAS)
     scan4_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
   extern __shared__ uint8_t smem_raw4[];
-  scan4::scan4_body<false>(&tmap, p, smem_raw4, sj_smem_u32(smem_raw4));
+  scan4::scan4_body<0>(&tmap, p, smem_raw4, sj_smem_u32(smem_raw4));
 }
 __global__ void __launch_bounds__(scan4::kThreads4, (SJB200_SCAN4_WARPS > 8) ? 1 : SJB200_SCAN4_MIN_CTAS)
     scan4_deferred_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
   extern __shared__ uint8_t smem_raw4[];
-  scan4::scan4_body<true>(&tmap, p, smem_raw4, sj_smem_u32(smem_raw4));
+  scan4::scan4_body<1>(&tmap, p, smem_raw4, sj_smem_u32(smem_raw4));
+}
+// minify on the scan4 structure (option minify_kernel=4; the block's bytes are fetched a second time, from L2, when it is emitted)
+__global__ void __launch_bounds__(scan4::kThreads4, (SJB200_SCAN4_WARPS > 8) ? 1 : SJB200_SCAN4_MIN_CTAS)
+    scan4_minify_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
+  extern __shared__ uint8_t smem_raw4[];
+  scan4::scan4_body<2>(&tmap, p, smem_raw4, sj_smem_u32(smem_raw4));
 }
 
 // ------------------------------------------------------------------ small helpers
@@ -902,17 +908,19 @@ static cudaError_t launch_kind(const CUtensorMap *tmap, const ScanParams &p, int
   return cudaGetLastError();
 }
 
-cudaError_t launch_scan4(const CUtensorMap *tmap, const ScanParams &p, int grid, bool deferred, cudaStream_t stream) {
+cudaError_t launch_scan4(const CUtensorMap *tmap, const ScanParams &p, int grid, int mode, cudaStream_t stream) {
   static bool configured[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(scan4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, scan4::kSmemBytes4);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(scan4_deferred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, scan4::kSmemBytes4);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(scan4_minify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, scan4::kSmemBytes4);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  if (deferred) scan4_deferred_kernel<<<grid, scan4::kThreads4, scan4::kSmemBytes4, stream>>>(*tmap, p);
+  if (mode == 2) scan4_minify_kernel<<<grid, scan4::kThreads4, scan4::kSmemBytes4, stream>>>(*tmap, p);
+  else if (mode == 1) scan4_deferred_kernel<<<grid, scan4::kThreads4, scan4::kSmemBytes4, stream>>>(*tmap, p);
   else scan4_kernel<<<grid, scan4::kThreads4, scan4::kSmemBytes4, stream>>>(*tmap, p);
   return cudaGetLastError();
 }

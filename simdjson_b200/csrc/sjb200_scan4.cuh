@@ -82,6 +82,7 @@ struct Smem {
   uint8_t ring[kScanWarps][2][kBlockBytes];   // per scan warp: two block buffers (TMA destination / emit staging)
   sj_u4 park[kPark][2][kScanWarps * 32];          // [pipeline buffer][polarity][thread]: candidate structural masks
   uint32_t parkpre[kPark][kScanWarps * 32];       // exclusive prefix of the lane's counts inside its block, both polarities packed
+  uint32_t compact_lut[16];                   // minify: see compact_entry
   uint32_t ticket[kNS];
   uint32_t summary[kNS][kScanWarps];          // c0 | c1<<16 | parity<<29 | ctl-hit0<<30 | ctl-hit1<<31
   uint32_t arrived[kNS];                      // scan warps done with the element (the last one composes and publishes)
@@ -304,12 +305,24 @@ SJ_DEV void load_unit(const uint8_t *T, uint32_t off, uint32_t w[8]) {
 // T: the block in shared memory.  pw0: the 4 bytes before the block (only lane 0's copy is used).  e_in / c_in: the two
 // locally known state bits entering the block.  Parks the two candidate masks and the lane's exclusive output prefix,
 // returns the block summary word (uniform).
+// kMin: the minify flavour (json_minifier.h L68-97): no UTF-8 validation, the two candidate masks are the bytes to KEEP
+// (everything but whitespace outside strings) among the first `valid_bytes` of the block, the counts are bytes.
+template <bool kMin>
 SJ_DEV uint32_t scan_block(const uint8_t *T, uint32_t pw0, uint32_t e_in, uint32_t c_in, unsigned lane, const ScanParams &p, sj_u4 *park0,
-                           sj_u4 *park1, uint32_t *parkpre) {
+                           sj_u4 *park1, uint32_t *parkpre, uint32_t valid_bytes) {
   const uint32_t lane_off = lane * 128u;
   uint32_t bs[4], qu[4], op[4], sc[4], cl[4];
   uint32_t uerr = 0;
-  {
+  if (kMin) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      uint32_t w8[8], pl[8];
+      load_unit(T, lane_off + 32u * u, w8);
+      transpose32(w8, pl);
+      const unit_classes c = classify(pl);
+      bs[u] = c.bs; qu[u] = c.qu; op[u] = c.op; sc[u] = c.sc; cl[u] = 0;
+    }
+  } else {
     const uint32_t pw = (lane == 0) ? pw0 : *reinterpret_cast<const uint32_t *>(T + swz(lane_off - 4));
     utf8_carry uc = utf8_carry_from_prev_word(pw);
     uint32_t pend = utf8_carry_pending(uc) ? 1u : 0u;  // the previous unit ended inside a multi-byte sequence
@@ -328,7 +341,7 @@ SJ_DEV uint32_t scan_block(const uint8_t *T, uint32_t pw0, uint32_t e_in, uint32
       }
     }
   }
-  if (sj_any(uerr != 0) && lane == 0) sj_atomic_or(p.flags, kFlagUtf8);
+  if (!kMin && sj_any(uerr != 0) && lane == 0) sj_atomic_or(p.flags, kFlagUtf8);
 
   // ---- escapes: which quotes are real (json_escape_scanner.h L96-143, resolved across lanes with one addition)
   uint32_t qr[4];
@@ -371,6 +384,15 @@ SJ_DEV uint32_t scan_block(const uint8_t *T, uint32_t pw0, uint32_t e_in, uint32
   for (int u = 0; u < 4; u++) {
     const uint32_t in_string = prefix_xor32(qr[u]) ^ (0u - instr);  // json_string_scanner.h L73
     instr = in_string >> 31;
+    if (kMin) {
+      const uint32_t ws = ~(op[u] | sc[u]);
+      const int nv = int(valid_bytes) - int(lane_off) - 32 * u;       // bytes of this unit that exist (the padding is never output)
+      const uint32_t valid = nv >= 32 ? 0xFFFFFFFFu : (nv <= 0 ? 0u : ((1u << nv) - 1u));
+      e0[u] = ~(ws & ~in_string) & valid;                             // json_minifier.h L37-40
+      e1[u] = ~(ws & in_string) & valid;
+      cnt += uint32_t(sj_popc(e0[u])) | (uint32_t(sj_popc(e1[u])) << 16);
+      continue;
+    }
     const uint32_t nq = sc[u] & ~qr[u];                              // json_scanner.h L148
     const uint32_t follows = shl_in(prev_nq, nq, 1);                 // L149
     prev_nq = nq;
@@ -480,6 +502,101 @@ SJ_DEV Parked load_parked(Smem *S, const ScanParams &p, uint32_t e, unsigned war
   return k;
 }
 
+// ------------------------------------------------------------------------------------------------ minify: emit one block
+// kept bytes of a 4-byte word packed to its low end: PRMT selector (unused positions select a zero byte) | count << 16
+// (computed once per CTA into shared memory: 16 words in 16 banks, any mix of nibbles across the lanes is one access)
+SJ_DEV uint32_t compact_entry(uint32_t nib) {
+  uint32_t sel = 0, cnt = 0;
+  for (uint32_t b = 0; b < 4; b++)
+    if ((nib >> b) & 1u) { sel |= b << (4 * cnt); cnt++; }
+  for (uint32_t i = cnt; i < 4; i++) sel |= 4u << (4 * i);
+  return sel | (cnt << 16);
+}
+
+// Block `warp` of this CTA's e-th element (resolved): fetch its bytes again (they are two scans old, still in L2) into
+// `slot`, pull the lane's row into registers, turn the slot into the staging area, pack the kept bytes of every word
+// with one PRMT, merge them into a running word with another, OR complete words into the (zeroed) staging area
+// (lanes share the words at their seams), and store the block's output as aligned 16-byte vectors.
+// Returns true when the slot's mbarrier completed a phase (the caller tracks parities).
+SJ_DEV bool emit_minify_block(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, uint64_t out_base, uint32_t e, unsigned warp, unsigned lane,
+                              const sj_u4 kv, uint32_t prew, uint8_t *slot, sj_mbar_t *bar, uint32_t parity, uint64_t launch_start) {
+  const int ns = int(e % kNS);
+  const uint32_t sum = S->summary[ns][warp];
+  const uint32_t pol = S->res_pol[ns][warp] & 1u;
+  const uint32_t total = pol ? ((sum >> 16) & 0x1FFFu) : (sum & 0xFFFFu);
+  if (total == 0) return false;
+  const uint32_t elem = S->ticket[ns];
+  const uint64_t bstart = launch_start + uint64_t(elem) * kElemBytes + uint64_t(warp) * kBlockBytes;
+  const uint64_t row = bstart / 128;
+  const bool by_tma = p.use_tma && (row + kBlockRows <= p.len / 128);
+  sj_syncwarp();
+  if (by_tma) {
+    if (lane == 0) {
+      sj_fence_proxy_async();
+      sj_mbar_arrive_expect_tx(bar, kBlockBytes);
+      sj_tma_load_rows(slot, tmap, bar, uint32_t(row));
+    }
+    wait_bar(bar, parity, p, 32);
+  } else {
+    fill_block_guarded(slot, p, bstart, lane);
+    sj_syncwarp();
+  }
+  uint32_t w[32];
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    const sj_u4 v = *reinterpret_cast<const sj_u4 *>(slot + swz(lane * 128u + 16u * c));
+    w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+  }
+  sj_syncwarp();  // every lane holds its row: the slot becomes the staging area (linear), zeroed because lanes OR into it
+#pragma unroll
+  for (int c = 0; c < 8; c++) *reinterpret_cast<sj_u4 *>(slot + lane * 128u + 16u * c) = sj_make_u4(0, 0, 0, 0);
+  sj_syncwarp();
+  uint32_t *stg = reinterpret_cast<uint32_t *>(slot);
+  const uint32_t off = (prew >> (16 * pol)) & 0xFFFFu;  // bytes of the block's output before this lane's
+  const uint32_t keep[4] = {kv.x, kv.y, kv.z, kv.w};
+  uint32_t carry = 0, fill = off & 3u, wp = off >> 2;
+#pragma unroll
+  for (int i = 0; i < 32; i++) {
+    const uint32_t ent = S->compact_lut[(keep[i >> 3] >> (4 * (i & 7))) & 15u];
+    const uint32_t comp = byte_perm(w[i], 0u, ent & 0xFFFFu);
+    const uint32_t cnt = ent >> 16;
+    // merged: the `fill` bytes waiting in carry, then the first bytes of comp
+    const uint32_t msel = uint32_t(0x4210541065407654ull >> (16 * fill)) & 0xFFFFu;
+    const uint32_t merged = byte_perm(carry, comp, msel);
+    const uint32_t tot = fill + cnt;
+    if (tot >= 4) {
+      sj_atomic_or(stg + wp, merged);
+      wp++;
+      carry = fill ? (comp >> (8 * (4 - fill))) : 0u;
+      fill = tot - 4;
+    } else {
+      carry = merged;
+      fill = tot;
+    }
+  }
+  if (fill) sj_atomic_or(stg + wp, carry);
+  sj_syncwarp();
+  // ---- copy-out: the destination's 16-byte groups, whatever its alignment
+  uint8_t *dst = p.dst + (out_base + S->res_base[ns][warp]);
+  const uint8_t *stgb = slot;
+  const uint32_t a = uint32_t(reinterpret_cast<uintptr_t>(dst) & 15u);
+  const uint32_t head = (total < ((16u - a) & 15u)) ? total : ((16u - a) & 15u);
+  const uint32_t nvec = (total - head) >> 4;
+  const uint32_t tail = total - head - (nvec << 4);
+  if (lane < head) dst[lane] = stgb[lane];
+  for (uint32_t i = lane; i < nvec; i += 32) {
+    const uint32_t sb = head + 16u * i;       // staging byte offset of this vector (any alignment)
+    const uint32_t w0 = sb >> 2, sh = 8u * (sb & 3u);
+    const uint32_t x0 = stg[w0], x1 = stg[w0 + 1], x2 = stg[w0 + 2], x3 = stg[w0 + 3];
+    const uint32_t x4 = sh ? stg[w0 + 4] : 0u;  // (w0 + 4 <= 1023 whenever it is needed)
+    *reinterpret_cast<sj_u4 *>(dst + sb) = sj_make_u4(sj_funnel_r(x0, x1, int(sh)), sj_funnel_r(x1, x2, int(sh)), sj_funnel_r(x2, x3, int(sh)), sj_funnel_r(x3, x4, int(sh)));
+  }
+  if (lane < tail) dst[head + (nvec << 4) + lane] = stgb[head + (nvec << 4) + lane];
+  sj_syncwarp();
+  if (p.debug != nullptr && warp == 0 && lane == 0) p.debug[uint64_t(elem) * 8 + 5] = sj_globaltimer();
+  return by_tma;
+}
+
 // ------------------------------------------------------------------------------------------------ element summary
 // Run by the LAST scan warp to finish an element (so the aggregate is out as early as possible, independent of how far
 // the chain warp is with older elements): compose the block summaries for either polarity at the start of the
@@ -546,12 +663,14 @@ SJ_DEV bool issue_load(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, 
   return full;
 }
 
-template <bool kDefer>
+// kMode: 0 stage 1, pipelined; 1 stage 1, deferred emit; 2 minify (pipelined)
+template <int kMode>
 SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, const Carry &cin, unsigned warp, unsigned lane) {
   const uint32_t nelem = elements_of(p);
   const uint64_t launch_start = uint64_t(p.tile_begin) * kTileBytes;
   const uint64_t launch_end = launch_start + uint64_t(p.ntiles) * kTileBytes;
   const uint64_t scan_limit = p.len < launch_end ? p.len : launch_end;  // blocks at or beyond it are not this launch's
+  constexpr bool kDefer = (kMode == 1), kMin = (kMode == 2);
   const uint64_t out_base = cin.count;
   uint32_t full_phase = 0;
   uint32_t pw_cur = 0x20202020u, pw_next = 0x20202020u;
@@ -612,10 +731,12 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
       const uint32_t st = boundary_state(p, bstart, launch_start, cin.state, pw0, lane);
       if (kDefer) {
         uint32_t *slot = park_slot(p, j);
-        summary = scan_block(T, pw0, st & 1u, (st >> 2) & 1u, lane, p, reinterpret_cast<sj_u4 *>(slot), reinterpret_cast<sj_u4 *>(slot) + kScanWarps * 32,
-                             slot + 2 * kScanWarps * 32 * 4);
+        summary = scan_block<false>(T, pw0, st & 1u, (st >> 2) & 1u, lane, p, reinterpret_cast<sj_u4 *>(slot),
+                                    reinterpret_cast<sj_u4 *>(slot) + kScanWarps * 32, slot + 2 * kScanWarps * 32 * 4, kBlockBytes);
       } else {
-        summary = scan_block(T, pw0, st & 1u, (st >> 2) & 1u, lane, p, S->park[j % kPark][0], S->park[j % kPark][1], S->parkpre[j % kPark]);
+        const uint64_t left = p.len - bstart;  // > 0: bytes of the block that exist
+        summary = scan_block<kMin>(T, pw0, st & 1u, (st >> 2) & 1u, lane, p, S->park[j % kPark][0], S->park[j % kPark][1], S->parkpre[j % kPark],
+                                   left < uint64_t(kBlockBytes) ? uint32_t(left) : uint32_t(kBlockBytes));
       }
     }
     {
@@ -642,7 +763,14 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
     }
     if (!kDefer && j >= uint32_t(kLag)) {  // pipelined: the chain warp has had kLag scans' time to resolve this one
       wait_bar(&S->resolved[ne % kNS], (ne / kNS) & 1u, p, 64);
-      emit_from_smem(S, p, out_base, ne, warp, lane, reinterpret_cast<uint32_t *>(T));
+      if (kMin) {
+        const uint32_t pol = S->res_pol[ne % kNS][warp] & 1u;
+        if (emit_minify_block(S, tmap, p, out_base, ne, warp, lane, S->park[ne % kPark][pol][warp * 32 + lane], S->parkpre[ne % kPark][warp * 32 + lane], T,
+                              &S->full[warp][r], (full_phase >> r) & 1u, launch_start))
+          full_phase ^= 1u << r;
+      } else {
+        emit_from_smem(S, p, out_base, ne, warp, lane, reinterpret_cast<uint32_t *>(T));
+      }
       ne++;
     }
     t = tn;
@@ -681,7 +809,14 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
   } else {
     while (ne < j) {
       wait_bar(&S->resolved[ne % kNS], (ne / kNS) & 1u, p, 64);
-      emit_from_smem(S, p, out_base, ne, warp, lane, reinterpret_cast<uint32_t *>(S->ring[warp][0]));
+      if (kMin) {
+        const uint32_t pol = S->res_pol[ne % kNS][warp] & 1u;
+        if (emit_minify_block(S, tmap, p, out_base, ne, warp, lane, S->park[ne % kPark][pol][warp * 32 + lane], S->parkpre[ne % kPark][warp * 32 + lane],
+                              S->ring[warp][0], &S->full[warp][0], full_phase & 1u, launch_start))
+          full_phase ^= 1u;
+      } else {
+        emit_from_smem(S, p, out_base, ne, warp, lane, reinterpret_cast<uint32_t *>(S->ring[warp][0]));
+      }
       ne++;
     }
   }
@@ -861,7 +996,7 @@ SJ_DEV void chain_role(Smem *S, const ScanParams &p, const Carry &cin, unsigned 
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel body
-template <bool kDefer>
+template <int kMode>
 SJ_DEV void scan4_body(const sj_tensor_map *tmap, const ScanParams &p, uint8_t *smem_raw, uint32_t smem_raw_addr) {
   // 1 KiB alignment for the 128B swizzle, computed on the shared-space address so the pointer keeps its address space
   Smem *S = reinterpret_cast<Smem *>(smem_raw + ((1024u - (smem_raw_addr & 1023u)) & 1023u));
@@ -882,8 +1017,9 @@ SJ_DEV void scan4_body(const sj_tensor_map *tmap, const ScanParams &p, uint8_t *
     }
     sj_fence_mbar_init();
   }
+  if (kMode == 2 && tid < 16) S->compact_lut[tid] = compact_entry(tid);
   sj_syncthreads();
-  if (warp < unsigned(kScanWarps)) scan_role<kDefer>(S, tmap, p, cin, warp, lane);
+  if (warp < unsigned(kScanWarps)) scan_role<kMode>(S, tmap, p, cin, warp, lane);
   else chain_role(S, p, cin, lane, warp - unsigned(kScanWarps));
   // last CTA out resets the ticket for the next launch on this context and hands the flags over
   sj_syncthreads();

@@ -123,6 +123,7 @@ SJ_DEV int sj_popc(uint32_t x) { return __builtin_popcount(x); }
 SJ_DEV int sj_ffs(uint32_t x) { return __builtin_ffs(int(x)); }
 SJ_DEV uint32_t sj_bfind(uint32_t x) { return x ? uint32_t(31 - __builtin_clz(x)) : 0xFFFFFFFFu; }
 SJ_DEV uint32_t sj_funnel_l(uint32_t lo, uint32_t hi, int n) { return n ? ((hi << n) | (lo >> (32 - n))) : hi; }
+SJ_DEV uint32_t sj_funnel_r(uint32_t lo, uint32_t hi, int n) { return n ? ((lo >> n) | (hi << (32 - n))) : lo; }
 
 SJ_DEV uint32_t sj_atomic_add(uint32_t *p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 SJ_DEV uint32_t sj_atomic_or(uint32_t *p, uint32_t v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
@@ -258,6 +259,7 @@ SJ_DEV uint32_t sj_bfind(uint32_t x) {  // index of the highest set bit (0xFFFFF
   return r;
 }
 SJ_DEV uint32_t sj_funnel_l(uint32_t lo, uint32_t hi, int n) { return __funnelshift_l(lo, hi, n); }
+SJ_DEV uint32_t sj_funnel_r(uint32_t lo, uint32_t hi, int n) { return __funnelshift_r(lo, hi, n); }
 
 SJ_DEV uint32_t sj_atomic_add(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
 SJ_DEV uint32_t sj_atomic_or(uint32_t *p, uint32_t v) { return atomicOr(p, v); }

@@ -32,7 +32,7 @@ struct LaunchArgs {
   unsigned grid;
   const sj_tensor_map *tmap;
   const ScanParams *p;
-  bool deferred;
+  int mode;  // 0 stage 1 pipelined, 1 stage 1 deferred, 2 minify
 };
 
 void *thread_main(void *arg);
@@ -50,14 +50,16 @@ void *thread_main(void *arg) {
   simt::tctx.nctas = a->la->grid;
   simt::tctx.warp = a->warp;
   simt::tctx.ctas = a->cta;
-  if (a->la->deferred) scan4::scan4_body<true>(a->la->tmap, *a->la->p, a->cta->smem, uint32_t(reinterpret_cast<uintptr_t>(a->cta->smem)));
-  else scan4::scan4_body<false>(a->la->tmap, *a->la->p, a->cta->smem, uint32_t(reinterpret_cast<uintptr_t>(a->cta->smem)));
+  const uint32_t sa = uint32_t(reinterpret_cast<uintptr_t>(a->cta->smem));
+  if (a->la->mode == 2) scan4::scan4_body<2>(a->la->tmap, *a->la->p, a->cta->smem, sa);
+  else if (a->la->mode == 1) scan4::scan4_body<1>(a->la->tmap, *a->la->p, a->cta->smem, sa);
+  else scan4::scan4_body<0>(a->la->tmap, *a->la->p, a->cta->smem, sa);
   return nullptr;
 }
 
-void emu_launch(unsigned grid, const sj_tensor_map &tmap, const ScanParams &p, bool deferred) {
+void emu_launch(unsigned grid, const sj_tensor_map &tmap, const ScanParams &p, int mode) {
   const unsigned T = scan4::kThreads4, W = T / 32;
-  LaunchArgs la{grid, &tmap, &p, deferred};
+  LaunchArgs la{grid, &tmap, &p, mode};
   std::vector<simt::CtaShared> ctas(grid);
   std::vector<simt::WarpShared> warps(size_t(grid) * W);
   std::vector<ThreadArg> args(size_t(grid) * T);
@@ -106,7 +108,7 @@ struct Result {
 
 // one document (or shard) through 1..n launches of chunk_tiles tiles each, like scan_host_document
 Result run_scan4(EmuCtx &cx, const uint8_t *buf, size_t len, uint32_t state_in, uint32_t chunk_tiles, unsigned grid, bool use_tma,
-                 bool sentinels) {
+                 bool sentinels, uint8_t *minify_dst = nullptr) {
   Result r;
   const uint32_t ntiles_total = uint32_t((len + kTileBytes - 1) / kTileBytes);
   if (cx.desc.size() < size_t(ntiles_total) + 1) cx.desc.assign(size_t(ntiles_total) + 1, 0ull);
@@ -130,8 +132,8 @@ Result run_scan4(EmuCtx &cx, const uint8_t *buf, size_t len, uint32_t state_in, 
     p.tile_begin = tb; p.ntiles = nt; p.sub_per_super = 1; p.nsuper = nt;
     p.full_tiles = uint32_t((len / 128) / kTileRows);
     p.epoch = ++cx.epoch;
-    p.idx_out = r.idx.data(); p.dst = nullptr;
-    p.write_sentinels = (sentinels && tb + nt == ntiles_total) ? 1u : 0u;
+    p.idx_out = r.idx.data(); p.dst = minify_dst;
+    p.write_sentinels = (sentinels && !minify_dst && tb + nt == ntiles_total) ? 1u : 0u;
     p.carry_in = &cx.carry[slot];
     p.carry_out = &cx.carry[slot + 1];
     p.flags = &cx.flags; p.count_desc = cx.desc.data(); p.ticket = cx.ticket; p.debug = nullptr;
@@ -139,7 +141,7 @@ Result run_scan4(EmuCtx &cx, const uint8_t *buf, size_t len, uint32_t state_in, 
     const unsigned g = std::min<unsigned>(grid, (nt * unsigned(kTileBytes) + scan4::kElemBytes - 1) / scan4::kElemBytes);
     cx.park.assign(size_t(g) * scan4::kParkD * scan4::kParkSlotWords + 4, 0xDEADBEEFu);
     p.park = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(cx.park.data()) + 15) & ~uintptr_t(15));
-    emu_launch(g, tmap, p, g_deferred);
+    emu_launch(g, tmap, p, minify_dst ? 2 : (g_deferred ? 1 : 0));
     if (cx.ticket[0] != 0 || cx.ticket[1] != 0 || cx.flags != 0) { fprintf(stderr, "BUG: ticket/flags not re-armed\n"); exit(2); }
     flags |= cx.carry[slot + 1].flags;
     slot++;
@@ -282,6 +284,42 @@ int test_look_back(std::mt19937_64 &rng, int cases) {
   return bad;
 }
 
+// minify on the scan4 structure against the oracle (json_minifier.h semantics: bytes and length when the document has no
+// unclosed string; UNCLOSED_STRING otherwise; nothing is ever written past dst[len))
+int check_minify(EmuCtx &cx, const std::vector<uint8_t> &store, size_t misalign, uint32_t chunk_tiles, unsigned grid, bool use_tma, size_t dst_misalign) {
+  const uint8_t *buf = store.data() + misalign;
+  const size_t len = store.size() - misalign;
+  if (len == 0) return 0;
+  std::vector<uint8_t> out(len + 64 + dst_misalign, 0xEE);
+  uint8_t *dst = out.data() + dst_misalign;
+  Result r = run_scan4(cx, buf, len, 0, chunk_tiles, grid, use_tma, false, dst);
+  std::vector<uint8_t> want(len + 1);
+  size_t wlen = 0;
+  const int werr = sjo_minify(buf, len, want.data(), &wlen);
+  int bad = 0;
+  const bool unclosed = (r.state >> 1) & 1u;
+  if (r.flags & kFlagInternal) bad = 1;
+  else if (unclosed != (werr == SJO_UNCLOSED_STRING)) bad = 2;
+  else if (!unclosed && (r.count != wlen || memcmp(dst, want.data(), wlen) != 0)) bad = 3;
+  else {
+    for (size_t i = size_t(r.count); i < len + 64 && !bad; i++)
+      if (dst[i] != 0xEE) bad = 4;  // wrote beyond the kept bytes
+    for (size_t i = 0; i < dst_misalign && !bad; i++)
+      if (out[i] != 0xEE) bad = 5;
+  }
+  if (bad) {
+    fprintf(stderr, "MINIFY MISMATCH kind=%d len=%zu misalign=%zu dst_misalign=%zu chunk_tiles=%u grid=%u tma=%d: got n=%llu | want err=%d n=%zu\n", bad, len, misalign,
+            dst_misalign, chunk_tiles, grid, int(use_tma), (unsigned long long)r.count, werr, wlen);
+    if (bad == 3)
+      for (size_t i = 0; i < wlen; i++)
+        if (dst[i] != want[i]) { fprintf(stderr, "  first difference at output byte %zu: got %02x want %02x\n", i, dst[i], want[i]); break; }
+    std::vector<uint8_t> v(buf, buf + len);
+    hexdump(v);
+    g_fail++;
+  }
+  return bad;
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -361,6 +399,8 @@ int main(int argc, char **argv) {
     g_deferred = (it & 1) != 0;  // alternate between the pipelined and the deferred variant
     check(cx, buf0, 0, state_in, 0, grid, true, g_deferred ? "tma, deferred" : "tma, pipelined");
     if (it % 3 == 0) check(cx, buf0, 0, state_in, 1 + uint32_t(rng() % 3), grid, true, "chunked");
+    if (it % 2 == 0) check_minify(cx, buf0, 0, (it % 6 == 0) ? 1 + uint32_t(rng() % 3) : 0, grid, it % 4 != 0, rng() % 17);
+    if (it % 5 == 1 && buf0.size() > 3) check_minify(cx, buf0, 1 + rng() % 3, 0, grid, true, rng() % 17);
     if (it % 4 == 1) check(cx, buf0, 0, state_in, 0, grid, false, "plain loads");
     if (it % 4 == 2 && buf0.size() > 3) check(cx, buf0, 1 + rng() % 3, state_in, 0, grid, true, "misaligned");
   }

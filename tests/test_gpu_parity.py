@@ -201,6 +201,31 @@ def test_stage1_kernel_variants(port, kernel, deferred):
         parser.close()
 
 
+@pytest.mark.skipif(os.environ.get("SJB200_TEST_EXPERIMENTAL") != "1",
+                    reason="minify on the scan4 structure (option minify_kernel=4) has run under the host SIMT emulation only "
+                           "(tests/simt_emul.cpp); set SJB200_TEST_EXPERIMENTAL=1 to run it on a GPU")
+def test_minify_on_scan4_experimental(port):
+    rc, parser = sj.get_active_implementation().create_dom_parser_implementation(32 << 20)
+    assert rc == sj.SUCCESS
+    parser.set_option("minify_kernel", 4)
+    try:
+        rng = random.Random(corpus.SEED ^ 0x3141)
+        for n in [1, 127, 4095, 4096, 4097, 2 * TILE, 2 * TILE + 1, 7 * TILE + 4100, 300 * TILE + 77]:
+            b = _big_adversarial(rng, n)
+            err, out = parser._minify_host(b)
+            werr, wout = port.minify(b)
+            assert err == werr and bytes(out) == wout, n
+        doc = corpus.random_json(20 << 20, pretty_bias=0.8, utf8_rate=0.15)
+        d = torch.from_numpy(doc.copy()).cuda()
+        dst = torch.empty(len(doc) + 16, dtype=torch.uint8, device="cuda")
+        for shift in (0, 1, 7):  # destination alignment
+            rcm, dl = parser.minify_device(d, dst[shift:])
+            werr, wout = port.minify(doc)
+            assert rcm == werr and dl == len(wout) and bytes(dst[shift:shift + dl].cpu().numpy()) == wout, shift
+    finally:
+        parser.close()
+
+
 def test_valid_documents_and_streams(parser, port):
     impl = sj.get_active_implementation()
     d = corpus.random_json(3 * (1 << 20) + 12345)
