@@ -67,6 +67,9 @@ constexpr int kParkSlotWords = 2 * kScanWarps * 32 * 4 + kScanWarps * 32;  // on
 #endif
 constexpr int kLookK = SJB200_SCAN4_LOOKK;       // descriptors per lane and look-back round trip (window of 320 elements >= one wave of CTAs)
 static_assert(kLag >= 1 && 2 * kLag + 3 <= kNS && 2 * (kParkD - 1) + 3 <= kNS && (kNS & (kNS - 1)) == 0, "slot ring");
+#ifndef SJB200_SCAN4_HELP
+#define SJB200_SCAN4_HELP 0  // 0: off; n > 0: a look-back that walked at least n elements publishes the inclusive prefixes it passed
+#endif
 #ifndef SJB200_SCAN4_SLEEP
 #define SJB200_SCAN4_SLEEP 1
 #endif
@@ -912,6 +915,36 @@ SJ_DEV void look_back(const ScanParams &p, uint32_t t, unsigned lane, uint32_t *
       ck = sj_shfl(ck, int(il));
       *s_in = sk ^ acc.p;
       *base = ck + (sk ? acc.b : acc.a);
+#if SJB200_SCAN4_HELP
+      // Option (off: measured slower with 296 chain warps, when every one of them also wrote 2.5 KB into the hot
+      // descriptor lines; kept for the one-CTA-per-SM configuration, where only walks longer than kHelpMin help):
+      // the walk has just computed what every element between the inclusive prefix and t needs, so publish THEIR
+      // inclusive prefixes too -- the owners would write exactly the same words -- and the other CTAs find an
+      // inclusive prefix right behind their element.
+      if (inc_dist >= uint32_t(SJB200_SCAN4_HELP)) {
+        uint32_t older_p = 0;   // parity of the used elements older than group k
+        uint32_t older_c = ck;  // outputs up to and including the used elements older than group k
+#pragma unroll
+        for (int k = kLookK - 1; k >= 0; k--) {
+          const bool u = (use >> k) & 1u;
+          const uint32_t rel = (uint32_t(sj_popc((bal[k] >> lane) >> 1)) ^ older_p ^ sk) & 1u;  // in-string entering my element
+          const uint32_t a = uint32_t(d[k]) & 0x7FFFFu, b = uint32_t(d[k] >> 19) & 0x7FFFFu;
+          const uint32_t mine = u ? (rel ? b : a) : 0u;
+          uint32_t suf = mine;  // suffix sum over lanes >= mine (older elements of the group first)
+#pragma unroll
+          for (int dd = 1; dd < 32; dd <<= 1) {
+            const uint32_t o = sj_shfl_down(suf, dd);
+            if (int(lane) + dd < 32) suf += o;
+          }
+          if (u) {
+            const uint32_t s_after = rel ^ (uint32_t(d[k] >> 38) & 1u);
+            sj_st_relaxed_u64(p.count_desc + (first - 32 * k), pack_inc(p.epoch, s_after, older_c + suf));
+          }
+          older_c += sj_shfl(suf, 0);
+          older_p ^= uint32_t(sj_popc(bal[k])) & 1u;
+        }
+      }
+#endif
       return;
     }
     newest -= 32 * kLookK;

@@ -6,8 +6,10 @@ SRCS="simdjson_b200/csrc/sjb200_kernels.cu simdjson_b200/csrc/sjb200_capi.cu sim
 FLAGS="-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-fvisibility=hidden -shared"
 mkdir -p tools/variants
 build() { name=$1; shift; nvcc $FLAGS "$@" -o tools/variants/lib_$name.so $SRCS & }
+# next to measure: helping look-back with one CTA per SM, two chain warps, lag 3
+build help64 -DSJB200_SCAN4_HELP=64
+build help1 -DSJB200_SCAN4_HELP=1
+build chain2 -DSJB200_SCAN4_CHAIN=2
 build park4 -DSJB200_SCAN4_PARK=4
-build park4k5 -DSJB200_SCAN4_PARK=4 -DSJB200_SCAN4_LOOKK=5
-build k5 -DSJB200_SCAN4_LOOKK=5
 wait
 ls -la tools/variants
