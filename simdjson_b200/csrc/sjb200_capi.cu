@@ -386,8 +386,8 @@ extern "C" int sjb200_create(int device, size_t capacity, sjb200_ctx **out) {
               ok(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "stream") &&
               ok(c, cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking), "stream") &&
               dev_alloc(c, &c->d_carry, kCarrySlots, "cudaMalloc(carry)") && dev_alloc(c, &c->d_flags, 1, "cudaMalloc(flags)") &&
-              dev_alloc(c, &c->d_ticket, 2, "cudaMalloc(ticket)") &&
-              ok(c, cudaMemset(c->d_ticket, 0, 2 * sizeof(uint32_t)), "memset ticket") &&
+              dev_alloc(c, &c->d_ticket, 4, "cudaMalloc(ticket)") &&
+              ok(c, cudaMemset(c->d_ticket, 0, 4 * sizeof(uint32_t)), "memset ticket") &&
               ok(c, cudaMemset(c->d_flags, 0, sizeof(uint32_t)), "memset flags");
   void *hp = nullptr;
   good = good && ok(c, cudaMallocHost(&hp, kCarrySlots * sizeof(Carry)), "cudaMallocHost");

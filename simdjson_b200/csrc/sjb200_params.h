@@ -76,7 +76,7 @@ struct ScanParams {
   Carry *carry_out_host;    // scan4: optional second copy of the result in pinned host memory (saves the copy engine a trip between launches)
   uint32_t *flags;          // accumulated with atomicOr; zero between launches (the last CTA moves it to carry_out->flags)
   unsigned long long *count_desc;  // [nsuper] the look-back chain
-  uint32_t *ticket;         // [0] next tile, [1] CTAs finished
+  uint32_t *ticket;         // [0] next ticket, [1] CTAs finished, [2] scan4: aggregates published so far (4 words, zero between launches)
   uint32_t *park;           // scan4, deferred mode: scratch ring for parked masks, scan4_park_words(grid) words (stays in L2)
   unsigned long long *debug;  // optional [ntiles][8] timeline (globaltimer ns) for tuning; null in production
 };

@@ -67,6 +67,9 @@ constexpr int kParkSlotWords = 2 * kScanWarps * 32 * 4 + kScanWarps * 32;  // on
 #endif
 constexpr int kLookK = SJB200_SCAN4_LOOKK;       // descriptors per lane and look-back round trip (window of 320 elements >= one wave of CTAs)
 static_assert(kLag >= 1 && 2 * kLag + 3 <= kNS && 2 * (kParkD - 1) + 3 <= kNS && (kNS & (kNS - 1)) == 0, "slot ring");
+#ifndef SJB200_SCAN4_COUNTER
+#define SJB200_SCAN4_COUNTER 0  // 1: a look-back first waits (polling ONE word) until t aggregates are out, then loads its window once
+#endif
 #ifndef SJB200_SCAN4_HELP
 #define SJB200_SCAN4_HELP 0  // 0: off; n > 0: a look-back that walked at least n elements publishes the inclusive prefixes it passed
 #endif
@@ -630,6 +633,10 @@ SJ_DEV void compose_element(Smem *S, const ScanParams &p, int ns, uint32_t t, un
     S->elem[ns][2] = b1;
     S->elem[ns][3] = hit0 | (hit1 << 1);
     if (t > 0) sj_st_relaxed_u64(p.count_desc + t, pack_agg(p.epoch, s0, b0, b1));  // element 0 goes straight to inclusive
+#if SJB200_SCAN4_COUNTER
+    sj_fence_gpu_release();
+    sj_atomic_add(p.ticket + 2, 1u);  // aggregates of this launch that are out (result unused: a reduction, nobody waits for it)
+#endif
   }
   sj_syncwarp();
 }
@@ -835,6 +842,19 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
 // that only one bit is order-dependent: the quote parities of a group of 32 elements are one ballot word, an element's
 // polarity relative to the oldest element of the window is a popcount, and the counts are then plain sums.
 SJ_DEV void look_back(const ScanParams &p, uint32_t t, unsigned lane, uint32_t *s_in, uint32_t *base) {
+#if SJB200_SCAN4_COUNTER
+  // Option: instead of polling 320 descriptors in the lines every other chain warp is polling, wait on one word until
+  // at least t aggregates of this launch are out (tickets are scanned roughly in order, so that is nearly always all of
+  // elements 0..t-1); the loop below then finds its window complete at the first load and still copes when it is not.
+  for (uint32_t spins = 0; spins < kSpinLimit4; spins++) {
+    uint32_t out = 0;
+    if (lane == 0) out = sj_ld_relaxed_u32(p.ticket + 2);
+    if (sj_shfl(out, 0) >= t) break;
+#if SJB200_SCAN4_SLEEP
+    sj_nanosleep(100);
+#endif
+  }
+#endif
   Eff acc;
   acc.p = 0; acc.a = 0; acc.b = 0;
   int64_t newest = int64_t(t) - 1;
@@ -1062,6 +1082,7 @@ SJ_DEV void scan4_body(const sj_tensor_map *tmap, const ScanParams &p, uint8_t *
     if (done == sj_nctas() - 1) {
       p.ticket[0] = 0;
       p.ticket[1] = 0;
+      p.ticket[2] = 0;
       const uint32_t fl = sj_atomic_exch(p.flags, 0u);
       p.carry_out->flags = fl;
       if (p.carry_out_host != nullptr) p.carry_out_host->flags = fl;

@@ -131,6 +131,8 @@ SJ_DEV uint32_t sj_atomic_exch(uint32_t *p, uint32_t v) { return __atomic_exchan
 SJ_DEV unsigned long long sj_ld_relaxed_u64(const unsigned long long *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 SJ_DEV void sj_st_relaxed_u64(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 SJ_DEV void sj_threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+SJ_DEV void sj_fence_gpu_release() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+SJ_DEV uint32_t sj_ld_relaxed_u32(const uint32_t *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 SJ_DEV void sj_fence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 SJ_DEV void sj_nanosleep(unsigned) {
   struct timespec ts = {0, 20000};
@@ -273,6 +275,12 @@ SJ_DEV void sj_st_relaxed_u64(unsigned long long *p, unsigned long long v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 SJ_DEV void sj_threadfence() { __threadfence(); }
+SJ_DEV void sj_fence_gpu_release() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+SJ_DEV uint32_t sj_ld_relaxed_u32(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 SJ_DEV void sj_fence_block() { __threadfence_block(); }
 SJ_DEV void sj_nanosleep(unsigned ns) { __nanosleep(ns); }
 SJ_DEV unsigned sj_smid() {

@@ -94,7 +94,7 @@ bool g_deferred = false;  // which variant of the kernel the next launches run
 struct EmuCtx {
   std::vector<unsigned long long> desc;
   std::vector<uint32_t> park;
-  uint32_t ticket[2] = {0, 0};
+  uint32_t ticket[4] = {0, 0, 0, 0};
   uint32_t flags = 0;
   uint32_t epoch = 0;
   Carry carry[64];
@@ -142,7 +142,7 @@ Result run_scan4(EmuCtx &cx, const uint8_t *buf, size_t len, uint32_t state_in, 
     cx.park.assign(size_t(g) * scan4::kParkD * scan4::kParkSlotWords + 4, 0xDEADBEEFu);
     p.park = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(cx.park.data()) + 15) & ~uintptr_t(15));
     emu_launch(g, tmap, p, minify_dst ? 2 : (g_deferred ? 1 : 0));
-    if (cx.ticket[0] != 0 || cx.ticket[1] != 0 || cx.flags != 0) { fprintf(stderr, "BUG: ticket/flags not re-armed\n"); exit(2); }
+    if (cx.ticket[0] != 0 || cx.ticket[1] != 0 || cx.ticket[2] != 0 || cx.flags != 0) { fprintf(stderr, "BUG: ticket/flags not re-armed\n"); exit(2); }
     flags |= cx.carry[slot + 1].flags;
     slot++;
     if (slot + 1 >= 64) { fprintf(stderr, "too many chunks\n"); exit(2); }
@@ -262,7 +262,8 @@ int test_look_back(std::mt19937_64 &rng, int cases) {
     }
     ScanParams p;
     memset(&p, 0, sizeof(p));
-    p.epoch = epoch; p.count_desc = desc.data(); p.flags = &flags;
+    uint32_t tick[4] = {0, 0, t, 0};  // (the published-aggregates counter of the SJB200_SCAN4_COUNTER build option)
+    p.epoch = epoch; p.count_desc = desc.data(); p.flags = &flags; p.ticket = tick;
     simt::WarpShared w;
     simt::CtaShared cta;
     pthread_barrier_init(&w.bar, nullptr, 32);

@@ -10,6 +10,8 @@ build() { name=$1; shift; nvcc $FLAGS "$@" -o tools/variants/lib_$name.so $SRCS 
 build help64 -DSJB200_SCAN4_HELP=64
 build help1 -DSJB200_SCAN4_HELP=1
 build chain2 -DSJB200_SCAN4_CHAIN=2
+build counter -DSJB200_SCAN4_COUNTER=1
+build counterhelp -DSJB200_SCAN4_COUNTER=1 -DSJB200_SCAN4_HELP=64
 build park4 -DSJB200_SCAN4_PARK=4
 wait
 ls -la tools/variants
