@@ -306,8 +306,8 @@ def run_ours(args, rank, world):
             "clocks": clocks.summary(),
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": DOC_BYTES, "d2h_bytes_per_step": int(4 * e2e_n + 24), "steps": e2e_steps},
             "gpu_launches": int(launches2 - launches1),
-            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
-                         "peak_source": peak_src, "kernel": "sjb200::scan4_deferred_kernel / scan4_kernel (sjb200_scan4.cuh)", "kernel_ms": round(kms, 5), "algorithmic_bytes": int(algo_bytes),
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": ncu_traffic()[0],
+                         "traffic_source": ncu_traffic()[1], "peak_source": peak_src, "kernel": "sjb200::scan4_deferred_kernel / scan4_kernel (sjb200_scan4.cuh)", "kernel_ms": round(kms, 5), "algorithmic_bytes": int(algo_bytes),
                          "input_gbs_kernel_only": round(DOC_BYTES / (kms * 1e-3) / 1e9, 1)},
         }
         line["cpu_baseline"] = cpu_baseline(docs[0])
@@ -315,6 +315,22 @@ def run_ours(args, rank, world):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def ncu_traffic():
+    """DRAM bytes of one launch of the stage-1 kernel on the bench document, from the committed `ncu --set full` capture
+    (profiles/, produced by tools/run_gpu_round.sh + tools/ncu_summary.py); None when there is no capture"""
+    path = os.path.join(ROOT, "profiles", "r1b_scan4_kernel_ncu_full.json")
+    try:
+        d = json.load(open(path))
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            v, u = d[k]
+            tot += float(v) * unit[u]
+        return int(tot), os.path.relpath(path, ROOT)
+    except Exception:  # noqa: BLE001
+        return None, None
 
 
 def cpu_baseline(doc):
