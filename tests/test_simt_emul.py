@@ -2,7 +2,8 @@
 the oracle: one OS thread per CUDA thread, warp collectives as rendezvous, mbarriers with deferred TMA copies
 (sjb200_simt.cuh, SJB200_HOST_EMU).  Covers the warp roles, the ticket / mbarrier pipeline, the both-polarity block
 scans, the look-back chain (several CTAs, windows), emit, launch carries, chunked launches, shard transducers, plain-load
-and misaligned paths.  No GPU involved; the GPU parity tests live in test_gpu_parity.py."""
+and misaligned paths, minify on the scan4 structure.  (Built with -fsanitize=thread the same program reports no data
+race in the shared-memory / mbarrier protocol; that build is too slow for the regular run.)  No GPU involved; the GPU parity tests live in test_gpu_parity.py."""
 import os
 import subprocess
 
