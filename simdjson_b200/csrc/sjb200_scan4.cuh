@@ -56,6 +56,9 @@ constexpr int kThreads4 = 32 * (kScanWarps + kChainWarps);
 #endif
 constexpr int kPark = SJB200_SCAN4_PARK;  // elements whose masks wait in shared memory: a scan warp emits element j-kLag after scanning j
 constexpr int kLag = kPark - 1;
+#ifndef SJB200_SCAN4_STAGGER
+#define SJB200_SCAN4_STAGGER 0  // 1: even scan warps emit one element earlier than odd ones (lag kLag-1 / kLag), so that at any time half of the
+#endif                          // CTA's warps are in the latency-bound emit loop while the other half are in the ALU-bound scan
 constexpr int kNS = 32;          // ring of element slots (tickets, summaries, resolutions)
 #ifndef SJB200_SCAN4_DEFER_PARK
 #define SJB200_SCAN4_DEFER_PARK 12
@@ -429,7 +432,20 @@ SJ_DEV uint32_t scan_block(const uint8_t *T, uint32_t pw0, uint32_t e_in, uint32
 // Each lane walks its own four mask words, column by column: every lane runs the trip count of the fullest word of the
 // column (uniform), pulls the highest set bit per iteration (one FLO) and stores its position -- descending, so the
 // store offset is an immediate of the unrolled loop.
+#ifndef SJB200_SCAN4_EMIT
+#define SJB200_SCAN4_EMIT 1  // 0: one loop per column (dependent chain of ~4 instructions per output); 1: the four columns in one loop (four independent chains); 2: two loops of two columns
+#endif
+// one step of one word's chain: store the position of the highest remaining bit at q[-k], clear it
+#define SJ_EMIT_STEP(m, q, pb)                   \
+  {                                              \
+    const bool has = (m) != 0;                   \
+    const uint32_t h = sj_bfind(m);              \
+    (q)--;                                       \
+    if (has) *(q) = (pb) + h;                    \
+    (m) &= ~(1u << (h & 31u));                   \
+  }
 SJ_DEV void emit_columns(const sj_u4 ev, uint32_t off, uint32_t pos_lane, uint32_t *dst) {
+#if SJB200_SCAN4_EMIT == 0
   const uint32_t m4[4] = {ev.x, ev.y, ev.z, ev.w};
 #pragma unroll
   for (int u = 0; u < 4; u++) {
@@ -440,12 +456,56 @@ SJ_DEV void emit_columns(const sj_u4 ev, uint32_t off, uint32_t pos_lane, uint32
     uint32_t *q = dst + (off + c);  // one past the word's last output
     off += c;
 #pragma unroll 4
-    for (uint32_t k = 1; k <= n; k++) {
-      const bool has = m != 0;
-      const uint32_t h = sj_bfind(m);
-      if (has) q[-int(k)] = pb + h;
-      m &= ~(1u << (h & 31u));
+    for (uint32_t k = 0; k < n; k++) SJ_EMIT_STEP(m, q, pb)
+  }
+#else
+  // The chains of different words are independent: run them side by side, so that the FLO -> shift -> clear latency of
+  // one is covered by the others (a warp that emits is otherwise latency-bound: ~4 dependent instructions per output).
+  uint32_t m0 = ev.x, m1 = ev.y, m2 = ev.z, m3 = ev.w;
+  const uint32_t c0 = uint32_t(sj_popc(m0)), c1 = uint32_t(sj_popc(m1)), c2 = uint32_t(sj_popc(m2)), c3 = uint32_t(sj_popc(m3));
+  uint32_t *q0 = dst + (off + c0);  // one past each word's last output
+  uint32_t *q1 = q0 + c1, *q2 = q1 + c2, *q3 = q2 + c3;
+  const uint32_t pb0 = pos_lane, pb1 = pos_lane + 32u, pb2 = pos_lane + 64u, pb3 = pos_lane + 96u;
+#if SJB200_SCAN4_EMIT == 1
+  const uint32_t c01 = c0 > c1 ? c0 : c1, c23 = c2 > c3 ? c2 : c3;
+  const uint32_t n = sj_reduce_max(c01 > c23 ? c01 : c23);
+#pragma unroll 2
+  for (uint32_t k = 0; k < n; k++) {
+    SJ_EMIT_STEP(m0, q0, pb0)
+    SJ_EMIT_STEP(m1, q1, pb1)
+    SJ_EMIT_STEP(m2, q2, pb2)
+    SJ_EMIT_STEP(m3, q3, pb3)
+  }
+#else
+  const uint32_t na = sj_reduce_max(c0 > c1 ? c0 : c1), nb = sj_reduce_max(c2 > c3 ? c2 : c3);
+#pragma unroll 2
+  for (uint32_t k = 0; k < na; k++) {
+    SJ_EMIT_STEP(m0, q0, pb0)
+    SJ_EMIT_STEP(m1, q1, pb1)
+  }
+#pragma unroll 2
+  for (uint32_t k = 0; k < nb; k++) {
+    SJ_EMIT_STEP(m2, q2, pb2)
+    SJ_EMIT_STEP(m3, q3, pb3)
+  }
+#endif
+#endif
+}
+#undef SJ_EMIT_STEP
+
+// the rare block with more than one output per four bytes: no staging, compact code (kept out of line: the kernel's
+// hot loops should stay resident in the instruction cache)
+SJ_DEV_NOINLINE void emit_columns_dense(const sj_u4 ev, uint32_t off, uint32_t pos_lane, uint32_t *dst) {
+  const uint32_t m4[4] = {ev.x, ev.y, ev.z, ev.w};
+  for (int u = 0; u < 4; u++) {
+    uint32_t m = m4[u];
+    uint32_t *q = dst + off;
+    while (m != 0) {
+      const uint32_t l = uint32_t(sj_ffs(m)) - 1u;
+      *q++ = pos_lane + 32u * uint32_t(u) + l;
+      m &= m - 1u;
     }
+    off += uint32_t(sj_popc(m4[u]));
   }
 }
 
@@ -480,7 +540,7 @@ SJ_DEV void emit_block(Smem *S, const ScanParams &p, uint64_t out_base, uint32_t
     if (lane < tail) out[head + (nvec << 2) + lane] = stg[a + head + (nvec << 2) + lane];
     sj_syncwarp();
   } else {
-    emit_columns(ev, off, pos_lane, out);  // > 1 structural per 4 bytes over 4 KiB: straight to global memory
+    emit_columns_dense(ev, off, pos_lane, out);  // > 1 structural per 4 bytes over 4 KiB: straight to global memory
   }
   if (p.debug != nullptr && warp == 0 && lane == 0) p.debug[uint64_t(elem) * 8 + 5] = sj_globaltimer();
 }
@@ -608,30 +668,39 @@ SJ_DEV bool emit_minify_block(Smem *S, const sj_tensor_map *tmap, const ScanPara
 // the chain warp is with older elements): compose the block summaries for either polarity at the start of the
 // element, publish the aggregate in the look-back chain, leave the per-block prefixes for the chain warp.
 SJ_DEV void compose_element(Smem *S, const ScanParams &p, int ns, uint32_t t, unsigned lane) {
-  const uint32_t mine = (lane < uint32_t(kScanWarps)) ? S->summary[ns][lane] : 0u;
-  uint32_t s0 = 0, s1 = 1, b0 = 0, b1 = 0, hit0 = 0, hit1 = 0;
-  uint32_t my0 = 0, my1 = 0;
+  // Lane w holds the summary of block w; an inclusive scan over the lanes with the (associative) composition of block
+  // effects gives, in four shuffle steps, what a serial walk over the blocks would (the aggregate is on the critical
+  // path of every later element, so it should not wait for sixteen dependent steps).
+  // Effect of a run of blocks: P quote parity, A / B outputs when entered outside / inside a string, HA / HB unescaped
+  // control character seen when entered outside / inside.  Packed: X = A | HA << 30 | P << 31, Y = B | HB << 30.
+  const uint32_t r = (lane < uint32_t(kScanWarps)) ? S->summary[ns][lane] : 0u;  // lanes beyond the element: identity
+  uint32_t X = (r & 0xFFFFu) | (((r >> 30) & 1u) << 30) | (((r >> 29) & 1u) << 31);
+  uint32_t Y = ((r >> 16) & 0x1FFFu) | ((r >> 31) << 30);
 #pragma unroll
-  for (int w = 0; w < kScanWarps; w++) {
-    const uint32_t r = sj_shfl(mine, w);
-    const uint32_t c0 = r & 0xFFFFu, c1 = (r >> 16) & 0x1FFFu, par = (r >> 29) & 1u, h0 = (r >> 30) & 1u, h1 = r >> 31;
-    if (int(lane) == w) { my0 = (s0 << 31) | b0; my1 = (s1 << 31) | b1; }
-    b0 += s0 ? c1 : c0;
-    hit0 |= s0 ? h1 : h0;
-    s0 ^= par;
-    b1 += s1 ? c1 : c0;
-    hit1 |= s1 ? h1 : h0;
-    s1 ^= par;
+  for (int d = 1; d < kScanWarps; d <<= 1) {
+    const uint32_t xo = sj_shfl_up(X, d), yo = sj_shfl_up(Y, d);  // the run that ends d blocks before mine
+    if (int(lane) >= d) {
+      const bool flip = (xo >> 31) != 0;  // the older run leaves the in-string state toggled: my run is entered the other way
+      const uint32_t xn = flip ? Y : X, yn = flip ? X : Y;
+      const uint32_t A = (xo & 0x3FFFFFFFu) + (xn & 0x3FFFFFFFu), B = (yo & 0x3FFFFFFFu) + (yn & 0x3FFFFFFFu);
+      const uint32_t HA = (xo | xn) & 0x40000000u, HB = (yo | yn) & 0x40000000u;
+      X = A | HA | ((xo ^ X) & 0x80000000u);
+      Y = B | HB;
+    }
   }
+  // exclusive prefixes: what precedes block `lane` inside the element
+  uint32_t xe = sj_shfl_up(X, 1), ye = sj_shfl_up(Y, 1);
+  if (lane == 0) { xe = 0; ye = 0; }
   if (lane < uint32_t(kScanWarps)) {
-    S->pre[ns][0][lane] = my0;
-    S->pre[ns][1][lane] = my1;
+    S->pre[ns][0][lane] = (xe & 0x80000000u) | (xe & 0x3FFFFFFFu);            // entered outside: polarity | outputs before the block
+    S->pre[ns][1][lane] = ((xe & 0x80000000u) ^ 0x80000000u) | (ye & 0x3FFFFFFFu);  // entered inside
   }
-  if (lane == 0) {
+  if (lane == uint32_t(kScanWarps - 1)) {
+    const uint32_t s0 = X >> 31, b0 = X & 0x3FFFFFFFu, b1 = Y & 0x3FFFFFFFu;
     S->elem[ns][0] = s0;  // quote parity of the element
     S->elem[ns][1] = b0;
     S->elem[ns][2] = b1;
-    S->elem[ns][3] = hit0 | (hit1 << 1);
+    S->elem[ns][3] = ((X >> 30) & 1u) | (((Y >> 30) & 1u) << 1);
     if (t > 0) sj_st_relaxed_u64(p.count_desc + t, pack_agg(p.epoch, s0, b0, b1));  // element 0 goes straight to inclusive
 #if SJB200_SCAN4_COUNTER
     sj_fence_gpu_release();
@@ -706,6 +775,7 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
   }
   uint32_t ne = 0;  // this CTA's next element to emit (elements are emitted in order)
   uint32_t j = 0;
+  const uint32_t my_lag = (SJB200_SCAN4_STAGGER && kLag >= 2 && (warp & 1u) == 0) ? uint32_t(kLag - 1) : uint32_t(kLag);
   for (;; j++) {
     if (t >= nelem) break;
     const int r = int(j & 1u);
@@ -749,6 +819,7 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
                                    left < uint64_t(kBlockBytes) ? uint32_t(left) : uint32_t(kBlockBytes));
       }
     }
+    if (p.debug != nullptr && warp == 0 && lane == 0) p.debug[uint64_t(t) * 8 + 1] = sj_globaltimer();
     {
       const int ns = int(j % kNS);
       uint32_t last = 0;
@@ -771,8 +842,9 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
       if (j == 0 && lane == 0) t_acq = sj_atomic_add(p.ticket, 1u);  // start-up: keep the third ticket behind everybody's second
       publish_ticket(S, j + 2, t_acq, lane);
     }
-    if (!kDefer && j >= uint32_t(kLag)) {  // pipelined: the chain warp has had kLag scans' time to resolve this one
+    if (!kDefer && j >= my_lag) {  // pipelined: the chain warp has had my_lag scans' time to resolve this one
       wait_bar(&S->resolved[ne % kNS], (ne / kNS) & 1u, p, 64);
+      if (p.debug != nullptr && warp == 0 && lane == 0) p.debug[uint64_t(S->ticket[ne % kNS]) * 8 + 2] = sj_globaltimer();
       if (kMin) {
         const uint32_t pol = S->res_pol[ne % kNS][warp] & 1u;
         if (emit_minify_block(S, tmap, p, out_base, ne, warp, lane, S->park[ne % kPark][pol][warp * 32 + lane], S->parkpre[ne % kPark][warp * 32 + lane], T,
