@@ -2,7 +2,9 @@
 // No torch, no CPU fallback: every scan runs in sjb200_kernels.cu or the call fails.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <ctype.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -13,6 +15,7 @@
 #include "../../include/sjb200.h"
 #include "sjb200_bits.cuh"
 #include "sjb200_finish.h"
+#include "sjb200_hostpipe.h"
 #include "sjb200_kernels.cuh"
 
 using namespace sjb200;
@@ -71,7 +74,7 @@ struct sjb200_ctx {
   int grid[3] = {0, 0, 0};
   long opt_kernel = 4;  // stage-1 kernel generation: 4 = scan4 (sjb200_scan4.cuh), 3 = the tile-synchronous scan_kernel<kIndex>
   int grid4 = 0;
-  long opt_sub_per_super = 0, opt_use_tma = 1, opt_grid = 0, opt_chunk_bytes = 4 << 20, opt_time_kernel = 0;
+  long opt_sub_per_super = 0, opt_use_tma = 1, opt_grid = 0, opt_chunk_bytes = 2 << 20, opt_time_kernel = 0;
   cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // around the last scan kernel when opt_time_kernel is set
   bool ev_valid = false;
   std::vector<cudaEvent_t> ev_pool;              // [2i], [2i+1] around launch i since the last kernel_ms_mean query
@@ -80,6 +83,16 @@ struct sjb200_ctx {
   unsigned long long *d_debug = nullptr; size_t debug_tiles = 0; uint32_t debug_last_tiles = 0;
   unsigned long long launches = 0;               // kernels of ours launched by this context
   PFN_encodeTiled encode = nullptr;
+  // host-pointer pipeline: ring of page-locked staging slots filled by copy threads (sjb200_hostpipe.h)
+  uint8_t *h_ring = nullptr; size_t ring_slot_bytes = 0; int ring_slots = 0;
+  std::vector<cudaEvent_t> ring_events;
+  CopyPool *pool = nullptr;
+  long opt_force_grid = 0;
+  long opt_copy_threads = 8;        // 0: no staging (cudaMemcpyAsync straight from the caller's memory)
+  long opt_ring_slots = 8;
+  long opt_stage_min_bytes = 1 << 20;  // smaller inputs go straight through the driver
+  long opt_zero_copy_out = 1;       // stage 1 stores indexes straight into a page-locked, mapped caller array
+  int last_input_path = 0, last_output_path = 0;  // stats: 0 driver copy, 1 staged ring, 2 caller memory is page-locked; 0 copy engine, 1 kernel stores
   PendingCall pending;
   std::string last_error;
 };
@@ -140,14 +153,16 @@ bool ensure_desc(sjb200_ctx *c, size_t len) {
   return true;
 }
 
-uint32_t next_epoch(sjb200_ctx *c) {
+// The wipe at the wrap of the 18-bit tag is ordered on the LAUNCH stream (a context is used on one stream at a time,
+// see sjb200.h): kernels queued earlier on it finish before the wipe, the next launch starts after it.
+bool next_epoch(sjb200_ctx *c, cudaStream_t launch_stream, uint32_t *epoch) {
   c->epoch++;
-  if (c->epoch >= (1u << 18)) {  // 18-bit tag wrapped: wipe the descriptors once
-    cudaMemsetAsync(c->d_count_desc, 0, c->desc_tiles * sizeof(unsigned long long), c->stream);
-    cudaStreamSynchronize(c->stream);
+  if (c->epoch >= (1u << 18)) {
+    if (!ok(c, cudaMemsetAsync(c->d_count_desc, 0, c->desc_tiles * sizeof(unsigned long long), launch_stream), "memset desc")) return false;
     c->epoch = 1;
   }
-  return c->epoch;
+  *epoch = c->epoch;
+  return true;
 }
 
 bool ensure_host_scratch(sjb200_ctx *c, uint8_t **p, size_t *have, size_t need) {
@@ -183,6 +198,10 @@ bool make_tensor_map(sjb200_ctx *c, CUtensorMap *map, const uint8_t *d_buf, size
 }
 
 bool use_scan4(const sjb200_ctx *c, int kind) { return (kind == kIndex && c->opt_kernel == 4) || (kind == kMinify && c->opt_minify_kernel == 4); }
+// the one tensor map the kernel selected for `kind` reads through (scan4: 4 KiB boxes; the tile-synchronous kernels: 32 KiB)
+bool map_for(sjb200_ctx *c, int kind, CUtensorMap *map, const uint8_t *d_buf, size_t len, bool *usable) {
+  return make_tensor_map(c, map, d_buf, len, usable, use_scan4(c, kind) ? kScan4BoxRows : kTileRows);
+}
 int grid_cap(sjb200_ctx *c, int kind) {
   if (use_scan4(c, kind)) {
     if (c->grid4 == 0) c->grid4 = scan4_max_ctas_per_sm() * c->sm_count;
@@ -192,6 +211,7 @@ int grid_cap(sjb200_ctx *c, int kind) {
   return c->opt_grid > 0 ? int(c->opt_grid) : c->grid[kind];
 }
 int grid_for(sjb200_ctx *c, int kind, uint32_t nelements) {
+  if (c->opt_force_grid > 0) return int(c->opt_force_grid);  // tuning: a full grid even for a tiny document (measures the fixed cost of a launch)
   return int(std::max<uint32_t>(1, std::min<uint32_t>(uint32_t(grid_cap(c, kind)), nelements)));
 }
 
@@ -221,7 +241,7 @@ bool enqueue_scan(sjb200_ctx *c, int kind, const CUtensorMap *map, bool tma, con
   p.sub_per_super = R;
   p.nsuper = (ntiles + R - 1) / R;
   p.full_tiles = uint32_t((len / 128) / kTileRows);
-  p.epoch = next_epoch(c);
+  if (!next_epoch(c, stream, &p.epoch)) return false;
   p.idx_out = d_idx;
   p.dst = d_dst;
   p.carry_in = (carry_in_slot < 0) ? nullptr : c->d_carry + carry_in_slot;
@@ -233,11 +253,12 @@ bool enqueue_scan(sjb200_ctx *c, int kind, const CUtensorMap *map, bool tma, con
   p.ticket = c->d_ticket;
   p.debug = nullptr;
   if (c->opt_debug_timeline) {
-    if (c->debug_tiles < ntiles) {
+    const uint32_t rows = std::max<uint32_t>(ntiles, 4096);  // (the trace build of scan4 writes 17 rows per CTA)
+    if (c->debug_tiles < rows) {
       cudaFree(c->d_debug); c->d_debug = nullptr; c->debug_tiles = 0;
-      if (dev_alloc(c, &c->d_debug, size_t(ntiles) * 8, "cudaMalloc(debug)")) c->debug_tiles = ntiles;
+      if (dev_alloc(c, &c->d_debug, size_t(rows) * 8, "cudaMalloc(debug)")) c->debug_tiles = rows;
     }
-    if (c->d_debug) { cudaMemsetAsync(c->d_debug, 0, size_t(ntiles) * 64, stream); p.debug = c->d_debug; c->debug_last_tiles = ntiles; }
+    if (c->d_debug) { cudaMemsetAsync(c->d_debug, 0, size_t(rows) * 64, stream); p.debug = c->d_debug; c->debug_last_tiles = rows; }
   }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (c->opt_time_kernel) {
@@ -251,11 +272,6 @@ bool enqueue_scan(sjb200_ctx *c, int kind, const CUtensorMap *map, bool tma, con
   }
   bool launched;
   if (use_scan4(c, kind)) {
-    // scan4 reads 4 KiB boxes: its own tensor map over the same bytes (an element of its chain is one tile)
-    CUtensorMap map4;
-    bool tma4 = false;
-    make_tensor_map(c, &map4, d_buf, len, &tma4, kScan4BoxRows);
-    p.use_tma = (tma && tma4) ? 1u : 0u;
     const uint32_t tpe = uint32_t(scan4_tiles_per_element());
     const uint32_t nelem = (ntiles + tpe - 1) / tpe;
     const int grid = grid_for(c, kind, nelem);
@@ -271,7 +287,7 @@ bool enqueue_scan(sjb200_ctx *c, int kind, const CUtensorMap *map, bool tma, con
       }
       p.park = c->d_park;
     }
-    launched = ok(c, launch_scan4(&map4, p, grid, kind == kMinify ? 2 : (deferred ? 1 : 0), stream), "launch scan4");
+    launched = ok(c, launch_scan4(map, p, grid, kind == kMinify ? 2 : (deferred ? 1 : 0), stream), "launch scan4");
   } else {
     launched = ok(c, launch_scan(kind, map, p, grid_for(c, kind, p.nsuper), stream), "launch scan");
   }
@@ -300,9 +316,10 @@ class DeviceTailReader final : public StructuralReader {
     const uint32_t count = n_ - new_lo;
     size_t hw = c_->h_window_words * 4;
     uint8_t *hwp = reinterpret_cast<uint8_t *>(c_->h_window);
-    if (!ensure_host_scratch(c_, &hwp, &hw, size_t(count) * 4)) { failed_ = true; return false; }
-    c_->h_window = reinterpret_cast<uint32_t *>(hwp);
+    const bool grown = ensure_host_scratch(c_, &hwp, &hw, size_t(count) * 4);
+    c_->h_window = reinterpret_cast<uint32_t *>(hwp);  // also on failure: the old block is gone
     c_->h_window_words = hw / 4;
+    if (!grown) { failed_ = true; return false; }
     if (!ensure_host_scratch(c_, &c_->h_chars, &c_->h_chars_bytes, count)) { failed_ = true; return false; }
     if (c_->d_chars_bytes < count) {
       cudaFree(c_->d_chars);
@@ -409,6 +426,12 @@ extern "C" int sjb200_create(int device, size_t capacity, sjb200_ctx **out) {
     sjb200_destroy(c);
     return SJB200_MEMALLOC;
   }
+  // tuning knobs of the host-pointer pipeline for callers that cannot reach sjb200_set_option (the C++ plug-in owns its contexts)
+  for (const char *key : {"copy_threads", "ring_slots", "chunk_bytes", "stage_min_bytes", "zero_copy_out"}) {
+    std::string env = std::string("SJB200_") + key;
+    for (auto &ch : env) ch = char(toupper((unsigned char)ch));
+    if (const char *v = getenv(env.c_str())) sjb200_set_option(c, key, atol(v));
+  }
   int rc = sjb200_set_capacity(c, capacity);
   if (rc != SJB200_SUCCESS) {
     sjb200_destroy(c);
@@ -429,6 +452,9 @@ extern "C" void sjb200_destroy(sjb200_ctx *c) {
   if (c->h_small) cudaFreeHost(c->h_small);
   if (c->h_chars) cudaFreeHost(c->h_chars);
   if (c->h_window) cudaFreeHost(c->h_window);
+  delete c->pool; c->pool = nullptr;
+  if (c->h_ring) cudaFreeHost(c->h_ring);
+  for (auto e : c->ring_events) cudaEventDestroy(e);
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   for (auto e : c->chunk_events) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -467,7 +493,7 @@ extern "C" long sjb200_get_debug_timeline(sjb200_ctx *c, unsigned long long *out
 extern "C" int sjb200_pin_host_memory(sjb200_ctx *c, void *ptr, size_t bytes) {
   if (!c || !ptr || bytes == 0) return SJB200_UNEXPECTED_ERROR;
   DeviceGuard g(c->device);
-  return ok(c, cudaHostRegister(ptr, bytes, cudaHostRegisterPortable), "cudaHostRegister") ? SJB200_SUCCESS : SJB200_MEMALLOC;
+  return ok(c, cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped), "cudaHostRegister") ? SJB200_SUCCESS : SJB200_MEMALLOC;
 }
 extern "C" int sjb200_unpin_host_memory(sjb200_ctx *c, void *ptr) {
   if (!c || !ptr) return SJB200_UNEXPECTED_ERROR;
@@ -499,6 +525,8 @@ extern "C" double sjb200_get_stat(sjb200_ctx *c, const char *key) {
   if (!strcmp(key, "launches")) return double(c->launches);
   if (!strcmp(key, "grid_index")) return double(grid_for(c, kIndex, 0xFFFFFFFFu));
   if (!strcmp(key, "sm_count")) return double(c->sm_count);
+  if (!strcmp(key, "input_path")) return double(c->last_input_path);
+  if (!strcmp(key, "output_path")) return double(c->last_output_path);
   return -1.0;
 }
 
@@ -512,7 +540,12 @@ extern "C" int sjb200_set_option(sjb200_ctx *c, const char *key, long value) {
   else if (!strcmp(key, "minify_kernel")) c->opt_minify_kernel = (value == 4) ? 4 : 3;
   else if (!strcmp(key, "time_kernel")) c->opt_time_kernel = value;
   else if (!strcmp(key, "debug_timeline")) c->opt_debug_timeline = value;
-  else if (!strcmp(key, "chunk_bytes")) c->opt_chunk_bytes = std::max<long>(kTileBytes, (value / kTileBytes) * kTileBytes);
+  else if (!strcmp(key, "chunk_bytes")) c->opt_chunk_bytes = std::max<long>(2 * kTileBytes, (value / (2 * kTileBytes)) * (2 * kTileBytes));
+  else if (!strcmp(key, "force_grid")) c->opt_force_grid = value;
+  else if (!strcmp(key, "copy_threads")) c->opt_copy_threads = std::max<long>(0, std::min<long>(value, 64));
+  else if (!strcmp(key, "ring_slots")) c->opt_ring_slots = std::max<long>(2, std::min<long>(value, 64));
+  else if (!strcmp(key, "stage_min_bytes")) c->opt_stage_min_bytes = std::max<long>(0, value);
+  else if (!strcmp(key, "zero_copy_out")) c->opt_zero_copy_out = value;
   else return SJB200_UNEXPECTED_ERROR;
   return SJB200_SUCCESS;
 }
@@ -539,7 +572,7 @@ void stage1_enqueue_into(sjb200_ctx *c, PendingCall &pc, const uint8_t *d_buf, s
   if (!ensure_desc(c, len)) { pc.early_error = SJB200_MEMALLOC; return; }
   CUtensorMap map;
   bool tma = false;
-  make_tensor_map(c, &map, d_buf, len, &tma);
+  map_for(c, kIndex, &map, d_buf, len, &tma);
   // scan4 stores its result in the pinned host mirror itself; the older kernel needs the copy engine for it
   if (!enqueue_scan(c, kIndex, &map, tma, d_buf, len, 0, tiles_of(len), true, 0x20202020u, d_idx, nullptr, -1, s, slot, true, nullptr,
                     c->h_carry + slot) ||
@@ -653,7 +686,7 @@ extern "C" int sjb200_minify_dev_enqueue(sjb200_ctx *c, const uint8_t *d_buf, si
   if (!ensure_desc(c, len)) { pc.early_error = SJB200_MEMALLOC; return SJB200_SUCCESS; }
   CUtensorMap map;
   bool tma = false;
-  make_tensor_map(c, &map, d_buf, len, &tma);
+  map_for(c, kMinify, &map, d_buf, len, &tma);
   if (!enqueue_scan(c, kMinify, &map, tma, d_buf, len, 0, tiles_of(len), true, 0x20202020u, nullptr, d_dst, -1, s, 1) ||
       !fetch_result(c, s))
     pc.early_error = SJB200_UNEXPECTED_ERROR;
@@ -692,7 +725,7 @@ extern "C" int sjb200_validate_utf8_dev_enqueue(sjb200_ctx *c, const uint8_t *d_
   if (len > kMaxBytes) { pc.early_error = SJB200_CAPACITY; return SJB200_SUCCESS; }
   CUtensorMap map;
   bool tma = false;
-  make_tensor_map(c, &map, d_buf, len, &tma);
+  map_for(c, kUtf8, &map, d_buf, len, &tma);
   if (!enqueue_scan(c, kUtf8, &map, tma, d_buf, len, 0, tiles_of(len), true, 0x20202020u, nullptr, nullptr, -1, s, 1) ||
       !fetch_result(c, s))
     pc.early_error = SJB200_UNEXPECTED_ERROR;
@@ -746,60 +779,139 @@ bool ensure_output(sjb200_ctx *c, size_t len) {
   return true;
 }
 
-// The host-pointer pipeline.  The document goes to the device chunk by chunk; one scan launch per chunk is
-// chained behind its copy (scanner state and output offset travel through d_carry[k] -> d_carry[k+1]); and as
-// soon as a chunk's launch has finished, the output it produced (indexes / minified bytes) starts its way
-// back while later chunks are still being copied in and scanned:  H2D(k+1) | scan(k) | D2H(k-1).
+// page-locked staging ring + copy threads for pageable input (created at the first large host-pointer call)
+bool ensure_ring(sjb200_ctx *c, size_t slot_bytes) {
+  const int slots = int(c->opt_ring_slots);
+  if (c->h_ring && c->ring_slot_bytes >= slot_bytes && c->ring_slots == slots) return true;
+  if (c->h_ring) { cudaFreeHost(c->h_ring); c->h_ring = nullptr; c->ring_slot_bytes = 0; c->ring_slots = 0; }
+  void *q = nullptr;
+  if (!ok(c, cudaMallocHost(&q, slot_bytes * size_t(slots)), "cudaMallocHost(ring)")) return false;
+  c->h_ring = static_cast<uint8_t *>(q);
+  c->ring_slot_bytes = slot_bytes;
+  c->ring_slots = slots;
+  while (c->ring_events.size() < size_t(slots)) {
+    cudaEvent_t e;
+    if (!ok(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event")) return false;
+    c->ring_events.push_back(e);
+  }
+  return true;
+}
+bool ensure_pool(sjb200_ctx *c) {
+  if (!c->pool) c->pool = new (std::nothrow) CopyPool();
+  return c->pool && c->pool->start(int(c->opt_copy_threads));
+}
+
+// The host-pointer pipeline.  The document goes to the device chunk by chunk; one scan launch per chunk is chained
+// behind its copy (scanner state and output offset travel through d_carry[k] -> d_carry[k+1], flags accumulate);
+// later chunks are copied while earlier ones are scanned:  stage(k+2) | H2D(k+1) | scan(k) [| D2H(k-1)].
+//   input:  page-locked caller memory -> copied from where it lies; pageable -> through the staging ring (copy threads),
+//           small documents straight through the driver.
+//   output: stage 1 into a page-locked, mapped caller array (what the plug-in and the Python mirror register) -> the
+//           scan kernels store the indexes there themselves (d_idx is then the device alias of host_out and nothing
+//           comes back through the copy engine); otherwise each chunk's output is copied back as soon as its launch is done.
 // elt = bytes per output element (4 for indexes, 1 for minify, 0 = no output to bring back).
 bool scan_host_document(sjb200_ctx *c, int kind, const uint8_t *buf, size_t len, uint32_t *d_idx, uint8_t *d_dst, void *host_out,
-                        size_t elt, int *final_slot) {
+                        size_t elt, bool direct_out, int *final_slot) {
   size_t chunk = size_t(c->opt_chunk_bytes);
-  const size_t min_chunk = ((len / (kCarrySlots - 2)) / kTileBytes + 1) * kTileBytes;  // at most kCarrySlots-1 chunks
+  const size_t min_chunk = ((len / (kCarrySlots - 2)) / (2 * kTileBytes) + 1) * (2 * kTileBytes);  // at most kCarrySlots-1 chunks
   if (chunk < min_chunk) chunk = min_chunk;
   const size_t nchunks = (len + chunk - 1) / chunk;
+  const bool drain = !direct_out && elt != 0 && host_out != nullptr;
   while (c->chunk_events.size() < 2 * nchunks) {
     cudaEvent_t e;
     if (!ok(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event")) return false;
     c->chunk_events.push_back(e);
   }
+  // where does the input come from?
+  int in_path = 0;
+  {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, buf) == cudaSuccess) {
+      if (attr.type == cudaMemoryTypeHost) in_path = 2;
+    } else {
+      (void)cudaGetLastError();
+    }
+    if (in_path == 0 && c->opt_copy_threads > 0 && len >= size_t(c->opt_stage_min_bytes) && ensure_ring(c, chunk) && ensure_pool(c)) in_path = 1;
+  }
+  c->last_input_path = in_path;
+  c->last_output_path = direct_out ? 1 : 0;
   CUtensorMap map;
   bool tma = false;
-  make_tensor_map(c, &map, c->d_in, len, &tma);
+  map_for(c, kind, &map, c->d_in, len, &tma);
   // calls are synchronous, so no earlier kernel still reads d_in when the first copy lands
-  for (size_t k = 0; k < nchunks; k++) {
+  auto launch_chunk = [&](size_t k, const uint8_t *src) -> bool {
     const size_t off = k * chunk;
     const size_t bytes = std::min(chunk, len - off);
     cudaEvent_t copied = c->chunk_events[2 * k], scanned = c->chunk_events[2 * k + 1];
-    if (!ok(c, cudaMemcpyAsync(c->d_in + off, buf + off, bytes, cudaMemcpyHostToDevice, c->copy_stream), "H2D chunk") ||
+    if (!ok(c, cudaMemcpyAsync(c->d_in + off, src, bytes, cudaMemcpyHostToDevice, c->copy_stream), "H2D chunk") ||
         !ok(c, cudaEventRecord(copied, c->copy_stream), "event record") || !ok(c, cudaStreamWaitEvent(c->stream, copied, 0), "wait event"))
       return false;
     const bool last = (k + 1 == nchunks);
     if (!enqueue_scan(c, kind, &map, tma, c->d_in, len, uint32_t(off / kTileBytes), tiles_of(bytes), last, 0x20202020u, d_idx, d_dst,
-                      k == 0 ? -1 : int(k), c->stream, int(k + 1)))
+                      k == 0 ? -1 : int(k), c->stream, int(k + 1), false, nullptr, c->h_carry + k + 1))
       return false;
-    if (!ok(c, cudaMemcpyAsync(c->h_carry + k + 1, c->d_carry + k + 1, sizeof(Carry), cudaMemcpyDeviceToHost, c->stream), "D2H carry") ||
-        !ok(c, cudaEventRecord(scanned, c->stream), "event record"))
+    if (!use_scan4(c, kind) &&  // scan4 mirrors its result to the pinned host slot itself
+        !ok(c, cudaMemcpyAsync(c->h_carry + k + 1, c->d_carry + k + 1, sizeof(Carry), cudaMemcpyDeviceToHost, c->stream), "D2H carry"))
       return false;
+    return !drain || ok(c, cudaEventRecord(scanned, c->stream), "event record");
+  };
+  if (in_path == 1) {
+    CopyPool &pool = *c->pool;
+    const int slots = c->ring_slots;
+    pool.begin(buf, len, chunk, c->h_ring, c->ring_slot_bytes, slots);
+    pool.allow(size_t(slots));
+    size_t issued = 0, released = 0;  // chunks handed to the copy engine / known to have left their slot
+    bool good = true;
+    while (good && issued < nchunks) {
+      while (released < issued && cudaEventQuery(c->ring_events[released % size_t(slots)]) == cudaSuccess) {
+        released++;
+        pool.allow(released + size_t(slots));
+      }
+      if (pool.chunk_ready(issued)) {
+        good = launch_chunk(issued, c->h_ring + (issued % size_t(slots)) * c->ring_slot_bytes) &&
+               ok(c, cudaEventRecord(c->ring_events[issued % size_t(slots)], c->copy_stream), "event record");
+        issued++;
+      } else {
+        SJB200_CPU_RELAX();
+      }
+    }
+    (void)cudaGetLastError();  // cudaEventQuery's cudaErrorNotReady is not an error
+    pool.end(!good);
+    if (!good) return false;
+  } else {
+    for (size_t k = 0; k < nchunks; k++)
+      if (!launch_chunk(k, buf + k * chunk)) return false;
   }
-  // drain: bring each chunk's output back as soon as that chunk is done
-  uint64_t have = 0;
-  for (size_t k = 0; k < nchunks; k++) {
-    if (!ok(c, cudaEventSynchronize(c->chunk_events[2 * k + 1]), "event sync")) return false;
-    const uint64_t upto = c->h_carry[k + 1].count;
-    if (elt && host_out && upto > have) {
-      const uint8_t *src = (kind == kIndex) ? reinterpret_cast<const uint8_t *>(d_idx) : d_dst;
-      if (!ok(c, cudaMemcpyAsync(static_cast<uint8_t *>(host_out) + have * elt, src + have * elt, size_t(upto - have) * elt,
-                                 cudaMemcpyDeviceToHost, c->out_stream), "D2H output"))
-        return false;
-      have = upto;
+  if (drain) {  // bring each chunk's output back as soon as that chunk is done
+    uint64_t have = 0;
+    for (size_t k = 0; k < nchunks; k++) {
+      if (!ok(c, cudaEventSynchronize(c->chunk_events[2 * k + 1]), "event sync")) return false;
+      const uint64_t upto = c->h_carry[k + 1].count;
+      if (upto > have) {
+        const uint8_t *src = (kind == kIndex) ? reinterpret_cast<const uint8_t *>(d_idx) : d_dst;
+        if (!ok(c, cudaMemcpyAsync(static_cast<uint8_t *>(host_out) + have * elt, src + have * elt, size_t(upto - have) * elt,
+                                   cudaMemcpyDeviceToHost, c->out_stream), "D2H output"))
+          return false;
+        have = upto;
+      }
     }
   }
+  if (!ok(c, cudaStreamSynchronize(c->stream), "sync") || (drain && !ok(c, cudaStreamSynchronize(c->out_stream), "sync"))) return false;
   // every launch reports (and clears) its own flags: the document's flags are their union
   uint32_t flags = 0;
   for (size_t k = 0; k < nchunks; k++) flags |= c->h_carry[k + 1].flags;
   *c->h_flags = flags;
   *final_slot = int(nchunks);
-  return ok(c, cudaStreamSynchronize(c->stream), "sync") && ok(c, cudaStreamSynchronize(c->out_stream), "sync");
+  return true;
+}
+
+// device alias of a caller array the kernels may store into directly: page-locked AND mapped host memory
+uint32_t *mapped_alias(sjb200_ctx *c, uint32_t *host_ptr) {
+  if (!c->opt_zero_copy_out || !host_ptr) return nullptr;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, host_ptr) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+  if (attr.type != cudaMemoryTypeHost || attr.devicePointer == nullptr) return nullptr;
+  return static_cast<uint32_t *>(attr.devicePointer);
 }
 
 }  // namespace
@@ -815,9 +927,11 @@ extern "C" int sjb200_stage1(sjb200_ctx *c, const uint8_t *buf, size_t len, int 
     if (len == 0) return SJB200_UTF8_ERROR;
   }
   DeviceGuard g(c->device);
-  if (!ensure_input(c, len) || !ensure_index(c, len) || !ensure_desc(c, len)) return SJB200_MEMALLOC;
+  uint32_t *alias = use_scan4(c, kIndex) ? mapped_alias(c, idx_out) : nullptr;
+  if (!ensure_input(c, len) || (!alias && !ensure_index(c, len)) || !ensure_desc(c, len)) return SJB200_MEMALLOC;
   int slot = 0;
-  if (!scan_host_document(c, kIndex, buf, len, c->d_idx, nullptr, idx_out, sizeof(uint32_t), &slot)) return SJB200_UNEXPECTED_ERROR;
+  if (!scan_host_document(c, kIndex, buf, len, alias ? alias : c->d_idx, nullptr, idx_out, sizeof(uint32_t), alias != nullptr, &slot))
+    return SJB200_UNEXPECTED_ERROR;
   FinishInput in;
   in.mode = mode; in.len = len;
   in.count = c->h_carry[slot].count;
@@ -839,7 +953,7 @@ extern "C" int sjb200_minify(sjb200_ctx *c, const uint8_t *buf, size_t len, uint
   if (!ensure_input(c, len) || !ensure_output(c, len) || !ensure_desc(c, len)) return SJB200_MEMALLOC;
   int slot = 0;
   // the padded tail is never output, so at most len bytes are written to dst (json_minifier.h L79-95)
-  if (!scan_host_document(c, kMinify, buf, len, nullptr, c->d_out, dst, 1, &slot)) return SJB200_UNEXPECTED_ERROR;
+  if (!scan_host_document(c, kMinify, buf, len, nullptr, c->d_out, dst, 1, false, &slot)) return SJB200_UNEXPECTED_ERROR;
   if (*c->h_flags & kFlagInternal) return SJB200_UNEXPECTED_ERROR;
   if ((c->h_carry[slot].state >> 1) & 1u) return SJB200_UNCLOSED_STRING;
   *dst_len = size_t(c->h_carry[slot].count);
@@ -853,7 +967,7 @@ extern "C" int sjb200_validate_utf8(sjb200_ctx *c, const uint8_t *buf, size_t le
   DeviceGuard g(c->device);
   if (!ensure_input(c, len)) return 0;
   int slot = 0;
-  if (!scan_host_document(c, kUtf8, buf, len, nullptr, nullptr, nullptr, 0, &slot)) return 0;
+  if (!scan_host_document(c, kUtf8, buf, len, nullptr, nullptr, nullptr, 0, false, &slot)) return 0;
   if (*c->h_flags & kFlagInternal) return 0;
   return (*c->h_flags & kFlagUtf8) ? 0 : 1;
 }
@@ -869,7 +983,7 @@ extern "C" int sjb200_stage1_shard_dev(sjb200_ctx *c, const uint8_t *d_buf, size
   if (!ensure_desc(c, len)) return SJB200_MEMALLOC;
   CUtensorMap map;
   bool tma = false;
-  make_tensor_map(c, &map, d_buf, len, &tma);
+  map_for(c, kIndex, &map, d_buf, len, &tma);
   c->h_carry[0].count = 0; c->h_carry[0].state = state_in & 7u; c->h_carry[0].ttable = 0;
   (void)last_shard;  // every shard checks its own end: cuts are at character boundaries (sjb200_shard_cut)
   c->h_carry[0].flags = 0; c->h_carry[0].reserved = 0;
@@ -895,7 +1009,7 @@ extern "C" int sjb200_stage1_shard_dev_enqueue(sjb200_ctx *c, const uint8_t *d_b
   if (!ensure_desc(c, len)) return SJB200_MEMALLOC;
   CUtensorMap map;
   bool tma = false;
-  make_tensor_map(c, &map, d_buf, len, &tma);
+  map_for(c, kIndex, &map, d_buf, len, &tma);
   if (!enqueue_scan(c, kIndex, &map, tma, d_buf, len, 0, tiles_of(len), true, 0x20202020u, d_idx, nullptr, -1, s, 1, false,
                     static_cast<Carry *>(d_result)))
     return SJB200_UNEXPECTED_ERROR;

@@ -34,6 +34,7 @@ constexpr int kMinCtasPerSm = SJB200_MIN_CTAS;  // __launch_bounds__ occupancy t
 #define SJB200_MAX_SUB 8
 #endif
 constexpr int kMaxSub = SJB200_MAX_SUB;
+constexpr int kMaxRanks = 8;                          // GPUs of one node that can share a scan (sjb200_comm)
 constexpr int kCtlBytes = 1024;                       // control block
 constexpr int kLutBytes = 64 * 64;                    // composed-transducer table
 constexpr int kEmitBytes = kWarps * 1024;             // per-warp emit scratch (128 mask words + 128 counts)
@@ -79,6 +80,26 @@ struct ScanParams {
   uint32_t *ticket;         // [0] next ticket, [1] CTAs finished, [2] scan4: aggregates published so far (4 words, zero between launches)
   uint32_t *park;           // scan4, deferred mode: scratch ring for parked masks, scan4_park_words(grid) words (stays in L2)
   unsigned long long *debug;  // optional [ntiles][8] timeline (globaltimer ns) for tuning; null in production
+  // multi-GPU exchange fused into the scan (scan4): the launch's last CTA stores the shard record {count, state out,
+  // transducer, flags} into EVERY rank's exchange window over NVLink (peer-mapped device memory), tagged with xchg_seq --
+  // the path's one exchange step without a collective launch.  xchg_nranks == 0: no exchange.
+  unsigned long long *xchg_peer[kMaxRanks];  // [r] = base of rank r's window: [slots][kMaxRanks][2] words
+  uint32_t xchg_nranks, xchg_rank, xchg_slot, xchg_seq;
 };
+
+#if defined(__CUDACC__)
+#define SJ_PARAMS_HD __host__ __device__
+#else
+#define SJ_PARAMS_HD
+#endif
+// one shard record as two independently tagged 64-bit words (8-byte stores are single transactions):
+//   w0 = seq[15:0] << 48 | count[47:0]        w1 = seq << 32 | flags << 16 | ttable << 8 | state_out
+SJ_PARAMS_HD inline unsigned long long xchg_word0(uint32_t seq, uint64_t count) { return ((unsigned long long)(seq & 0xFFFFu) << 48) | (count & 0xFFFFFFFFFFFFull); }
+SJ_PARAMS_HD inline unsigned long long xchg_word1(uint32_t seq, uint32_t state, uint32_t ttable, uint32_t flags) {
+  return ((unsigned long long)seq << 32) | ((unsigned long long)(flags & 0xFFu) << 16) | ((unsigned long long)(ttable & 0x3Fu) << 8) | (state & 7u);
+}
+SJ_PARAMS_HD inline bool xchg_complete(unsigned long long w0, unsigned long long w1, uint32_t seq) {
+  return uint32_t(w0 >> 48) == (seq & 0xFFFFu) && uint32_t(w1 >> 32) == seq;
+}
 
 }  // namespace sjb200

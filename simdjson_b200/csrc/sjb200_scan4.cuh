@@ -79,6 +79,18 @@ static_assert(kLag >= 1 && 2 * kLag + 3 <= kNS && 2 * (kParkD - 1) + 3 <= kNS &&
 #ifndef SJB200_SCAN4_SLEEP
 #define SJB200_SCAN4_SLEEP 1
 #endif
+#ifndef SJB200_SCAN4_TRACE
+#define SJB200_SCAN4_TRACE 0  // 1: tuning build that records where a scan warp's time goes (shared memory, dumped to ScanParams::debug at exit)
+#endif
+constexpr int kTraceIters = 8, kTracePoints = 12;
+#if SJB200_SCAN4_TRACE
+#define SJ_TRACE4(pt)                                                                                              \
+  do {                                                                                                             \
+    if (lane == 0 && (warp == 0 || warp == 9) && j < uint32_t(kTraceIters)) S->trace[warp ? 1 : 0][j][pt] = sj_clock32(); \
+  } while (0)
+#else
+#define SJ_TRACE4(pt) do { } while (0)
+#endif
 constexpr uint32_t kSpinLimit4 = 1u << 21;  // bounded waits: a stuck protocol becomes kFlagInternal, never a hang
 constexpr uint32_t kStageWords = kBlockBytes / 4;
 constexpr int kElemBytes = kScanWarps * kBlockBytes;  // 32 KiB or 64 KiB: what one CTA scans per ticket, one look-back descriptor
@@ -103,6 +115,10 @@ struct Smem {
   sj_mbar_t ticket_ready[kNS];
   sj_mbar_t scanned[kNS];
   sj_mbar_t resolved[kNS];
+#if SJB200_SCAN4_TRACE
+  uint32_t trace[2][kTraceIters][kTracePoints];  // tuning build: SM cycle counter at the phase boundaries of scan warps 0 and 9
+  unsigned long long trace_cta[4];               // globaltimer: kernel entry, roles start, scan role done, before exit
+#endif
 };
 constexpr int kSmemBytes4 = int(sizeof(Smem)) + 1024;
 
@@ -342,7 +358,11 @@ SJ_DEV uint32_t scan_block(const uint8_t *T, uint32_t pw0, uint32_t e_in, uint32
       transpose32(w8, pl);
       const unit_classes c = classify(pl);
       bs[u] = c.bs; qu[u] = c.qu; op[u] = c.op; sc[u] = c.sc; cl[u] = c.ctl;
+#if defined(SJB200_DIAG_NO_UTF8)  // ablation for tuning only (results are wrong for non-ASCII input)
+      if (false) {
+#else
       if (sj_any((pl[7] | pend) != 0)) {  // all-ASCII units of a warp (and nothing pending) need no check
+#endif
         uerr |= utf8_check_unit(pl, uc);
         pend = (uc.n1 >> 31) | (uc.n2 >> 30) | (uc.n3 >> 29);
       } else {
@@ -445,6 +465,9 @@ SJ_DEV uint32_t scan_block(const uint8_t *T, uint32_t pw0, uint32_t e_in, uint32
     (m) &= ~(1u << (h & 31u));                   \
   }
 SJ_DEV void emit_columns(const sj_u4 ev, uint32_t off, uint32_t pos_lane, uint32_t *dst) {
+#if defined(SJB200_DIAG_NO_EMIT)  // ablation for tuning only (no output)
+  return;
+#endif
 #if SJB200_SCAN4_EMIT == 0
   const uint32_t m4[4] = {ev.x, ev.y, ev.z, ev.w};
 #pragma unroll
@@ -542,7 +565,7 @@ SJ_DEV void emit_block(Smem *S, const ScanParams &p, uint64_t out_base, uint32_t
   } else {
     emit_columns_dense(ev, off, pos_lane, out);  // > 1 structural per 4 bytes over 4 KiB: straight to global memory
   }
-  if (p.debug != nullptr && warp == 0 && lane == 0) p.debug[uint64_t(elem) * 8 + 5] = sj_globaltimer();
+  if (!SJB200_SCAN4_TRACE && p.debug != nullptr && warp == 0 && lane == 0) p.debug[uint64_t(elem) * 8 + 5] = sj_globaltimer();
 }
 
 // pipelined mode: the masks wait in shared memory
@@ -788,13 +811,16 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
         ne++;
       }
     }
+    SJ_TRACE4(0);
     uint32_t t_acq = 0;
     if (warp == 0 && lane == 0 && j > 0) t_acq = sj_atomic_add(p.ticket, 1u);  // element j+2 of this CTA (see below for j == 0)
     const uint32_t tn = wait_ticket(S, j + 1, p);
+    SJ_TRACE4(1);
     if (tn < nelem) tma_next = issue_load(S, tmap, p, tn, warp, lane, r ^ 1, &pw_next, scan_limit);
+    SJ_TRACE4(2);
     uint8_t *T = S->ring[warp][r];
     const uint64_t bstart = launch_start + uint64_t(t) * kElemBytes + uint64_t(warp) * kBlockBytes;
-    if (p.debug != nullptr && warp == 0 && lane == 0) {
+    if (!SJB200_SCAN4_TRACE && p.debug != nullptr && warp == 0 && lane == 0) {
       p.debug[uint64_t(t) * 8 + 0] = sj_globaltimer();
       p.debug[uint64_t(t) * 8 + 7] = ((unsigned long long)sj_smid() << 48) | ((unsigned long long)sj_cta() << 32) | j;
     }
@@ -807,8 +833,10 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
         fill_block_guarded(T, p, bstart, lane);
         sj_syncwarp();
       }
+      SJ_TRACE4(3);
       const uint32_t pw0 = sj_shfl(pw_cur, 0);
       const uint32_t st = boundary_state(p, bstart, launch_start, cin.state, pw0, lane);
+      SJ_TRACE4(4);
       if (kDefer) {
         uint32_t *slot = park_slot(p, j);
         summary = scan_block<false>(T, pw0, st & 1u, (st >> 2) & 1u, lane, p, reinterpret_cast<sj_u4 *>(slot),
@@ -819,7 +847,8 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
                                    left < uint64_t(kBlockBytes) ? uint32_t(left) : uint32_t(kBlockBytes));
       }
     }
-    if (p.debug != nullptr && warp == 0 && lane == 0) p.debug[uint64_t(t) * 8 + 1] = sj_globaltimer();
+    if (!SJB200_SCAN4_TRACE && p.debug != nullptr && warp == 0 && lane == 0) p.debug[uint64_t(t) * 8 + 1] = sj_globaltimer();
+    SJ_TRACE4(5);
     {
       const int ns = int(j % kNS);
       uint32_t last = 0;
@@ -830,7 +859,7 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
       }
       if (sj_shfl(last, 0)) {
         sj_fence_block();
-        if (p.debug != nullptr && lane == 0) p.debug[uint64_t(t) * 8 + 3] = sj_globaltimer();
+        if (!SJB200_SCAN4_TRACE && p.debug != nullptr && lane == 0) p.debug[uint64_t(t) * 8 + 3] = sj_globaltimer();
         compose_element(S, p, ns, t, lane);
         if (lane == 0) {
           S->arrived[ns] = 0;
@@ -838,13 +867,16 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
         }
       }
     }
+    SJ_TRACE4(6);
     if (warp == 0) {
       if (j == 0 && lane == 0) t_acq = sj_atomic_add(p.ticket, 1u);  // start-up: keep the third ticket behind everybody's second
       publish_ticket(S, j + 2, t_acq, lane);
     }
+    SJ_TRACE4(7);
     if (!kDefer && j >= my_lag) {  // pipelined: the chain warp has had my_lag scans' time to resolve this one
       wait_bar(&S->resolved[ne % kNS], (ne / kNS) & 1u, p, 64);
-      if (p.debug != nullptr && warp == 0 && lane == 0) p.debug[uint64_t(S->ticket[ne % kNS]) * 8 + 2] = sj_globaltimer();
+      SJ_TRACE4(8);
+      if (!SJB200_SCAN4_TRACE && p.debug != nullptr && warp == 0 && lane == 0) p.debug[uint64_t(S->ticket[ne % kNS]) * 8 + 2] = sj_globaltimer();
       if (kMin) {
         const uint32_t pol = S->res_pol[ne % kNS][warp] & 1u;
         if (emit_minify_block(S, tmap, p, out_base, ne, warp, lane, S->park[ne % kPark][pol][warp * 32 + lane], S->parkpre[ne % kPark][warp * 32 + lane], T,
@@ -854,6 +886,7 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
         emit_from_smem(S, p, out_base, ne, warp, lane, reinterpret_cast<uint32_t *>(T));
       }
       ne++;
+      SJ_TRACE4(9);
     }
     t = tn;
     tma_cur = tma_next;
@@ -1099,7 +1132,7 @@ SJ_DEV void chain_role(Smem *S, const ScanParams &p, const Carry &cin, unsigned 
     const uint32_t t = wait_ticket(S, j, p);
     if (t >= nelem) break;
     wait_bar(&S->scanned[ns], (j / kNS) & 1u, p, 200);
-    if (p.debug != nullptr && lane == 0) p.debug[uint64_t(t) * 8 + 6] = sj_globaltimer();
+    if (!SJB200_SCAN4_TRACE && p.debug != nullptr && lane == 0) p.debug[uint64_t(t) * 8 + 6] = sj_globaltimer();
     const uint32_t par = S->elem[ns][0], b0 = S->elem[ns][1], b1 = S->elem[ns][2], hits = S->elem[ns][3];
     uint32_t s_in = (cin.state >> 1) & 1u, base = 0;
     if (t > 0) look_back(p, t, lane, &s_in, &base);
@@ -1115,7 +1148,7 @@ SJ_DEV void chain_role(Smem *S, const ScanParams &p, const Carry &cin, unsigned 
     if (lane == 0 && (s_in ? hit1 : hit0)) sj_atomic_or(p.flags, kFlagCtl);
     sj_syncwarp();
     if (lane == 0) sj_mbar_arrive(&S->resolved[ns]);
-    if (p.debug != nullptr && lane == 0) p.debug[uint64_t(t) * 8 + 4] = sj_globaltimer();
+    if (!SJB200_SCAN4_TRACE && p.debug != nullptr && lane == 0) p.debug[uint64_t(t) * 8 + 4] = sj_globaltimer();
     if (t == nelem - 1) finalize_launch(p, cin, s_out, cin.count + base + mine_total, lane);
   }
 }
@@ -1126,6 +1159,14 @@ SJ_DEV void scan4_body(const sj_tensor_map *tmap, const ScanParams &p, uint8_t *
   // 1 KiB alignment for the 128B swizzle, computed on the shared-space address so the pointer keeps its address space
   Smem *S = reinterpret_cast<Smem *>(smem_raw + ((1024u - (smem_raw_addr & 1023u)) & 1023u));
   const unsigned tid = sj_tid(), lane = tid & 31u, warp = tid >> 5;
+#if SJB200_SCAN4_TRACE
+  if (tid == 0) {
+    S->trace_cta[0] = sj_globaltimer();
+    for (int a = 0; a < 2; a++)
+      for (int b = 0; b < kTraceIters; b++)
+        for (int cc = 0; cc < kTracePoints; cc++) S->trace[a][b][cc] = 0;
+  }
+#endif
   Carry cin;
   cin.count = 0; cin.state = 0; cin.ttable = 0; cin.flags = 0; cin.reserved = 0;
   if (p.carry_in != nullptr) cin = *p.carry_in;
@@ -1144,10 +1185,27 @@ SJ_DEV void scan4_body(const sj_tensor_map *tmap, const ScanParams &p, uint8_t *
   }
   if (kMode == 2 && tid < 16) S->compact_lut[tid] = compact_entry(tid);
   sj_syncthreads();
+#if SJB200_SCAN4_TRACE
+  if (tid == 0) S->trace_cta[1] = sj_globaltimer();
+#endif
   if (warp < unsigned(kScanWarps)) scan_role<kMode>(S, tmap, p, cin, warp, lane);
   else chain_role(S, p, cin, lane, warp - unsigned(kScanWarps));
+#if SJB200_SCAN4_TRACE
+  if (tid == 0) S->trace_cta[2] = sj_globaltimer();
+#endif
   // last CTA out resets the ticket for the next launch on this context and hands the flags over
   sj_syncthreads();
+#if SJB200_SCAN4_TRACE
+  if (tid == 0 && p.debug != nullptr) {  // rows: [cta][0] = 4 CTA times + smid; [cta][1 + a * kTraceIters + b] = the 12 points of warp a, iteration b
+    unsigned long long *row = p.debug + size_t(sj_cta()) * (1 + 2 * kTraceIters) * 8;
+    row[0] = S->trace_cta[0]; row[1] = S->trace_cta[1]; row[2] = S->trace_cta[2]; row[3] = sj_globaltimer(); row[4] = sj_smid();
+    for (int a = 0; a < 2; a++)
+      for (int b = 0; b < kTraceIters; b++) {
+        unsigned long long *q = row + size_t(1 + a * kTraceIters + b) * 8;
+        for (int cc = 0; cc < 6; cc++) q[cc] = (unsigned long long)S->trace[a][b][2 * cc] | ((unsigned long long)S->trace[a][b][2 * cc + 1] << 32);
+      }
+  }
+#endif
   if (tid == 0) {
     sj_threadfence();
     const uint32_t done = sj_atomic_add(p.ticket + 1, 1u);
@@ -1158,6 +1216,17 @@ SJ_DEV void scan4_body(const sj_tensor_map *tmap, const ScanParams &p, uint8_t *
       const uint32_t fl = sj_atomic_exch(p.flags, 0u);
       p.carry_out->flags = fl;
       if (p.carry_out_host != nullptr) p.carry_out_host->flags = fl;
+      if (p.xchg_nranks != 0) {
+        // the exchange step of a sharded scan, fused: this launch's record goes straight into every rank's window
+        // (finalize_launch's stores are visible here: its CTA fenced before it counted itself out)
+        const volatile Carry *co = p.carry_out;
+        const unsigned long long w0 = xchg_word0(p.xchg_seq, co->count), w1 = xchg_word1(p.xchg_seq, co->state, co->ttable, fl);
+        for (uint32_t r = 0; r < p.xchg_nranks; r++) {
+          unsigned long long *rec = p.xchg_peer[r] + (size_t(p.xchg_slot) * kMaxRanks + p.xchg_rank) * 2;
+          sj_st_sys_u64(rec, w0);
+          sj_st_sys_u64(rec + 1, w1);
+        }
+      }
       sj_threadfence();
     }
   }

@@ -131,6 +131,7 @@ SJ_DEV uint32_t sj_atomic_exch(uint32_t *p, uint32_t v) { return __atomic_exchan
 SJ_DEV unsigned long long sj_ld_relaxed_u64(const unsigned long long *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 SJ_DEV void sj_st_relaxed_u64(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 SJ_DEV void sj_threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+SJ_DEV void sj_st_sys_u64(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 SJ_DEV void sj_fence_gpu_release() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 SJ_DEV uint32_t sj_ld_relaxed_u32(const uint32_t *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 SJ_DEV void sj_fence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
@@ -139,6 +140,7 @@ SJ_DEV void sj_nanosleep(unsigned) {
   nanosleep(&ts, nullptr);
 }
 SJ_DEV unsigned sj_smid() { return simt::tctx.cta; }
+SJ_DEV uint32_t sj_clock32() { return uint32_t(sj_globaltimer()); }
 SJ_DEV unsigned long long sj_globaltimer() {
   struct timespec ts;
   clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -275,6 +277,10 @@ SJ_DEV void sj_st_relaxed_u64(unsigned long long *p, unsigned long long v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 SJ_DEV void sj_threadfence() { __threadfence(); }
+// a word of another GPU's memory (peer-mapped over NVLink): system scope
+SJ_DEV void sj_st_sys_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 SJ_DEV void sj_fence_gpu_release() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 SJ_DEV uint32_t sj_ld_relaxed_u32(const uint32_t *p) {
   uint32_t v;
@@ -293,6 +299,7 @@ SJ_DEV unsigned long long sj_globaltimer() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+SJ_DEV uint32_t sj_clock32() { return uint32_t(clock64()); }  // SM-local cycle counter (cheap; for intervals on one SM)
 
 typedef CUtensorMap sj_tensor_map;
 typedef unsigned long long sj_mbar_t;

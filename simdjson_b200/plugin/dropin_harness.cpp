@@ -2,7 +2,9 @@
 // parse_many, ondemand::parser::iterate, simdjson::minify, simdjson::validate_utf8) with either the "b200"
 // plug-in or a CPU implementation active, so the pytest drop-in tests can compare the two.  It is the
 // reference-side usage a maintainer would write, wrapped for ctypes.
+#include <chrono>
 #include <cstring>
+#include <memory>
 #include <string>
 
 #include "b200_implementation.h"
@@ -116,4 +118,37 @@ HARNESS_API int dropin_minify(int use_b200, const uint8_t *buf, size_t len, uint
 HARNESS_API int dropin_validate_utf8(int use_b200, const uint8_t *buf, size_t len) {
   scoped_impl g(pick(use_b200, 0));
   return simdjson::validate_utf8(reinterpret_cast<const char *>(buf), len) ? 1 : 0;
+}
+
+// Stage 1 alone through the reference's own boundary, timed inside the process: what `bench.py` reports as e2e.
+// get_active_implementation()->create_dom_parser_implementation(...)->stage1(buf, len, regular) on a pageable
+// padded_string (the memory dom::parser::parse hands its implementation), `iters` calls after two warm-up calls.
+// Returns the error code of the last call; seconds[0] = total of the timed calls, seconds[1] = the fastest call.
+// idx_out (optional, idx_cap words): the n + 3 index words of the last call, for the parity gate.
+HARNESS_API int dropin_stage1_timed(int use_b200, const uint8_t *buf, size_t len, int iters, double *seconds, uint32_t *n_out,
+                                    uint32_t *idx_out, size_t idx_cap, unsigned long long *gpu_calls) {
+  scoped_impl g(pick(use_b200, 0));
+  std::unique_ptr<internal::dom_parser_implementation> p;
+  auto err = get_active_implementation()->create_dom_parser_implementation(len, 1024, p);
+  if (err) return int(err);
+  padded_string json(reinterpret_cast<const char *>(buf), len);
+  const uint8_t *b = reinterpret_cast<const uint8_t *>(json.data());
+  for (int i = 0; i < 2; i++) err = p->stage1(b, len, stage1_mode::regular);
+  double total = 0, best = 1e30;
+  for (int i = 0; i < iters; i++) {
+    const auto t0 = std::chrono::steady_clock::now();
+    err = p->stage1(b, len, stage1_mode::regular);
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    total += dt;
+    if (dt < best) best = dt;
+  }
+  seconds[0] = total;
+  seconds[1] = best;
+  *n_out = p->n_structural_indexes;
+  if (idx_out && size_t(p->n_structural_indexes) + 3 <= idx_cap) std::memcpy(idx_out, p->structural_indexes.get(), (size_t(p->n_structural_indexes) + 3) * 4);
+  if (gpu_calls) {
+    auto *bp = dynamic_cast<b200::dom_parser_implementation *>(p.get());
+    *gpu_calls = bp ? bp->gpu_stage1_calls() : 0;
+  }
+  return int(err);
 }

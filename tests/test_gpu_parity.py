@@ -450,3 +450,41 @@ def test_config4_utf8_256mib(port):
     assert p.validate_utf8_device(d) == 1
     p.close()
     assert port.validate_utf8(u[: 1 << 20])
+
+
+# --------------------------------------------------------------------------- host-pointer pipeline (every input / output path)
+def test_host_pointer_paths(port):
+    """sjb200_stage1 / _minify / _validate_utf8 with host buffers: pageable input through the staging ring (copy
+    threads), through the driver, page-locked input; indexes stored by the kernel into the page-locked caller array or
+    copied back chunk by chunk -- all bit-identical to the oracle (include/simdjson/internal/dom_parser_implementation.h L80)."""
+    rc, p = sj.get_active_implementation().create_dom_parser_implementation(40 << 20)
+    assert rc == sj.SUCCESS
+    try:
+        rng = random.Random(corpus.SEED ^ 0x7077)
+        docs = [corpus.random_json(n) for n in (100, (1 << 20) - 3, (5 << 20) + 17, (33 << 20) + 4099)]
+        docs.append(_big_adversarial(rng, 3 * (1 << 20) + 333))
+        want = [(port.stage1(d, 0), port.stage1(d, 2)) for d in docs]
+        for threads, zero_copy, chunk in ((8, 1, 2 << 20), (3, 1, 1 << 20), (0, 1, 4 << 20), (5, 0, 2 << 20), (0, 0, 64 << 10)):
+            p.set_option("copy_threads", threads)
+            p.set_option("zero_copy_out", zero_copy)
+            p.set_option("chunk_bytes", chunk)
+            p.set_option("stage_min_bytes", 1 << 20)
+            for d, (w0, w2) in zip(docs, want):
+                assert_same(run_stage1(p, d, 0), w0, ("pageable", threads, zero_copy, len(d)))
+                assert p.get_stat("input_path") == (1 if threads and len(d) >= (1 << 20) else 0)
+                assert p.get_stat("output_path") == zero_copy
+                assert_same(run_stage1(p, d, 2), w2, ("pageable streaming_final", threads, zero_copy, len(d)))
+            pinned = torch.from_numpy(docs[2].copy()).pin_memory()
+            assert_same(run_stage1(p, pinned.numpy(), 0), want[2][0], ("page-locked input", threads))
+            assert p.get_stat("input_path") == 2
+            # the same pipeline feeds minify and validate_utf8
+            werr, wout = port.minify(docs[3])
+            err, out = p._minify_host(docs[3])
+            assert err == werr and bytes(out) == wout
+            assert p._validate_utf8_host(docs[3]) == port.validate_utf8(docs[3])
+            bad = docs[2].copy()
+            bad[len(bad) - 70000] = 0xFF
+            assert p._validate_utf8_host(bad) is False
+            assert_same(run_stage1(p, bad, 0), port.stage1(bad, 0), ("invalid utf-8", threads))
+    finally:
+        p.close()

@@ -52,6 +52,11 @@ if os.environ.get("PROBE_KERNEL", "4") == "4":
                   ("resolved - (all predecessors scanned)", t[:, 4] - ready), ("emitted - resolved", t[:, 5] - t[:, 4]),
                   ("emitted - scan start", t[:, 5] - t[:, 0])):
         print("%-40s mean %7.2f us  p50 %7.2f  p90 %7.2f  max %7.2f" % ((nm,) + us(a.astype(np.float64))))
+    v = (t[:, 1] > 0) & (t[:, 2] > 0)
+    if v.any():
+        for nm, a in (("warp 0: its own block scan (slot1 - slot0)", (t[:, 1] - t[:, 0])[v]), ("warp 0: emit (slot5 - slot2: resolved seen -> stored)", (t[:, 5] - t[:, 2])[v]),
+                      ("warp 0: emit start - resolved (slot2 - slot4)", (t[:, 2] - t[:, 4])[v])):
+            print("%-52s mean %7.2f us  p50 %7.2f  p90 %7.2f  max %7.2f" % ((nm,) + us(a.astype(np.float64))))
     dur = (t[:, 3] - t[:, 0]) / 1e3
     print("slowest scans (element, cta, sm, iteration, start us, duration us):")
     for i in np.argsort(-dur)[:14]:
@@ -67,6 +72,7 @@ if os.environ.get("PROBE_KERNEL", "4") == "4":
         rows = t[ctas == c]
         rows = rows[np.argsort(rows[:, 0])]
         print("cta", int(c), " ".join("[#%d: %.1f %.1f %.1f %.1f %.1f]" % (int(np.where((t == r).all(axis=1))[0][0]), (r[0] - t0) / 1e3, (r[3] - t0) / 1e3, (r[6] - t0) / 1e3, (r[4] - t0) / 1e3, (r[5] - t0) / 1e3) for i, r in enumerate(rows)))
+        print("   warp 0 (scan start, scan end, emit start, emit end):", " ".join("[%.1f %.1f | %.1f %.1f]" % ((r[0] - t0) / 1e3, (r[1] - t0) / 1e3, (r[2] - t0) / 1e3, (r[5] - t0) / 1e3) for r in rows))
     sys.exit(0)
 front = (t[:, 3] - t[:, 0]) / 1e3
 v6 = t[:, 6] > 0
