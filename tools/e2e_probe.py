@@ -1,21 +1,61 @@
-"""host-pointer path throughput vs chunk size (tuning aid)"""
-import os, sys, time
-import numpy as np, torch
+"""e2e probe: stage 1 through the plug-in (libsimdjson_b200.so, unmodified reference API, pageable padded_string) and
+through the Python mirror of the C ABI; sweeps the host-pipeline knobs via the SJB200_* environment.
+  python tools/e2e_probe.py            one line per configuration"""
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
-import simdjson_b200 as sj
-from simdjson_b200 import corpus
-doc = corpus.random_json(64 << 20)
-pin = torch.from_numpy(doc.copy()).pin_memory(); hb = pin.numpy()
-rc, p = sj.get_active_implementation().create_dom_parser_implementation(len(doc))
-# raw PCIe reference: H2D and D2H of the same sizes with torch
-d = torch.empty(len(doc), dtype=torch.uint8, device="cuda")
-for _ in range(3):
-    torch.cuda.synchronize(); t0 = time.perf_counter(); d.copy_(pin, non_blocking=True); torch.cuda.synchronize(); dt = time.perf_counter() - t0
-print(f"raw H2D 64 MiB pinned: {len(doc)/dt/1e9:.1f} GB/s")
-for chunk in (1 << 20, 4 << 20, 16 << 20, 64 << 20):
-    p.set_option("chunk_bytes", chunk)
-    ts = []
-    for _ in range(6):
-        t0 = time.perf_counter(); rc = p.stage1(hb, 0); ts.append(time.perf_counter() - t0)
-    print(f"chunk {chunk>>20:3d} MiB: best {len(doc)/min(ts)/1e9:6.2f} GB/s  median {len(doc)/sorted(ts)[3]/1e9:6.2f} GB/s  rc={rc} n={p.n_structural_indexes}")
+PLUGIN = os.path.join(ROOT, "simdjson_b200", "plugin", "libsimdjson_b200.so")
+
+
+def one():
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from simdjson_b200 import corpus
+    size = int(os.environ.get("PROBE_BYTES", 64 << 20))
+    cache = f"/tmp/probe_cache_{size}.npz"
+    z = np.load(cache) if os.path.exists(cache) else None
+    doc = z["doc"] if z is not None else corpus.random_json(size).copy()
+    L = C.CDLL(PLUGIN)
+    L.dropin_stage1_timed.restype = C.c_int
+    L.dropin_stage1_timed.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.c_void_p, C.c_size_t,
+                                      C.POINTER(C.c_ulonglong)]
+    secs = (C.c_double * 2)()
+    n = C.c_uint32(0)
+    calls = C.c_ulonglong(0)
+    idx = np.zeros(len(doc) // 4 + 16, dtype=np.uint32)
+    use = int(os.environ.get("PROBE_USE_B200", 1))
+    iters = int(os.environ.get("PROBE_ITERS", 10))
+    rc = L.dropin_stage1_timed(use, doc.ctypes.data, len(doc), iters, secs, C.byref(n), idx.ctypes.data, len(idx), C.byref(calls))
+    res = {"tag": os.environ.get("PROBE_TAG", ""), "bytes": size, "rc": rc, "n": int(n.value), "gpu_calls": int(calls.value),
+           "gbs_mean": size * iters / secs[0] / 1e9, "gbs_best": size / secs[1] / 1e9, "ms_best": secs[1] * 1e3}
+    if z is not None:
+        res["parity"] = bool(rc == int(z["err"]) and int(n.value) == int(z["n"]) and np.array_equal(idx[: int(z["n"]) + 3], z["words"]))
+    print(json.dumps(res), flush=True)
+    with open(os.path.join(ROOT, "gpurun_out", "e2e_probe.jsonl"), "a") as f:
+        f.write(json.dumps(res) + "\n")
+
+
+if __name__ == "__main__":
+    if os.environ.get("PROBE_CHILD"):
+        one()
+        sys.exit(0)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    configs = [("cpu reference (1 thread)", {"PROBE_USE_B200": "0", "PROBE_ITERS": "3"}),
+               ("threads8 chunk2M", {}),
+               ("threads0 (driver pageable copy)", {"SJB200_COPY_THREADS": "0"}),
+               ("threads4", {"SJB200_COPY_THREADS": "4"}),
+               ("threads12", {"SJB200_COPY_THREADS": "12"}),
+               ("threads16 chunk4M", {"SJB200_COPY_THREADS": "16", "SJB200_CHUNK_BYTES": str(4 << 20)}),
+               ("threads8 chunk1M slots16", {"SJB200_CHUNK_BYTES": str(1 << 20), "SJB200_RING_SLOTS": "16"}),
+               ("threads8 chunk4M", {"SJB200_CHUNK_BYTES": str(4 << 20)}),
+               ("threads8 chunk8M", {"SJB200_CHUNK_BYTES": str(8 << 20)}),
+               ("threads8 copy-engine D2H", {"SJB200_ZERO_COPY_OUT": "0"})]
+    for tag, env in configs:
+        e = dict(os.environ, PROBE_CHILD="1", PROBE_TAG=tag, **env)
+        subprocess.run([sys.executable, os.path.abspath(__file__)], env=e)
