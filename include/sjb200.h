@@ -154,10 +154,46 @@ SJB200_API int sjb200_stage1_shard_dev(sjb200_ctx *ctx, const uint8_t *d_buf, si
  * all-gather enqueued behind the scan on the same stream */
 SJB200_API int sjb200_stage1_shard_dev_enqueue(sjb200_ctx *ctx, const uint8_t *d_buf, size_t len, uint32_t *d_idx, void *d_result,
                                     void *stream);
+/* ---- the sharded scan as one call per rank, exchange fused into the scan kernel (no collective launch).
+ * One sjb200_comm per rank (one process per GPU, or several contexts in one process).  Each comm owns an exchange
+ * window in its device's memory; peers map each other's windows (CUDA IPC across processes: get_handle -> exchange the
+ * 64-byte handles by any means, e.g. one NCCL/gloo all-gather at start-up -> connect).  During a pass the scan
+ * kernel's last CTA stores the shard's 16-byte record {count, state, transducer, flags} straight into every rank's
+ * window over NVLink; finish() folds the true incoming state / 64-bit index base from the local window and, only if
+ * some rank's speculation (state 0) was wrong, re-scans that rank and runs a second round.  Indexes stay
+ * shard-relative (uint32) + base, like document_stream's batch_start + structural_indexes[i]
+ * (include/simdjson/dom/document_stream-inl.h L250).  Up to 32 passes may be in flight per rank. */
+typedef struct sjb200_comm sjb200_comm;
+#define SJB200_COMM_HANDLE_BYTES 64
+typedef struct {
+  uint64_t count;        /* structurals of this shard (after a re-scan: the corrected count) */
+  uint64_t base;         /* structurals of all earlier shards: global index i of this shard = base + i */
+  uint64_t total_count;  /* structurals of all shards */
+  uint32_t state_in;     /* true scanner state entering this shard (0 = the speculation held) */
+  uint32_t state_out;
+  uint32_t final_state;  /* state after the last shard (bit1: the document ends inside a string) */
+  uint32_t flags;        /* this shard: bit0 utf-8 error, bit1 unescaped control char in string, bit2 internal */
+  uint32_t flags_all;    /* union over all shards */
+  uint32_t rescanned;    /* 1: this rank scanned twice */
+} sjb200_sharded_result;
+SJB200_API int sjb200_comm_create(sjb200_ctx *ctx, int rank, int nranks /* <= 8 */, sjb200_comm **out);
+SJB200_API void sjb200_comm_destroy(sjb200_comm *comm);
+SJB200_API int sjb200_comm_get_handle(sjb200_comm *comm, void *handle /* SJB200_COMM_HANDLE_BYTES */);
+SJB200_API int sjb200_comm_connect(sjb200_comm *comm, const void *handles /* nranks x 64 bytes, by rank */);
+SJB200_API int sjb200_comm_connect_local(sjb200_comm *comm, sjb200_comm *const *all /* nranks comms of this process, by rank */);
+SJB200_API int sjb200_stage1_sharded(sjb200_comm *comm, const uint8_t *d_shard, size_t len, int last_shard, uint32_t *d_idx,
+                          sjb200_sharded_result *out, void *stream);
+SJB200_API int sjb200_stage1_sharded_enqueue(sjb200_comm *comm, const uint8_t *d_shard, size_t len, int last_shard, uint32_t *d_idx,
+                                  void *stream);
+SJB200_API int sjb200_stage1_sharded_finish(sjb200_comm *comm, sjb200_sharded_result *out); /* completes the oldest pass in flight */
+
 /* fold: state entering shard r given the ttables of shards 0..r-1 and the document's initial state 0 */
 SJB200_API uint32_t sjb200_fold_state(const uint32_t *ttables, int nshards_before);
 /* largest cut <= nominal such that buf[cut] is not a UTF-8 continuation byte (host pointer) */
 SJB200_API size_t sjb200_shard_cut(const uint8_t *buf, size_t len, size_t nominal);
+/* the same, preferring the byte after a raw line feed within `window` bytes below nominal: a raw 0x0A cannot occur
+ * inside a JSON string, so for valid input the next shard starts in state 0 and the speculation always holds */
+SJB200_API size_t sjb200_shard_cut_line(const uint8_t *buf, size_t len, size_t nominal, size_t window);
 
 #ifdef __cplusplus
 }

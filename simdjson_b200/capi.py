@@ -17,8 +17,11 @@ EXPORTS = [
     "sjb200_stage1_dev", "sjb200_minify_dev", "sjb200_validate_utf8_dev", "sjb200_stage1_dev_batch",
     "sjb200_stage1_dev_enqueue", "sjb200_stage1_dev_finish", "sjb200_minify_dev_enqueue", "sjb200_minify_dev_finish",
     "sjb200_validate_utf8_dev_enqueue", "sjb200_validate_utf8_dev_finish",
-    "sjb200_stage1_shard_dev", "sjb200_stage1_shard_dev_enqueue", "sjb200_fold_state", "sjb200_shard_cut",
+    "sjb200_stage1_shard_dev", "sjb200_stage1_shard_dev_enqueue", "sjb200_fold_state", "sjb200_shard_cut", "sjb200_shard_cut_line",
+    "sjb200_comm_create", "sjb200_comm_destroy", "sjb200_comm_get_handle", "sjb200_comm_connect", "sjb200_comm_connect_local",
+    "sjb200_stage1_sharded", "sjb200_stage1_sharded_enqueue", "sjb200_stage1_sharded_finish",
 ]
+COMM_HANDLE_BYTES = 64
 
 # simdjson::error_code values of this path (include/simdjson/error.h L19-54)
 SUCCESS, CAPACITY, MEMALLOC, UTF8_ERROR, EMPTY, UNESCAPED_CHARS, UNCLOSED_STRING, UNSUPPORTED_ARCHITECTURE, UNEXPECTED_ERROR = 0, 1, 2, 11, 13, 14, 15, 16, 24
@@ -35,6 +38,11 @@ class Doc(C.Structure):
 
 class ShardResult(C.Structure):
     _fields_ = [("ttable", C.c_uint32), ("state_out", C.c_uint32), ("flags", C.c_uint32), ("reserved", C.c_uint32), ("count", C.c_uint64)]
+
+
+class ShardedResult(C.Structure):
+    _fields_ = [("count", C.c_uint64), ("base", C.c_uint64), ("total_count", C.c_uint64), ("state_in", C.c_uint32), ("state_out", C.c_uint32),
+                ("final_state", C.c_uint32), ("flags", C.c_uint32), ("flags_all", C.c_uint32), ("rescanned", C.c_uint32)]
 
 
 def load():
@@ -74,6 +82,15 @@ def load():
         "sjb200_stage1_shard_dev_enqueue": (C.c_int, [vp, vp, sz, vp, vp, vp]),
         "sjb200_fold_state": (C.c_uint32, [u32p, C.c_int]),
         "sjb200_shard_cut": (sz, [vp, sz, sz]),
+        "sjb200_shard_cut_line": (sz, [vp, sz, sz, sz]),
+        "sjb200_comm_create": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp)]),
+        "sjb200_comm_destroy": (None, [vp]),
+        "sjb200_comm_get_handle": (C.c_int, [vp, vp]),
+        "sjb200_comm_connect": (C.c_int, [vp, vp]),
+        "sjb200_comm_connect_local": (C.c_int, [vp, C.POINTER(vp)]),
+        "sjb200_stage1_sharded": (C.c_int, [vp, vp, sz, C.c_int, vp, C.POINTER(ShardedResult), vp]),
+        "sjb200_stage1_sharded_enqueue": (C.c_int, [vp, vp, sz, C.c_int, vp, vp]),
+        "sjb200_stage1_sharded_finish": (C.c_int, [vp, C.POINTER(ShardedResult)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <new>
 #include <string>
 #include <vector>
@@ -62,6 +63,8 @@ struct sjb200_ctx {
   size_t desc_tiles = 0;
   uint8_t *d_chars = nullptr; size_t d_chars_bytes = 0;
   uint32_t *d_park = nullptr; size_t d_park_words = 0;  // scan4 deferred mode: parked masks (a per-CTA ring, independent of the input size)
+  long opt_utf8_kernel = 2;    // 2: utf8v2 (independent warps, sjb200_utf8.cuh); 1: scan_kernel<kUtf8> (tile-synchronous)
+  int grid_u = 0;
   long opt_minify_kernel = 3;  // 3: scan_kernel<kMinify>; 4: minify on the scan4 structure (not yet measured on hardware)
   long opt_deferred = 0;  // 0: never use the deferred variant of scan4 (default until measured better); 1: for launches that fit; 2: always
   // pinned host mirrors
@@ -198,9 +201,10 @@ bool make_tensor_map(sjb200_ctx *c, CUtensorMap *map, const uint8_t *d_buf, size
 }
 
 bool use_scan4(const sjb200_ctx *c, int kind) { return (kind == kIndex && c->opt_kernel == 4) || (kind == kMinify && c->opt_minify_kernel == 4); }
+bool use_utf8v2(const sjb200_ctx *c, int kind) { return kind == kUtf8 && c->opt_utf8_kernel == 2; }
 // the one tensor map the kernel selected for `kind` reads through (scan4: 4 KiB boxes; the tile-synchronous kernels: 32 KiB)
 bool map_for(sjb200_ctx *c, int kind, CUtensorMap *map, const uint8_t *d_buf, size_t len, bool *usable) {
-  return make_tensor_map(c, map, d_buf, len, usable, use_scan4(c, kind) ? kScan4BoxRows : kTileRows);
+  return make_tensor_map(c, map, d_buf, len, usable, (use_scan4(c, kind) || use_utf8v2(c, kind)) ? kScan4BoxRows : kTileRows);
 }
 int grid_cap(sjb200_ctx *c, int kind) {
   if (use_scan4(c, kind)) {
@@ -215,11 +219,17 @@ int grid_for(sjb200_ctx *c, int kind, uint32_t nelements) {
   return int(std::max<uint32_t>(1, std::min<uint32_t>(uint32_t(grid_cap(c, kind)), nelements)));
 }
 
+// where a sharded launch publishes its record (sjb200_comm)
+struct XchgTarget {
+  unsigned long long *peer[kMaxRanks];
+  uint32_t nranks, rank, slot, seq;
+};
+
 // Enqueue the scan of document tiles [tile_begin, tile_begin+ntiles) of (d_buf,len).
 bool enqueue_scan(sjb200_ctx *c, int kind, const CUtensorMap *map, bool tma, const uint8_t *d_buf, size_t len, uint32_t tile_begin,
                   uint32_t ntiles, bool has_last_tile, uint32_t prev_word, uint32_t *d_idx, uint8_t *d_dst, int carry_in_slot,
                   cudaStream_t stream, int carry_out_slot = -1, bool write_sentinels = false, Carry *external_out = nullptr,
-                  Carry *host_out = nullptr) {
+                  Carry *host_out = nullptr, const XchgTarget *xchg = nullptr) {
   // carry_in_slot < 0: the launch starts a document (zero state, zero count)
   if (carry_out_slot < 0) carry_out_slot = (carry_in_slot < 0) ? 1 : (carry_in_slot ^ 1);
   ScanParams p;
@@ -251,6 +261,10 @@ bool enqueue_scan(sjb200_ctx *c, int kind, const CUtensorMap *map, bool tma, con
   p.flags = c->d_flags;
   p.count_desc = c->d_count_desc;
   p.ticket = c->d_ticket;
+  if (xchg && use_scan4(c, kind)) {
+    for (int r = 0; r < kMaxRanks; r++) p.xchg_peer[r] = xchg->peer[r];
+    p.xchg_nranks = xchg->nranks; p.xchg_rank = xchg->rank; p.xchg_slot = xchg->slot; p.xchg_seq = xchg->seq;
+  }
   p.debug = nullptr;
   if (c->opt_debug_timeline) {
     const uint32_t rows = std::max<uint32_t>(ntiles, 4096);  // (the trace build of scan4 writes 17 rows per CTA)
@@ -288,6 +302,13 @@ bool enqueue_scan(sjb200_ctx *c, int kind, const CUtensorMap *map, bool tma, con
       p.park = c->d_park;
     }
     launched = ok(c, launch_scan4(map, p, grid, kind == kMinify ? 2 : (deferred ? 1 : 0), stream), "launch scan4");
+  } else if (use_utf8v2(c, kind)) {
+    if (c->grid_u == 0) c->grid_u = utf8v2_max_ctas_per_sm() * c->sm_count;
+    const uint64_t nblocks = (uint64_t(ntiles) * kTileBytes + 4095) / 4096;
+    const uint64_t want = (nblocks + uint64_t(utf8v2_warps_per_cta()) - 1) / uint64_t(utf8v2_warps_per_cta());
+    const int grid = c->opt_force_grid > 0 ? int(c->opt_force_grid) : int(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(c->opt_grid > 0 ? c->opt_grid : c->grid_u), want)));
+    p.carry_out_host = host_out;
+    launched = ok(c, launch_utf8v2(map, p, grid, stream), "launch utf8v2");
   } else {
     launched = ok(c, launch_scan(kind, map, p, grid_for(c, kind, p.nsuper), stream), "launch scan");
   }
@@ -538,6 +559,7 @@ extern "C" int sjb200_set_option(sjb200_ctx *c, const char *key, long value) {
   else if (!strcmp(key, "kernel")) c->opt_kernel = (value == 3) ? 3 : 4;
   else if (!strcmp(key, "deferred")) c->opt_deferred = value;
   else if (!strcmp(key, "minify_kernel")) c->opt_minify_kernel = (value == 4) ? 4 : 3;
+  else if (!strcmp(key, "utf8_kernel")) c->opt_utf8_kernel = (value == 1) ? 1 : 2;
   else if (!strcmp(key, "time_kernel")) c->opt_time_kernel = value;
   else if (!strcmp(key, "debug_timeline")) c->opt_debug_timeline = value;
   else if (!strcmp(key, "chunk_bytes")) c->opt_chunk_bytes = std::max<long>(2 * kTileBytes, (value / (2 * kTileBytes)) * (2 * kTileBytes));
@@ -1016,6 +1038,225 @@ extern "C" int sjb200_stage1_shard_dev_enqueue(sjb200_ctx *c, const uint8_t *d_b
   return SJB200_SUCCESS;
 }
 
+// =============================================================================== sharded scan with the exchange fused in
+// One object per rank.  The exchange window lives in device memory; peers map it through CUDA IPC (one process per GPU,
+// the torch.distributed / MPI layout) or directly (several contexts in one process).  A pass = every rank scans its
+// shard with the speculated state 0; the scan kernel's last CTA stores the 16-byte record {count, state, transducer,
+// flags} into every rank's window over NVLink -- no collective launch.  finish() reads the local window, folds the
+// true incoming state and index base, and -- only when somebody's speculation was wrong -- re-scans and runs a second
+// round.  Up to kXchgSteps / 2 passes may be in flight per rank (enqueue ... enqueue, finish ... finish).
+struct sjb200_comm {
+  sjb200_ctx *ctx = nullptr;
+  int rank = 0, nranks = 1;
+  unsigned long long *window = nullptr;            // [kXchgSteps][2 rounds][kMaxRanks][2]
+  unsigned long long *peer[kMaxRanks] = {};        // peer[r] = rank r's window as seen from this device
+  bool opened[kMaxRanks] = {};                     // mapped through cudaIpcOpenMemHandle (to be closed)
+  bool connected = false;
+  unsigned long long *h_rec = nullptr;             // pinned [kMaxRanks][2]
+  Carry *d_result = nullptr;                       // [kXchgSteps] the launches' own result blocks
+  cudaStream_t poll_stream = nullptr;
+  cudaEvent_t done[kXchgSteps] = {};
+  struct Step { const uint8_t *d_buf; size_t len; uint32_t *d_idx; cudaStream_t stream; uint32_t seq; int last; } steps[kXchgSteps];
+  uint32_t head = 0, tail = 0;                     // passes enqueued / finished
+  long poll_timeout_ms = 20000;
+};
+
+namespace {
+constexpr size_t kWindowWords = size_t(kXchgSteps) * 2 * kMaxRanks * 2;
+uint32_t window_slot(uint32_t seq, int round) { return (seq % uint32_t(kXchgSteps)) * 2u + uint32_t(round); }
+
+// wait (host polling, bounded) until every rank's record of (seq, round) is in the local window; records -> comm->h_rec
+int comm_collect(sjb200_comm *m, uint32_t seq, int round) {
+  sjb200_ctx *c = m->ctx;
+  const unsigned long long *src = m->window + size_t(window_slot(seq, round)) * kMaxRanks * 2;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (;;) {
+    if (!ok(c, cudaMemcpyAsync(m->h_rec, src, size_t(m->nranks) * 16, cudaMemcpyDeviceToHost, m->poll_stream), "D2H window") ||
+        !ok(c, cudaStreamSynchronize(m->poll_stream), "sync"))
+      return SJB200_UNEXPECTED_ERROR;
+    bool all = true;
+    for (int r = 0; r < m->nranks; r++) all = all && xchg_complete(m->h_rec[2 * r], m->h_rec[2 * r + 1], seq);
+    if (all) return SJB200_SUCCESS;
+    if (std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count() > m->poll_timeout_ms) {
+      c->last_error = "sharded scan: a peer's record did not arrive";
+      return SJB200_UNEXPECTED_ERROR;
+    }
+  }
+}
+}  // namespace
+
+extern "C" int sjb200_comm_create(sjb200_ctx *c, int rank, int nranks, sjb200_comm **out) {
+  if (!c || !out || nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks) return SJB200_UNEXPECTED_ERROR;
+  *out = nullptr;
+  DeviceGuard g(c->device);
+  sjb200_comm *m = new (std::nothrow) sjb200_comm();
+  if (!m) return SJB200_MEMALLOC;
+  m->ctx = c; m->rank = rank; m->nranks = nranks;
+  void *hp = nullptr;
+  bool good = dev_alloc(c, &m->window, kWindowWords, "cudaMalloc(window)") &&
+              ok(c, cudaMemset(m->window, 0, kWindowWords * sizeof(unsigned long long)), "memset window") &&
+              dev_alloc(c, &m->d_result, kXchgSteps, "cudaMalloc(results)") &&
+              ok(c, cudaMallocHost(&hp, kMaxRanks * 16), "cudaMallocHost") &&
+              ok(c, cudaStreamCreateWithFlags(&m->poll_stream, cudaStreamNonBlocking), "stream");
+  m->h_rec = static_cast<unsigned long long *>(hp);
+  for (int i = 0; good && i < kXchgSteps; i++) good = ok(c, cudaEventCreateWithFlags(&m->done[i], cudaEventDisableTiming), "event");
+  if (!good) { sjb200_comm_destroy(m); return SJB200_MEMALLOC; }
+  m->peer[rank] = m->window;
+  m->connected = (nranks == 1);
+  *out = m;
+  return SJB200_SUCCESS;
+}
+
+extern "C" void sjb200_comm_destroy(sjb200_comm *m) {
+  if (!m) return;
+  DeviceGuard g(m->ctx->device);
+  cudaDeviceSynchronize();
+  for (int r = 0; r < kMaxRanks; r++)
+    if (m->opened[r] && m->peer[r]) cudaIpcCloseMemHandle(m->peer[r]);
+  cudaFree(m->window); cudaFree(m->d_result);
+  if (m->h_rec) cudaFreeHost(m->h_rec);
+  if (m->poll_stream) cudaStreamDestroy(m->poll_stream);
+  for (auto e : m->done) if (e) cudaEventDestroy(e);
+  (void)cudaGetLastError();
+  delete m;
+}
+
+extern "C" int sjb200_comm_get_handle(sjb200_comm *m, void *handle) {
+  if (!m || !handle) return SJB200_UNEXPECTED_ERROR;
+  static_assert(sizeof(cudaIpcMemHandle_t) == SJB200_COMM_HANDLE_BYTES, "handle size");
+  DeviceGuard g(m->ctx->device);
+  cudaIpcMemHandle_t h;
+  if (!ok(m->ctx, cudaIpcGetMemHandle(&h, m->window), "cudaIpcGetMemHandle")) return SJB200_UNEXPECTED_ERROR;
+  memcpy(handle, &h, sizeof(h));
+  return SJB200_SUCCESS;
+}
+
+extern "C" int sjb200_comm_connect(sjb200_comm *m, const void *handles) {
+  if (!m || !handles) return SJB200_UNEXPECTED_ERROR;
+  DeviceGuard g(m->ctx->device);
+  for (int r = 0; r < m->nranks; r++) {
+    if (r == m->rank || m->peer[r]) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const uint8_t *>(handles) + size_t(r) * sizeof(h), sizeof(h));
+    void *q = nullptr;
+    if (!ok(m->ctx, cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle")) return SJB200_UNEXPECTED_ERROR;
+    m->peer[r] = static_cast<unsigned long long *>(q);
+    m->opened[r] = true;
+  }
+  m->connected = true;
+  return SJB200_SUCCESS;
+}
+
+// ranks that live in ONE process (several contexts, same or different devices): plain pointers, peer access enabled
+extern "C" int sjb200_comm_connect_local(sjb200_comm *m, sjb200_comm *const *all) {
+  if (!m || !all) return SJB200_UNEXPECTED_ERROR;
+  DeviceGuard g(m->ctx->device);
+  for (int r = 0; r < m->nranks; r++) {
+    if (!all[r] || all[r]->nranks != m->nranks || all[r]->rank != r) return SJB200_UNEXPECTED_ERROR;
+    if (all[r]->ctx->device != m->ctx->device) {
+      cudaError_t e = cudaDeviceEnablePeerAccess(all[r]->ctx->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { ok(m->ctx, e, "cudaDeviceEnablePeerAccess"); return SJB200_UNEXPECTED_ERROR; }
+      (void)cudaGetLastError();
+    }
+    m->peer[r] = all[r]->window;
+  }
+  m->connected = true;
+  return SJB200_SUCCESS;
+}
+
+extern "C" int sjb200_stage1_sharded_enqueue(sjb200_comm *m, const uint8_t *d_shard, size_t len, int last_shard, uint32_t *d_idx, void *stream) {
+  if (!m || !m->connected || !d_shard || !d_idx || len == 0 || len > kMaxBytes) return SJB200_UNEXPECTED_ERROR;
+  if (m->head - m->tail >= uint32_t(kXchgSteps / 2)) return SJB200_CAPACITY;  // too many passes in flight: finish some first
+  sjb200_ctx *c = m->ctx;
+  if (!use_scan4(c, kIndex)) return SJB200_UNEXPECTED_ERROR;
+  DeviceGuard g(c->device);
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+  if (!ensure_desc(c, len)) return SJB200_MEMALLOC;
+  const uint32_t seq = m->head + 1;  // tags start at 1: a zeroed window never matches
+  XchgTarget x;
+  for (int r = 0; r < kMaxRanks; r++) x.peer[r] = m->peer[r];
+  x.nranks = uint32_t(m->nranks); x.rank = uint32_t(m->rank); x.slot = window_slot(seq, 0); x.seq = seq;
+  CUtensorMap map;
+  bool tma = false;
+  map_for(c, kIndex, &map, d_shard, len, &tma);
+  sjb200_comm::Step &st = m->steps[m->head % uint32_t(kXchgSteps)];
+  st.d_buf = d_shard; st.len = len; st.d_idx = d_idx; st.stream = s; st.seq = seq; st.last = last_shard;
+  if (!enqueue_scan(c, kIndex, &map, tma, d_shard, len, 0, tiles_of(len), true, 0x20202020u, d_idx, nullptr, -1, s, 1, false,
+                    m->d_result + (m->head % uint32_t(kXchgSteps)), nullptr, &x) ||
+      !ok(c, cudaEventRecord(m->done[m->head % uint32_t(kXchgSteps)], s), "event record"))
+    return SJB200_UNEXPECTED_ERROR;
+  m->head++;
+  return SJB200_SUCCESS;
+}
+
+extern "C" int sjb200_stage1_sharded_finish(sjb200_comm *m, sjb200_sharded_result *out) {
+  if (!m || !out || m->tail == m->head) return SJB200_UNEXPECTED_ERROR;
+  sjb200_ctx *c = m->ctx;
+  DeviceGuard g(c->device);
+  memset(out, 0, sizeof(*out));
+  const sjb200_comm::Step st = m->steps[m->tail % uint32_t(kXchgSteps)];
+  const uint32_t slot_i = m->tail % uint32_t(kXchgSteps);
+  m->tail++;
+  if (!ok(c, cudaEventSynchronize(m->done[slot_i]), "event sync")) return SJB200_UNEXPECTED_ERROR;  // own scan (and its stores) done
+  int rc = comm_collect(m, st.seq, 0);
+  if (rc != SJB200_SUCCESS) return rc;
+  uint32_t tt[kMaxRanks], flags_all = 0;
+  bool any_wrong = false;
+  uint32_t state = 0, my_state = 0;
+  for (int r = 0; r < m->nranks; r++) {
+    tt[r] = uint32_t(m->h_rec[2 * r + 1] >> 8) & 0x3Fu;
+    if (r == m->rank) my_state = state;
+    if (state != 0) any_wrong = true;
+    state = tt_apply(tt[r], state);
+  }
+  out->state_in = my_state;
+  out->state_out = tt_apply(tt[m->rank], my_state);
+  out->final_state = state;
+  uint64_t my_count = xchg_count(m->h_rec[2 * m->rank]);
+  uint32_t my_flags = uint32_t(m->h_rec[2 * m->rank + 1] >> 16) & 0xFFu;
+  if (any_wrong) {
+    // second round: ranks whose speculation failed scan again with their true state; everybody republishes
+    if (my_state != 0) {
+      sjb200_shard_result sr;
+      rc = sjb200_stage1_shard_dev(c, st.d_buf, st.len, my_state, st.last, st.d_idx, &sr, st.stream);
+      if (rc != SJB200_SUCCESS) return rc;
+      my_count = sr.count;
+      my_flags = sr.flags;
+      out->rescanned = 1;
+    }
+    ScanParams p;
+    memset(&p, 0, sizeof(p));
+    for (int r = 0; r < kMaxRanks; r++) p.xchg_peer[r] = m->peer[r];
+    p.xchg_nranks = uint32_t(m->nranks); p.xchg_rank = uint32_t(m->rank); p.xchg_slot = window_slot(st.seq, 1); p.xchg_seq = st.seq;
+    if (!ok(c, launch_xchg_post(p, xchg_word0(st.seq, my_count), xchg_word1(st.seq, out->state_out, tt[m->rank], my_flags), st.stream), "xchg post") ||
+        !ok(c, cudaStreamSynchronize(st.stream), "sync"))
+      return SJB200_UNEXPECTED_ERROR;
+    c->launches++;
+    rc = comm_collect(m, st.seq, 1);
+    if (rc != SJB200_SUCCESS) return rc;
+  }
+  uint64_t base = 0, total = 0;
+  for (int r = 0; r < m->nranks; r++) {
+    const uint64_t cnt = xchg_count(m->h_rec[2 * r]);
+    if (r < m->rank) base += cnt;
+    total += cnt;
+    flags_all |= uint32_t(m->h_rec[2 * r + 1] >> 16) & 0xFFu;
+  }
+  out->count = my_count;
+  out->base = base;
+  out->total_count = total;
+  out->flags = my_flags;
+  out->flags_all = flags_all;
+  return ((my_flags | flags_all) & kFlagInternal) ? SJB200_UNEXPECTED_ERROR : SJB200_SUCCESS;
+}
+
+extern "C" int sjb200_stage1_sharded(sjb200_comm *m, const uint8_t *d_shard, size_t len, int last_shard, uint32_t *d_idx,
+                                     sjb200_sharded_result *out, void *stream) {
+  int rc = sjb200_stage1_sharded_enqueue(m, d_shard, len, last_shard, d_idx, stream);
+  if (rc != SJB200_SUCCESS) return rc;
+  return sjb200_stage1_sharded_finish(m, out);
+}
+
 extern "C" uint32_t sjb200_fold_state(const uint32_t *ttables, int nshards_before) {
   uint32_t state = 0;
   for (int i = 0; i < nshards_before; i++) state = tt_apply(ttables[i], state);
@@ -1027,4 +1268,12 @@ extern "C" size_t sjb200_shard_cut(const uint8_t *buf, size_t len, size_t nomina
   size_t cut = nominal;
   for (int k = 0; k < 3 && cut > 0 && (buf[cut] & 0xC0) == 0x80; k++) cut--;
   return cut;
+}
+
+extern "C" size_t sjb200_shard_cut_line(const uint8_t *buf, size_t len, size_t nominal, size_t window) {
+  if (nominal >= len) return len;
+  const size_t lo = nominal > window ? nominal - window : 0;
+  for (size_t cut = nominal; cut > lo; cut--)
+    if (buf[cut - 1] == 0x0A) return cut;
+  return sjb200_shard_cut(buf, len, nominal);
 }

@@ -28,6 +28,7 @@
 
 #include "sjb200_bits.cuh"
 #include "sjb200_scan4.cuh"
+#include "sjb200_utf8.cuh"
 
 namespace sjb200 {
 
@@ -882,6 +883,13 @@ __global__ void __launch_bounds__(scan4::kThreads4, (SJB200_SCAN4_WARPS > 8) ? 1
   scan4::scan4_body<2>(&tmap, p, smem_raw4, sj_smem_u32(smem_raw4));
 }
 
+// validate_utf8, every warp on its own (sjb200_utf8.cuh)
+__global__ void __launch_bounds__(utf8v2::kThreadsU, utf8v2::kCtasPerSmU)
+    utf8v2_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
+  extern __shared__ uint8_t smem_raw_u[];
+  utf8v2::utf8_body(&tmap, p, smem_raw_u, sj_smem_u32(smem_raw_u));
+}
+
 // ------------------------------------------------------------------ small helpers
 __global__ void gather_chars_kernel(const uint8_t *buf, const uint32_t *idx, uint32_t first, uint32_t count, uint8_t *out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -891,6 +899,16 @@ __global__ void write_sentinels_kernel(uint32_t *idx, uint32_t n, uint32_t a, ui
   idx[n] = a;
   idx[n + 1] = b;
   idx[n + 2] = c;
+}
+
+// second round of a sharded pass (after re-scans): republish this rank's record in every rank's exchange window
+__global__ void xchg_post_kernel(ScanParams p, unsigned long long w0, unsigned long long w1) {
+  const uint32_t r = threadIdx.x;
+  if (r < p.xchg_nranks) {
+    unsigned long long *rec = p.xchg_peer[r] + (size_t(p.xchg_slot) * kMaxRanks + p.xchg_rank) * 2;
+    sj_st_sys_u64(rec, w0);
+    sj_st_sys_u64(rec + 1, w1);
+  }
 }
 
 // ------------------------------------------------------------------ launchers
@@ -924,6 +942,26 @@ cudaError_t launch_scan4(const CUtensorMap *tmap, const ScanParams &p, int grid,
   else scan4_kernel<<<grid, scan4::kThreads4, scan4::kSmemBytes4, stream>>>(*tmap, p);
   return cudaGetLastError();
 }
+
+cudaError_t launch_utf8v2(const CUtensorMap *tmap, const ScanParams &p, int grid, cudaStream_t stream) {
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(utf8v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, utf8v2::kSmemBytesU);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  utf8v2_kernel<<<grid, utf8v2::kThreadsU, utf8v2::kSmemBytesU, stream>>>(*tmap, p);
+  return cudaGetLastError();
+}
+int utf8v2_max_ctas_per_sm() {
+  int n = 0;
+  cudaFuncSetAttribute(utf8v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, utf8v2::kSmemBytesU);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, utf8v2_kernel, utf8v2::kThreadsU, utf8v2::kSmemBytesU);
+  return (e == cudaSuccess && n > 0) ? n : 1;
+}
+int utf8v2_warps_per_cta() { return utf8v2::kWarpsU; }
 
 size_t scan4_park_words(int grid) { return size_t(grid) * scan4::kParkD * scan4::kParkSlotWords; }
 int scan4_deferred_capacity() { return scan4::kParkD; }
@@ -968,6 +1006,11 @@ cudaError_t launch_gather_chars(const uint8_t *buf, const uint32_t *idx, uint32_
                                 cudaStream_t stream) {
   if (count == 0) return cudaSuccess;
   gather_chars_kernel<<<(count + 255) / 256, 256, 0, stream>>>(buf, idx, first, count, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_xchg_post(const ScanParams &p, unsigned long long w0, unsigned long long w1, cudaStream_t stream) {
+  xchg_post_kernel<<<1, 32, 0, stream>>>(p, w0, w1);
   return cudaGetLastError();
 }
 

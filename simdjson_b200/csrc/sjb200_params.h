@@ -35,6 +35,7 @@ constexpr int kMinCtasPerSm = SJB200_MIN_CTAS;  // __launch_bounds__ occupancy t
 #endif
 constexpr int kMaxSub = SJB200_MAX_SUB;
 constexpr int kMaxRanks = 8;                          // GPUs of one node that can share a scan (sjb200_comm)
+constexpr int kXchgSteps = 64;                        // sharded passes whose exchange records an exchange window holds (two rounds each)
 constexpr int kCtlBytes = 1024;                       // control block
 constexpr int kLutBytes = 64 * 64;                    // composed-transducer table
 constexpr int kEmitBytes = kWarps * 1024;             // per-warp emit scratch (128 mask words + 128 counts)
@@ -93,13 +94,16 @@ struct ScanParams {
 #define SJ_PARAMS_HD
 #endif
 // one shard record as two independently tagged 64-bit words (8-byte stores are single transactions):
-//   w0 = seq[15:0] << 48 | count[47:0]        w1 = seq << 32 | flags << 16 | ttable << 8 | state_out
-SJ_PARAMS_HD inline unsigned long long xchg_word0(uint32_t seq, uint64_t count) { return ((unsigned long long)(seq & 0xFFFFu) << 48) | (count & 0xFFFFFFFFFFFFull); }
+//   w0 = seq[30:0] << 33 | count[32:0]        w1 = seq << 32 | flags << 16 | ttable << 8 | state_out
+SJ_PARAMS_HD inline unsigned long long xchg_word0(uint32_t seq, uint64_t count) {
+  return ((unsigned long long)(seq & 0x7FFFFFFFu) << 33) | (count & 0x1FFFFFFFFull);
+}
 SJ_PARAMS_HD inline unsigned long long xchg_word1(uint32_t seq, uint32_t state, uint32_t ttable, uint32_t flags) {
   return ((unsigned long long)seq << 32) | ((unsigned long long)(flags & 0xFFu) << 16) | ((unsigned long long)(ttable & 0x3Fu) << 8) | (state & 7u);
 }
 SJ_PARAMS_HD inline bool xchg_complete(unsigned long long w0, unsigned long long w1, uint32_t seq) {
-  return uint32_t(w0 >> 48) == (seq & 0xFFFFu) && uint32_t(w1 >> 32) == seq;
+  return uint32_t(w0 >> 33) == (seq & 0x7FFFFFFFu) && uint32_t(w1 >> 32) == seq;
 }
+SJ_PARAMS_HD inline uint64_t xchg_count(unsigned long long w0) { return w0 & 0x1FFFFFFFFull; }
 
 }  // namespace sjb200

@@ -140,12 +140,12 @@ SJ_DEV void sj_nanosleep(unsigned) {
   nanosleep(&ts, nullptr);
 }
 SJ_DEV unsigned sj_smid() { return simt::tctx.cta; }
-SJ_DEV uint32_t sj_clock32() { return uint32_t(sj_globaltimer()); }
 SJ_DEV unsigned long long sj_globaltimer() {
   struct timespec ts;
   clock_gettime(CLOCK_MONOTONIC, &ts);
   return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
 }
+SJ_DEV uint32_t sj_clock32() { return uint32_t(sj_globaltimer()); }
 
 // ---- mbarrier with deferred TMA copies
 struct sj_tensor_map {  // what the emulated TMA needs to know about the 2-D uint8 [rows][128] tensor

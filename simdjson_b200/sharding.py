@@ -33,6 +33,77 @@ def shard_cuts(buf, nshards):
     return cuts
 
 
+def shard_cuts_at_lines(buf, nshards, window=1 << 20):
+    """the same, preferring cuts right after a raw line feed (a raw 0x0A cannot lie inside a JSON string, so for valid
+    input every shard starts in state 0 and no rank ever scans twice)"""
+    L = _lib()
+    a = np.ascontiguousarray(buf, dtype=np.uint8)
+    cuts = [0]
+    for k in range(1, nshards):
+        cuts.append(max(cuts[-1], int(L.sjb200_shard_cut_line(a.ctypes.data, len(a), (len(a) * k) // nshards, window))))
+    cuts.append(len(a))
+    return cuts
+
+
+class Comm:
+    """sjb200_comm: the per-rank object of the sharded scan with the exchange fused into the scan kernel
+    (include/sjb200.h).  connect() maps the peers' exchange windows: pass `all_gather_bytes`, a callable that all-gathers
+    a 64-byte uint8 array over the job's process group (torch.distributed over NCCL or gloo) -- the only collective of
+    the path, once per job -- or, for ranks living in one process, connect_local()."""
+
+    def __init__(self, parser, rank, world):
+        from . import capi
+        self._capi = capi
+        self.parser, self.rank, self.world = parser, rank, world
+        self._h = C.c_void_p()
+        rc = _lib().sjb200_comm_create(parser._ctx, rank, world, C.byref(self._h))
+        if rc != 0:
+            raise RuntimeError(f"sjb200_comm_create failed ({rc}): " + parser.last_cuda_error())
+
+    def handle(self):
+        h = np.zeros(self._capi.COMM_HANDLE_BYTES, dtype=np.uint8)
+        rc = _lib().sjb200_comm_get_handle(self._h, h.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("sjb200_comm_get_handle failed: " + self.parser.last_cuda_error())
+        return h
+
+    def connect(self, all_gather_bytes):
+        if self.world == 1:
+            return
+        handles = np.ascontiguousarray(all_gather_bytes(self.handle()), dtype=np.uint8).reshape(self.world, self._capi.COMM_HANDLE_BYTES)
+        rc = _lib().sjb200_comm_connect(self._h, handles.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("sjb200_comm_connect failed: " + self.parser.last_cuda_error())
+
+    @staticmethod
+    def connect_local(comms):
+        arr = (C.c_void_p * len(comms))(*[c._h for c in comms])
+        for c in comms:
+            rc = _lib().sjb200_comm_connect_local(c._h, arr)
+            if rc != 0:
+                raise RuntimeError("sjb200_comm_connect_local failed: " + c.parser.last_cuda_error())
+
+    def enqueue(self, d_shard, d_idx, last_shard, stream=None):
+        from .implementation import _stream_ptr
+        return _lib().sjb200_stage1_sharded_enqueue(self._h, d_shard.data_ptr(), d_shard.numel(), int(last_shard), d_idx.data_ptr(), _stream_ptr(stream))
+
+    def finish(self):
+        res = self._capi.ShardedResult()
+        rc = _lib().sjb200_stage1_sharded_finish(self._h, C.byref(res))
+        return rc, res
+
+    def scan(self, d_shard, d_idx, last_shard, stream=None):
+        rc = self.enqueue(d_shard, d_idx, last_shard, stream)
+        if rc != 0:
+            return rc, None
+        return self.finish()
+
+    def close(self):
+        if self._h:
+            _lib().sjb200_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+
 def exchange(scan, rank, world, all_gather):
     """Run the protocol on one rank.
       scan(state_in) -> (ttable, count, flags)   scans this rank's shard (GPU: sjb200_stage1_shard_dev)

@@ -10,6 +10,7 @@
 // build: see tests/test_simt_emul.py
 #define SJB200_HOST_EMU 1
 #include "sjb200_scan4.cuh"
+#include "sjb200_utf8.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -51,14 +52,16 @@ void *thread_main(void *arg) {
   simt::tctx.warp = a->warp;
   simt::tctx.ctas = a->cta;
   const uint32_t sa = uint32_t(reinterpret_cast<uintptr_t>(a->cta->smem));
-  if (a->la->mode == 2) scan4::scan4_body<2>(a->la->tmap, *a->la->p, a->cta->smem, sa);
+  if (a->la->mode == 3) utf8v2::utf8_body(a->la->tmap, *a->la->p, a->cta->smem, sa);
+  else if (a->la->mode == 2) scan4::scan4_body<2>(a->la->tmap, *a->la->p, a->cta->smem, sa);
   else if (a->la->mode == 1) scan4::scan4_body<1>(a->la->tmap, *a->la->p, a->cta->smem, sa);
   else scan4::scan4_body<0>(a->la->tmap, *a->la->p, a->cta->smem, sa);
   return nullptr;
 }
 
 void emu_launch(unsigned grid, const sj_tensor_map &tmap, const ScanParams &p, int mode) {
-  const unsigned T = scan4::kThreads4, W = T / 32;
+  const unsigned T = (mode == 3) ? unsigned(utf8v2::kThreadsU) : unsigned(scan4::kThreads4), W = T / 32;
+  const size_t smem_bytes = (mode == 3) ? size_t(utf8v2::kSmemBytesU) : size_t(scan4::kSmemBytes4);
   LaunchArgs la{grid, &tmap, &p, mode};
   std::vector<simt::CtaShared> ctas(grid);
   std::vector<simt::WarpShared> warps(size_t(grid) * W);
@@ -66,8 +69,8 @@ void emu_launch(unsigned grid, const sj_tensor_map &tmap, const ScanParams &p, i
   std::vector<pthread_t> th(size_t(grid) * T);
   for (unsigned c = 0; c < grid; c++) {
     pthread_barrier_init(&ctas[c].bar, nullptr, T);
-    ctas[c].smem = static_cast<uint8_t *>(aligned_alloc(1024, (size_t(scan4::kSmemBytes4) + 1023) & ~size_t(1023)));
-    memset(ctas[c].smem, 0xCD, scan4::kSmemBytes4);
+    ctas[c].smem = static_cast<uint8_t *>(aligned_alloc(1024, (smem_bytes + 1023) & ~size_t(1023)));
+    memset(ctas[c].smem, 0xCD, smem_bytes);
     for (unsigned w = 0; w < W; w++) pthread_barrier_init(&warps[c * W + w].bar, nullptr, 32);
   }
   pthread_attr_t attr;
@@ -321,6 +324,43 @@ int check_minify(EmuCtx &cx, const std::vector<uint8_t> &store, size_t misalign,
   return bad;
 }
 
+// validate_utf8 with independent warps (sjb200_utf8.cuh) against the oracle; chunk_tiles > 0: several launches like the host path
+int check_utf8v2(EmuCtx &cx, const std::vector<uint8_t> &store, size_t misalign, uint32_t chunk_tiles, unsigned grid, bool use_tma) {
+  const uint8_t *buf = store.data() + misalign;
+  const size_t len = store.size() - misalign;
+  if (len == 0) return 0;
+  const uint32_t ntiles_total = uint32_t((len + kTileBytes - 1) / kTileBytes);
+  sj_tensor_map tmap;
+  tmap.base = buf; tmap.rows = len / 128; tmap.box_rows = utf8v2::kBlockRowsU;
+  const bool tma_ok = use_tma && (reinterpret_cast<uintptr_t>(buf) & 15u) == 0 && tmap.rows > 0;
+  if (chunk_tiles == 0) chunk_tiles = ntiles_total;
+  uint32_t flags = 0;
+  for (uint32_t tb = 0; tb < ntiles_total; tb += chunk_tiles) {
+    const uint32_t nt = std::min(chunk_tiles, ntiles_total - tb);
+    ScanParams p;
+    memset(&p, 0, sizeof(p));
+    p.buf = buf; p.len = len; p.prev_word = 0x20202020u;
+    p.check_eof = (tb + nt == ntiles_total) ? 1u : 0u;
+    p.use_tma = tma_ok ? 1u : 0u;
+    p.tile_begin = tb; p.ntiles = nt;
+    p.carry_out = &cx.carry[1];
+    p.flags = &cx.flags; p.ticket = cx.ticket;
+    cx.carry[1] = Carry();
+    emu_launch(grid, tmap, p, 3);
+    if (cx.ticket[1] != 0 || cx.flags != 0) { fprintf(stderr, "BUG: utf8v2 ticket/flags not re-armed\n"); exit(2); }
+    flags |= cx.carry[1].flags;
+  }
+  const bool got = !(flags & kFlagUtf8), want = sjo_validate_utf8(buf, len) != 0;
+  if (got != want || (flags & kFlagInternal)) {
+    fprintf(stderr, "UTF8V2 MISMATCH len=%zu misalign=%zu chunk_tiles=%u grid=%u tma=%d: got %d want %d flags=%u\n", len, misalign, chunk_tiles, grid, int(use_tma), int(got), int(want), flags);
+    std::vector<uint8_t> v(buf, buf + len);
+    hexdump(v);
+    g_fail++;
+    return 1;
+  }
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -402,6 +442,10 @@ int main(int argc, char **argv) {
     if (it % 3 == 0) check(cx, buf0, 0, state_in, 1 + uint32_t(rng() % 3), grid, true, "chunked");
     if (it % 2 == 0) check_minify(cx, buf0, 0, (it % 6 == 0) ? 1 + uint32_t(rng() % 3) : 0, grid, it % 4 != 0, rng() % 17);
     if (it % 5 == 1 && buf0.size() > 3) check_minify(cx, buf0, 1 + rng() % 3, 0, grid, true, rng() % 17);
+    if (kind == 1 || kind == 2 || kind == 4 || it % 3 == 0) {
+      check_utf8v2(cx, buf0, 0, (it % 4 == 0) ? 1 + uint32_t(rng() % 2) : 0, grid, it % 5 != 0);
+      if (it % 3 == 1 && buf0.size() > 3) check_utf8v2(cx, buf0, 1 + rng() % 3, 0, grid, true);
+    }
     if (it % 4 == 1) check(cx, buf0, 0, state_in, 0, grid, false, "plain loads");
     if (it % 4 == 2 && buf0.size() > 3) check(cx, buf0, 1 + rng() % 3, state_in, 0, grid, true, "misaligned");
   }

@@ -488,3 +488,93 @@ def test_host_pointer_paths(port):
             assert_same(run_stage1(p, bad, 0), port.stage1(bad, 0), ("invalid utf-8", threads))
     finally:
         p.close()
+
+
+# --------------------------------------------------------------------------- sharded scan, exchange fused into the scan kernel
+def _raw_scan(port, doc):
+    """the oracle's raw structural list of a whole buffer (no finish() logic): what the shards together must reproduce"""
+    import ctypes as C
+    L = port.L
+    L.sjo_scan_shard.restype = C.c_uint64
+    L.sjo_scan_shard.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)]
+    idx = np.zeros(len(doc) + 1, dtype=np.uint32)
+    so = C.c_uint32(0)
+    n = L.sjo_scan_shard(doc.ctypes.data, len(doc), 0, idx.ctypes.data, C.byref(so))
+    return idx[:n].astype(np.int64), int(so.value)
+
+
+def _run_ranks_in_threads(doc, cuts, device=0):
+    """one sjb200_comm per rank, all ranks in this process (connect_local), one thread per rank like one process per GPU"""
+    from simdjson_b200 import sharding
+    world = len(cuts) - 1
+    impl = sj.get_active_implementation(device)
+    parsers, comms = [], []
+    for r in range(world):
+        rc, p = impl.create_dom_parser_implementation(max(cuts[r + 1] - cuts[r], 64))
+        assert rc == sj.SUCCESS
+        parsers.append(p)
+        comms.append(sharding.Comm(p, r, world))
+    sharding.Comm.connect_local(comms)
+    out = [None] * world
+
+    def work(r):
+        try:
+            torch.cuda.set_device(device)
+            shard = torch.from_numpy(doc[cuts[r]: cuts[r + 1]].copy()).cuda()
+            d_idx = torch.empty(int(sj.lib().sjb200_index_words(shard.numel())), dtype=torch.int32, device="cuda")
+            stream = torch.cuda.Stream()
+            results = []
+            for rep in range(3):  # several passes in flight: enqueue all, then finish all
+                assert comms[r].enqueue(shard, d_idx, r == world - 1, stream) == 0
+            for rep in range(3):
+                rc, res = comms[r].finish()
+                results.append((rc, res.count, res.base, res.total_count, res.state_in, res.final_state, res.flags_all, res.rescanned))
+            torch.cuda.synchronize()
+            idx = d_idx.cpu().numpy().view(np.uint32)[: results[-1][1]].astype(np.int64) + cuts[r]
+            out[r] = (results, idx)
+        except Exception as e:  # noqa: BLE001
+            out[r] = e
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    [t.start() for t in th]
+    [t.join(timeout=300) for t in th]
+    for c in comms:
+        c.close()
+    for p in parsers:
+        p.close()
+    for o in out:
+        if isinstance(o, Exception) or o is None:
+            raise AssertionError(o)
+    return out
+
+
+def test_sharded_scan_fused_exchange(port):
+    """SURVEY.md 8(e) through sjb200_stage1_sharded: ONE buffer cut into 2 / 4 / 8 shards -- at arbitrary character
+    boundaries (mid-row, mid-string: carry-in != 0, wrong speculations, second round) and at line feeds (the sharder's
+    choice: no rank scans twice) -- every rank's base + indexes against one scan of the whole buffer by the oracle."""
+    from simdjson_b200 import sharding
+    rng = random.Random(corpus.SEED ^ 0x5a5a)
+    docs = [corpus.ndjson_rows(24 << 20), corpus.random_json((6 << 20) + 4321, pretty_bias=0.9),
+            np.frombuffer(_big_adversarial(rng, 9 * TILE + 777), dtype=np.uint8).copy()]
+    for di, doc in enumerate(docs):
+        want, want_state = _raw_scan(port, doc)
+        utf8_ok = port.validate_utf8(doc)
+        for world in (2, 4, 8):
+            for mode, cuts in (("bytes", sharding.shard_cuts(doc, world)), ("lines", sharding.shard_cuts_at_lines(doc, world))):
+                if any(cuts[k + 1] <= cuts[k] for k in range(world)):
+                    continue
+                out = _run_ranks_in_threads(doc, cuts)
+                got = np.concatenate([o[1] for o in out])
+                assert len(got) == len(want) and np.array_equal(got, want), (di, world, mode)
+                base = 0
+                for r, (results, idx) in enumerate(out):
+                    for rc, count, b, total, state_in, final_state, flags_all, rescanned in results:
+                        assert rc == 0 and b == base and total == len(want) and count == len(idx), (di, world, mode, r)
+                        assert final_state == want_state and bool(flags_all & 1) == (not utf8_ok)
+                        assert rescanned == (1 if state_in != 0 else 0)
+                    base += len(idx)
+                if mode == "lines" and di < 2:
+                    assert all(res[7] == 0 for o in out for res in o[0]), "valid JSON cut after a line feed never needs a second scan"
+        if di == 0:  # arbitrary cuts of NDJSON land inside strings: the second round really ran
+            out = _run_ranks_in_threads(doc, sharding.shard_cuts(doc, 8))
+            assert any(res[7] for o in out for res in o[0])
