@@ -1,33 +1,42 @@
 #!/usr/bin/env python
 """bench.py -- stage-1 structural indexing throughput on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config NAME] [--check]
 
-One "step" = one stage-1 pass (structural indexing + UTF-8 validation) over one synthetic
-document per GPU.  Workload at N=1: configs[1] of BASELINE.json, "synthetic 64 MiB
-random-structure JSON, stage1 index on 1xB200" (seeded generator simdjson_b200/corpus.py,
-SURVEY.md section 8(d) item 2).  At N>1 every rank holds one 64 MiB shard of an N x 64 MiB stream
-(byte-range sharding): each rank scans its shard with a speculated incoming
-scanner state, the ranks all-gather {6-bit carry transducer, count} over NCCL (the path's one
-real exchange step), fold their true incoming state / index base, and re-scan only if the
-speculation was wrong -> weak scaling.
+One "step" = one stage-1 pass (structural indexing + UTF-8 validation) over one batch of synthetic input per GPU.
+
+Configurations (`--config`, BASELINE.json `configs`):
+  stage1_64m   (default) configs[1]: synthetic 64 MiB random-structure JSON, stage 1 on 1xB200.  At N>1 every rank
+               holds one 64 MiB shard of ONE N x 64 MiB document (a JSON array cut after line feeds, so no shard is a
+               document of its own); every step is a sharded pass through sjb200_stage1_sharded: the scan kernel itself
+               stores each shard's {count, state, transducer, flags} record into every rank's exchange window over
+               NVLink (the path's one exchange), the host folds state / index base -> weak scaling.
+  jsonexamples configs[0]: twitter.json / citm_catalog.json / amazon_cellphones.ndjson (latency-bound: one launch each)
+  ndjson_1g    configs[2]: 1 GiB NDJSON (amazon_cellphones-style rows), streaming_final; N>1: cut after line feeds
+  utf8_minify_256m  configs[3]: validate_utf8 on 256 MiB mixed ASCII / UTF-8 text, minify on 256 MiB pretty JSON
+  concat_8g    configs[4]: twitter + citm repeated to 8 GiB, 8 shards of ~1 GiB with 64-bit index bases, round-robin
+               over the N ranks
+`--check` runs the parity gate of the multi-rank path on adversarial cuts (mid-row, mid-string: carry-in != 0, second
+round, re-scans) through the real IPC / NCCL plumbing and prints one JSON line; exit code 1 on a mismatch.
 
 The JSON line carries:
   value     input GB/s with the input resident in HBM (device-timed, max over ranks)
-  e2e       the same metric through the host-pointer C-ABI call (pinned host input, H2D copy and
-            D2H of the n indexes inside the timed region)
-  roofline  algorithmic bytes (1 B read per input byte + 4 B written per structural + 12 B of
-            sentinels) / the scan kernel's mean duration, measured with CUDA events
-            recorded around the kernel on its launch stream, against MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline  the reference's own CPU stage 1 (oracle/_ref, compiled from the unmodified
-            reference) timed on this box's host cores on the same document (bounded sample)
+  e2e       the same metric through the reference's own boundary: libsimdjson_b200.so (the C++ plug-in),
+            get_active_implementation()->create_dom_parser_implementation()->stage1() on a PAGEABLE padded_string;
+            H2D copy, scan and the indexes' way back to the parser's structural_indexes inside the timed region
+  roofline  algorithmic bytes (1 B read per input byte + 4 B written per structural + 12 B of sentinels, SURVEY.md
+            section 8(d)) / the scan kernel's mean duration, measured with CUDA events recorded around every scan kernel
+            of the timed region on its launch stream, against MEASURED_PEAKS.json hbm_gbs
+  parity    every distinct document of the timed region: (n + 3) index words of its last step against the CPU oracle
+  cpu_baseline  the reference's own CPU stage 1 (oracle/_ref, the unmodified reference) on this box's host cores:
+            pre-spawned threads, one private copy of the document per thread; all cores and one core
 `--impl reference` times that CPU implementation as its own arm (rank 0 only).
 """
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -41,6 +50,14 @@ DOC_BYTES = 64 << 20
 ROTATE = 4  # distinct 64 MiB inputs used round-robin: 256 MiB > 126 MB of L2, so no step finds its input in L2
 METRIC = "stage1 GB/s (bytes in / s) vs HBM roofline at 1/2/4/8 B200; CPU ref GB/s"
 UNIT = "GB/s"
+PLUGIN = os.path.join(ROOT, "simdjson_b200", "plugin", "libsimdjson_b200.so")
+KERNEL_SOURCES = ["sjb200_scan4.cuh", "sjb200_bits.cuh", "sjb200_simt.cuh", "sjb200_params.h", "sjb200_kernels.cu", "sjb200_utf8.cuh"]
+
+
+def workload_name(world):
+    if world == 1:
+        return "synthetic 64 MiB random-structure JSON, stage1 index on 1xB200 (BASELINE.json configs[1])"
+    return f"synthetic {world} x 64 MiB random-structure JSON, stage1 sharded by byte range over {world}xB200 (BASELINE.json configs[1] per GPU)"
 
 
 def peaks():
@@ -51,6 +68,39 @@ def peaks():
         except Exception:  # noqa: BLE001
             pass
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def kernel_source_hash():
+    h = hashlib.sha256()
+    for f in KERNEL_SOURCES:
+        with open(os.path.join(ROOT, "simdjson_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic(kernel="scan4"):
+    """DRAM bytes of one launch of the kernel on the bench document, from an `ncu --set full` capture under profiles/
+    -- reported ONLY when that capture was taken from the kernel sources this run was built from (the summary records
+    their hash); otherwise null: a stale constant is worse than no number."""
+    want = kernel_source_hash()
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    for name in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
+        if not (name.endswith("_ncu_full.json") and kernel in name):
+            continue
+        try:
+            d = json.load(open(os.path.join(pdir, name)))
+            if d.get("kernel_src_sha16") != want:
+                continue
+            unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            tot = 0.0
+            for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                v, u = d[k]
+                tot += float(v) * unit[u]
+            best = (int(tot), os.path.join("profiles", name))
+        except Exception:  # noqa: BLE001
+            continue
+    return best if best else (None, f"no ncu capture of kernel sources {want} under profiles/")
 
 
 class ClockSampler:
@@ -106,53 +156,112 @@ class ClockSampler:
         return {"sm_mhz": float(sm[len(sm) // 2]), "sm_max_mhz": float(self.max_sm), "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
+# =============================================================================== workloads
 def make_doc(seed_offset):
     from simdjson_b200 import corpus
     return corpus.random_json(DOC_BYTES, seed=corpus.SEED + 7919 * seed_offset)
 
 
-# =============================================================================== reference arm
-def run_reference(args, rank):
-    """the reference's own CPU stage 1 (oracle/_ref = unmodified reference, compiled in the build
-    container) on this box's host cores; else the oracle port.  Rank 0 only."""
-    if rank != 0:
-        return
+def make_stream(world, k):
+    """ONE document of world x 64 MiB: '[' + pieces separated by ',\\n' + ']' -- a single JSON array, so that a shard cut
+    anywhere is not a document of its own.  Deterministic in (world, k); every rank builds the same buffer."""
+    from simdjson_b200 import corpus
+    total = world * DOC_BYTES
+    parts, size = [b"["], 1
+    i = 0
+    while True:
+        piece = bytes(corpus.random_json(8 << 20, seed=corpus.SEED + 104729 * k + 31 * i))
+        extra = len(piece) + (2 if i else 0)
+        if size + extra + 64 > total:
+            break
+        if i:
+            parts.append(b",\n")
+        parts.append(piece)
+        size += extra
+        i += 1
+    pad = total - size - len(b',\n"') - len(b'"]')
+    parts.append(b',\n"' + b"x" * pad + b'"]')
+    doc = np.frombuffer(b"".join(parts), dtype=np.uint8)
+    assert len(doc) == total
+    return doc
+
+
+def oracle():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
-    doc = make_doc(0)
+    return O
+
+
+def raw_scan(O, port, buf, state_in=0):
+    """the oracle's raw structural list of a buffer entered in state_in (no finish() logic)"""
+    L = port.L
+    L.sjo_scan_shard.restype = C.c_uint64
+    L.sjo_scan_shard.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)]
+    a = np.ascontiguousarray(buf, dtype=np.uint8)
+    idx = np.zeros(len(a) + 1, dtype=np.uint32)
+    so = C.c_uint32(0)
+    n = L.sjo_scan_shard(a.ctypes.data, len(a), state_in, idx.ctypes.data, C.byref(so))
+    return idx[:n], int(so.value)
+
+
+def cpu_baseline(doc, steps=3):
+    """the reference's CPU stage 1 on this host: all cores (pre-spawned threads, one private copy of the document per
+    thread: DRAM-bound, not cache-luck-bound) and one core; a bounded sample (a few rounds)"""
+    O = oracle()
     cores = os.cpu_count() or 1
-    threads = max(1, min(cores, int(os.environ.get("SJB200_REF_THREADS", cores))))
     if O.have_ref():
         ref = O.Ref("")
-        kind, name = "reference", ref.name
-        # bounded sample: every thread runs one full 64 MiB stage-1 call per round (independent parsers, the only
-        # way the reference can use more than one core for this path); `steps` rounds after `warmup` rounds
-        for _ in range(max(0, args.warmup - 1)):
-            ref.time(0, doc, 0, threads, 1)
-        t0 = time.perf_counter()
-        best, err = ref.time(0, doc, 0, threads, max(1, args.steps))
-        wall = time.perf_counter() - t0
-        gbs = threads * len(doc) / best / 1e9
-        one, _ = ref.time(0, doc, 0, 1, 2)
-        sample = f"{threads} threads x one {DOC_BYTES >> 20} MiB stage1 call per round, best of {args.steps} rounds ({wall:.1f} s wall); 1 thread: {len(doc)/one/1e9:.2f} GB/s"
-    else:
-        port = O.Port()
-        kind, name, threads = "port", "oracle port (scalar C)", 1
-        t0 = time.perf_counter()
-        r = port.stage1(doc[: 16 << 20], 0)
-        best = time.perf_counter() - t0
-        gbs = (16 << 20) / best / 1e9
-        err = r.err
-        sample = "1 thread x 16 MiB prefix of the document, one pass"
+        threads = max(1, min(cores, int(os.environ.get("SJB200_REF_THREADS", cores))))
+        best1, mean1, _ = ref.time_rounds(0, doc, 0, 1, 1, 3)
+        bestn, meann, err = ref.time_rounds(0, doc, 0, threads, 1, max(2, steps))
+        return {"value": round(threads * len(doc) / meann / 1e9, 3), "unit": UNIT, "cores": threads, "kind": "reference",
+                "value_best_round": round(threads * len(doc) / bestn / 1e9, 3), "one_core": round(len(doc) / mean1 / 1e9, 3),
+                "sample": f"{ref.name} kernel; {threads} pre-spawned threads x one private {len(doc) >> 20} MiB document each, mean of {max(2, steps)} rounds after 1 warm-up round",
+                "error_code": err}
+    port = O.Port()
+    t0 = time.perf_counter()
+    port.stage1(doc[: 16 << 20], 0)
+    dt = time.perf_counter() - t0
+    return {"value": round((16 << 20) / dt / 1e9, 3), "unit": UNIT, "cores": 1, "kind": "port", "sample": "scalar C port, 16 MiB prefix, one pass"}
+
+
+# =============================================================================== reference arm
+def run_reference(args, rank, world):
+    """the reference's own CPU stage 1 (oracle/_ref = unmodified reference, compiled in the build container) on this box's
+    host cores; else the oracle port.  Rank 0 only."""
+    if rank != 0:
+        return
+    doc = make_doc(0)
+    cb = cpu_baseline(doc, steps=max(2, min(args.steps, 8)))
     line = {
-        "impl": "reference", "metric": METRIC, "value": round(gbs, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(best * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "synthetic 64 MiB random-structure JSON, stage1 (CPU reference, %s kernel)" % name, "bytes_per_call": DOC_BYTES, "threads": threads},
-        "cpu_baseline": {"value": round(gbs, 3), "unit": UNIT, "cores": threads, "kind": kind, "sample": sample, "error_code": err},
-        "e2e": {"value": round(gbs, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(len(doc) * cb["cores"] / (cb["value"] * 1e9) * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic",
+        "config": {"workload": workload_name(max(1, args.gpus)), "bytes_per_call": DOC_BYTES, "threads": cb["cores"],
+                   "how": "CPU reference: every host thread runs the whole 64 MiB stage-1 call on its own copy of the document (the reference has no intra-call parallelism)"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# =============================================================================== e2e through the plug-in
+def plugin_e2e(doc, iters, want_words=None):
+    """stage 1 through libsimdjson_b200.so on a pageable padded_string (dropin_stage1_timed, plugin/dropin_harness.cpp)"""
+    L = C.CDLL(PLUGIN)
+    L.dropin_stage1_timed.restype = C.c_int
+    L.dropin_stage1_timed.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.c_void_p, C.c_size_t,
+                                      C.POINTER(C.c_ulonglong)]
+    secs = (C.c_double * 2)()
+    n = C.c_uint32(0)
+    calls = C.c_ulonglong(0)
+    idx = np.zeros(len(doc) // 4 + 16, dtype=np.uint32)
+    rc = L.dropin_stage1_timed(1, doc.ctypes.data, len(doc), iters, secs, C.byref(n), idx.ctypes.data, len(idx), C.byref(calls))
+    ok = None
+    if want_words is not None:
+        ok = bool(rc == 0 and np.array_equal(idx[: len(want_words)], want_words))
+    return {"rc": rc, "n": int(n.value), "seconds_total": secs[0], "seconds_best": secs[1], "gpu_calls": int(calls.value), "parity": ok}
 
 
 # =============================================================================== our arm
@@ -161,7 +270,7 @@ def run_ours(args, rank, world):
     import torch.distributed as dist
 
     import simdjson_b200 as sj
-    from simdjson_b200 import capi
+    from simdjson_b200 import capi, sharding
 
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
@@ -170,46 +279,40 @@ def run_ours(args, rank, world):
         dist.init_process_group("nccl", device_id=dev)
     impl = sj.get_active_implementation(local)
     L = sj.lib()
+    O = oracle()
+    port = O.Port()
 
-    # ---- workload: ROTATE distinct documents per rank, resident in HBM before the timed region
-    docs = [make_doc(rank * ROTATE + k) for k in range(ROTATE)]
-    # (N>1: rank r's document is shard r of the stream doc_0 doc_1 ... doc_{N-1}; every shard is a complete document)
-    d_docs = [torch.from_numpy(d.copy()).to(dev) for d in docs]
-    pinned = [torch.from_numpy(d.copy()).pin_memory() for d in docs]
     rc, parser = impl.create_dom_parser_implementation(DOC_BYTES)
     if rc != sj.SUCCESS:
         raise RuntimeError("create_dom_parser_implementation failed: " + capi.ERROR_NAMES.get(rc, str(rc)))
     parser.set_option("time_kernel", 1)
-    parsers = [parser]
     stream = torch.cuda.Stream(device=dev)  # the stream every scan of the timed region is launched on
     torch.cuda.set_stream(stream)
     words = L.sjb200_index_words(DOC_BYTES)
-    d_idxs = [torch.empty(words, dtype=torch.int32, device=dev) for _ in range(2)]
-    shard_res = [torch.zeros(3, dtype=torch.int64, device=dev) for _ in range(128)]
-    shard_gather = [torch.zeros(3 * world, dtype=torch.int64, device=dev) for _ in range(128)] if world > 1 else []
-    gather_in = torch.zeros(4, dtype=torch.int64, device=dev)
-    gather_out = torch.zeros(4 * world, dtype=torch.int64, device=dev) if world > 1 else None
+    d_idxs = [torch.empty(words, dtype=torch.int32, device=dev) for _ in range(ROTATE)]  # one per distinct input: the last step's output of each stays for the parity gate
 
-    kernel_ms, n_struct = [], []
+    # ---- workload, resident in HBM before the timed region
+    if world == 1:
+        docs = [make_doc(k) for k in range(ROTATE)]
+        shards, cuts = docs, None
+    else:
+        streams = [make_stream(world, k) for k in range(ROTATE)]
+        cuts = [sharding.shard_cuts_at_lines(s, world) for s in streams]
+        shards = [np.ascontiguousarray(s[c[rank]: c[rank + 1]]) for s, c in zip(streams, cuts)]
+        del streams
+    d_docs = [torch.from_numpy(d.copy()).to(dev) for d in shards]
+    comm = None
+    if world > 1:
+        comm = sharding.Comm(parser, rank, world)
 
-    def sharded_step(i):
-        """one sharded pass (simdjson_b200/sharding.py): scan with speculated state 0, all-gather {transducer,count,flags},
-        fold, re-scan if the speculation was wrong"""
-        from simdjson_b200 import sharding
+        def all_gather_bytes(h):
+            t = torch.from_numpy(h.copy()).to(dev)
+            out = torch.empty(world * t.numel(), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(out, t)  # NCCL: the 64-byte IPC handles of the exchange windows, once per job
+            return out.cpu().numpy()
+        comm.connect(all_gather_bytes)
 
-        def scan(state_in):
-            rc, res = parser.stage1_shard_device(d_docs[i % ROTATE], state_in, rank == world - 1, d_idx=d_idxs[i % 2], stream=stream)
-            if rc != 0:
-                raise RuntimeError("shard scan failed: " + parser.last_cuda_error())
-            return int(res.ttable), int(res.count), int(res.flags)
-
-        def all_gather(v):
-            gather_in.copy_(torch.from_numpy(v))
-            dist.all_gather_into_tensor(gather_out, gather_in)
-            return gather_out.view(world, 4).cpu().numpy()
-
-        r = sharding.exchange(scan, rank, world, all_gather)
-        return r["count"], r["base"]
+    kernel_ms, n_struct, results = [], [], {}
 
     def run_steps(k, record):
         t_ev0, t_ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -220,46 +323,44 @@ def run_ours(args, rank, world):
         t_ev0.record(stream)
         if world == 1:
             # K steps = K documents through the batch entry point: every scan is queued back to back on `stream`
-            res = parser.stage1_device_batch([d_docs[i % ROTATE] for i in range(k)], [d_idxs[i % 2] for i in range(k)], sj.REGULAR, stream=stream)
-            for err, n in res:
+            res = parser.stage1_device_batch([d_docs[i % ROTATE] for i in range(k)], [d_idxs[i % ROTATE] for i in range(k)], sj.REGULAR, stream=stream)
+            for i, (err, n) in enumerate(res):
                 if err != sj.SUCCESS:
                     raise RuntimeError("stage1 failed: " + capi.ERROR_NAMES.get(err, str(err)) + " " + parser.last_cuda_error())
                 if record:
                     n_struct.append(n)
+                    results[i % ROTATE] = (n, 0, 0)
         else:
-            # pipelined speculation: scan_k -> all_gather_k are queued for every step without a host round trip; the
-            # host verifies all K speculations afterwards and falls back to the synchronous protocol for a step whose
-            # speculation was wrong (never the case for shards that start at a document boundary)
-            from simdjson_b200 import sharding
-            for i in range(k):
-                rc = parser.stage1_shard_device_enqueue(d_docs[i % ROTATE], shard_res[i % len(shard_res)], d_idx=d_idxs[i % 2], stream=stream)
-                if rc != 0:
-                    raise RuntimeError("shard scan failed: " + parser.last_cuda_error())
-                dist.all_gather_into_tensor(shard_gather[i % len(shard_res)], shard_res[i % len(shard_res)])
-            t_ev1.record(stream)
-            torch.cuda.synchronize()
-            for i in range(min(k, len(shard_res))):
-                okk, state_in, _base = sharding.verify_speculation(shard_gather[i].view(world, 3).cpu().numpy(), rank)
-                if not okk:
-                    sharded_step(i)
-                if record:
-                    n_struct.append(sharding.unpack_result(shard_res[i].cpu().numpy())[1])
-        if world == 1:
-            t_ev1.record(stream)
-            torch.cuda.synchronize()
+            # sharded passes, up to 24 in flight: enqueue (scan + fused exchange, no host round trip), then finish
+            # (fold state / base from the local exchange window; re-scan + second round only on a wrong speculation)
+            i = 0
+            while i < k:
+                w = min(24, k - i)
+                for j in range(i, i + w):
+                    rcq = comm.enqueue(d_docs[j % ROTATE], d_idxs[j % ROTATE], rank == world - 1, stream)
+                    if rcq != 0:
+                        raise RuntimeError("sharded enqueue failed: " + parser.last_cuda_error())
+                for j in range(i, i + w):
+                    rcf, res = comm.finish()
+                    if rcf != 0:
+                        raise RuntimeError("sharded finish failed: " + parser.last_cuda_error())
+                    if record:
+                        n_struct.append(int(res.count))
+                        results[j % ROTATE] = (int(res.count), int(res.base), int(res.state_in), int(res.rescanned), int(res.total_count))
+                i += w
+        t_ev1.record(stream)
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         if record:
             kernel_ms.append(parser.get_stat("kernel_ms_mean"))
         return t_ev0.elapsed_time(t_ev1)
 
-    launches0 = sum(p.get_stat("launches") for p in parsers)
     run_steps(max(3, args.warmup), False)
-    launches1 = sum(p.get_stat("launches") for p in parsers)
+    launches1 = parser.get_stat("launches")
     with ClockSampler(local) as clocks:
         total_ms = run_steps(args.steps, True)
-    launches2 = sum(p.get_stat("launches") for p in parsers)
-    _ = launches0
+    launches2 = parser.get_stat("launches")
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -267,23 +368,52 @@ def run_ours(args, rank, world):
     ms_per_step = total_ms / args.steps
     value = world * DOC_BYTES / (ms_per_step * 1e-3) / 1e9
 
-    # ---- e2e through the host-pointer C-ABI call (pinned host input; H2D + D2H inside the timed region)
-    p = parsers[0]
-    hosts = [x.numpy() for x in pinned]
-    for i in range(3):
-        p.stage1(hosts[i % ROTATE], sj.REGULAR)
+    # ---- parity gate: the output every distinct input left behind in the timed region, against the oracle
+    parity_ok, checked, rescans = True, 0, 0
+    first_words = None
+    for k in range(min(ROTATE, args.steps)):
+        got = d_idxs[k].cpu().numpy().view(np.uint32)
+        if world == 1:
+            want = port.stage1(shards[k], 0)
+            n = results[k][0]
+            okk = want.err == 0 and want.n == n and np.array_equal(got[: n + 3], want.words())
+            if k == 0:
+                first_words = want.words().copy()
+        else:
+            count, base, state_in, rescanned, total = results[k]
+            widx, _ = raw_scan(O, port, shards[k], state_in)
+            counts = torch.tensor([count], dtype=torch.int64, device=dev)
+            allc = torch.empty(world, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(allc, counts)
+            allc = allc.cpu().numpy()
+            okk = len(widx) == count and np.array_equal(got[:count], widx) and base == int(allc[:rank].sum()) and total == int(allc.sum())
+            rescans += rescanned
+        parity_ok = parity_ok and bool(okk)
+        checked += 1
+    if world > 1:
+        flag = torch.tensor([1 if parity_ok else 0], dtype=torch.int64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        parity_ok = bool(flag.item())
+
+    # ---- e2e: stage 1 through the plug-in (the reference's own boundary), pageable input, every rank its own shard
     e2e_steps = max(3, min(args.steps, 10))
     if world > 1:
         dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    e2e_n = 0
-    for i in range(e2e_steps):
-        rc = p.stage1(hosts[i % ROTATE], sj.REGULAR)
-        assert rc == 0, rc
-        e2e_n = p.n_structural_indexes
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    e2e_info = None
+    if os.path.exists(PLUGIN):
+        r = plugin_e2e(shards[0], e2e_steps, first_words)
+        e2e_s, e2e_n = r["seconds_total"], r["n"]
+        e2e_info = {"through": "libsimdjson_b200.so: create_dom_parser_implementation()->stage1() on a pageable padded_string", "rc": r["rc"], "parity": r["parity"],
+                    "gbs_best_call": round(len(shards[0]) / r["seconds_best"] / 1e9, 3), "gpu_stage1_calls": r["gpu_calls"]}
+    else:  # the plug-in needs the reference headers to build; without it the same C-ABI call through the Python mirror, pageable numpy input
+        host = shards[0].copy()
+        for _ in range(2):
+            parser.stage1(host, sj.REGULAR)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            rcx = parser.stage1(host, sj.REGULAR)
+        e2e_s, e2e_n = time.perf_counter() - t0, parser.n_structural_indexes
+        e2e_info = {"through": "sjb200_stage1 (C ABI, Python mirror), pageable input", "rc": rcx}
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -295,61 +425,32 @@ def run_ours(args, rank, world):
         nmean = float(np.mean(n_struct))
         algo_bytes = DOC_BYTES + 4.0 * nmean + 12.0
         achieved = algo_bytes / (kms * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic("scan4")
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "synthetic 64 MiB random-structure JSON, stage1 index on 1xB200 (BASELINE.json configs[1])" if world == 1 else
-                       f"{world} x 64 MiB shards of one random-structure JSON stream, stage1 sharded by byte range + NCCL carry/offset all-gather",
-                       "bytes_per_gpu_per_step": DOC_BYTES, "mode": "regular" if world == 1 else "shard", "structurals_per_step": int(nmean),
+            "config": {"workload": workload_name(world), "bytes_per_gpu_per_step": DOC_BYTES, "mode": "regular" if world == 1 else "shard", "structurals_per_step": int(nmean),
                        "l2": f"{ROTATE} distinct inputs used round-robin ({ROTATE * DOC_BYTES >> 20} MiB > 126 MB L2)",
-                       "api": "sjb200_stage1_dev_batch: the K documents of the timed region are queued back to back on one stream" if world == 1 else "sjb200_stage1_shard_dev_enqueue + NCCL all_gather_into_tensor per step, verified after the timed region"},
+                       "content": "random sequence of 48 distinct 96 KiB random subtrees per document (corpus.random_json): DRAM behaviour of 64 MiB, 4.6 MB of distinct structure",
+                       "api": "sjb200_stage1_dev_batch: the K documents of the timed region are queued back to back on one stream" if world == 1 else
+                              "sjb200_stage1_sharded_enqueue / _finish: exchange record stored by the scan kernel into every rank's window over NVLink (CUDA IPC); NCCL only for the handle exchange at start-up"},
             "clocks": clocks.summary(),
-            "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": DOC_BYTES, "d2h_bytes_per_step": int(4 * e2e_n + 24), "steps": e2e_steps},
+            "parity": {"ok": parity_ok, "documents_checked": checked, "against": "CPU oracle (oracle/sj_oracle.c), (n+3) index words" if world == 1 else "CPU oracle raw scan of every rank's shard + index bases", "rescans": rescans},
+            "e2e": dict({"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": DOC_BYTES, "d2h_bytes_per_step": int(4 * e2e_n + 24), "steps": e2e_steps}, **(e2e_info or {})),
             "gpu_launches": int(launches2 - launches1),
-            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": ncu_traffic()[0],
-                         "traffic_source": ncu_traffic()[1], "peak_source": peak_src, "kernel": "sjb200::scan4_deferred_kernel / scan4_kernel (sjb200_scan4.cuh)", "kernel_ms": round(kms, 5), "algorithmic_bytes": int(algo_bytes),
-                         "input_gbs_kernel_only": round(DOC_BYTES / (kms * 1e-3) / 1e9, 1)},
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+                         "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "sjb200::scan4_kernel (sjb200_scan4.cuh)", "kernel_ms": round(kms, 5), "algorithmic_bytes": int(algo_bytes),
+                         "input_gbs_kernel_only": round(DOC_BYTES / (kms * 1e-3) / 1e9, 1), "kernel_src_sha16": kernel_source_hash()},
         }
-        line["cpu_baseline"] = cpu_baseline(docs[0])
+        line["cpu_baseline"] = cpu_baseline(shards[0])
         print(json.dumps(line), flush=True)
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-
-
-def ncu_traffic():
-    """DRAM bytes of one launch of the stage-1 kernel on the bench document, from the committed `ncu --set full` capture
-    (profiles/, produced by tools/run_gpu_round.sh + tools/ncu_summary.py); None when there is no capture"""
-    path = os.path.join(ROOT, "profiles", "r1b_scan4_kernel_ncu_full.json")
-    try:
-        d = json.load(open(path))
-        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        tot = 0.0
-        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            v, u = d[k]
-            tot += float(v) * unit[u]
-        return int(tot), os.path.relpath(path, ROOT)
-    except Exception:  # noqa: BLE001
-        return None, None
-
-
-def cpu_baseline(doc):
-    """rank 0, N=1 style bounded sample of the reference's CPU stage 1 on this host"""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_lib as O
-    cores = os.cpu_count() or 1
-    if O.have_ref():
-        ref = O.Ref("")
-        one, _ = ref.time(0, doc, 0, 1, 3)
-        threads = max(1, min(cores, int(os.environ.get("SJB200_REF_THREADS", cores))))
-        many, _ = ref.time(0, doc, 0, threads, 3)
-        return {"value": round(threads * len(doc) / many / 1e9, 3), "unit": UNIT, "cores": threads, "kind": "reference",
-                "sample": f"{ref.name} kernel; {threads} threads x one 64 MiB stage1 call, best of 3 rounds; single thread: {len(doc)/one/1e9:.2f} GB/s"}
-    port = O.Port()
-    t0 = time.perf_counter()
-    port.stage1(doc[: 16 << 20], 0)
-    dt = time.perf_counter() - t0
-    return {"value": round((16 << 20) / dt / 1e9, 3), "unit": UNIT, "cores": 1, "kind": "port", "sample": "scalar C port, 16 MiB prefix, one pass"}
+    if not parity_ok:
+        sys.exit(1)
 
 
 def main():
@@ -358,14 +459,20 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="stage1_64m", choices=["stage1_64m", "jsonexamples", "ndjson_1g", "utf8_minify_256m", "concat_8g"])
+    ap.add_argument("--check", action="store_true", help="parity gate of the multi-rank path on adversarial cuts")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, world)
         return
     if world != args.gpus and args.gpus > 1:
         sys.stderr.write(f"bench.py: --gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})\n")
+    if args.check or args.config != "stage1_64m":
+        import bench_configs
+        bench_configs.run(args, rank, world)
+        return
     run_ours(args, rank, world)
 
 

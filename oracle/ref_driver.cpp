@@ -139,6 +139,62 @@ SJR_API double sjr_time(const char *name, int op, const uint8_t *buf, size_t len
   return best;
 }
 
+// The same measurement with the hygiene a stable number needs: the T threads are created ONCE and reused for every
+// round (thread creation is outside the timed window), every thread works on its OWN copy of the document (so the
+// figure is bounded by DRAM bandwidth and not by how much of one shared buffer happens to sit in the last-level cache),
+// a round starts on a flag all threads spin on and ends when the last one reports.  out[0] = best round, out[1] = mean
+// round (seconds; every round = every thread doing one call).  Returns 0, or a negative value on error.
+SJR_API int sjr_time_rounds(const char *name, int op, const uint8_t *buf, size_t len, int mode, int threads, int warmup, int iters,
+                            double *out, int *err_out) {
+  auto impl = find_impl(name);
+  if (!impl) return -1;
+  if (threads < 1) threads = 1;
+  struct worker_state {
+    std::unique_ptr<internal::dom_parser_implementation> parser;
+    std::unique_ptr<uint8_t[]> src, dst;
+    int err{0};
+  };
+  std::vector<worker_state> ws(threads);
+  std::atomic<int> round{0}, done{0}, ready{0};
+  std::atomic<bool> failed{false};
+  const int rounds = warmup + iters;
+  auto body = [&](int t) {
+    worker_state &w = ws[t];
+    w.src.reset(new (std::nothrow) uint8_t[len + SIMDJSON_PADDING]);
+    if (!w.src) failed = true;
+    else { std::memcpy(w.src.get(), buf, len); std::memset(w.src.get() + len, 0x20, SIMDJSON_PADDING); }
+    if (op == 0 && impl->create_dom_parser_implementation(len, 1024, w.parser)) failed = true;
+    if (op == 1) { w.dst.reset(new (std::nothrow) uint8_t[len + SIMDJSON_PADDING]); if (!w.dst) failed = true; }
+    ready++;
+    for (int r = 1; r <= rounds; r++) {
+      while (round.load(std::memory_order_acquire) < r) {}
+      if (!failed) {
+        if (op == 0) w.err = int(w.parser->stage1(w.src.get(), len, stage1_mode(mode)));
+        else if (op == 1) { size_t n = 0; w.err = int(impl->minify(w.src.get(), len, w.dst.get(), n)); }
+        else w.err = impl->validate_utf8(reinterpret_cast<const char *>(w.src.get()), len) ? 0 : int(UTF8_ERROR);
+      }
+      done.fetch_add(1, std::memory_order_release);
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 0; t < threads; t++) th.emplace_back(body, t);
+  while (ready.load() < threads) std::this_thread::yield();
+  double best = 1e30, sum = 0;
+  for (int r = 1; r <= rounds; r++) {
+    const auto t0 = std::chrono::steady_clock::now();
+    round.store(r, std::memory_order_release);
+    while (done.load(std::memory_order_acquire) < r * threads) {}
+    const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (r > warmup) { sum += s; if (s < best) best = s; }
+  }
+  for (auto &t : th) t.join();
+  if (failed) return -2;
+  out[0] = best;
+  out[1] = sum / iters;
+  if (err_out) *err_out = ws[0].err;
+  return 0;
+}
+
 // ------------------------------------------------- DOM-level reference hooks
 // Used by the drop-in tests to get what dom::parser::parse / parse_many /
 // simdjson::minify produce through a CPU implementation, for comparison with

@@ -71,6 +71,23 @@ SJ_HD uint32_t bitsel(uint32_t m, uint32_t a, uint32_t b) {
 #endif
 }
 
+// x >> d for a constant d, on the FMA pipe (IMAD.HI) instead of the ALU pipe (SHF): the scan is bound by the ALU pipe's
+// issue rate, the FMA pipe is mostly idle.  Build option; the multiply is slower per instruction, so it only pays if
+// it overlaps (measured per build in profiles/).
+#ifndef SJB200_SHR_IMAD
+#define SJB200_SHR_IMAD 0
+#endif
+template <int D>
+SJ_HD uint32_t shr_const(uint32_t x) {
+#if defined(__CUDA_ARCH__) && SJB200_SHR_IMAD
+  uint32_t r;
+  asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "n"(1u << (32 - D)));
+  return r;
+#else
+  return x >> D;
+#endif
+}
+
 // ------------------------------------------------------------- transpose
 // w[i] (i=0..7) holds input bytes 4i..4i+3 little-endian.  On return p[k] bit n
 // = bit k of byte n (n = 0..31).
@@ -89,7 +106,7 @@ SJ_HD void transpose32(const uint32_t w[8], uint32_t p[8]) {
 #define SJ_DSWAP(lo, hi, d, m)                      \
   {                                                 \
     const uint32_t nl = bitsel(m, lo, (hi) << (d)); \
-    const uint32_t nh = bitsel(m, (lo) >> (d), hi); \
+    const uint32_t nh = bitsel(m, shr_const<d>(lo), hi); \
     lo = nl; hi = nh;                               \
   }
   SJ_DSWAP(a0, a1, 1, 0x55555555u) SJ_DSWAP(a2, a3, 1, 0x55555555u)

@@ -77,7 +77,7 @@ struct sjb200_ctx {
   int grid[3] = {0, 0, 0};
   long opt_kernel = 4;  // stage-1 kernel generation: 4 = scan4 (sjb200_scan4.cuh), 3 = the tile-synchronous scan_kernel<kIndex>
   int grid4 = 0;
-  long opt_sub_per_super = 0, opt_use_tma = 1, opt_grid = 0, opt_chunk_bytes = 2 << 20, opt_time_kernel = 0;
+  long opt_sub_per_super = 0, opt_use_tma = 1, opt_grid = 0, opt_chunk_bytes = 4 << 20, opt_time_kernel = 0;
   cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // around the last scan kernel when opt_time_kernel is set
   bool ev_valid = false;
   std::vector<cudaEvent_t> ev_pool;              // [2i], [2i+1] around launch i since the last kernel_ms_mean query
@@ -883,6 +883,7 @@ bool scan_host_document(sjb200_ctx *c, int kind, const uint8_t *buf, size_t len,
     pool.begin(buf, len, chunk, c->h_ring, c->ring_slot_bytes, slots);
     pool.allow(size_t(slots));
     size_t issued = 0, released = 0;  // chunks handed to the copy engine / known to have left their slot
+    uint32_t idle = 0;
     bool good = true;
     while (good && issued < nchunks) {
       while (released < issued && cudaEventQuery(c->ring_events[released % size_t(slots)]) == cudaSuccess) {
@@ -893,8 +894,11 @@ bool scan_host_document(sjb200_ctx *c, int kind, const uint8_t *buf, size_t len,
         good = launch_chunk(issued, c->h_ring + (issued % size_t(slots)) * c->ring_slot_bytes) &&
                ok(c, cudaEventRecord(c->ring_events[issued % size_t(slots)], c->copy_stream), "event record");
         issued++;
-      } else {
+        idle = 0;
+      } else if (++idle < 512) {
         SJB200_CPU_RELAX();
+      } else {
+        std::this_thread::sleep_for(std::chrono::microseconds(10));  // (no unbounded spinning: see sjb200_hostpipe.h)
       }
     }
     (void)cudaGetLastError();  // cudaEventQuery's cudaErrorNotReady is not an error

@@ -16,6 +16,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <memory>
 #include <mutex>
@@ -90,7 +91,11 @@ class CopyPool {
   // wait until every worker has left the session (abort = true makes them leave early)
   void end(bool abort) {
     if (abort) abort_.store(true, std::memory_order_release);
-    while (active_.load(std::memory_order_acquire) != 0) SJB200_CPU_RELAX();
+    uint32_t spins = 0;
+    while (active_.load(std::memory_order_acquire) != 0) {
+      if (++spins < 256) SJB200_CPU_RELAX();
+      else std::this_thread::sleep_for(std::chrono::microseconds(20));
+    }
   }
 
  private:
@@ -106,8 +111,9 @@ class CopyPool {
       for (size_t k = 0; k < nchunks_; k++) {
         uint32_t spins = 0;
         while (allowed_.load(std::memory_order_acquire) <= k && !abort_.load(std::memory_order_acquire)) {
-          if (++spins < 2000) SJB200_CPU_RELAX();
-          else std::this_thread::yield();
+          // a short spin, then sleep: a pool that spins on a machine with a CPU quota (containers) starves its own copies
+          if (++spins < 256) SJB200_CPU_RELAX();
+          else std::this_thread::sleep_for(std::chrono::microseconds(20));
         }
         if (abort_.load(std::memory_order_acquire)) break;
         const size_t off = k * chunk_;

@@ -79,6 +79,12 @@ static_assert(kLag >= 1 && 2 * kLag + 3 <= kNS && 2 * (kParkD - 1) + 3 <= kNS &&
 #ifndef SJB200_SCAN4_SLEEP
 #define SJB200_SCAN4_SLEEP 1
 #endif
+#ifndef SJB200_SCAN4_EARLY_LOOKBACK
+#define SJB200_SCAN4_EARLY_LOOKBACK 1  // 1: the chain warp walks back over the predecessors of an element while the element is being scanned
+#endif
+#ifndef SJB200_SCAN4_UTF8_BLOCK
+#define SJB200_SCAN4_UTF8_BLOCK 1  // 1: ASCII / non-ASCII decided once per 4 KiB block (two specialised copies of the unit loop); 0: once per unit
+#endif
 #ifndef SJB200_SCAN4_TRACE
 #define SJB200_SCAN4_TRACE 0  // 1: tuning build that records where a scan warp's time goes (shared memory, dumped to ScanParams::debug at exit)
 #endif
@@ -348,6 +354,43 @@ SJ_DEV uint32_t scan_block(const uint8_t *T, uint32_t pw0, uint32_t e_in, uint32
       bs[u] = c.bs; qu[u] = c.qu; op[u] = c.op; sc[u] = c.sc; cl[u] = 0;
     }
   } else {
+#if SJB200_SCAN4_UTF8_BLOCK
+    // One decision per block instead of one per unit: does any lane hold a byte >= 0x80?  (The lane's row is read
+    // twice -- the load pipe has room, the ALU pipe does not.)  An all-ASCII block needs no UTF-8 code at all, any other
+    // block runs the check in every unit without the per-unit vote, pending-carry bookkeeping and carry reset.
+    uint32_t hi = 0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      const sj_u4 v = *reinterpret_cast<const sj_u4 *>(T + swz(lane_off + 16u * c));
+      hi |= v.x | v.y | v.z | v.w;
+    }
+    if (!sj_any((hi & 0x80808080u) != 0)) {
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        uint32_t w8[8], pl[8];
+        load_unit(T, lane_off + 32u * u, w8);
+        transpose32(w8, pl);
+        const unit_classes c = classify(pl);
+        bs[u] = c.bs; qu[u] = c.qu; op[u] = c.op; sc[u] = c.sc; cl[u] = c.ctl;
+      }
+      // only the block before this one can have left a sequence open: it ends in ASCII here, which is an error
+      if (lane == 0 && utf8_carry_pending(utf8_carry_from_prev_word(pw0))) uerr = 1u;
+    } else {
+      const uint32_t pw = (lane == 0) ? pw0 : *reinterpret_cast<const uint32_t *>(T + swz(lane_off - 4));
+      utf8_carry uc = utf8_carry_from_prev_word(pw);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        uint32_t w8[8], pl[8];
+        load_unit(T, lane_off + 32u * u, w8);
+        transpose32(w8, pl);
+        const unit_classes c = classify(pl);
+        bs[u] = c.bs; qu[u] = c.qu; op[u] = c.op; sc[u] = c.sc; cl[u] = c.ctl;
+#if !defined(SJB200_DIAG_NO_UTF8)
+        uerr |= utf8_check_unit(pl, uc);
+#endif
+      }
+    }
+#else
     const uint32_t pw = (lane == 0) ? pw0 : *reinterpret_cast<const uint32_t *>(T + swz(lane_off - 4));
     utf8_carry uc = utf8_carry_from_prev_word(pw);
     uint32_t pend = utf8_carry_pending(uc) ? 1u : 0u;  // the previous unit ended inside a multi-byte sequence
@@ -369,6 +412,7 @@ SJ_DEV uint32_t scan_block(const uint8_t *T, uint32_t pw0, uint32_t e_in, uint32
         uc = utf8_carry_zero();
       }
     }
+#endif
   }
   if (!kMin && sj_any(uerr != 0) && lane == 0) sj_atomic_or(p.flags, kFlagUtf8);
 
@@ -1136,11 +1180,21 @@ SJ_DEV void chain_role(Smem *S, const ScanParams &p, const Carry &cin, unsigned 
     const int ns = int(j % kNS);
     const uint32_t t = wait_ticket(S, j, p);
     if (t >= nelem) break;
+    uint32_t s_in = (cin.state >> 1) & 1u, base = 0;
+#if SJB200_SCAN4_EARLY_LOOKBACK
+    // The look-back needs the elements BEFORE t, not t itself: it runs while this CTA is still scanning t, so that the
+    // element is resolved as soon as its own summary is there (with the look-back after the scan, an element was
+    // resolved ~3.6 us after the last of its predecessors had been scanned: pick-up + poll round trips + fold).
+    if (t > 0) look_back(p, t, lane, &s_in, &base);
+    wait_bar(&S->scanned[ns], (j / kNS) & 1u, p, 64);
+    if (!SJB200_SCAN4_TRACE && p.debug != nullptr && lane == 0) p.debug[uint64_t(t) * 8 + 6] = sj_globaltimer();
+    const uint32_t par = S->elem[ns][0], b0 = S->elem[ns][1], b1 = S->elem[ns][2], hits = S->elem[ns][3];
+#else
     wait_bar(&S->scanned[ns], (j / kNS) & 1u, p, 200);
     if (!SJB200_SCAN4_TRACE && p.debug != nullptr && lane == 0) p.debug[uint64_t(t) * 8 + 6] = sj_globaltimer();
     const uint32_t par = S->elem[ns][0], b0 = S->elem[ns][1], b1 = S->elem[ns][2], hits = S->elem[ns][3];
-    uint32_t s_in = (cin.state >> 1) & 1u, base = 0;
     if (t > 0) look_back(p, t, lane, &s_in, &base);
+#endif
     const uint32_t mine_total = s_in ? b1 : b0;
     const uint32_t s_out = s_in ^ par;
     if (lane == 0) sj_st_relaxed_u64(p.count_desc + t, pack_inc(p.epoch, s_out, base + mine_total));

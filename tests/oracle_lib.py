@@ -113,6 +113,8 @@ class Ref:
         L.sjr_validate_utf8.argtypes = [C.c_char_p, C.POINTER(C.c_uint8), C.c_size_t]
         L.sjr_time.restype = C.c_double
         L.sjr_time.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_uint8), C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.sjr_time_rounds.restype = C.c_int
+        L.sjr_time_rounds.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_uint8), C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.sjr_dom_roundtrip.restype = C.c_int
         L.sjr_dom_roundtrip.argtypes = [C.c_char_p, C.POINTER(C.c_uint8), C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.sjr_dom_parse_many.restype = C.c_long
@@ -150,6 +152,16 @@ class Ref:
         err = C.c_int(0)
         s = self.L.sjr_time(self.impl, op, _ptr(a), len(a), mode, threads, iters, C.byref(err))
         return s, err.value
+
+    def time_rounds(self, op, buf, mode=REGULAR, threads=1, warmup=1, iters=3):
+        """pre-spawned threads, one private copy of the document per thread; returns (best_s, mean_s, error_code)"""
+        a = _u8(buf)
+        out = (C.c_double * 2)()
+        err = C.c_int(0)
+        rc = self.L.sjr_time_rounds(self.impl, op, _ptr(a), len(a), mode, threads, warmup, iters, out, C.byref(err))
+        if rc != 0:
+            raise RuntimeError(f"sjr_time_rounds failed ({rc})")
+        return out[0], out[1], err.value
 
     def dom_roundtrip(self, buf):
         a = _u8(buf)
