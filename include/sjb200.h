@@ -125,6 +125,21 @@ typedef struct {
 } sjb200_doc;
 SJB200_API int sjb200_stage1_dev_batch(sjb200_ctx *ctx, sjb200_doc *docs, int ndocs, int mode, void *stream);
 
+/* every place a document of a whitespace-separated stream (NDJSON, concatenated documents) starts, from the
+ * device-resident output (d_idx, n) of a stage-1 call: (structural index, byte offset) pairs in stream order, built on
+ * the device.  Structural i >= 1 starts a document when it is a value or an opening bracket and
+ * structural i-1 is neither an opening bracket nor ',' / ':' -- the predicate of find_next_document_index
+ * (src/generic/stage1/find_next_document_index.h L60-88), applied to every position instead of the last one only, so a
+ * consumer can hand the documents of ONE big stage-1 pass to many stage-2 workers instead of discovering them window by
+ * window (include/simdjson/dom/document_stream-inl.h L245-271).  *ndocs_out = number of starts found (entries beyond
+ * `capacity` are not stored). */
+typedef struct {
+  uint32_t index; /* structural index at which a document starts */
+  uint32_t byte;  /* = structural_indexes[index] */
+} sjb200_doc_boundary;
+SJB200_API int sjb200_document_table_dev(sjb200_ctx *ctx, const uint8_t *d_buf, const uint32_t *d_idx, uint32_t n, sjb200_doc_boundary *d_table,
+                              uint32_t capacity, uint32_t *ndocs_out, void *stream);
+
 /* split form of the same calls for pipelining / timing: enqueue returns as soon as the work is on the
  * stream, finish waits for it and completes the reference's finish() logic. */
 SJB200_API int sjb200_stage1_dev_enqueue(sjb200_ctx *ctx, const uint8_t *d_buf, size_t len, int mode, uint32_t *d_idx, void *stream);

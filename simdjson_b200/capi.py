@@ -15,7 +15,7 @@ EXPORTS = [
     "sjb200_last_cuda_error", "sjb200_set_option", "sjb200_get_stat", "sjb200_pin_host_memory", "sjb200_unpin_host_memory", "sjb200_get_debug_timeline",
     "sjb200_stage1", "sjb200_minify", "sjb200_validate_utf8",
     "sjb200_stage1_dev", "sjb200_minify_dev", "sjb200_validate_utf8_dev", "sjb200_stage1_dev_batch",
-    "sjb200_stage1_dev_enqueue", "sjb200_stage1_dev_finish", "sjb200_minify_dev_enqueue", "sjb200_minify_dev_finish",
+    "sjb200_document_table_dev", "sjb200_stage1_dev_enqueue", "sjb200_stage1_dev_finish", "sjb200_minify_dev_enqueue", "sjb200_minify_dev_finish",
     "sjb200_validate_utf8_dev_enqueue", "sjb200_validate_utf8_dev_finish",
     "sjb200_stage1_shard_dev", "sjb200_stage1_shard_dev_enqueue", "sjb200_fold_state", "sjb200_shard_cut", "sjb200_shard_cut_line",
     "sjb200_comm_create", "sjb200_comm_destroy", "sjb200_comm_get_handle", "sjb200_comm_connect", "sjb200_comm_connect_local",
@@ -72,6 +72,7 @@ def load():
         "sjb200_minify_dev": (C.c_int, [vp, vp, sz, vp, C.POINTER(sz), vp]),
         "sjb200_validate_utf8_dev": (C.c_int, [vp, vp, sz, vp]),
         "sjb200_stage1_dev_batch": (C.c_int, [vp, C.POINTER(Doc), C.c_int, C.c_int, vp]),
+        "sjb200_document_table_dev": (C.c_int, [vp, vp, vp, C.c_uint32, vp, C.c_uint32, u32p, vp]),
         "sjb200_stage1_dev_enqueue": (C.c_int, [vp, vp, sz, C.c_int, vp, vp]),
         "sjb200_stage1_dev_finish": (C.c_int, [vp, u32p]),
         "sjb200_minify_dev_enqueue": (C.c_int, [vp, vp, sz, vp, vp]),

@@ -15,6 +15,7 @@
 
 #include "../../include/sjb200.h"
 #include "sjb200_bits.cuh"
+#include "sjb200_docs.h"
 #include "sjb200_finish.h"
 #include "sjb200_hostpipe.h"
 #include "sjb200_kernels.cuh"
@@ -61,7 +62,8 @@ struct sjb200_ctx {
   uint32_t *d_ticket = nullptr;
   unsigned long long *d_count_desc = nullptr;
   size_t desc_tiles = 0;
-  uint8_t *d_chars = nullptr; size_t d_chars_bytes = 0;
+  StreamFinish *d_sfin = nullptr;  // [kCarrySlots] results of the device-side streaming epilogue
+  uint32_t *d_doc_scratch = nullptr; size_t doc_scratch_words = 0; uint32_t *d_ndocs = nullptr;
   uint32_t *d_park = nullptr; size_t d_park_words = 0;  // scan4 deferred mode: parked masks (a per-CTA ring, independent of the input size)
   long opt_utf8_kernel = 2;    // 2: utf8v2 (independent warps, sjb200_utf8.cuh); 1: scan_kernel<kUtf8> (tile-synchronous)
   int grid_u = 0;
@@ -71,8 +73,8 @@ struct sjb200_ctx {
   Carry *h_carry = nullptr;     // [kCarrySlots]
   uint32_t *h_flags = nullptr;
   uint8_t *h_small = nullptr;   // 64 B scratch
-  uint8_t *h_chars = nullptr;   size_t h_chars_bytes = 0;
-  uint32_t *h_window = nullptr; size_t h_window_words = 0;
+  StreamFinish *h_sfin = nullptr;  // pinned mirror
+  uint8_t *h_tails = nullptr; uint8_t *d_tails = nullptr; const uint8_t **d_tail_ptrs = nullptr; size_t tails_cap = 0;  // batch: last 3 bytes of every document
   uint32_t epoch = 0;
   int grid[3] = {0, 0, 0};
   long opt_kernel = 4;  // stage-1 kernel generation: 4 = scan4 (sjb200_scan4.cuh), 3 = the tile-synchronous scan_kernel<kIndex>
@@ -317,77 +319,16 @@ bool enqueue_scan(sjb200_ctx *c, int kind, const CUtensorMap *map, bool tma, con
   return launched;
 }
 
-// ---- structural characters of a device-resident index array, fetched in growing windows from the end
-class DeviceTailReader final : public StructuralReader {
+// (the streaming modes' walk over the tail of a device-resident index array lives on the device: sjb200_docs.cu)
+class NullIndexWriter final : public IndexWriter {  // regular mode behind a device-resident scan: the kernel stored the sentinels already
  public:
-  DeviceTailReader(sjb200_ctx *c, const uint8_t *d_buf, const uint32_t *d_idx, uint32_t n, cudaStream_t s)
-      : c_(c), d_buf_(d_buf), d_idx_(d_idx), n_(n), s_(s), lo_(n), hi_(n) {}
-  bool failed() const { return failed_; }
-  uint32_t position(uint32_t i) override { return fetch(i) ? c_->h_window[i - lo_] : 0; }
-  uint8_t character(uint32_t i) override { return fetch(i) ? c_->h_chars[i - lo_] : 0; }
-
- private:
-  bool fetch(uint32_t i) {
-    if (failed_) return false;
-    if (i >= lo_ && i < hi_) return true;
-    // (re)load [new_lo, n): window doubles every time the walk runs off its low end
-    uint32_t want = std::max<uint32_t>(1024, 2 * (n_ - std::min(i, lo_)));
-    uint32_t new_lo = (want >= n_) ? 0 : n_ - want;
-    if (i < new_lo) new_lo = i;
-    const uint32_t count = n_ - new_lo;
-    size_t hw = c_->h_window_words * 4;
-    uint8_t *hwp = reinterpret_cast<uint8_t *>(c_->h_window);
-    const bool grown = ensure_host_scratch(c_, &hwp, &hw, size_t(count) * 4);
-    c_->h_window = reinterpret_cast<uint32_t *>(hwp);  // also on failure: the old block is gone
-    c_->h_window_words = hw / 4;
-    if (!grown) { failed_ = true; return false; }
-    if (!ensure_host_scratch(c_, &c_->h_chars, &c_->h_chars_bytes, count)) { failed_ = true; return false; }
-    if (c_->d_chars_bytes < count) {
-      cudaFree(c_->d_chars);
-      c_->d_chars = nullptr; c_->d_chars_bytes = 0;
-      if (!dev_alloc(c_, &c_->d_chars, count, "cudaMalloc(chars)")) { failed_ = true; return false; }
-      c_->d_chars_bytes = count;
-    }
-    bool good = ok(c_, launch_gather_chars(d_buf_, d_idx_, new_lo, count, c_->d_chars, s_), "gather") &&
-                ok(c_, cudaMemcpyAsync(c_->h_chars, c_->d_chars, count, cudaMemcpyDeviceToHost, s_), "D2H chars") &&
-                ok(c_, cudaMemcpyAsync(c_->h_window, d_idx_ + new_lo, size_t(count) * 4, cudaMemcpyDeviceToHost, s_), "D2H idx") &&
-                ok(c_, cudaStreamSynchronize(s_), "sync");
-    if (!good) { failed_ = true; return false; }
-    lo_ = new_lo;
-    hi_ = n_;
-    return true;
-  }
-  sjb200_ctx *c_;
-  const uint8_t *d_buf_;
-  const uint32_t *d_idx_;
-  uint32_t n_;
-  cudaStream_t s_;
-  uint32_t lo_, hi_;
-  bool failed_ = false;
+  bool set3(uint32_t, uint32_t, uint32_t, uint32_t) override { return false; }
+  bool final_fixup(uint32_t, uint32_t) override { return false; }
 };
-
-__global__ void final_fixup_kernel(uint32_t *idx, uint32_t m, uint32_t len) {
-  idx[m + 1] = idx[m];
-  idx[m] = len;
-}
-
-class DeviceIndexWriter final : public IndexWriter {
+class NullReader final : public StructuralReader {
  public:
-  DeviceIndexWriter(sjb200_ctx *c, uint32_t *d_idx, cudaStream_t s) : c_(c), d_idx_(d_idx), s_(s) {}
-  bool set3(uint32_t n, uint32_t a, uint32_t b, uint32_t cc) override {
-    c_->launches++;
-    return ok(c_, launch_write_sentinels(d_idx_, n, a, b, cc, s_), "sentinels");
-  }
-  bool final_fixup(uint32_t m, uint32_t len) override {
-    c_->launches++;
-    final_fixup_kernel<<<1, 1, 0, s_>>>(d_idx_, m, len);
-    return ok(c_, cudaGetLastError(), "fixup");
-  }
-
- private:
-  sjb200_ctx *c_;
-  uint32_t *d_idx_;
-  cudaStream_t s_;
+  uint32_t position(uint32_t) override { return 0; }
+  uint8_t character(uint32_t) override { return 0; }
 };
 
 bool is_filter_mode(int mode) { return mode >= SJB200_JSON_SEQUENCE_PARTIAL; }
@@ -434,6 +375,9 @@ extern "C" int sjb200_create(int device, size_t capacity, sjb200_ctx **out) {
   c->h_flags = static_cast<uint32_t *>(hp);
   good = good && ok(c, cudaMallocHost(&hp, 64), "cudaMallocHost");
   c->h_small = static_cast<uint8_t *>(hp);
+  good = good && ok(c, cudaMallocHost(&hp, kCarrySlots * sizeof(StreamFinish)), "cudaMallocHost");
+  c->h_sfin = static_cast<StreamFinish *>(hp);
+  good = good && dev_alloc(c, &c->d_sfin, kCarrySlots, "cudaMalloc(stream finish)") && dev_alloc(c, &c->d_ndocs, 1, "cudaMalloc(ndocs)");
   if (good) {
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -467,12 +411,12 @@ extern "C" void sjb200_destroy(sjb200_ctx *c) {
   DeviceGuard g(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   free_sized(c);
-  cudaFree(c->d_carry); cudaFree(c->d_flags); cudaFree(c->d_ticket); cudaFree(c->d_chars); cudaFree(c->d_debug); cudaFree(c->d_park);
+  cudaFree(c->d_carry); cudaFree(c->d_flags); cudaFree(c->d_ticket); cudaFree(c->d_sfin); cudaFree(c->d_doc_scratch); cudaFree(c->d_ndocs); cudaFree(c->d_tails); cudaFree(c->d_tail_ptrs); cudaFree(c->d_debug); cudaFree(c->d_park);
   if (c->h_carry) cudaFreeHost(c->h_carry);
   if (c->h_flags) cudaFreeHost(c->h_flags);
   if (c->h_small) cudaFreeHost(c->h_small);
-  if (c->h_chars) cudaFreeHost(c->h_chars);
-  if (c->h_window) cudaFreeHost(c->h_window);
+  if (c->h_sfin) cudaFreeHost(c->h_sfin);
+  if (c->h_tails) cudaFreeHost(c->h_tails);
   delete c->pool; c->pool = nullptr;
   if (c->h_ring) cudaFreeHost(c->h_ring);
   for (auto e : c->ring_events) cudaEventDestroy(e);
@@ -576,7 +520,7 @@ extern "C" int sjb200_set_option(sjb200_ctx *c, const char *key, long value) {
 namespace {
 // enqueue one device-resident stage-1 scan; its {count,state,flags} come back in h_carry[slot]
 void stage1_enqueue_into(sjb200_ctx *c, PendingCall &pc, const uint8_t *d_buf, size_t len, int mode, uint32_t *d_idx, cudaStream_t s,
-                         int slot) {
+                         int slot, const uint8_t *tail3 = nullptr /* host copy of the last min(3, len) bytes, when the caller fetched it */) {
   pc = PendingCall();
   pc.kind = kIndex; pc.mode = mode; pc.d_buf = d_buf; pc.d_idx = d_idx; pc.stream = s; pc.len = len; pc.carry_slot = slot;
   if (mode < SJB200_REGULAR || mode > SJB200_COMMA_DELIMITED_FINAL) { pc.early_error = SJB200_UNEXPECTED_ERROR; return; }
@@ -584,10 +528,13 @@ void stage1_enqueue_into(sjb200_ctx *c, PendingCall &pc, const uint8_t *d_buf, s
   if (len == 0) { pc.early_error = SJB200_EMPTY; return; }                // L197
   if (mode != SJB200_REGULAR) {                                           // L198-204
     const size_t k = std::min<size_t>(3, len);
-    if (!ok(c, cudaMemcpyAsync(c->h_small, d_buf + len - k, k, cudaMemcpyDeviceToHost, s), "D2H tail") ||
-        !ok(c, cudaStreamSynchronize(s), "sync"))
-      { pc.early_error = SJB200_UNEXPECTED_ERROR; return; }
-    len = trim_partial_utf8_tail(c->h_small, k, len);
+    if (!tail3) {
+      if (!ok(c, cudaMemcpyAsync(c->h_small, d_buf + len - k, k, cudaMemcpyDeviceToHost, s), "D2H tail") ||
+          !ok(c, cudaStreamSynchronize(s), "sync"))
+        { pc.early_error = SJB200_UNEXPECTED_ERROR; return; }
+      tail3 = c->h_small;
+    }
+    len = trim_partial_utf8_tail(tail3, k, len);
     pc.len = len;
     if (len == 0) { pc.early_error = SJB200_UTF8_ERROR; return; }
   }
@@ -600,19 +547,30 @@ void stage1_enqueue_into(sjb200_ctx *c, PendingCall &pc, const uint8_t *d_buf, s
                     c->h_carry + slot) ||
       (!use_scan4(c, kIndex) &&
        !ok(c, cudaMemcpyAsync(c->h_carry + slot, c->d_carry + slot, sizeof(Carry), cudaMemcpyDeviceToHost, s), "D2H result")))
-    pc.early_error = SJB200_UNEXPECTED_ERROR;
+    { pc.early_error = SJB200_UNEXPECTED_ERROR; return; }
+  // whitespace-separated streams: the rest of finish() (find_next_document_index, the final fix-up) runs on the device
+  // right behind the scan -- no host round trip between the two (sjb200_docs.cu)
+  if (mode == SJB200_STREAMING_PARTIAL || mode == SJB200_STREAMING_FINAL) {
+    c->launches++;
+    if (!ok(c, launch_stream_finish(d_buf, d_idx, c->d_carry + slot, uint32_t(len), mode, c->d_sfin + slot, c->h_sfin + slot, s), "stream finish"))
+      pc.early_error = SJB200_UNEXPECTED_ERROR;
+  }
 }
 
 // complete one enqueued scan (the stream has been synchronised by the caller)
 int stage1_finish_from(sjb200_ctx *c, const PendingCall &pc, uint32_t *n_inout) {
   if (pc.early_error >= 0) return pc.early_error;
+  if (pc.mode == SJB200_STREAMING_PARTIAL || pc.mode == SJB200_STREAMING_FINAL) {
+    const StreamFinish &r = c->h_sfin[pc.carry_slot];  // written by stream_finish_kernel behind the scan
+    if (r.n_written && n_inout) *n_inout = r.n;
+    return r.err;
+  }
   FinishInput in;
   in.mode = pc.mode; in.len = pc.len;
   in.count = c->h_carry[pc.carry_slot].count;
   in.state = c->h_carry[pc.carry_slot].state;
   in.flags = c->h_carry[pc.carry_slot].flags;
   in.sentinels_written = true;
-  DeviceIndexWriter writer(c, pc.d_idx, pc.stream);
   int rc;
   uint32_t n_local = n_inout ? *n_inout : 0;
   if (is_filter_mode(pc.mode)) {
@@ -635,12 +593,11 @@ int stage1_finish_from(sjb200_ctx *c, const PendingCall &pc, uint32_t *n_inout) 
           !ok(c, cudaStreamSynchronize(pc.stream), "sync"))
         return SJB200_UNEXPECTED_ERROR;
     }
-  } else {
-    DeviceTailReader reader(c, pc.d_buf, pc.d_idx, uint32_t(in.count), pc.stream);
+  } else {  // regular: error precedence only, nothing to read or write (the scan stored the sentinels)
+    NullReader reader;
+    NullIndexWriter writer;
     bool dirty = false;
     rc = finish_stage1(in, reader, writer, &n_local, nullptr, nullptr, &dirty);
-    if (reader.failed()) return SJB200_UNEXPECTED_ERROR;
-    if (!ok(c, cudaStreamSynchronize(pc.stream), "sync")) return SJB200_UNEXPECTED_ERROR;
   }
   if (n_inout) *n_inout = n_local;
   return rc;
@@ -675,9 +632,37 @@ extern "C" int sjb200_stage1_dev_batch(sjb200_ctx *c, sjb200_doc *docs, int ndoc
   while (done < ndocs) {
     const int group = std::min(ndocs - done, kCarrySlots - 2);  // one result slot per document in flight
     calls.assign(size_t(group), PendingCall());
+    const uint8_t *tails = nullptr;
+    if (mode != SJB200_REGULAR) {
+      // streaming modes look at every document's last three bytes before its scan (partial UTF-8 tail): fetch them for
+      // the whole group with one launch and one copy instead of one synchronous copy per document
+      if (c->tails_cap < size_t(group)) {
+        if (c->h_tails) cudaFreeHost(c->h_tails);
+        cudaFree(c->d_tails); cudaFree(c->d_tail_ptrs);
+        c->h_tails = nullptr; c->d_tails = nullptr; c->d_tail_ptrs = nullptr; c->tails_cap = 0;
+        void *hp = nullptr;
+        // host block: [group] pointers, [group] lengths, then 4 bytes per document coming back
+        if (!ok(c, cudaMallocHost(&hp, size_t(group) * 20), "cudaMallocHost(tails)") || !dev_alloc(c, &c->d_tails, size_t(group) * 4, "cudaMalloc(tails)") ||
+            !dev_alloc(c, &c->d_tail_ptrs, size_t(group) * 2, "cudaMalloc(tail ptrs)"))
+          return SJB200_MEMALLOC;
+        c->h_tails = static_cast<uint8_t *>(hp);
+        c->tails_cap = size_t(group);
+      }
+      const uint8_t **hptr = reinterpret_cast<const uint8_t **>(c->h_tails);
+      uint64_t *hlen = reinterpret_cast<uint64_t *>(c->h_tails + size_t(group) * 8);
+      uint8_t *hout = c->h_tails + size_t(group) * 16;
+      for (int i = 0; i < group; i++) { hptr[i] = docs[done + i].d_buf; hlen[i] = (docs[done + i].len <= c->capacity) ? docs[done + i].len : 0; }
+      const uint64_t *dlen = reinterpret_cast<const uint64_t *>(c->d_tail_ptrs + group);
+      if (!ok(c, cudaMemcpyAsync(c->d_tail_ptrs, c->h_tails, size_t(group) * 16, cudaMemcpyHostToDevice, s), "H2D tail ptrs") ||
+          !ok(c, launch_gather_tails(c->d_tail_ptrs, dlen, uint32_t(group), c->d_tails, s), "gather tails") ||
+          !ok(c, cudaMemcpyAsync(hout, c->d_tails, size_t(group) * 4, cudaMemcpyDeviceToHost, s), "D2H tails") || !ok(c, cudaStreamSynchronize(s), "sync"))
+        return SJB200_UNEXPECTED_ERROR;
+      c->launches++;
+      tails = hout;
+    }
     for (int i = 0; i < group; i++) {
       sjb200_doc &d = docs[done + i];
-      stage1_enqueue_into(c, calls[size_t(i)], d.d_buf, d.len, mode, d.d_idx, s, 1 + i);
+      stage1_enqueue_into(c, calls[size_t(i)], d.d_buf, d.len, mode, d.d_idx, s, 1 + i, tails ? tails + 4 * size_t(i) : nullptr);
     }
     if (!ok(c, cudaStreamSynchronize(s), "sync")) return SJB200_UNEXPECTED_ERROR;
     for (int i = 0; i < group; i++) {
@@ -686,6 +671,30 @@ extern "C" int sjb200_stage1_dev_batch(sjb200_ctx *c, sjb200_doc *docs, int ndoc
     }
     done += group;
   }
+  return SJB200_SUCCESS;
+}
+
+// every place a document of a whitespace-separated stream starts: built on the device from a
+// device-resident index array, in stream order
+extern "C" int sjb200_document_table_dev(sjb200_ctx *c, const uint8_t *d_buf, const uint32_t *d_idx, uint32_t n, sjb200_doc_boundary *d_table,
+                                         uint32_t capacity, uint32_t *ndocs_out, void *stream) {
+  if (!c || !d_buf || !d_idx || !ndocs_out || (capacity && !d_table)) return SJB200_UNEXPECTED_ERROR;
+  *ndocs_out = 0;
+  if (n == 0) return SJB200_SUCCESS;
+  DeviceGuard g(c->device);
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+  const size_t need = doc_table_scratch_words(n);
+  if (c->doc_scratch_words < need) {
+    cudaFree(c->d_doc_scratch); c->d_doc_scratch = nullptr; c->doc_scratch_words = 0;
+    if (!dev_alloc(c, &c->d_doc_scratch, need, "cudaMalloc(doc scratch)")) return SJB200_MEMALLOC;
+    c->doc_scratch_words = need;
+  }
+  static_assert(sizeof(sjb200_doc_boundary) == sizeof(sjb200_doc_boundary_t), "layout");
+  if (!ok(c, launch_doc_table(d_buf, d_idx, n, c->d_doc_scratch, reinterpret_cast<sjb200_doc_boundary_t *>(d_table), capacity, c->d_ndocs, s), "doc table") ||
+      !ok(c, cudaMemcpyAsync(c->h_small, c->d_ndocs, sizeof(uint32_t), cudaMemcpyDeviceToHost, s), "D2H ndocs") || !ok(c, cudaStreamSynchronize(s), "sync"))
+    return SJB200_UNEXPECTED_ERROR;
+  c->launches += 3;
+  memcpy(ndocs_out, c->h_small, sizeof(uint32_t));
   return SJB200_SUCCESS;
 }
 

@@ -32,6 +32,8 @@
 
 namespace sjb200 {
 
+void copy_to_staging(void *dst, const void *src, size_t n);  // sjb200_hostcopy.cpp: streaming stores
+
 class CopyPool {
  public:
   static constexpr size_t kMaxChunks = 4096;
@@ -120,7 +122,7 @@ class CopyPool {
         const size_t bytes = (len_ - off < chunk_) ? (len_ - off) : chunk_;
         const size_t per = ((bytes + size_t(nt) - 1) / size_t(nt) + 4095) & ~size_t(4095);  // whole pages per thread
         const size_t lo = size_t(me) * per;
-        if (lo < bytes) memcpy(ring_ + size_t(k % size_t(nslots_)) * slot_bytes_ + lo, src_ + off + lo, (bytes - lo < per) ? (bytes - lo) : per);
+        if (lo < bytes) copy_to_staging(ring_ + size_t(k % size_t(nslots_)) * slot_bytes_ + lo, src_ + off + lo, (bytes - lo < per) ? (bytes - lo) : per);
         done_[k].fetch_add(1, std::memory_order_release);
       }
       active_.fetch_sub(1, std::memory_order_release);

@@ -891,9 +891,14 @@ __global__ void __launch_bounds__(utf8v2::kThreadsU, utf8v2::kCtasPerSmU)
 }
 
 // ------------------------------------------------------------------ small helpers
-__global__ void gather_chars_kernel(const uint8_t *buf, const uint32_t *idx, uint32_t first, uint32_t count, uint8_t *out) {
+// last min(3, len) bytes of many device-resident documents into one small array (streaming modes trim a partial UTF-8
+// tail before the scan: json_structural_indexer.h L198-204) -- one launch + one copy for a whole batch
+__global__ void gather_tails_kernel(const uint8_t *const *bufs, const uint64_t *lens, uint32_t ndocs, uint8_t *out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < count) out[i] = buf[idx[first + i]];
+  if (i >= ndocs) return;
+  const uint64_t len = lens[i];
+  const uint32_t k = len < 3 ? uint32_t(len) : 3u;
+  for (uint32_t b = 0; b < 4; b++) out[4 * i + b] = (b < k) ? bufs[i][len - k + b] : 0;
 }
 __global__ void write_sentinels_kernel(uint32_t *idx, uint32_t n, uint32_t a, uint32_t b, uint32_t c) {
   idx[n] = a;
@@ -1002,10 +1007,9 @@ int scan_max_ctas_per_sm(int kind) {
   return (e == cudaSuccess && n > 0) ? n : 1;
 }
 
-cudaError_t launch_gather_chars(const uint8_t *buf, const uint32_t *idx, uint32_t first, uint32_t count, uint8_t *out,
-                                cudaStream_t stream) {
-  if (count == 0) return cudaSuccess;
-  gather_chars_kernel<<<(count + 255) / 256, 256, 0, stream>>>(buf, idx, first, count, out);
+cudaError_t launch_gather_tails(const uint8_t *const *bufs, const uint64_t *lens, uint32_t ndocs, uint8_t *out, cudaStream_t stream) {
+  if (ndocs == 0) return cudaSuccess;
+  gather_tails_kernel<<<(ndocs + 127) / 128, 128, 0, stream>>>(bufs, lens, ndocs, out);
   return cudaGetLastError();
 }
 

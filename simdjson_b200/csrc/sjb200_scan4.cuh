@@ -50,7 +50,15 @@ constexpr int kBlockRows = kBlockBytes / 128;
 #define SJB200_SCAN4_CHAIN 1
 #endif
 constexpr int kChainWarps = SJB200_SCAN4_CHAIN;  // chain warp c resolves this CTA's elements j = c, c + kChainWarps, ...
-constexpr int kThreads4 = 32 * (kScanWarps + kChainWarps);
+#ifndef SJB200_SCAN4_EMITW
+#define SJB200_SCAN4_EMITW 7
+#endif
+// Emit warps (stage 1 only): the scan is bound by the ALU pipe, the emit by FLO / shared-memory latency.  When the warp
+// that scanned a block also emits it, all warps of the CTA sit in the emit loop together (measured: ~2300 of the ~9200
+// cycles of an iteration with the ALU pipe nearly idle).  Dedicated warps take resolved blocks from a CTA-wide queue
+// and emit them while the scan warps go on scanning.  0: every scan warp emits its own blocks (minify always does).
+constexpr int kEmitWarps = SJB200_SCAN4_EMITW;
+constexpr int kThreads4 = 32 * (kScanWarps + kChainWarps + kEmitWarps);
 #ifndef SJB200_SCAN4_PARK
 #define SJB200_SCAN4_PARK 3
 #endif
@@ -121,6 +129,12 @@ struct Smem {
   sj_mbar_t ticket_ready[kNS];
   sj_mbar_t scanned[kNS];
   sj_mbar_t resolved[kNS];
+  // emit warps
+  alignas(16) uint8_t estage[kEmitWarps > 0 ? kEmitWarps : 1][kEmitWarps > 0 ? kBlockBytes : 16];  // their staging areas
+  sj_mbar_t park_free[kPark];    // phase k: every block of element (slot + k * kPark) has been emitted, the parked masks may be overwritten
+  uint32_t emitted_cnt[kNS];     // blocks of the element emitted so far
+  uint32_t emit_next;            // next (element, block) item: element = item / kScanWarps
+  uint32_t scan_done;            // 0xFFFFFFFF while the scan warps are running, then the number of elements this CTA scanned
 #if SJB200_SCAN4_TRACE
   uint32_t trace[2][kTraceIters][kTracePoints];  // tuning build: SM cycle counter at the phase boundaries of scan warps 0 and 9
   unsigned long long trace_cta[4];               // globaltimer: kernel entry, roles start, scan role done, before exit
@@ -735,44 +749,39 @@ SJ_DEV bool emit_minify_block(Smem *S, const sj_tensor_map *tmap, const ScanPara
 // the chain warp is with older elements): compose the block summaries for either polarity at the start of the
 // element, publish the aggregate in the look-back chain, leave the per-block prefixes for the chain warp.
 SJ_DEV void compose_element(Smem *S, const ScanParams &p, int ns, uint32_t t, unsigned lane) {
-  // Lane w holds the summary of block w; an inclusive scan over the lanes with the (associative) composition of block
-  // effects gives, in four shuffle steps, what a serial walk over the blocks would (the aggregate is on the critical
-  // path of every later element, so it should not wait for sixteen dependent steps).
-  // Effect of a run of blocks: P quote parity, A / B outputs when entered outside / inside a string, HA / HB unescaped
-  // control character seen when entered outside / inside.  Packed: X = A | HA << 30 | P << 31, Y = B | HB << 30.
+  // Lane w holds the summary of block w.  Only one bit is order-dependent: the quote parities of the blocks are one
+  // ballot word, the polarity entering block w (for an element entered outside a string) is a popcount, and what a block
+  // contributes for either polarity of the element is then known per lane -- the element's aggregate is two REDUX sums.
+  // It is published at once (it gates every later element of the launch); the per-block prefixes the chain warp needs
+  // to post the blocks' output offsets are computed after that.
   const uint32_t r = (lane < uint32_t(kScanWarps)) ? S->summary[ns][lane] : 0u;  // lanes beyond the element: identity
-  uint32_t X = (r & 0xFFFFu) | (((r >> 30) & 1u) << 30) | (((r >> 29) & 1u) << 31);
-  uint32_t Y = ((r >> 16) & 0x1FFFu) | ((r >> 31) << 30);
-#pragma unroll
-  for (int d = 1; d < kScanWarps; d <<= 1) {
-    const uint32_t xo = sj_shfl_up(X, d), yo = sj_shfl_up(Y, d);  // the run that ends d blocks before mine
-    if (int(lane) >= d) {
-      const bool flip = (xo >> 31) != 0;  // the older run leaves the in-string state toggled: my run is entered the other way
-      const uint32_t xn = flip ? Y : X, yn = flip ? X : Y;
-      const uint32_t A = (xo & 0x3FFFFFFFu) + (xn & 0x3FFFFFFFu), B = (yo & 0x3FFFFFFFu) + (yn & 0x3FFFFFFFu);
-      const uint32_t HA = (xo | xn) & 0x40000000u, HB = (yo | yn) & 0x40000000u;
-      X = A | HA | ((xo ^ X) & 0x80000000u);
-      Y = B | HB;
-    }
-  }
-  // exclusive prefixes: what precedes block `lane` inside the element
-  uint32_t xe = sj_shfl_up(X, 1), ye = sj_shfl_up(Y, 1);
-  if (lane == 0) { xe = 0; ye = 0; }
-  if (lane < uint32_t(kScanWarps)) {
-    S->pre[ns][0][lane] = (xe & 0x80000000u) | (xe & 0x3FFFFFFFu);            // entered outside: polarity | outputs before the block
-    S->pre[ns][1][lane] = ((xe & 0x80000000u) ^ 0x80000000u) | (ye & 0x3FFFFFFFu);  // entered inside
-  }
-  if (lane == uint32_t(kScanWarps - 1)) {
-    const uint32_t s0 = X >> 31, b0 = X & 0x3FFFFFFFu, b1 = Y & 0x3FFFFFFFu;
-    S->elem[ns][0] = s0;  // quote parity of the element
-    S->elem[ns][1] = b0;
-    S->elem[ns][2] = b1;
-    S->elem[ns][3] = ((X >> 30) & 1u) | (((Y >> 30) & 1u) << 1);
-    if (t > 0) sj_st_relaxed_u64(p.count_desc + t, pack_agg(p.epoch, s0, b0, b1));  // element 0 goes straight to inclusive
+  const uint32_t c0 = r & 0xFFFFu, c1 = (r >> 16) & 0x1FFFu, h0 = (r >> 30) & 1u, h1 = r >> 31;
+  const uint32_t P = sj_ballot(((r >> 29) & 1u) != 0);
+  const uint32_t s = uint32_t(sj_popc(P & ((1u << lane) - 1u))) & 1u;
+  const uint32_t a = s ? c1 : c0, b = s ? c0 : c1;      // this block's outputs when the ELEMENT is entered outside / inside a string
+  const uint32_t A = sj_reduce_add(a), B = sj_reduce_add(b);
+  const uint32_t HA = sj_any((s ? h1 : h0) != 0) ? 1u : 0u, HB = sj_any((s ? h0 : h1) != 0) ? 1u : 0u;
+  const uint32_t par = uint32_t(sj_popc(P)) & 1u;
+  if (lane == 0) {
+    if (t > 0) sj_st_relaxed_u64(p.count_desc + t, pack_agg(p.epoch, par, A, B));  // element 0 goes straight to inclusive
 #if SJB200_SCAN4_COUNTER
     sj_fence_gpu_release();
     sj_atomic_add(p.ticket + 2, 1u);  // aggregates of this launch that are out (result unused: a reduction, nobody waits for it)
 #endif
+    S->elem[ns][0] = par;
+    S->elem[ns][1] = A;
+    S->elem[ns][2] = B;
+    S->elem[ns][3] = HA | (HB << 1);
+  }
+  uint32_t ia = a, ib = b;  // inclusive prefixes over the blocks
+#pragma unroll
+  for (int d = 1; d < kScanWarps; d <<= 1) {
+    const uint32_t xa = sj_shfl_up(ia, d), xb = sj_shfl_up(ib, d);
+    if (int(lane) >= d) { ia += xa; ib += xb; }
+  }
+  if (lane < uint32_t(kScanWarps)) {
+    S->pre[ns][0][lane] = (s << 31) | (ia - a);         // entered outside: polarity | outputs before the block
+    S->pre[ns][1][lane] = ((s ^ 1u) << 31) | (ib - b);  // entered inside
   }
   sj_syncwarp();
 }
@@ -850,6 +859,7 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
   uint32_t ne = 0;  // this CTA's next element to emit (elements are emitted in order)
   uint32_t j = 0;
   const uint32_t my_lag = (SJB200_SCAN4_STAGGER && kLag >= 2 && (warp & 1u) == 0) ? uint32_t(kLag - 1) : uint32_t(kLag);
+  constexpr bool kEmitW = (kMode == 0) && (kEmitWarps > 0);  // the emit warps take the blocks from here: this warp only scans
   for (;; j++) {
     if (t >= nelem) break;
     const int r = int(j & 1u);
@@ -895,6 +905,8 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
         summary = scan_block<false>(T, pw0, st & 1u, (st >> 2) & 1u, lane, p, reinterpret_cast<sj_u4 *>(slot),
                                     reinterpret_cast<sj_u4 *>(slot) + kScanWarps * 32, slot + 2 * kScanWarps * 32 * 4, kBlockBytes);
       } else {
+        // the parked masks of element j - kPark must have been emitted before this element's take their place
+        if (kEmitW && j >= uint32_t(kPark)) wait_bar(&S->park_free[j % kPark], ((j / kPark) - 1u) & 1u, p, 64);
         const uint64_t left = p.len - bstart;  // > 0: bytes of the block that exist
         summary = scan_block<kMin>(T, pw0, st & 1u, (st >> 2) & 1u, lane, p, S->park[j % kPark][0], S->park[j % kPark][1], S->parkpre[j % kPark],
                                    left < uint64_t(kBlockBytes) ? uint32_t(left) : uint32_t(kBlockBytes));
@@ -922,7 +934,7 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
     }
     SJ_TRACE4(6);
     SJ_TRACE4(7);
-    if (!kDefer && j >= my_lag) {  // pipelined: the chain warp has had my_lag scans' time to resolve this one
+    if (!kDefer && !kEmitW && j >= my_lag) {  // pipelined: the chain warp has had my_lag scans' time to resolve this one
       wait_bar(&S->resolved[ne % kNS], (ne / kNS) & 1u, p, 64);
       SJ_TRACE4(8);
       if (!SJB200_SCAN4_TRACE && p.debug != nullptr && warp == 0 && lane == 0) p.debug[uint64_t(S->ticket[ne % kNS]) * 8 + 2] = sj_globaltimer();
@@ -942,7 +954,9 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
     pw_cur = pw_next;
   }
   // drain: what this CTA scanned and has not emitted yet (no load is in flight: both ring slots are free)
-  if (kDefer) {
+  if (kEmitW) {
+    if (warp == 0 && lane == 0) sj_st_release_u32(&S->scan_done, j);  // the emit warps stop after element j - 1
+  } else if (kDefer) {
     // deferred mode emits everything here: the scan phase ran without ever waiting for the chain.  The parked words of
     // the next element are fetched while the current one is emitted.
     bool have = false;
@@ -982,6 +996,46 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
         emit_from_smem(S, p, out_base, ne, warp, lane, reinterpret_cast<uint32_t *>(S->ring[warp][0]));
       }
       ne++;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ emit warps
+// Items are (element, block) pairs in the order the CTA scanned them; a warp takes the next item, waits until the
+// element is resolved, emits the block exactly as the scanning warp would have (same parked words, same staging scheme,
+// its own staging area), and reports it.  The last block of an element frees the element's parked masks.
+SJ_DEV void emit_role(Smem *S, const ScanParams &p, const Carry &cin, unsigned ewarp, unsigned lane) {
+  const uint64_t out_base = cin.count;
+  uint32_t *stg = reinterpret_cast<uint32_t *>(S->estage[ewarp]);
+  for (;;) {
+    uint32_t q = 0;
+    if (lane == 0) q = sj_atomic_add(&S->emit_next, 1u);
+    q = sj_shfl(q, 0);
+    const uint32_t e = q / uint32_t(kScanWarps), b = q % uint32_t(kScanWarps);
+    // until element e is resolved -- or the scan warps report that this CTA never drew an element e
+    uint32_t spins = 0;
+    for (;;) {
+      if (sj_mbar_try_wait(&S->resolved[e % kNS], (e / kNS) & 1u)) break;
+      const uint32_t done = sj_ld_acquire_u32(&S->scan_done);
+      if (done != 0xFFFFFFFFu && e >= done) return;
+      if (++spins > kSpinLimit4) {
+        sj_atomic_or(p.flags, kFlagInternal);
+        return;
+      }
+#if SJB200_SCAN4_SLEEP
+      sj_nanosleep(64);
+#endif
+    }
+    const uint32_t pol = S->res_pol[e % kNS][b] & 1u;
+    const unsigned tid = b * 32u + lane;
+    emit_block(S, p, out_base, e, b, lane, S->park[e % kPark][pol][tid], S->parkpre[e % kPark][tid], stg);
+    sj_syncwarp();
+    if (lane == 0) {
+      sj_fence_block();
+      if (sj_atomic_add(&S->emitted_cnt[e % kNS], 1u) == uint32_t(kScanWarps - 1)) {
+        S->emitted_cnt[e % kNS] = 0;
+        sj_mbar_arrive(&S->park_free[e % kPark]);
+      }
     }
   }
 }
@@ -1238,8 +1292,12 @@ SJ_DEV void scan4_body(const sj_tensor_map *tmap, const ScanParams &p, uint8_t *
       sj_mbar_init(&S->ticket_ready[i], 1);
       sj_mbar_init(&S->scanned[i], 1);
       S->arrived[i] = 0;
+      S->emitted_cnt[i] = 0;
       sj_mbar_init(&S->resolved[i], 1);
     }
+    for (int i = 0; i < kPark; i++) sj_mbar_init(&S->park_free[i], 1);
+    S->emit_next = 0;
+    S->scan_done = 0xFFFFFFFFu;
     sj_fence_mbar_init();
   }
   if (kMode == 2 && tid < 16) S->compact_lut[tid] = compact_entry(tid);
@@ -1248,7 +1306,8 @@ SJ_DEV void scan4_body(const sj_tensor_map *tmap, const ScanParams &p, uint8_t *
   if (tid == 0) S->trace_cta[1] = sj_globaltimer();
 #endif
   if (warp < unsigned(kScanWarps)) scan_role<kMode>(S, tmap, p, cin, warp, lane);
-  else chain_role(S, p, cin, lane, warp - unsigned(kScanWarps));
+  else if (warp < unsigned(kScanWarps + kChainWarps)) chain_role(S, p, cin, lane, warp - unsigned(kScanWarps));
+  else if (kMode == 0) emit_role(S, p, cin, warp - unsigned(kScanWarps + kChainWarps), lane);
 #if SJB200_SCAN4_TRACE
   if (tid == 0) S->trace_cta[2] = sj_globaltimer();
 #endif

@@ -135,6 +135,8 @@ SJ_DEV void sj_st_sys_u64(unsigned long long *p, unsigned long long v) { __atomi
 SJ_DEV void sj_fence_gpu_release() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 SJ_DEV uint32_t sj_ld_relaxed_u32(const uint32_t *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 SJ_DEV void sj_fence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+SJ_DEV void sj_st_release_u32(uint32_t *p, uint32_t v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+SJ_DEV uint32_t sj_ld_acquire_u32(const uint32_t *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 SJ_DEV void sj_nanosleep(unsigned) {
   struct timespec ts = {0, 20000};
   nanosleep(&ts, nullptr);
@@ -288,6 +290,16 @@ SJ_DEV uint32_t sj_ld_relaxed_u32(const uint32_t *p) {
   return v;
 }
 SJ_DEV void sj_fence_block() { __threadfence_block(); }
+// a flag in shared memory between warps of one CTA
+SJ_DEV void sj_st_release_u32(uint32_t *p, uint32_t v) {
+  __threadfence_block();
+  *reinterpret_cast<volatile uint32_t *>(p) = v;
+}
+SJ_DEV uint32_t sj_ld_acquire_u32(const uint32_t *p) {
+  const uint32_t v = *reinterpret_cast<const volatile uint32_t *>(p);
+  __threadfence_block();
+  return v;
+}
 SJ_DEV void sj_nanosleep(unsigned ns) { __nanosleep(ns); }
 SJ_DEV unsigned sj_smid() {
   unsigned r;

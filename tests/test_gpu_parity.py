@@ -578,3 +578,68 @@ def test_sharded_scan_fused_exchange(port):
         if di == 0:  # arbitrary cuts of NDJSON land inside strings: the second round really ran
             out = _run_ranks_in_threads(doc, sharding.shard_cuts(doc, 8))
             assert any(res[7] for o in out for res in o[0])
+
+
+# --------------------------------------------------------------------------- streams of documents, epilogue on the device
+def _doc_starts(doc, idx):
+    """python restatement of the boundary predicate (find_next_document_index.h L60-88) applied to every structural"""
+    role = {ord(":"): 1, ord(","): 1, ord("{"): 2, ord("}"): 3, ord("["): 4, ord("]"): 5}
+    r = np.array([role.get(int(b), 0) for b in doc[idx]], dtype=np.int64) if len(idx) < 200000 else None
+    if r is None:
+        lut = np.zeros(256, dtype=np.int64)
+        for k, v in role.items():
+            lut[k] = v
+        r = lut[doc[idx]]
+    cur, before = r[1:], r[:-1]
+    start = ~np.isin(cur, (1, 3, 5)) & ~np.isin(before, (1, 2, 4))
+    return np.concatenate([[0], np.nonzero(start)[0] + 1]) if len(idx) else np.zeros(0, np.int64)
+
+
+def test_device_stream_epilogue_and_document_table(port):
+    """streaming_partial / streaming_final with device-resident data: finish() incl. find_next_document_index runs on the
+    device behind the scan (sjb200_docs.cu) -- same n, same sentinel words, same error code as the oracle; the document
+    boundary table lists every document start in stream order."""
+    import ctypes as C
+    rng = random.Random(corpus.SEED ^ 0xd0c5)
+    rc, p = sj.get_active_implementation().create_dom_parser_implementation(8 << 20)
+    assert rc == sj.SUCCESS
+    try:
+        inputs = [corpus.multi_document(rng) for _ in range(60)]
+        inputs += [corpus.adversarial(rng) for _ in range(40)]
+        inputs += [bytes(corpus.ndjson_rows(3 << 20)), bytes(corpus.ndjson_rows(3 << 20))[:-777], b"[1,2,3]  {\"a\":1} [1,2  ", b"{\"a\":[1,2", b"   ", b"1 2 3",
+                   bytes(corpus.tile_documents([b'{"k":[1,2,{"z":null}]}', b"[]", b"7", b'"s"'], 2 << 20)), b"\"unclosed", b"[1,2] \xe2\x82", b"\xe2\x82"]
+        for b in inputs:
+            a = np.frombuffer(bytes(b), dtype=np.uint8)
+            if len(a) == 0:
+                continue
+            d = torch.from_numpy(a.copy()).cuda()
+            for mode in (1, 2):
+                want = port.stage1(a, mode)
+                p.n_structural_indexes = O.N_SENTINEL
+                rcd = p.stage1_device(d, mode)
+                got = O.Stage1Result(rcd, p.n_structural_indexes, p.device_index_buffer().cpu().numpy().view(np.uint32))
+                assert_same(got, want, ("device stream epilogue", mode, len(a), bytes(b[:40])))
+        # a batch of streams through one call (the tails of all documents are fetched together)
+        docs = [np.frombuffer(bytes(corpus.multi_document(rng)), dtype=np.uint8) for _ in range(50)]
+        d_bufs = [torch.from_numpy(x.copy()).cuda() for x in docs]
+        d_idxs = [torch.empty(int(sj.lib().sjb200_index_words(len(x))), dtype=torch.int32, device="cuda") for x in docs]
+        res = p.stage1_device_batch(d_bufs, d_idxs, 2)
+        for x, di, (err, n) in zip(docs, d_idxs, res):
+            want = port.stage1(x, 2)
+            assert err == want.err and (not want.wrote or (n == want.n and np.array_equal(di.cpu().numpy().view(np.uint32)[: n + 3], want.words())))
+        # the document table of a big NDJSON buffer and of mixed streams
+        for doc in (corpus.ndjson_rows(5 << 20), np.frombuffer(bytes(corpus.tile_documents([b'{"k":[1,2,{"z":null}]}', b"[]", b"7", b'"s"', b"[[],{}]"], 1 << 20)), dtype=np.uint8)):
+            d = torch.from_numpy(doc.copy()).cuda()
+            assert p.stage1_device(d, 2) == 0
+            n = p.n_structural_indexes
+            idx = p.device_index_buffer().cpu().numpy().view(np.uint32)[:n].astype(np.int64)
+            want_starts = _doc_starts(doc, idx)
+            table = torch.zeros(2 * (len(want_starts) + 8), dtype=torch.int32, device="cuda")
+            nd = C.c_uint32(0)
+            rct = sj.lib().sjb200_document_table_dev(p._ctx, d.data_ptr(), p.device_index_buffer().data_ptr(), n, table.data_ptr(), len(want_starts) + 8, C.byref(nd), None)
+            assert rct == 0 and nd.value == len(want_starts)
+            t = table.cpu().numpy().view(np.uint32).reshape(-1, 2)[: nd.value]
+            assert np.array_equal(t[:, 0], want_starts) and np.array_equal(t[:, 1], idx[want_starts])
+            assert all(doc[b] in b'[{"0123456789-tfn' for b in t[:50, 1])
+    finally:
+        p.close()
