@@ -93,7 +93,7 @@ struct sjb200_ctx {
   std::vector<cudaEvent_t> ring_events;
   CopyPool *pool = nullptr;
   long opt_force_grid = 0;
-  long opt_copy_threads = 8;        // 0: no staging (cudaMemcpyAsync straight from the caller's memory)
+  long opt_copy_threads = 4;        // 0: no staging (cudaMemcpyAsync straight from the caller's memory)
   long opt_ring_slots = 8;
   long opt_stage_min_bytes = 1 << 20;  // smaller inputs go straight through the driver
   long opt_zero_copy_out = 1;       // stage 1 stores indexes straight into a page-locked, mapped caller array
