@@ -70,7 +70,10 @@ typedef struct sjb200_ctx sjb200_ctx;
 
 /* ---- lifetime: one context per dom_parser_implementation instance (own stream + scratch; contexts
  * are independent, so two parsers may run from two host threads concurrently, as document_stream's
- * stage-1 worker requires: include/simdjson/dom/document_stream-inl.h L16-85). */
+ * stage-1 worker requires: include/simdjson/dom/document_stream-inl.h L16-85).
+ * A context is used by ONE host thread and on ONE stream at a time: its look-back descriptors, ticket and flag words
+ * are shared by all of its launches, which are therefore meant to run one after the other (calls that take a `stream`
+ * may be given any stream, but consecutive calls on different streams must be ordered by the caller). */
 SJB200_API int sjb200_create(int device, size_t capacity_bytes, sjb200_ctx **out);
 SJB200_API void sjb200_destroy(sjb200_ctx *ctx);
 SJB200_API int sjb200_set_capacity(sjb200_ctx *ctx, size_t capacity_bytes); /* > 0xFFFFFFFF -> CAPACITY */
@@ -103,7 +106,9 @@ SJB200_API int sjb200_unpin_host_memory(sjb200_ctx *ctx, void *ptr);
 SJB200_API int sjb200_stage1(sjb200_ctx *ctx, const uint8_t *buf, size_t len, int mode, uint32_t *idx_out, uint32_t *n_inout);
 /* dst needs len bytes (the reference's tests give it exactly len: tests/dom/basictests.cpp L1916). */
 SJB200_API int sjb200_minify(sjb200_ctx *ctx, const uint8_t *buf, size_t len, uint8_t *dst, size_t *dst_len);
-/* returns 1 valid / 0 invalid; a CUDA failure reports 0 and sets sjb200_last_cuda_error. */
+/* returns 1 valid / 0 invalid; a CUDA failure reports 0 and sets sjb200_last_cuda_error.  No size limit (inputs beyond
+ * 4 GiB are validated piece by piece); sjb200_minify and the *_dev variants accept at most 0xFFFFFFFF bytes per call
+ * (CAPACITY beyond that -- a deviation from the reference, whose minify is unbounded). */
 SJB200_API int sjb200_validate_utf8(sjb200_ctx *ctx, const uint8_t *buf, size_t len);
 
 /* ---- device-resident entry points.  d_* are device pointers on the context's device; `stream` is a

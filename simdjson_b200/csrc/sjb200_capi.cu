@@ -574,25 +574,33 @@ int stage1_finish_from(sjb200_ctx *c, const PendingCall &pc, uint32_t *n_inout) 
   int rc;
   uint32_t n_local = n_inout ? *n_inout : 0;
   if (is_filter_mode(pc.mode)) {
-    // RS / comma-delimited streams: the serial filters run on host copies, then go back
-    const uint32_t n = uint32_t(in.count);
-    std::vector<uint8_t> hbuf(pc.len);
-    std::vector<uint32_t> hidx(size_t(n) + 3);
-    if (!ok(c, cudaMemcpyAsync(hbuf.data(), pc.d_buf, pc.len, cudaMemcpyDeviceToHost, pc.stream), "D2H buf") ||
-        !ok(c, cudaMemcpyAsync(hidx.data(), pc.d_idx, size_t(n) * 4, cudaMemcpyDeviceToHost, pc.stream), "D2H idx") ||
+    // RS / comma-delimited streams: the filters and the rest of finish() run on the device-resident array (sjb200_docs.cu);
+    // only the error precedence that needs no data is decided here (json_structural_indexer.h L249-291)
+    if (in.flags & kFlagInternal) return SJB200_UNEXPECTED_ERROR;
+    if (in.flags & kFlagCtl) return SJB200_UNESCAPED_CHARS;
+    uint32_t n = uint32_t(in.count);
+    n_local = n;
+    if (n == 0) { if (n_inout) *n_inout = 0; return SJB200_EMPTY; }
+    const bool unclosed = (in.state >> 1) & 1u;
+    const bool partial = (pc.mode == SJB200_JSON_SEQUENCE_PARTIAL || pc.mode == SJB200_COMMA_DELIMITED_PARTIAL);
+    if (unclosed) {
+      n--;
+      if (partial) { n_local = n; if (n == 0) { if (n_inout) *n_inout = 0; return SJB200_CAPACITY; } }
+    }
+    const size_t need = filter_scratch_words(n);
+    if (c->doc_scratch_words < need) {
+      cudaFree(c->d_doc_scratch); c->d_doc_scratch = nullptr; c->doc_scratch_words = 0;
+      if (!dev_alloc(c, &c->d_doc_scratch, need, "cudaMalloc(filter scratch)")) return SJB200_MEMALLOC;
+      c->doc_scratch_words = need;
+    }
+    c->launches += 4;
+    if (!ok(c, launch_stream_filter(pc.d_buf, uint32_t(pc.len), pc.d_idx, n, pc.mode, in.flags, c->d_doc_scratch, c->d_sfin + pc.carry_slot,
+                                    c->h_sfin + pc.carry_slot, pc.stream), "stream filter") ||
         !ok(c, cudaStreamSynchronize(pc.stream), "sync"))
       return SJB200_UNEXPECTED_ERROR;
-    HostStructuralReader reader(hbuf.data(), hidx.data());
-    HostIndexWriter hw(hidx.data());
-    in.sentinels_written = false;  // the host copy holds only the n indexes
-    bool dirty = false;
-    rc = finish_stage1(in, reader, hw, &n_local, hbuf.data(), hidx.data(), &dirty);
-    const bool wrote = !(rc == SJB200_UNCLOSED_STRING && pc.mode == SJB200_REGULAR) && rc != SJB200_UNESCAPED_CHARS && rc != SJB200_UNEXPECTED_ERROR;
-    if (wrote) {
-      if (!ok(c, cudaMemcpyAsync(pc.d_idx, hidx.data(), (size_t(n) + 3) * 4, cudaMemcpyHostToDevice, pc.stream), "H2D idx") ||
-          !ok(c, cudaStreamSynchronize(pc.stream), "sync"))
-        return SJB200_UNEXPECTED_ERROR;
-    }
+    const StreamFinish &r = c->h_sfin[pc.carry_slot];
+    if (n_inout) *n_inout = r.n;
+    return r.err;
   } else {  // regular: error precedence only, nothing to read or write (the scan stored the sentinels)
     NullReader reader;
     NullIndexWriter writer;
@@ -998,7 +1006,19 @@ extern "C" int sjb200_minify(sjb200_ctx *c, const uint8_t *buf, size_t len, uint
 extern "C" int sjb200_validate_utf8(sjb200_ctx *c, const uint8_t *buf, size_t len) {
   if (!c) return 0;
   if (len == 0) return 1;
-  if (len > kMaxBytes) return 0;
+  if (len > kMaxBytes) {
+    // the reference's validate_utf8 has no size limit (only stage 1 is bounded by SIMDJSON_MAXSIZE_BYTES): longer inputs
+    // go through as consecutive pieces cut at character boundaries -- validity needs no state beyond that
+    const size_t piece = size_t(1) << 30;
+    size_t off = 0;
+    while (off < len) {
+      size_t end = (len - off > piece) ? sjb200_shard_cut(buf, len, off + piece) : len;
+      if (end <= off) end = std::min(len, off + piece);  // a run of > 3 continuation bytes: invalid anyway, the piece will say so
+      if (sjb200_validate_utf8(c, buf + off, end - off) != 1) return 0;
+      off = end;
+    }
+    return 1;
+  }
   DeviceGuard g(c->device);
   if (!ensure_input(c, len)) return 0;
   int slot = 0;

@@ -619,6 +619,29 @@ def test_device_stream_epilogue_and_document_table(port):
                 rcd = p.stage1_device(d, mode)
                 got = O.Stage1Result(rcd, p.n_structural_indexes, p.device_index_buffer().cpu().numpy().view(np.uint32))
                 assert_same(got, want, ("device stream epilogue", mode, len(a), bytes(b[:40])))
+        # RS-delimited (RFC 7464) and comma-delimited streams: the filters are device compactions of the index array
+        for b, mode in _fuzz_inputs(rng, 600):
+            a = np.frombuffer(bytes(b), dtype=np.uint8)
+            if len(a) == 0 or mode < 3:
+                continue
+            d = torch.from_numpy(a.copy()).cuda()
+            for md in ((3, 4) if mode in (3, 4) else (5, 6)):
+                want = port.stage1(a, md)
+                p.n_structural_indexes = O.N_SENTINEL
+                rcd = p.stage1_device(d, md)
+                got = O.Stage1Result(rcd, p.n_structural_indexes, p.device_index_buffer().cpu().numpy().view(np.uint32))
+                assert_same(got, want, ("device filter", md, len(a), bytes(b[:60])))
+        big_rs = b"\x1e" + b"\x1e".join(bytes(corpus.random_json(20000 + 977 * k, seed=k)) + b"\n" for k in range(40))
+        big_comma = b",".join(bytes(corpus.random_json(20000 + 977 * k, seed=100 + k)) for k in range(40))
+        for a, modes in ((np.frombuffer(big_rs, dtype=np.uint8), (3, 4)), (np.frombuffer(big_comma, dtype=np.uint8), (5, 6)),
+                         (np.frombuffer(big_rs[:-5000], dtype=np.uint8), (3, 4)), (np.frombuffer(big_comma[:-5000], dtype=np.uint8), (5, 6))):
+            d = torch.from_numpy(a.copy()).cuda()
+            for md in modes:
+                want = port.stage1(a, md)
+                p.n_structural_indexes = O.N_SENTINEL
+                rcd = p.stage1_device(d, md)
+                got = O.Stage1Result(rcd, p.n_structural_indexes, p.device_index_buffer().cpu().numpy().view(np.uint32))
+                assert_same(got, want, ("device filter, big", md, len(a)))
         # a batch of streams through one call (the tails of all documents are fetched together)
         docs = [np.frombuffer(bytes(corpus.multi_document(rng)), dtype=np.uint8) for _ in range(50)]
         d_bufs = [torch.from_numpy(x.copy()).cuda() for x in docs]
