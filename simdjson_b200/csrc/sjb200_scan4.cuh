@@ -115,6 +115,7 @@ enum : uint32_t { kDescNone = 0, kDescAgg = 1, kDescInc = 2 };
 
 struct Smem {
   uint8_t ring[kScanWarps][2][kBlockBytes];   // per scan warp: two block buffers (TMA destination / emit staging)
+  uint8_t estage[kEmitWarps > 0 ? kEmitWarps : 1][kBlockBytes];  // emit warps: staging areas (1 KiB aligned like the ring: minify fetches blocks into them by TMA)
   sj_u4 park[kPark][2][kScanWarps * 32];          // [pipeline buffer][polarity][thread]: candidate structural masks
   uint32_t parkpre[kPark][kScanWarps * 32];       // exclusive prefix of the lane's counts inside its block, both polarities packed
   uint32_t compact_lut[16];                   // minify: see compact_entry
@@ -130,7 +131,7 @@ struct Smem {
   sj_mbar_t scanned[kNS];
   sj_mbar_t resolved[kNS];
   // emit warps
-  alignas(16) uint8_t estage[kEmitWarps > 0 ? kEmitWarps : 1][kEmitWarps > 0 ? kBlockBytes : 16];  // their staging areas
+  sj_mbar_t efull[kEmitWarps > 0 ? kEmitWarps : 1];  // minify: completion of an emit warp's block fetch
   sj_mbar_t park_free[kPark];    // phase k: every block of element (slot + k * kPark) has been emitted, the parked masks may be overwritten
   uint32_t emitted_cnt[kNS];     // blocks of the element emitted so far
   uint32_t emit_next;            // next (element, block) item: element = item / kScanWarps
@@ -859,7 +860,7 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
   uint32_t ne = 0;  // this CTA's next element to emit (elements are emitted in order)
   uint32_t j = 0;
   const uint32_t my_lag = (SJB200_SCAN4_STAGGER && kLag >= 2 && (warp & 1u) == 0) ? uint32_t(kLag - 1) : uint32_t(kLag);
-  constexpr bool kEmitW = (kMode == 0) && (kEmitWarps > 0);  // the emit warps take the blocks from here: this warp only scans
+  constexpr bool kEmitW = (kMode != 1) && (kEmitWarps > 0);  // the emit warps take the blocks from here: this warp only scans
   for (;; j++) {
     if (t >= nelem) break;
     const int r = int(j & 1u);
@@ -1004,9 +1005,12 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
 // Items are (element, block) pairs in the order the CTA scanned them; a warp takes the next item, waits until the
 // element is resolved, emits the block exactly as the scanning warp would have (same parked words, same staging scheme,
 // its own staging area), and reports it.  The last block of an element frees the element's parked masks.
-SJ_DEV void emit_role(Smem *S, const ScanParams &p, const Carry &cin, unsigned ewarp, unsigned lane) {
+template <int kMode>
+SJ_DEV void emit_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, const Carry &cin, unsigned ewarp, unsigned lane) {
   const uint64_t out_base = cin.count;
+  const uint64_t launch_start = uint64_t(p.tile_begin) * kTileBytes;
   uint32_t *stg = reinterpret_cast<uint32_t *>(S->estage[ewarp]);
+  uint32_t fetch_phase = 0;  // minify: parity of the next completion of this warp's fetch barrier
   for (;;) {
     uint32_t q = 0;
     if (lane == 0) q = sj_atomic_add(&S->emit_next, 1u);
@@ -1028,7 +1032,13 @@ SJ_DEV void emit_role(Smem *S, const ScanParams &p, const Carry &cin, unsigned e
     }
     const uint32_t pol = S->res_pol[e % kNS][b] & 1u;
     const unsigned tid = b * 32u + lane;
-    emit_block(S, p, out_base, e, b, lane, S->park[e % kPark][pol][tid], S->parkpre[e % kPark][tid], stg);
+    if (kMode == 2) {
+      if (emit_minify_block(S, tmap, p, out_base, e, b, lane, S->park[e % kPark][pol][tid], S->parkpre[e % kPark][tid], S->estage[ewarp], &S->efull[ewarp],
+                            fetch_phase, launch_start))
+        fetch_phase ^= 1u;
+    } else {
+      emit_block(S, p, out_base, e, b, lane, S->park[e % kPark][pol][tid], S->parkpre[e % kPark][tid], stg);
+    }
     sj_syncwarp();
     if (lane == 0) {
       sj_fence_block();
@@ -1296,6 +1306,7 @@ SJ_DEV void scan4_body(const sj_tensor_map *tmap, const ScanParams &p, uint8_t *
       sj_mbar_init(&S->resolved[i], 1);
     }
     for (int i = 0; i < kPark; i++) sj_mbar_init(&S->park_free[i], 1);
+    for (int i = 0; i < (kEmitWarps > 0 ? kEmitWarps : 1); i++) sj_mbar_init(&S->efull[i], 1);
     S->emit_next = 0;
     S->scan_done = 0xFFFFFFFFu;
     sj_fence_mbar_init();
@@ -1307,7 +1318,7 @@ SJ_DEV void scan4_body(const sj_tensor_map *tmap, const ScanParams &p, uint8_t *
 #endif
   if (warp < unsigned(kScanWarps)) scan_role<kMode>(S, tmap, p, cin, warp, lane);
   else if (warp < unsigned(kScanWarps + kChainWarps)) chain_role(S, p, cin, lane, warp - unsigned(kScanWarps));
-  else if (kMode == 0) emit_role(S, p, cin, warp - unsigned(kScanWarps + kChainWarps), lane);
+  else if (kMode != 1) emit_role<kMode>(S, tmap, p, cin, warp - unsigned(kScanWarps + kChainWarps), lane);
 #if SJB200_SCAN4_TRACE
   if (tid == 0) S->trace_cta[2] = sj_globaltimer();
 #endif
