@@ -95,6 +95,7 @@ struct sjb200_ctx {
   long opt_force_grid = 0;
   long opt_copy_threads = 4;        // 0: no staging (cudaMemcpyAsync straight from the caller's memory)
   long opt_ring_slots = 8;
+  long opt_first_chunk_bytes = 512 << 10;  // first chunk of the host-pointer pipeline; the following ones double up to chunk_bytes
   long opt_stage_min_bytes = 1 << 20;  // smaller inputs go straight through the driver
   long opt_zero_copy_out = 1;       // stage 1 stores indexes straight into a page-locked, mapped caller array
   int last_input_path = 0, last_output_path = 0;  // stats: 0 driver copy, 1 staged ring, 2 caller memory is page-locked; 0 copy engine, 1 kernel stores
@@ -392,7 +393,7 @@ extern "C" int sjb200_create(int device, size_t capacity, sjb200_ctx **out) {
     return SJB200_MEMALLOC;
   }
   // tuning knobs of the host-pointer pipeline for callers that cannot reach sjb200_set_option (the C++ plug-in owns its contexts)
-  for (const char *key : {"copy_threads", "ring_slots", "chunk_bytes", "stage_min_bytes", "zero_copy_out"}) {
+  for (const char *key : {"copy_threads", "ring_slots", "chunk_bytes", "first_chunk_bytes", "stage_min_bytes", "zero_copy_out"}) {
     std::string env = std::string("SJB200_") + key;
     for (auto &ch : env) ch = char(toupper((unsigned char)ch));
     if (const char *v = getenv(env.c_str())) sjb200_set_option(c, key, atol(v));
@@ -511,6 +512,7 @@ extern "C" int sjb200_set_option(sjb200_ctx *c, const char *key, long value) {
   else if (!strcmp(key, "copy_threads")) c->opt_copy_threads = std::max<long>(0, std::min<long>(value, 64));
   else if (!strcmp(key, "ring_slots")) c->opt_ring_slots = std::max<long>(2, std::min<long>(value, 64));
   else if (!strcmp(key, "stage_min_bytes")) c->opt_stage_min_bytes = std::max<long>(0, value);
+  else if (!strcmp(key, "first_chunk_bytes")) c->opt_first_chunk_bytes = std::max<long>(2 * kTileBytes, (value / (2 * kTileBytes)) * (2 * kTileBytes));
   else if (!strcmp(key, "zero_copy_out")) c->opt_zero_copy_out = value;
   else return SJB200_UNEXPECTED_ERROR;
   return SJB200_SUCCESS;
@@ -852,9 +854,17 @@ bool ensure_pool(sjb200_ctx *c) {
 bool scan_host_document(sjb200_ctx *c, int kind, const uint8_t *buf, size_t len, uint32_t *d_idx, uint8_t *d_dst, void *host_out,
                         size_t elt, bool direct_out, int *final_slot) {
   size_t chunk = size_t(c->opt_chunk_bytes);
-  const size_t min_chunk = ((len / (kCarrySlots - 2)) / (2 * kTileBytes) + 1) * (2 * kTileBytes);  // at most kCarrySlots-1 chunks
+  const size_t min_chunk = ((len / (kCarrySlots - 8)) / (2 * kTileBytes) + 1) * (2 * kTileBytes);  // at most kCarrySlots-1 chunks
   if (chunk < min_chunk) chunk = min_chunk;
-  const size_t nchunks = (len + chunk - 1) / chunk;
+  // chunk boundaries: the first chunks are small and double up to the full size, so that the copy engine and the first
+  // scan start early (what precedes the first launch is not overlapped with anything), then equal chunks to the end
+  std::vector<size_t> bounds;
+  bounds.push_back(0);
+  for (size_t c0 = std::min<size_t>(chunk, size_t(c->opt_first_chunk_bytes)); bounds.back() < len;) {
+    bounds.push_back(std::min(len, bounds.back() + c0));
+    c0 = std::min(chunk, c0 * 2);
+  }
+  const size_t nchunks = bounds.size() - 1;
   const bool drain = !direct_out && elt != 0 && host_out != nullptr;
   while (c->chunk_events.size() < 2 * nchunks) {
     cudaEvent_t e;
@@ -879,8 +889,8 @@ bool scan_host_document(sjb200_ctx *c, int kind, const uint8_t *buf, size_t len,
   map_for(c, kind, &map, c->d_in, len, &tma);
   // calls are synchronous, so no earlier kernel still reads d_in when the first copy lands
   auto launch_chunk = [&](size_t k, const uint8_t *src) -> bool {
-    const size_t off = k * chunk;
-    const size_t bytes = std::min(chunk, len - off);
+    const size_t off = bounds[k];
+    const size_t bytes = bounds[k + 1] - off;
     cudaEvent_t copied = c->chunk_events[2 * k], scanned = c->chunk_events[2 * k + 1];
     if (!ok(c, cudaMemcpyAsync(c->d_in + off, src, bytes, cudaMemcpyHostToDevice, c->copy_stream), "H2D chunk") ||
         !ok(c, cudaEventRecord(copied, c->copy_stream), "event record") || !ok(c, cudaStreamWaitEvent(c->stream, copied, 0), "wait event"))
@@ -897,7 +907,7 @@ bool scan_host_document(sjb200_ctx *c, int kind, const uint8_t *buf, size_t len,
   if (in_path == 1) {
     CopyPool &pool = *c->pool;
     const int slots = c->ring_slots;
-    pool.begin(buf, len, chunk, c->h_ring, c->ring_slot_bytes, slots);
+    pool.begin(buf, bounds.data(), nchunks, c->h_ring, c->ring_slot_bytes, slots);
     pool.allow(size_t(slots));
     size_t issued = 0, released = 0;  // chunks handed to the copy engine / known to have left their slot
     uint32_t idle = 0;
@@ -923,7 +933,7 @@ bool scan_host_document(sjb200_ctx *c, int kind, const uint8_t *buf, size_t len,
     if (!good) return false;
   } else {
     for (size_t k = 0; k < nchunks; k++)
-      if (!launch_chunk(k, buf + k * chunk)) return false;
+      if (!launch_chunk(k, buf + bounds[k])) return false;
   }
   if (drain) {  // bring each chunk's output back as soon as that chunk is done
     uint64_t have = 0;

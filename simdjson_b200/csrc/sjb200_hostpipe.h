@@ -72,11 +72,11 @@ class CopyPool {
     threads_.clear();
   }
 
-  // One session = one document: chunk k (bytes [k*chunk, min(len, (k+1)*chunk))) goes to ring slot k % nslots as soon
-  // as allow() has covered it.  nchunks <= kMaxChunks.
-  void begin(const uint8_t *src, size_t len, size_t chunk, uint8_t *ring, size_t slot_bytes, int nslots) {
-    src_ = src; len_ = len; chunk_ = chunk; ring_ = ring; slot_bytes_ = slot_bytes; nslots_ = nslots;
-    nchunks_ = (len + chunk - 1) / chunk;
+  // One session = one document: chunk k (bytes [bounds[k], bounds[k+1])) goes to ring slot k % nslots as soon as allow()
+  // has covered it.  nchunks <= kMaxChunks, every chunk <= slot_bytes; `bounds` stays valid until end().
+  void begin(const uint8_t *src, const size_t *bounds, size_t nchunks, uint8_t *ring, size_t slot_bytes, int nslots) {
+    src_ = src; bounds_ = bounds; ring_ = ring; slot_bytes_ = slot_bytes; nslots_ = nslots;
+    nchunks_ = nchunks;
     for (size_t k = 0; k < nchunks_; k++) done_[k].store(0, std::memory_order_relaxed);
     allowed_.store(0, std::memory_order_relaxed);
     abort_.store(false, std::memory_order_relaxed);
@@ -118,8 +118,8 @@ class CopyPool {
           else std::this_thread::sleep_for(std::chrono::microseconds(20));
         }
         if (abort_.load(std::memory_order_acquire)) break;
-        const size_t off = k * chunk_;
-        const size_t bytes = (len_ - off < chunk_) ? (len_ - off) : chunk_;
+        const size_t off = bounds_[k];
+        const size_t bytes = bounds_[k + 1] - off;
         const size_t per = ((bytes + size_t(nt) - 1) / size_t(nt) + 4095) & ~size_t(4095);  // whole pages per thread
         const size_t lo = size_t(me) * per;
         if (lo < bytes) copy_to_staging(ring_ + size_t(k % size_t(nslots_)) * slot_bytes_ + lo, src_ + off + lo, (bytes - lo < per) ? (bytes - lo) : per);
@@ -136,7 +136,8 @@ class CopyPool {
   bool quit_ = false;
   const uint8_t *src_ = nullptr;
   uint8_t *ring_ = nullptr;
-  size_t len_ = 0, chunk_ = 0, slot_bytes_ = 0, nchunks_ = 0;
+  const size_t *bounds_ = nullptr;
+  size_t slot_bytes_ = 0, nchunks_ = 0;
   int nslots_ = 0;
   std::atomic<size_t> allowed_{0};
   std::atomic<bool> abort_{false};

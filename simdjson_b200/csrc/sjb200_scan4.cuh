@@ -87,6 +87,9 @@ static_assert(kLag >= 1 && 2 * kLag + 3 <= kNS && 2 * (kParkD - 1) + 3 <= kNS &&
 #ifndef SJB200_SCAN4_SLEEP
 #define SJB200_SCAN4_SLEEP 1
 #endif
+#ifndef SJB200_SCAN4_LB_SLEEP
+#define SJB200_SCAN4_LB_SLEEP 0  // ns between two polls of the look-back window (0: poll again at once)
+#endif
 #ifndef SJB200_SCAN4_EARLY_LOOKBACK
 #define SJB200_SCAN4_EARLY_LOOKBACK 1  // 1: the chain warp walks back over the predecessors of an element while the element is being scanned
 #endif
@@ -832,15 +835,13 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
   uint32_t full_phase = 0;
   uint32_t pw_cur = 0x20202020u, pw_next = 0x20202020u;
   bool tma_cur = false, tma_next = false;
-  // Warp 0 is the ticket master.  Tickets must not depend on the chain warp's progress (it may sit in a look-back
-  // while the scan warps run ahead).  A ticket is drawn two iterations before it is needed and published one iteration
-  // before (at the top of warp 0's loop, straight from a register): nobody waits for the atomic's round trip to L2, and
-  // nobody waits for warp 0's scan either (measured with the trace build: with the ticket published after warp 0's
-  // scan, every other warp waited ~1100 cycles per iteration at its loop top).
+  // Tickets must not depend on the chain warp's progress (it may sit in a look-back while the scan warps run ahead),
+  // and nobody should wait for a ticket at the top of an iteration (measured with the trace build: with the ticket
+  // published after warp 0's scan, every other warp waited ~1100 cycles per iteration): the ticket of element j + 2 is
+  // drawn and published at the top of iteration j, it is needed at the top of iteration j + 1.
   // Tickets should be scanned in roughly the order they were taken (every element waits for ALL lower tickets): at
-  // start-up the second and third tickets are therefore taken only once the first block has arrived, when every CTA
-  // of the launch has drawn its first one.
-  uint32_t held = 0;  // lane 0 of warp 0: the ticket of this CTA's element j + 2, published at the top of iteration j
+  // start-up the second ticket is therefore taken only once the first block has arrived, when every CTA of the launch
+  // has drawn its first one.
   if (warp == 0) {
     uint32_t a0 = 0;
     if (lane == 0) a0 = sj_atomic_add(p.ticket, 1u);
@@ -851,10 +852,7 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
   if (warp == 0) {
     if (tma_cur) wait_bar(&S->full[0][0], 0u, p, 32);
     uint32_t a1 = 0;
-    if (lane == 0) {
-      a1 = sj_atomic_add(p.ticket, 1u);
-      held = sj_atomic_add(p.ticket, 1u);
-    }
+    if (lane == 0) a1 = sj_atomic_add(p.ticket, 1u);
     publish_ticket(S, 1, a1, lane);
   }
   uint32_t ne = 0;  // this CTA's next element to emit (elements are emitted in order)
@@ -874,11 +872,17 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
       }
     }
     SJ_TRACE4(0);
-    if (warp == 0) {
-      publish_ticket(S, j + 2, held, lane);
-      if (lane == 0) held = sj_atomic_add(p.ticket, 1u);  // element j + 3 of this CTA: needed one iteration from now
-    }
     const uint32_t tn = wait_ticket(S, j + 1, p);
+    if (warp == (j % uint32_t(kScanWarps))) {
+      // ticket duty rotates: this warp draws the CTA's element j + 2 and waits for the atomic's round trip (~700 cycles)
+      // before it goes on; the others need that ticket one iteration from now.  (A ticket is scanned two iterations after
+      // it was drawn -- every element of the launch waits for ALL lower tickets, so tickets should not be held longer
+      // than the TMA pipeline needs -- and no warp is always the one that pays for the round trip.)  Drawn only after
+      // ticket j + 1 has been seen: a CTA's tickets must increase with j (the loops stop at the first one beyond the end).
+      uint32_t a = 0;
+      if (lane == 0) a = sj_atomic_add(p.ticket, 1u);
+      publish_ticket(S, j + 2, a, lane);
+    }
     SJ_TRACE4(1);
     if (tn < nelem) tma_next = issue_load(S, tmap, p, tn, warp, lane, r ^ 1, &pw_next, scan_limit);
     SJ_TRACE4(2);
@@ -1027,7 +1031,7 @@ SJ_DEV void emit_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
         return;
       }
 #if SJB200_SCAN4_SLEEP
-      sj_nanosleep(64);
+      sj_nanosleep(32);
 #endif
     }
     const uint32_t pol = S->res_pol[e % kNS][b] & 1u;
@@ -1117,8 +1121,8 @@ SJ_DEV void look_back(const ScanParams &p, uint32_t t, unsigned lane, uint32_t *
         sj_atomic_or(p.flags, kFlagInternal);
         break;
       }
-#if SJB200_SCAN4_SLEEP
-      sj_nanosleep(100);
+#if SJB200_SCAN4_LB_SLEEP > 0
+      sj_nanosleep(SJB200_SCAN4_LB_SLEEP);  // (a poll is a round trip to L2, ~700 cycles of waiting on loads: it takes no issue slots worth saving)
 #endif
     }
     // ---- fold the aggregates newer than the inclusive prefix

@@ -46,14 +46,12 @@ if __name__ == "__main__":
         one()
         sys.exit(0)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    configs = [("threads4 chunk4M (default)", {}),
-               ("threads2", {"SJB200_COPY_THREADS": "2"}),
-               ("threads3", {"SJB200_COPY_THREADS": "3"}),
+    configs = [("threads4 chunk4M first512K (default)", {}),
                ("threads6", {"SJB200_COPY_THREADS": "6"}),
-               ("threads8", {"SJB200_COPY_THREADS": "8"}),
-               ("threads4 chunk2M", {"SJB200_CHUNK_BYTES": str(2 << 20)}),
-               ("threads4 chunk8M slots6", {"SJB200_CHUNK_BYTES": str(8 << 20), "SJB200_RING_SLOTS": "6"}),
-               ("threads4 copy-engine D2H", {"SJB200_ZERO_COPY_OUT": "0"})]
+               ("threads6 chunk2M", {"SJB200_COPY_THREADS": "6", "SJB200_CHUNK_BYTES": str(2 << 20)}),
+               ("threads4 chunk2M first256K", {"SJB200_CHUNK_BYTES": str(2 << 20), "SJB200_FIRST_CHUNK_BYTES": str(256 << 10)}),
+               ("threads4 no ramp", {"SJB200_FIRST_CHUNK_BYTES": str(4 << 20)}),
+               ("threads6 chunk2M slots16", {"SJB200_COPY_THREADS": "6", "SJB200_CHUNK_BYTES": str(2 << 20), "SJB200_RING_SLOTS": "16"})]
     for tag, env in configs:
         e = dict(os.environ, PROBE_CHILD="1", PROBE_TAG=tag, **env)
         subprocess.run([sys.executable, os.path.abspath(__file__)], env=e)
