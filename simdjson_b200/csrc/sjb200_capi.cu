@@ -294,12 +294,13 @@ bool enqueue_scan(sjb200_ctx *c, int kind, const CUtensorMap *map, bool tma, con
     const int grid = grid_for(c, kind, nelem);
     // deferred emit when every CTA can hold all the elements it will draw (small launches: one wave of CTAs)
     bool deferred = kind == kIndex && (c->opt_deferred == 2 || (c->opt_deferred == 1 && uint64_t(nelem) * 4 <= uint64_t(grid) * uint64_t(scan4_deferred_capacity()) * 3));
-    if (deferred) {
+    if (deferred || scan4_parks_in_global()) {
       const size_t need = scan4_park_words(grid_cap(c, kind));
       if (c->d_park_words < need) {
         cudaStreamSynchronize(c->stream);
         cudaFree(c->d_park); c->d_park = nullptr; c->d_park_words = 0;
         if (dev_alloc(c, &c->d_park, need, "cudaMalloc(park)")) c->d_park_words = need;
+        else if (scan4_parks_in_global()) return false;
         else deferred = false;
       }
       p.park = c->d_park;

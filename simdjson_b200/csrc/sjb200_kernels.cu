@@ -968,8 +968,9 @@ int utf8v2_max_ctas_per_sm() {
 }
 int utf8v2_warps_per_cta() { return utf8v2::kWarpsU; }
 
-size_t scan4_park_words(int grid) { return size_t(grid) * scan4::kParkD * scan4::kParkSlotWords; }
-int scan4_deferred_capacity() { return scan4::kParkD; }
+size_t scan4_park_words(int grid) { return size_t(grid) * scan4::kParkRing * scan4::kParkSlotWords + 8; }
+int scan4_parks_in_global() { return scan4::kGPark > 0 ? 1 : 0; }
+int scan4_deferred_capacity() { return scan4::kParkRing; }
 int scan4_tiles_per_element() { return scan4::kElemBytes / kTileBytes; }
 
 int scan4_max_ctas_per_sm() {

@@ -17,6 +17,7 @@ cudaError_t launch_scan4(const CUtensorMap *tmap, const ScanParams &p, int grid,
                          cudaStream_t stream);
 size_t scan4_park_words(int grid);   // uint32 words of ScanParams::park for a deferred launch of `grid` CTAs
 int scan4_tiles_per_element();      // 32 KiB tiles of the launch parameter block per scan4 element
+int scan4_parks_in_global();         // 1: every scan4 launch needs ScanParams::park (emit warps read the parked masks from an L2-resident ring)
 int scan4_deferred_capacity();       // elements per CTA the deferred variant can hold at once
 int scan4_max_ctas_per_sm();
 constexpr int kScan4BoxRows = 32;

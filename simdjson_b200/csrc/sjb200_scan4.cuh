@@ -73,11 +73,21 @@ constexpr int kNS = 32;          // ring of element slots (tickets, summaries, r
 #endif
 constexpr int kParkD = SJB200_SCAN4_DEFER_PARK;  // deferred mode: elements of a CTA whose masks may wait in the L2-resident scratch ring
 constexpr int kParkSlotWords = 2 * kScanWarps * 32 * 4 + kScanWarps * 32;  // one element's parked words (both polarities + prefixes)
+#ifndef SJB200_SCAN4_GPARK
+#define SJB200_SCAN4_GPARK 8
+#endif
+// With emit warps the parked masks may wait in an L2-resident scratch ring in global memory (ScanParams::park) instead of
+// shared memory: the emit warps do not care about the extra latency, and the ring can be deep -- the scan warps then
+// never wait for the chain as long as an element is resolved and emitted within kGPark - 1 scans (with three elements
+// parked in shared memory, every hiccup of the look-back chain stalled the scan).  0: park in shared memory.
+constexpr int kGPark = (SJB200_SCAN4_EMITW > 0) ? SJB200_SCAN4_GPARK : 0;
+constexpr int kParkRing = (kGPark > 0) ? kGPark : kParkD;  // slots per CTA of the global scratch ring
+constexpr int kParkFree = (kGPark > 0) ? kGPark : kPark;   // elements whose masks may be parked at once (emit-warp mode)
 #ifndef SJB200_SCAN4_LOOKK
 #define SJB200_SCAN4_LOOKK 10
 #endif
 constexpr int kLookK = SJB200_SCAN4_LOOKK;       // descriptors per lane and look-back round trip (window of 320 elements >= one wave of CTAs)
-static_assert(kLag >= 1 && 2 * kLag + 3 <= kNS && 2 * (kParkD - 1) + 3 <= kNS && (kNS & (kNS - 1)) == 0, "slot ring");
+static_assert(kLag >= 1 && 2 * kLag + 3 <= kNS && 2 * (kParkD - 1) + 3 <= kNS && 2 * kGPark + 4 <= kNS && (kNS & (kNS - 1)) == 0, "slot ring");
 #ifndef SJB200_SCAN4_COUNTER
 #define SJB200_SCAN4_COUNTER 0  // 1: a look-back first waits (polling ONE word) until t aggregates are out, then loads its window once
 #endif
@@ -119,8 +129,8 @@ enum : uint32_t { kDescNone = 0, kDescAgg = 1, kDescInc = 2 };
 struct Smem {
   uint8_t ring[kScanWarps][2][kBlockBytes];   // per scan warp: two block buffers (TMA destination / emit staging)
   uint8_t estage[kEmitWarps > 0 ? kEmitWarps : 1][kBlockBytes];  // emit warps: staging areas (1 KiB aligned like the ring: minify fetches blocks into them by TMA)
-  sj_u4 park[kPark][2][kScanWarps * 32];          // [pipeline buffer][polarity][thread]: candidate structural masks
-  uint32_t parkpre[kPark][kScanWarps * 32];       // exclusive prefix of the lane's counts inside its block, both polarities packed
+  sj_u4 park[kGPark > 0 ? 1 : kPark][2][kGPark > 0 ? 1 : kScanWarps * 32];  // [pipeline buffer][polarity][thread]: candidate structural masks (shared-memory parking)
+  uint32_t parkpre[kGPark > 0 ? 1 : kPark][kGPark > 0 ? 1 : kScanWarps * 32];  // exclusive prefix of the lane's counts inside its block, both polarities packed
   uint32_t compact_lut[16];                   // minify: see compact_entry
   uint32_t ticket[kNS];
   uint32_t summary[kNS][kScanWarps];          // c0 | c1<<16 | parity<<29 | ctl-hit0<<30 | ctl-hit1<<31
@@ -135,7 +145,7 @@ struct Smem {
   sj_mbar_t resolved[kNS];
   // emit warps
   sj_mbar_t efull[kEmitWarps > 0 ? kEmitWarps : 1];  // minify: completion of an emit warp's block fetch
-  sj_mbar_t park_free[kPark];    // phase k: every block of element (slot + k * kPark) has been emitted, the parked masks may be overwritten
+  sj_mbar_t park_free[kParkFree];  // phase k: every block of element (slot + k * kParkFree) has been emitted, the parked masks may be overwritten
   uint32_t emitted_cnt[kNS];     // blocks of the element emitted so far
   uint32_t emit_next;            // next (element, block) item: element = item / kScanWarps
   uint32_t scan_done;            // 0xFFFFFFFF while the scan warps are running, then the number of elements this CTA scanned
@@ -634,7 +644,7 @@ SJ_DEV void emit_block(Smem *S, const ScanParams &p, uint64_t out_base, uint32_t
 SJ_DEV void emit_from_smem(Smem *S, const ScanParams &p, uint64_t out_base, uint32_t e, unsigned warp, unsigned lane, uint32_t *stg) {
   const uint32_t pol = S->res_pol[e % kNS][warp] & 1u;
   const unsigned tid = warp * 32 + lane;
-  emit_block(S, p, out_base, e, warp, lane, S->park[e % kPark][pol][tid], S->parkpre[e % kPark][tid], stg);
+  emit_block(S, p, out_base, e, warp, lane, S->park[kGPark > 0 ? 0 : e % kPark][pol][kGPark > 0 ? 0 : tid], S->parkpre[kGPark > 0 ? 0 : e % kPark][kGPark > 0 ? 0 : tid], stg);
 }
 
 // deferred mode: the masks wait in the scratch ring of ScanParams::park (it stays in L2)
@@ -642,7 +652,7 @@ struct Parked {
   sj_u4 ev;
   uint32_t prew;
 };
-SJ_DEV uint32_t *park_slot(const ScanParams &p, uint32_t e) { return p.park + (size_t(sj_cta()) * kParkD + (e % uint32_t(kParkD))) * size_t(kParkSlotWords); }
+SJ_DEV uint32_t *park_slot(const ScanParams &p, uint32_t e) { return p.park + (size_t(sj_cta()) * kParkRing + (e % uint32_t(kParkRing))) * size_t(kParkSlotWords); }
 SJ_DEV Parked load_parked(Smem *S, const ScanParams &p, uint32_t e, unsigned warp, unsigned lane) {
   const uint32_t pol = S->res_pol[e % kNS][warp] & 1u;
   const uint32_t *slot = park_slot(p, e);
@@ -863,8 +873,8 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
     if (t >= nelem) break;
     const int r = int(j & 1u);
     if (kDefer) {
-      // the scratch slot of element j must be free (only binds when a CTA draws more than kParkD elements)
-      while (ne + uint32_t(kParkD) <= j) {
+      // the scratch slot of element j must be free (only binds when a CTA draws more than kParkRing elements)
+      while (ne + uint32_t(kParkRing) <= j) {
         wait_bar(&S->resolved[ne % kNS], (ne / kNS) & 1u, p, 64);
         const Parked k = load_parked(S, p, ne, warp, lane);
         emit_block(S, p, out_base, ne, warp, lane, k.ev, k.prew, reinterpret_cast<uint32_t *>(S->ring[warp][r ^ 1]));
@@ -910,11 +920,17 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
         summary = scan_block<false>(T, pw0, st & 1u, (st >> 2) & 1u, lane, p, reinterpret_cast<sj_u4 *>(slot),
                                     reinterpret_cast<sj_u4 *>(slot) + kScanWarps * 32, slot + 2 * kScanWarps * 32 * 4, kBlockBytes);
       } else {
-        // the parked masks of element j - kPark must have been emitted before this element's take their place
-        if (kEmitW && j >= uint32_t(kPark)) wait_bar(&S->park_free[j % kPark], ((j / kPark) - 1u) & 1u, p, 64);
+        // the parked masks of element j - kParkFree must have been emitted before this element's take their place
+        if (kEmitW && j >= uint32_t(kParkFree)) wait_bar(&S->park_free[j % kParkFree], ((j / kParkFree) - 1u) & 1u, p, 64);
         const uint64_t left = p.len - bstart;  // > 0: bytes of the block that exist
-        summary = scan_block<kMin>(T, pw0, st & 1u, (st >> 2) & 1u, lane, p, S->park[j % kPark][0], S->park[j % kPark][1], S->parkpre[j % kPark],
-                                   left < uint64_t(kBlockBytes) ? uint32_t(left) : uint32_t(kBlockBytes));
+        const uint32_t valid = left < uint64_t(kBlockBytes) ? uint32_t(left) : uint32_t(kBlockBytes);
+        if (kEmitW && kGPark > 0) {
+          uint32_t *slot = park_slot(p, j);
+          summary = scan_block<kMin>(T, pw0, st & 1u, (st >> 2) & 1u, lane, p, reinterpret_cast<sj_u4 *>(slot), reinterpret_cast<sj_u4 *>(slot) + kScanWarps * 32,
+                                     slot + 2 * kScanWarps * 32 * 4, valid);
+        } else {
+          summary = scan_block<kMin>(T, pw0, st & 1u, (st >> 2) & 1u, lane, p, S->park[j % kPark][0], S->park[j % kPark][1], S->parkpre[j % kPark], valid);
+        }
       }
     }
     if (!SJB200_SCAN4_TRACE && p.debug != nullptr && warp == 0 && lane == 0) p.debug[uint64_t(t) * 8 + 1] = sj_globaltimer();
@@ -945,7 +961,7 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
       if (!SJB200_SCAN4_TRACE && p.debug != nullptr && warp == 0 && lane == 0) p.debug[uint64_t(S->ticket[ne % kNS]) * 8 + 2] = sj_globaltimer();
       if (kMin) {
         const uint32_t pol = S->res_pol[ne % kNS][warp] & 1u;
-        if (emit_minify_block(S, tmap, p, out_base, ne, warp, lane, S->park[ne % kPark][pol][warp * 32 + lane], S->parkpre[ne % kPark][warp * 32 + lane], T,
+        if (emit_minify_block(S, tmap, p, out_base, ne, warp, lane, S->park[kGPark > 0 ? 0 : ne % kPark][pol][kGPark > 0 ? 0 : warp * 32 + lane], S->parkpre[kGPark > 0 ? 0 : ne % kPark][kGPark > 0 ? 0 : warp * 32 + lane], T,
                               &S->full[warp][r], (full_phase >> r) & 1u, launch_start))
           full_phase ^= 1u << r;
       } else {
@@ -994,7 +1010,7 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
       wait_bar(&S->resolved[ne % kNS], (ne / kNS) & 1u, p, 64);
       if (kMin) {
         const uint32_t pol = S->res_pol[ne % kNS][warp] & 1u;
-        if (emit_minify_block(S, tmap, p, out_base, ne, warp, lane, S->park[ne % kPark][pol][warp * 32 + lane], S->parkpre[ne % kPark][warp * 32 + lane],
+        if (emit_minify_block(S, tmap, p, out_base, ne, warp, lane, S->park[kGPark > 0 ? 0 : ne % kPark][pol][kGPark > 0 ? 0 : warp * 32 + lane], S->parkpre[kGPark > 0 ? 0 : ne % kPark][kGPark > 0 ? 0 : warp * 32 + lane],
                               S->ring[warp][0], &S->full[warp][0], full_phase & 1u, launch_start))
           full_phase ^= 1u;
       } else {
@@ -1036,19 +1052,27 @@ SJ_DEV void emit_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
     }
     const uint32_t pol = S->res_pol[e % kNS][b] & 1u;
     const unsigned tid = b * 32u + lane;
-    if (kMode == 2) {
-      if (emit_minify_block(S, tmap, p, out_base, e, b, lane, S->park[e % kPark][pol][tid], S->parkpre[e % kPark][tid], S->estage[ewarp], &S->efull[ewarp],
-                            fetch_phase, launch_start))
-        fetch_phase ^= 1u;
+    sj_u4 ev;
+    uint32_t prew;
+    if (kGPark > 0) {
+      const uint32_t *slot = park_slot(p, e);
+      ev = sj_ld_u4(slot + (pol * kScanWarps * 32 + tid) * 4);
+      prew = sj_ld_u32(slot + 2 * kScanWarps * 32 * 4 + tid);
     } else {
-      emit_block(S, p, out_base, e, b, lane, S->park[e % kPark][pol][tid], S->parkpre[e % kPark][tid], stg);
+      ev = S->park[kGPark > 0 ? 0 : e % kPark][pol][kGPark > 0 ? 0 : tid];
+      prew = S->parkpre[kGPark > 0 ? 0 : e % kPark][kGPark > 0 ? 0 : tid];
+    }
+    if (kMode == 2) {
+      if (emit_minify_block(S, tmap, p, out_base, e, b, lane, ev, prew, S->estage[ewarp], &S->efull[ewarp], fetch_phase, launch_start)) fetch_phase ^= 1u;
+    } else {
+      emit_block(S, p, out_base, e, b, lane, ev, prew, stg);
     }
     sj_syncwarp();
     if (lane == 0) {
       sj_fence_block();
       if (sj_atomic_add(&S->emitted_cnt[e % kNS], 1u) == uint32_t(kScanWarps - 1)) {
         S->emitted_cnt[e % kNS] = 0;
-        sj_mbar_arrive(&S->park_free[e % kPark]);
+        sj_mbar_arrive(&S->park_free[e % kParkFree]);
       }
     }
   }
@@ -1309,7 +1333,7 @@ SJ_DEV void scan4_body(const sj_tensor_map *tmap, const ScanParams &p, uint8_t *
       S->emitted_cnt[i] = 0;
       sj_mbar_init(&S->resolved[i], 1);
     }
-    for (int i = 0; i < kPark; i++) sj_mbar_init(&S->park_free[i], 1);
+    for (int i = 0; i < kParkFree; i++) sj_mbar_init(&S->park_free[i], 1);
     for (int i = 0; i < (kEmitWarps > 0 ? kEmitWarps : 1); i++) sj_mbar_init(&S->efull[i], 1);
     S->emit_next = 0;
     S->scan_done = 0xFFFFFFFFu;

@@ -142,7 +142,7 @@ Result run_scan4(EmuCtx &cx, const uint8_t *buf, size_t len, uint32_t state_in, 
     p.flags = &cx.flags; p.count_desc = cx.desc.data(); p.ticket = cx.ticket; p.debug = nullptr;
     cx.carry[slot + 1] = Carry();
     const unsigned g = std::min<unsigned>(grid, (nt * unsigned(kTileBytes) + scan4::kElemBytes - 1) / scan4::kElemBytes);
-    cx.park.assign(size_t(g) * scan4::kParkD * scan4::kParkSlotWords + 4, 0xDEADBEEFu);
+    cx.park.assign(size_t(g) * scan4::kParkRing * scan4::kParkSlotWords + 8, 0xDEADBEEFu);
     p.park = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(cx.park.data()) + 15) & ~uintptr_t(15));
     emu_launch(g, tmap, p, minify_dst ? 2 : (g_deferred ? 1 : 0));
     if (cx.ticket[0] != 0 || cx.ticket[1] != 0 || cx.ticket[2] != 0 || cx.flags != 0) { fprintf(stderr, "BUG: ticket/flags not re-armed\n"); exit(2); }
