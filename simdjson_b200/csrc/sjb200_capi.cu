@@ -98,6 +98,7 @@ struct sjb200_ctx {
   long opt_first_chunk_bytes = 512 << 10;  // first chunk of the host-pointer pipeline; the following ones double up to chunk_bytes
   long opt_stage_min_bytes = 1 << 20;  // smaller inputs go straight through the driver
   long opt_zero_copy_out = 1;       // stage 1 stores indexes straight into a page-locked, mapped caller array
+  double t_wait_ms = 0, t_issue_ms = 0, t_sync_ms = 0;  // last host-pointer call: waiting for staged chunks / inside CUDA calls / final synchronise
   int last_input_path = 0, last_output_path = 0;  // stats: 0 driver copy, 1 staged ring, 2 caller memory is page-locked; 0 copy engine, 1 kernel stores
   PendingCall pending;
   std::string last_error;
@@ -492,6 +493,9 @@ extern "C" double sjb200_get_stat(sjb200_ctx *c, const char *key) {
   if (!strcmp(key, "launches")) return double(c->launches);
   if (!strcmp(key, "grid_index")) return double(grid_for(c, kIndex, 0xFFFFFFFFu));
   if (!strcmp(key, "sm_count")) return double(c->sm_count);
+  if (!strcmp(key, "host_wait_ms")) return c->t_wait_ms;
+  if (!strcmp(key, "host_issue_ms")) return c->t_issue_ms;
+  if (!strcmp(key, "host_sync_ms")) return c->t_sync_ms;
   if (!strcmp(key, "input_path")) return double(c->last_input_path);
   if (!strcmp(key, "output_path")) return double(c->last_output_path);
   return -1.0;
@@ -913,14 +917,22 @@ bool scan_host_document(sjb200_ctx *c, int kind, const uint8_t *buf, size_t len,
     size_t issued = 0, released = 0;  // chunks handed to the copy engine / known to have left their slot
     uint32_t idle = 0;
     bool good = true;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [&](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::milli>(now() - t0).count(); };
+    c->t_wait_ms = c->t_issue_ms = c->t_sync_ms = 0;
+    auto t_mark = now();
     while (good && issued < nchunks) {
       while (released < issued && cudaEventQuery(c->ring_events[released % size_t(slots)]) == cudaSuccess) {
         released++;
         pool.allow(released + size_t(slots));
       }
       if (pool.chunk_ready(issued)) {
+        c->t_wait_ms += ms_since(t_mark);
+        t_mark = now();
         good = launch_chunk(issued, c->h_ring + (issued % size_t(slots)) * c->ring_slot_bytes) &&
                ok(c, cudaEventRecord(c->ring_events[issued % size_t(slots)], c->copy_stream), "event record");
+        c->t_issue_ms += ms_since(t_mark);
+        t_mark = now();
         issued++;
         idle = 0;
       } else if (++idle < 512) {
@@ -950,7 +962,9 @@ bool scan_host_document(sjb200_ctx *c, int kind, const uint8_t *buf, size_t len,
       }
     }
   }
+  const auto t_sync0 = std::chrono::steady_clock::now();
   if (!ok(c, cudaStreamSynchronize(c->stream), "sync") || (drain && !ok(c, cudaStreamSynchronize(c->out_stream), "sync"))) return false;
+  c->t_sync_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_sync0).count();
   // every launch reports (and clears) its own flags: the document's flags are their union
   uint32_t flags = 0;
   for (size_t k = 0; k < nchunks; k++) flags |= c->h_carry[k + 1].flags;
