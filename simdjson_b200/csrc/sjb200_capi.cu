@@ -64,11 +64,8 @@ struct sjb200_ctx {
   size_t desc_tiles = 0;
   StreamFinish *d_sfin = nullptr;  // [kCarrySlots] results of the device-side streaming epilogue
   uint32_t *d_doc_scratch = nullptr; size_t doc_scratch_words = 0; uint32_t *d_ndocs = nullptr;
-  uint32_t *d_park = nullptr; size_t d_park_words = 0;  // scan4 deferred mode: parked masks (a per-CTA ring, independent of the input size)
-  long opt_utf8_kernel = 2;    // 2: utf8v2 (independent warps, sjb200_utf8.cuh); 1: scan_kernel<kUtf8> (tile-synchronous)
+  uint32_t *d_park = nullptr; size_t d_park_words = 0;  // scan4 with emit warps: parked masks (a per-CTA ring, independent of the input size)
   int grid_u = 0;
-  long opt_minify_kernel = 3;  // 3: scan_kernel<kMinify>; 4: minify on the scan4 structure (not yet measured on hardware)
-  long opt_deferred = 0;  // 0: never use the deferred variant of scan4 (default until measured better); 1: for launches that fit; 2: always
   // pinned host mirrors
   Carry *h_carry = nullptr;     // [kCarrySlots]
   uint32_t *h_flags = nullptr;
@@ -76,10 +73,8 @@ struct sjb200_ctx {
   StreamFinish *h_sfin = nullptr;  // pinned mirror
   uint8_t *h_tails = nullptr; uint8_t *d_tails = nullptr; const uint8_t **d_tail_ptrs = nullptr; size_t tails_cap = 0;  // batch: last 3 bytes of every document
   uint32_t epoch = 0;
-  int grid[3] = {0, 0, 0};
-  long opt_kernel = 4;  // stage-1 kernel generation: 4 = scan4 (sjb200_scan4.cuh), 3 = the tile-synchronous scan_kernel<kIndex>
   int grid4 = 0;
-  long opt_sub_per_super = 0, opt_use_tma = 1, opt_grid = 0, opt_chunk_bytes = 4 << 20, opt_time_kernel = 0;
+  long opt_use_tma = 1, opt_grid = 0, opt_chunk_bytes = 4 << 20, opt_time_kernel = 0;
   cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // around the last scan kernel when opt_time_kernel is set
   bool ev_valid = false;
   std::vector<cudaEvent_t> ev_pool;              // [2i], [2i+1] around launch i since the last kernel_ms_mean query
@@ -183,7 +178,7 @@ bool ensure_host_scratch(sjb200_ctx *c, uint8_t **p, size_t *have, size_t need) 
   return true;
 }
 
-bool make_tensor_map(sjb200_ctx *c, CUtensorMap *map, const uint8_t *d_buf, size_t len, bool *usable, int box_rows = kTileRows) {
+bool make_tensor_map(sjb200_ctx *c, CUtensorMap *map, const uint8_t *d_buf, size_t len, bool *usable, int box_rows = kScan4BoxRows) {
   memset(map, 0, sizeof(*map));
   *usable = false;
   const uint64_t rows = len / 128;
@@ -204,19 +199,18 @@ bool make_tensor_map(sjb200_ctx *c, CUtensorMap *map, const uint8_t *d_buf, size
   return true;
 }
 
-bool use_scan4(const sjb200_ctx *c, int kind) { return (kind == kIndex && c->opt_kernel == 4) || (kind == kMinify && c->opt_minify_kernel == 4); }
-bool use_utf8v2(const sjb200_ctx *c, int kind) { return kind == kUtf8 && c->opt_utf8_kernel == 2; }
+// stage 1 and minify run on the scan4 structure (sjb200_scan4.cuh), validate_utf8 on utf8v2 (sjb200_utf8.cuh)
+bool use_scan4(const sjb200_ctx *, int kind) { return kind == kIndex || kind == kMinify; }
+bool use_utf8v2(const sjb200_ctx *, int kind) { return kind == kUtf8; }
 // the one tensor map the kernel selected for `kind` reads through (scan4: 4 KiB boxes; the tile-synchronous kernels: 32 KiB)
 bool map_for(sjb200_ctx *c, int kind, CUtensorMap *map, const uint8_t *d_buf, size_t len, bool *usable) {
-  return make_tensor_map(c, map, d_buf, len, usable, (use_scan4(c, kind) || use_utf8v2(c, kind)) ? kScan4BoxRows : kTileRows);
+  (void)kind;  // every kernel reads 4 KiB boxes of 32 rows
+  return make_tensor_map(c, map, d_buf, len, usable, kScan4BoxRows);
 }
 int grid_cap(sjb200_ctx *c, int kind) {
-  if (use_scan4(c, kind)) {
-    if (c->grid4 == 0) c->grid4 = scan4_max_ctas_per_sm() * c->sm_count;
-    return c->opt_grid > 0 ? int(c->opt_grid) : c->grid4;
-  }
-  if (c->grid[kind] == 0) c->grid[kind] = scan_max_ctas_per_sm(kind) * c->sm_count;
-  return c->opt_grid > 0 ? int(c->opt_grid) : c->grid[kind];
+  (void)kind;
+  if (c->grid4 == 0) c->grid4 = scan4_max_ctas_per_sm() * c->sm_count;
+  return c->opt_grid > 0 ? int(c->opt_grid) : c->grid4;
 }
 int grid_for(sjb200_ctx *c, int kind, uint32_t nelements) {
   if (c->opt_force_grid > 0) return int(c->opt_force_grid);  // tuning: a full grid even for a tiny document (measures the fixed cost of a launch)
@@ -246,15 +240,6 @@ bool enqueue_scan(sjb200_ctx *c, int kind, const CUtensorMap *map, bool tma, con
   p.use_tma = tma ? 1u : 0u;
   p.tile_begin = tile_begin;
   p.ntiles = ntiles;
-  // super-tiles: enough consecutive tiles per CTA that one wave of CTAs covers the launch (up to kMaxSub), so the
-  // look-back chain is consulted once per CTA instead of once per 32 KiB
-  const int cap = grid_cap(c, kind);
-  uint32_t R = 1;
-  if (kind == kIndex) R = std::min<uint32_t>(kMaxSub, std::max<uint32_t>(1, (ntiles + uint32_t(cap) - 1) / uint32_t(cap)));
-  if (c->opt_sub_per_super > 0 && kind == kIndex) R = std::min<uint32_t>(kMaxSub, uint32_t(c->opt_sub_per_super));
-  p.sub_per_super = R;
-  p.nsuper = (ntiles + R - 1) / R;
-  p.full_tiles = uint32_t((len / 128) / kTileRows);
   if (!next_epoch(c, stream, &p.epoch)) return false;
   p.idx_out = d_idx;
   p.dst = d_dst;
@@ -293,29 +278,24 @@ bool enqueue_scan(sjb200_ctx *c, int kind, const CUtensorMap *map, bool tma, con
     const uint32_t tpe = uint32_t(scan4_tiles_per_element());
     const uint32_t nelem = (ntiles + tpe - 1) / tpe;
     const int grid = grid_for(c, kind, nelem);
-    // deferred emit when every CTA can hold all the elements it will draw (small launches: one wave of CTAs)
-    bool deferred = kind == kIndex && (c->opt_deferred == 2 || (c->opt_deferred == 1 && uint64_t(nelem) * 4 <= uint64_t(grid) * uint64_t(scan4_deferred_capacity()) * 3));
-    if (deferred || scan4_parks_in_global()) {
+    if (scan4_parks_in_global()) {  // emit-warp builds: the parked masks wait in an L2-resident ring of the context
       const size_t need = scan4_park_words(grid_cap(c, kind));
       if (c->d_park_words < need) {
         cudaStreamSynchronize(c->stream);
         cudaFree(c->d_park); c->d_park = nullptr; c->d_park_words = 0;
-        if (dev_alloc(c, &c->d_park, need, "cudaMalloc(park)")) c->d_park_words = need;
-        else if (scan4_parks_in_global()) return false;
-        else deferred = false;
+        if (!dev_alloc(c, &c->d_park, need, "cudaMalloc(park)")) return false;
+        c->d_park_words = need;
       }
       p.park = c->d_park;
     }
-    launched = ok(c, launch_scan4(map, p, grid, kind == kMinify ? 2 : (deferred ? 1 : 0), stream), "launch scan4");
-  } else if (use_utf8v2(c, kind)) {
+    launched = ok(c, launch_scan4(map, p, grid, kind == kMinify ? 2 : 0, stream), "launch scan4");
+  } else {
     if (c->grid_u == 0) c->grid_u = utf8v2_max_ctas_per_sm() * c->sm_count;
     const uint64_t nblocks = (uint64_t(ntiles) * kTileBytes + 4095) / 4096;
     const uint64_t want = (nblocks + uint64_t(utf8v2_warps_per_cta()) - 1) / uint64_t(utf8v2_warps_per_cta());
     const int grid = c->opt_force_grid > 0 ? int(c->opt_force_grid) : int(std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(c->opt_grid > 0 ? c->opt_grid : c->grid_u), want)));
     p.carry_out_host = host_out;
     launched = ok(c, launch_utf8v2(map, p, grid, stream), "launch utf8v2");
-  } else {
-    launched = ok(c, launch_scan(kind, map, p, grid_for(c, kind, p.nsuper), stream), "launch scan");
   }
   if (e1) { cudaEventRecord(e1, stream); c->ev_k0 = e0; c->ev_k1 = e1; c->ev_valid = launched; }
   c->launches += launched ? 1 : 0;
@@ -505,11 +485,6 @@ extern "C" int sjb200_set_option(sjb200_ctx *c, const char *key, long value) {
   if (!c || !key) return SJB200_UNEXPECTED_ERROR;
   if (!strcmp(key, "use_tma")) c->opt_use_tma = value;
   else if (!strcmp(key, "grid")) c->opt_grid = value;
-  else if (!strcmp(key, "sub_per_super")) c->opt_sub_per_super = value;
-  else if (!strcmp(key, "kernel")) c->opt_kernel = (value == 3) ? 3 : 4;
-  else if (!strcmp(key, "deferred")) c->opt_deferred = value;
-  else if (!strcmp(key, "minify_kernel")) c->opt_minify_kernel = (value == 4) ? 4 : 3;
-  else if (!strcmp(key, "utf8_kernel")) c->opt_utf8_kernel = (value == 1) ? 1 : 2;
   else if (!strcmp(key, "time_kernel")) c->opt_time_kernel = value;
   else if (!strcmp(key, "debug_timeline")) c->opt_debug_timeline = value;
   else if (!strcmp(key, "chunk_bytes")) c->opt_chunk_bytes = std::max<long>(2 * kTileBytes, (value / (2 * kTileBytes)) * (2 * kTileBytes));

@@ -10,15 +10,12 @@
 namespace sjb200 {
 
 // launchers (defined in sjb200_kernels.cu)
-cudaError_t launch_scan(int kind, const CUtensorMap *tmap, const ScanParams &p, int grid, cudaStream_t stream);
-int scan_max_ctas_per_sm(int kind);
 // scan4: the stage-1 indexer of sjb200_scan4.cuh (4 KiB blocks; its tensor map has a 32-row box)
-cudaError_t launch_scan4(const CUtensorMap *tmap, const ScanParams &p, int grid, int mode /*0 stage 1, 1 stage 1 deferred, 2 minify*/,
+cudaError_t launch_scan4(const CUtensorMap *tmap, const ScanParams &p, int grid, int mode /*0 stage 1, 2 minify*/,
                          cudaStream_t stream);
-size_t scan4_park_words(int grid);   // uint32 words of ScanParams::park for a deferred launch of `grid` CTAs
+size_t scan4_park_words(int grid);   // uint32 words of ScanParams::park for a launch of `grid` CTAs (emit-warp builds)
 int scan4_tiles_per_element();      // 32 KiB tiles of the launch parameter block per scan4 element
 int scan4_parks_in_global();         // 1: every scan4 launch needs ScanParams::park (emit warps read the parked masks from an L2-resident ring)
-int scan4_deferred_capacity();       // elements per CTA the deferred variant can hold at once
 int scan4_max_ctas_per_sm();
 constexpr int kScan4BoxRows = 32;
 // utf8v2: validate_utf8 with independent warps (sjb200_utf8.cuh); same 32-row boxes

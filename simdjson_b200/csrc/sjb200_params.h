@@ -7,42 +7,15 @@
 
 namespace sjb200 {
 
-// ---- geometry (one "tile" is what one CTA scans per loop iteration)
-constexpr int kUnitsPerLane = 4;                     // 32-byte transposition units per lane
-constexpr int kLaneBytes = 32 * kUnitsPerLane;       // 128 B = one TMA 128B-swizzle row
-constexpr int kWarpBytes = 32 * kLaneBytes;          // 4 KiB
-constexpr int kWarps = 8;
-constexpr int kThreads = 32 * kWarps;
-constexpr int kTileBytes = kWarps * kWarpBytes;      // 32 KiB
-constexpr int kTileRows = kTileBytes / 128;          // 256 rows of 128 B (max TMA box dim)
-#ifndef SJB200_STAGES
-#define SJB200_STAGES 1
-#endif
-#ifndef SJB200_MIN_CTAS
-#define SJB200_MIN_CTAS 2
-#endif
-constexpr int kStages = SJB200_STAGES;      // shared-memory tile buffers per CTA
-constexpr int kMinCtasPerSm = SJB200_MIN_CTAS;  // __launch_bounds__ occupancy target
-// A CTA scans a "super-tile" of up to kMaxSub consecutive tiles before it consults the look-back chain once:
-// the masks of every tile wait in shared memory (8 words per lane per tile) until the incoming state is known.
-// (Parking them in an L2-resident global scratch instead, to fit 4 CTAs per SM, was measured slower: the SM is
-// issue-bound, not latency-bound.)
-#ifndef SJB200_SCAN4_MIN_CTAS
-#define SJB200_SCAN4_MIN_CTAS 2
-#endif
-#ifndef SJB200_MAX_SUB
-#define SJB200_MAX_SUB 8
-#endif
-constexpr int kMaxSub = SJB200_MAX_SUB;
+// ---- geometry: launch parameters count the document in 32 KiB "tiles" (chunk launches start at tile boundaries);
+// the kernels read it in 4 KiB blocks of 32 rows x 128 B
+constexpr int kTileBytes = 32 * 1024;
+constexpr int kTileRows = kTileBytes / 128;
 constexpr int kMaxRanks = 8;                          // GPUs of one node that can share a scan (sjb200_comm)
 constexpr int kXchgSteps = 64;                        // sharded passes whose exchange records an exchange window holds (two rounds each)
-constexpr int kCtlBytes = 1024;                       // control block
-constexpr int kLutBytes = 64 * 64;                    // composed-transducer table
-constexpr int kEmitBytes = kWarps * 1024;             // per-warp emit scratch (128 mask words + 128 counts)
-constexpr int kMaskSlotBytes = kThreads * 8 * 4;      // one tile's masks
-constexpr int kSmemBytesScan = kStages * kTileBytes + 1024 /*alignment slack*/ + kCtlBytes + kLutBytes + kEmitBytes + kMaxSub * kMaskSlotBytes;
-constexpr int kSmemBytesUtf8 = kStages * kTileBytes + 1024 + kCtlBytes;
-constexpr int smem_bytes_for(int kind) { return kind == 2 ? kSmemBytesUtf8 : kSmemBytesScan; }
+#ifndef SJB200_SCAN4_MIN_CTAS
+#define SJB200_SCAN4_MIN_CTAS 2                       // CTAs per SM of the 8-scan-warp build of scan4
+#endif
 
 // ---- scan kinds
 enum : int { kIndex = 0, kMinify = 1, kUtf8 = 2 };
@@ -66,9 +39,6 @@ struct ScanParams {
   uint32_t use_tma;         // 1: full tiles arrive by cp.async.bulk.tensor (buf 16 B aligned)
   uint32_t tile_begin;      // first document tile of this launch (chunked streaming)
   uint32_t ntiles;          // tiles in this launch: document tiles [tile_begin, tile_begin+ntiles)
-  uint32_t sub_per_super;   // R: tiles per super-tile (1..kMaxSub); the look-back chain has one element per super-tile
-  uint32_t nsuper;          // ceil(ntiles / R)
-  uint32_t full_tiles;      // document tiles that lie entirely inside floor(len/128) rows
   uint32_t epoch;           // tags look-back descriptors so they need no per-launch reset
   uint32_t *idx_out;        // kIndex: device index array
   uint8_t *dst;             // kMinify: device output
@@ -77,9 +47,9 @@ struct ScanParams {
   Carry *carry_out;
   Carry *carry_out_host;    // scan4: optional second copy of the result in pinned host memory (saves the copy engine a trip between launches)
   uint32_t *flags;          // accumulated with atomicOr; zero between launches (the last CTA moves it to carry_out->flags)
-  unsigned long long *count_desc;  // [nsuper] the look-back chain
+  unsigned long long *count_desc;  // the look-back chain: one descriptor per scan4 element of the launch
   uint32_t *ticket;         // [0] next ticket, [1] CTAs finished, [2] scan4: aggregates published so far (4 words, zero between launches)
-  uint32_t *park;           // scan4, deferred mode: scratch ring for parked masks, scan4_park_words(grid) words (stays in L2)
+  uint32_t *park;           // scan4 with emit warps: scratch ring for parked masks, scan4_park_words(grid) words (stays in L2)
   unsigned long long *debug;  // optional [ntiles][8] timeline (globaltimer ns) for tuning; null in production
   // multi-GPU exchange fused into the scan (scan4): the launch's last CTA stores the shard record {count, state out,
   // transducer, flags} into EVERY rank's exchange window over NVLink (peer-mapped device memory), tagged with xchg_seq --

@@ -46,12 +46,9 @@ constexpr int kScanWarps = SJB200_SCAN4_WARPS;  // scan warps per CTA = blocks p
                                                 // polling the descriptors, half the elements to resolve
 constexpr int kBlockBytes = 4096;
 constexpr int kBlockRows = kBlockBytes / 128;
-#ifndef SJB200_SCAN4_CHAIN
-#define SJB200_SCAN4_CHAIN 1
-#endif
-constexpr int kChainWarps = SJB200_SCAN4_CHAIN;  // chain warp c resolves this CTA's elements j = c, c + kChainWarps, ...
+constexpr int kChainWarps = 1;  // the warp that resolves this CTA's elements
 #ifndef SJB200_SCAN4_EMITW
-#define SJB200_SCAN4_EMITW 7
+#define SJB200_SCAN4_EMITW 0
 #endif
 // Emit warps (stage 1 only): the scan is bound by the ALU pipe, the emit by FLO / shared-memory latency.  When the warp
 // that scanned a block also emits it, all warps of the CTA sit in the emit loop together (measured: ~2300 of the ~9200
@@ -64,14 +61,7 @@ constexpr int kThreads4 = 32 * (kScanWarps + kChainWarps + kEmitWarps);
 #endif
 constexpr int kPark = SJB200_SCAN4_PARK;  // elements whose masks wait in shared memory: a scan warp emits element j-kLag after scanning j
 constexpr int kLag = kPark - 1;
-#ifndef SJB200_SCAN4_STAGGER
-#define SJB200_SCAN4_STAGGER 0  // 1: even scan warps emit one element earlier than odd ones (lag kLag-1 / kLag), so that at any time half of the
-#endif                          // CTA's warps are in the latency-bound emit loop while the other half are in the ALU-bound scan
 constexpr int kNS = 32;          // ring of element slots (tickets, summaries, resolutions)
-#ifndef SJB200_SCAN4_DEFER_PARK
-#define SJB200_SCAN4_DEFER_PARK 12
-#endif
-constexpr int kParkD = SJB200_SCAN4_DEFER_PARK;  // deferred mode: elements of a CTA whose masks may wait in the L2-resident scratch ring
 constexpr int kParkSlotWords = 2 * kScanWarps * 32 * 4 + kScanWarps * 32;  // one element's parked words (both polarities + prefixes)
 #ifndef SJB200_SCAN4_GPARK
 #define SJB200_SCAN4_GPARK 8
@@ -81,31 +71,13 @@ constexpr int kParkSlotWords = 2 * kScanWarps * 32 * 4 + kScanWarps * 32;  // on
 // never wait for the chain as long as an element is resolved and emitted within kGPark - 1 scans (with three elements
 // parked in shared memory, every hiccup of the look-back chain stalled the scan).  0: park in shared memory.
 constexpr int kGPark = (SJB200_SCAN4_EMITW > 0) ? SJB200_SCAN4_GPARK : 0;
-constexpr int kParkRing = (kGPark > 0) ? kGPark : kParkD;  // slots per CTA of the global scratch ring
+constexpr int kParkRing = (kGPark > 0) ? kGPark : 1;  // slots per CTA of the global scratch ring
 constexpr int kParkFree = (kGPark > 0) ? kGPark : kPark;   // elements whose masks may be parked at once (emit-warp mode)
 #ifndef SJB200_SCAN4_LOOKK
 #define SJB200_SCAN4_LOOKK 10
 #endif
 constexpr int kLookK = SJB200_SCAN4_LOOKK;       // descriptors per lane and look-back round trip (window of 320 elements >= one wave of CTAs)
-static_assert(kLag >= 1 && 2 * kLag + 3 <= kNS && 2 * (kParkD - 1) + 3 <= kNS && 2 * kGPark + 4 <= kNS && (kNS & (kNS - 1)) == 0, "slot ring");
-#ifndef SJB200_SCAN4_COUNTER
-#define SJB200_SCAN4_COUNTER 0  // 1: a look-back first waits (polling ONE word) until t aggregates are out, then loads its window once
-#endif
-#ifndef SJB200_SCAN4_HELP
-#define SJB200_SCAN4_HELP 0  // 0: off; n > 0: a look-back that walked at least n elements publishes the inclusive prefixes it passed
-#endif
-#ifndef SJB200_SCAN4_SLEEP
-#define SJB200_SCAN4_SLEEP 1
-#endif
-#ifndef SJB200_SCAN4_LB_SLEEP
-#define SJB200_SCAN4_LB_SLEEP 0  // ns between two polls of the look-back window (0: poll again at once)
-#endif
-#ifndef SJB200_SCAN4_EARLY_LOOKBACK
-#define SJB200_SCAN4_EARLY_LOOKBACK 1  // 1: the chain warp walks back over the predecessors of an element while the element is being scanned
-#endif
-#ifndef SJB200_SCAN4_UTF8_BLOCK
-#define SJB200_SCAN4_UTF8_BLOCK 1  // 1: ASCII / non-ASCII decided once per 4 KiB block (two specialised copies of the unit loop); 0: once per unit
-#endif
+static_assert(kLag >= 1 && 2 * kLag + 3 <= kNS && 2 * kGPark + 4 <= kNS && (kNS & (kNS - 1)) == 0, "slot ring");
 #ifndef SJB200_SCAN4_TRACE
 #define SJB200_SCAN4_TRACE 0  // 1: tuning build that records where a scan warp's time goes (shared memory, dumped to ScanParams::debug at exit)
 #endif
@@ -193,9 +165,7 @@ SJ_DEV bool wait_bar(sj_mbar_t *bar, uint32_t parity, const ScanParams &p, unsig
       sj_atomic_or(p.flags, kFlagInternal);
       return false;
     }
-#if SJB200_SCAN4_SLEEP
     sj_nanosleep(ns);
-#endif
   }
   return true;
 }
@@ -382,7 +352,6 @@ SJ_DEV uint32_t scan_block(const uint8_t *T, uint32_t pw0, uint32_t e_in, uint32
       bs[u] = c.bs; qu[u] = c.qu; op[u] = c.op; sc[u] = c.sc; cl[u] = 0;
     }
   } else {
-#if SJB200_SCAN4_UTF8_BLOCK
     // One decision per block instead of one per unit: does any lane hold a byte >= 0x80?  (The lane's row is read
     // twice -- the load pipe has room, the ALU pipe does not.)  An all-ASCII block needs no UTF-8 code at all, any other
     // block runs the check in every unit without the per-unit vote, pending-carry bookkeeping and carry reset.
@@ -413,34 +382,9 @@ SJ_DEV uint32_t scan_block(const uint8_t *T, uint32_t pw0, uint32_t e_in, uint32
         transpose32(w8, pl);
         const unit_classes c = classify(pl);
         bs[u] = c.bs; qu[u] = c.qu; op[u] = c.op; sc[u] = c.sc; cl[u] = c.ctl;
-#if !defined(SJB200_DIAG_NO_UTF8)
         uerr |= utf8_check_unit(pl, uc);
-#endif
       }
     }
-#else
-    const uint32_t pw = (lane == 0) ? pw0 : *reinterpret_cast<const uint32_t *>(T + swz(lane_off - 4));
-    utf8_carry uc = utf8_carry_from_prev_word(pw);
-    uint32_t pend = utf8_carry_pending(uc) ? 1u : 0u;  // the previous unit ended inside a multi-byte sequence
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      uint32_t w8[8], pl[8];
-      load_unit(T, lane_off + 32u * u, w8);
-      transpose32(w8, pl);
-      const unit_classes c = classify(pl);
-      bs[u] = c.bs; qu[u] = c.qu; op[u] = c.op; sc[u] = c.sc; cl[u] = c.ctl;
-#if defined(SJB200_DIAG_NO_UTF8)  // ablation for tuning only (results are wrong for non-ASCII input)
-      if (false) {
-#else
-      if (sj_any((pl[7] | pend) != 0)) {  // all-ASCII units of a warp (and nothing pending) need no check
-#endif
-        uerr |= utf8_check_unit(pl, uc);
-        pend = (uc.n1 >> 31) | (uc.n2 >> 30) | (uc.n3 >> 29);
-      } else {
-        uc = utf8_carry_zero();
-      }
-    }
-#endif
   }
   if (!kMin && sj_any(uerr != 0) && lane == 0) sj_atomic_or(p.flags, kFlagUtf8);
 
@@ -524,9 +468,6 @@ SJ_DEV uint32_t scan_block(const uint8_t *T, uint32_t pw0, uint32_t e_in, uint32
 // Each lane walks its own four mask words, column by column: every lane runs the trip count of the fullest word of the
 // column (uniform), pulls the highest set bit per iteration (one FLO) and stores its position -- descending, so the
 // store offset is an immediate of the unrolled loop.
-#ifndef SJB200_SCAN4_EMIT
-#define SJB200_SCAN4_EMIT 1  // 0: one loop per column (dependent chain of ~4 instructions per output); 1: the four columns in one loop (four independent chains); 2: two loops of two columns
-#endif
 // one step of one word's chain: store the position of the highest remaining bit at q[-k], clear it
 #define SJ_EMIT_STEP(m, q, pb)                   \
   {                                              \
@@ -537,23 +478,6 @@ SJ_DEV uint32_t scan_block(const uint8_t *T, uint32_t pw0, uint32_t e_in, uint32
     (m) &= ~(1u << (h & 31u));                   \
   }
 SJ_DEV void emit_columns(const sj_u4 ev, uint32_t off, uint32_t pos_lane, uint32_t *dst) {
-#if defined(SJB200_DIAG_NO_EMIT)  // ablation for tuning only (no output)
-  return;
-#endif
-#if SJB200_SCAN4_EMIT == 0
-  const uint32_t m4[4] = {ev.x, ev.y, ev.z, ev.w};
-#pragma unroll
-  for (int u = 0; u < 4; u++) {
-    uint32_t m = m4[u];
-    const uint32_t c = uint32_t(sj_popc(m));
-    const uint32_t n = sj_reduce_max(c);
-    const uint32_t pb = pos_lane + 32u * u;
-    uint32_t *q = dst + (off + c);  // one past the word's last output
-    off += c;
-#pragma unroll 4
-    for (uint32_t k = 0; k < n; k++) SJ_EMIT_STEP(m, q, pb)
-  }
-#else
   // The chains of different words are independent: run them side by side, so that the FLO -> shift -> clear latency of
   // one is covered by the others (a warp that emits is otherwise latency-bound: ~4 dependent instructions per output).
   uint32_t m0 = ev.x, m1 = ev.y, m2 = ev.z, m3 = ev.w;
@@ -561,7 +485,6 @@ SJ_DEV void emit_columns(const sj_u4 ev, uint32_t off, uint32_t pos_lane, uint32
   uint32_t *q0 = dst + (off + c0);  // one past each word's last output
   uint32_t *q1 = q0 + c1, *q2 = q1 + c2, *q3 = q2 + c3;
   const uint32_t pb0 = pos_lane, pb1 = pos_lane + 32u, pb2 = pos_lane + 64u, pb3 = pos_lane + 96u;
-#if SJB200_SCAN4_EMIT == 1
   const uint32_t c01 = c0 > c1 ? c0 : c1, c23 = c2 > c3 ? c2 : c3;
   const uint32_t n = sj_reduce_max(c01 > c23 ? c01 : c23);
 #pragma unroll 2
@@ -571,20 +494,6 @@ SJ_DEV void emit_columns(const sj_u4 ev, uint32_t off, uint32_t pos_lane, uint32
     SJ_EMIT_STEP(m2, q2, pb2)
     SJ_EMIT_STEP(m3, q3, pb3)
   }
-#else
-  const uint32_t na = sj_reduce_max(c0 > c1 ? c0 : c1), nb = sj_reduce_max(c2 > c3 ? c2 : c3);
-#pragma unroll 2
-  for (uint32_t k = 0; k < na; k++) {
-    SJ_EMIT_STEP(m0, q0, pb0)
-    SJ_EMIT_STEP(m1, q1, pb1)
-  }
-#pragma unroll 2
-  for (uint32_t k = 0; k < nb; k++) {
-    SJ_EMIT_STEP(m2, q2, pb2)
-    SJ_EMIT_STEP(m3, q3, pb3)
-  }
-#endif
-#endif
 }
 #undef SJ_EMIT_STEP
 
@@ -647,21 +556,8 @@ SJ_DEV void emit_from_smem(Smem *S, const ScanParams &p, uint64_t out_base, uint
   emit_block(S, p, out_base, e, warp, lane, S->park[kGPark > 0 ? 0 : e % kPark][pol][kGPark > 0 ? 0 : tid], S->parkpre[kGPark > 0 ? 0 : e % kPark][kGPark > 0 ? 0 : tid], stg);
 }
 
-// deferred mode: the masks wait in the scratch ring of ScanParams::park (it stays in L2)
-struct Parked {
-  sj_u4 ev;
-  uint32_t prew;
-};
+// emit-warp mode: the masks wait in the scratch ring of ScanParams::park (it stays in L2)
 SJ_DEV uint32_t *park_slot(const ScanParams &p, uint32_t e) { return p.park + (size_t(sj_cta()) * kParkRing + (e % uint32_t(kParkRing))) * size_t(kParkSlotWords); }
-SJ_DEV Parked load_parked(Smem *S, const ScanParams &p, uint32_t e, unsigned warp, unsigned lane) {
-  const uint32_t pol = S->res_pol[e % kNS][warp] & 1u;
-  const uint32_t *slot = park_slot(p, e);
-  const unsigned tid = warp * 32 + lane;
-  Parked k;
-  k.ev = sj_ld_u4(slot + (pol * kScanWarps * 32 + tid) * 4);
-  k.prew = sj_ld_u32(slot + 2 * kScanWarps * 32 * 4 + tid);
-  return k;
-}
 
 // ------------------------------------------------------------------------------------------------ minify: emit one block
 // kept bytes of a 4-byte word packed to its low end: PRMT selector (unused positions select a zero byte) | count << 16
@@ -778,10 +674,6 @@ SJ_DEV void compose_element(Smem *S, const ScanParams &p, int ns, uint32_t t, un
   const uint32_t par = uint32_t(sj_popc(P)) & 1u;
   if (lane == 0) {
     if (t > 0) sj_st_relaxed_u64(p.count_desc + t, pack_agg(p.epoch, par, A, B));  // element 0 goes straight to inclusive
-#if SJB200_SCAN4_COUNTER
-    sj_fence_gpu_release();
-    sj_atomic_add(p.ticket + 2, 1u);  // aggregates of this launch that are out (result unused: a reduction, nobody waits for it)
-#endif
     S->elem[ns][0] = par;
     S->elem[ns][1] = A;
     S->elem[ns][2] = B;
@@ -833,14 +725,14 @@ SJ_DEV bool issue_load(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, 
   return full;
 }
 
-// kMode: 0 stage 1, pipelined; 1 stage 1, deferred emit; 2 minify (pipelined)
+// kMode: 0 stage 1; 2 minify
 template <int kMode>
 SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, const Carry &cin, unsigned warp, unsigned lane) {
   const uint32_t nelem = elements_of(p);
   const uint64_t launch_start = uint64_t(p.tile_begin) * kTileBytes;
   const uint64_t launch_end = launch_start + uint64_t(p.ntiles) * kTileBytes;
   const uint64_t scan_limit = p.len < launch_end ? p.len : launch_end;  // blocks at or beyond it are not this launch's
-  constexpr bool kDefer = (kMode == 1), kMin = (kMode == 2);
+  constexpr bool kMin = (kMode == 2);
   const uint64_t out_base = cin.count;
   uint32_t full_phase = 0;
   uint32_t pw_cur = 0x20202020u, pw_next = 0x20202020u;
@@ -867,20 +759,10 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
   }
   uint32_t ne = 0;  // this CTA's next element to emit (elements are emitted in order)
   uint32_t j = 0;
-  const uint32_t my_lag = (SJB200_SCAN4_STAGGER && kLag >= 2 && (warp & 1u) == 0) ? uint32_t(kLag - 1) : uint32_t(kLag);
-  constexpr bool kEmitW = (kMode != 1) && (kEmitWarps > 0);  // the emit warps take the blocks from here: this warp only scans
+  constexpr bool kEmitW = (kEmitWarps > 0);  // the emit warps take the blocks from here: this warp only scans
   for (;; j++) {
     if (t >= nelem) break;
     const int r = int(j & 1u);
-    if (kDefer) {
-      // the scratch slot of element j must be free (only binds when a CTA draws more than kParkRing elements)
-      while (ne + uint32_t(kParkRing) <= j) {
-        wait_bar(&S->resolved[ne % kNS], (ne / kNS) & 1u, p, 64);
-        const Parked k = load_parked(S, p, ne, warp, lane);
-        emit_block(S, p, out_base, ne, warp, lane, k.ev, k.prew, reinterpret_cast<uint32_t *>(S->ring[warp][r ^ 1]));
-        ne++;
-      }
-    }
     SJ_TRACE4(0);
     const uint32_t tn = wait_ticket(S, j + 1, p);
     if (warp == (j % uint32_t(kScanWarps))) {
@@ -915,11 +797,7 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
       const uint32_t pw0 = sj_shfl(pw_cur, 0);
       const uint32_t st = boundary_state(p, bstart, launch_start, cin.state, pw0, lane);
       SJ_TRACE4(4);
-      if (kDefer) {
-        uint32_t *slot = park_slot(p, j);
-        summary = scan_block<false>(T, pw0, st & 1u, (st >> 2) & 1u, lane, p, reinterpret_cast<sj_u4 *>(slot),
-                                    reinterpret_cast<sj_u4 *>(slot) + kScanWarps * 32, slot + 2 * kScanWarps * 32 * 4, kBlockBytes);
-      } else {
+      {
         // the parked masks of element j - kParkFree must have been emitted before this element's take their place
         if (kEmitW && j >= uint32_t(kParkFree)) wait_bar(&S->park_free[j % kParkFree], ((j / kParkFree) - 1u) & 1u, p, 64);
         const uint64_t left = p.len - bstart;  // > 0: bytes of the block that exist
@@ -955,7 +833,7 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
     }
     SJ_TRACE4(6);
     SJ_TRACE4(7);
-    if (!kDefer && !kEmitW && j >= my_lag) {  // pipelined: the chain warp has had my_lag scans' time to resolve this one
+    if (!kEmitW && j >= uint32_t(kLag)) {  // pipelined: the chain warp has had kLag scans' time to resolve this one
       wait_bar(&S->resolved[ne % kNS], (ne / kNS) & 1u, p, 64);
       SJ_TRACE4(8);
       if (!SJB200_SCAN4_TRACE && p.debug != nullptr && warp == 0 && lane == 0) p.debug[uint64_t(S->ticket[ne % kNS]) * 8 + 2] = sj_globaltimer();
@@ -977,34 +855,6 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
   // drain: what this CTA scanned and has not emitted yet (no load is in flight: both ring slots are free)
   if (kEmitW) {
     if (warp == 0 && lane == 0) sj_st_release_u32(&S->scan_done, j);  // the emit warps stop after element j - 1
-  } else if (kDefer) {
-    // deferred mode emits everything here: the scan phase ran without ever waiting for the chain.  The parked words of
-    // the next element are fetched while the current one is emitted.
-    bool have = false;
-    Parked cur;
-    cur.ev = sj_make_u4(0, 0, 0, 0);
-    cur.prew = 0;
-    while (ne < j) {
-      if (!have) {
-        wait_bar(&S->resolved[ne % kNS], (ne / kNS) & 1u, p, 64);
-        cur = load_parked(S, p, ne, warp, lane);
-      }
-      have = false;
-      Parked nxt;
-      nxt.ev = sj_make_u4(0, 0, 0, 0);
-      nxt.prew = 0;
-      if (ne + 1 < j) {
-        uint32_t ready = 0;
-        if (lane == 0) ready = sj_mbar_try_wait(&S->resolved[(ne + 1) % kNS], ((ne + 1) / kNS) & 1u) ? 1u : 0u;
-        if (sj_shfl(ready, 0)) {
-          nxt = load_parked(S, p, ne + 1, warp, lane);
-          have = true;
-        }
-      }
-      emit_block(S, p, out_base, ne, warp, lane, cur.ev, cur.prew, reinterpret_cast<uint32_t *>(S->ring[warp][ne & 1u]));
-      cur = nxt;
-      ne++;
-    }
   } else {
     while (ne < j) {
       wait_bar(&S->resolved[ne % kNS], (ne / kNS) & 1u, p, 64);
@@ -1046,9 +896,7 @@ SJ_DEV void emit_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
         sj_atomic_or(p.flags, kFlagInternal);
         return;
       }
-#if SJB200_SCAN4_SLEEP
       sj_nanosleep(32);
-#endif
     }
     const uint32_t pol = S->res_pol[e % kNS][b] & 1u;
     const unsigned tid = b * 32u + lane;
@@ -1088,19 +936,6 @@ SJ_DEV void emit_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
 // that only one bit is order-dependent: the quote parities of a group of 32 elements are one ballot word, an element's
 // polarity relative to the oldest element of the window is a popcount, and the counts are then plain sums.
 SJ_DEV void look_back(const ScanParams &p, uint32_t t, unsigned lane, uint32_t *s_in, uint32_t *base) {
-#if SJB200_SCAN4_COUNTER
-  // Option: instead of polling 320 descriptors in the lines every other chain warp is polling, wait on one word until
-  // at least t aggregates of this launch are out (tickets are scanned roughly in order, so that is nearly always all of
-  // elements 0..t-1); the loop below then finds its window complete at the first load and still copes when it is not.
-  for (uint32_t spins = 0; spins < kSpinLimit4; spins++) {
-    uint32_t out = 0;
-    if (lane == 0) out = sj_ld_relaxed_u32(p.ticket + 2);
-    if (sj_shfl(out, 0) >= t) break;
-#if SJB200_SCAN4_SLEEP
-    sj_nanosleep(100);
-#endif
-  }
-#endif
   Eff acc;
   acc.p = 0; acc.a = 0; acc.b = 0;
   int64_t newest = int64_t(t) - 1;
@@ -1145,9 +980,6 @@ SJ_DEV void look_back(const ScanParams &p, uint32_t t, unsigned lane, uint32_t *
         sj_atomic_or(p.flags, kFlagInternal);
         break;
       }
-#if SJB200_SCAN4_LB_SLEEP > 0
-      sj_nanosleep(SJB200_SCAN4_LB_SLEEP);  // (a poll is a round trip to L2, ~700 cycles of waiting on loads: it takes no issue slots worth saving)
-#endif
     }
     // ---- fold the aggregates newer than the inclusive prefix
     const uint32_t use = want & ~pend & needed;
@@ -1181,36 +1013,6 @@ SJ_DEV void look_back(const ScanParams &p, uint32_t t, unsigned lane, uint32_t *
       ck = sj_shfl(ck, int(il));
       *s_in = sk ^ acc.p;
       *base = ck + (sk ? acc.b : acc.a);
-#if SJB200_SCAN4_HELP
-      // Option (off: measured slower with 296 chain warps, when every one of them also wrote 2.5 KB into the hot
-      // descriptor lines; kept for the one-CTA-per-SM configuration, where only walks longer than kHelpMin help):
-      // the walk has just computed what every element between the inclusive prefix and t needs, so publish THEIR
-      // inclusive prefixes too -- the owners would write exactly the same words -- and the other CTAs find an
-      // inclusive prefix right behind their element.
-      if (inc_dist >= uint32_t(SJB200_SCAN4_HELP)) {
-        uint32_t older_p = 0;   // parity of the used elements older than group k
-        uint32_t older_c = ck;  // outputs up to and including the used elements older than group k
-#pragma unroll
-        for (int k = kLookK - 1; k >= 0; k--) {
-          const bool u = (use >> k) & 1u;
-          const uint32_t rel = (uint32_t(sj_popc((bal[k] >> lane) >> 1)) ^ older_p ^ sk) & 1u;  // in-string entering my element
-          const uint32_t a = uint32_t(d[k]) & 0x7FFFFu, b = uint32_t(d[k] >> 19) & 0x7FFFFu;
-          const uint32_t mine = u ? (rel ? b : a) : 0u;
-          uint32_t suf = mine;  // suffix sum over lanes >= mine (older elements of the group first)
-#pragma unroll
-          for (int dd = 1; dd < 32; dd <<= 1) {
-            const uint32_t o = sj_shfl_down(suf, dd);
-            if (int(lane) + dd < 32) suf += o;
-          }
-          if (u) {
-            const uint32_t s_after = rel ^ (uint32_t(d[k] >> 38) & 1u);
-            sj_st_relaxed_u64(p.count_desc + (first - 32 * k), pack_inc(p.epoch, s_after, older_c + suf));
-          }
-          older_c += sj_shfl(suf, 0);
-          older_p ^= uint32_t(sj_popc(bal[k])) & 1u;
-        }
-      }
-#endif
       return;
     }
     newest -= 32 * kLookK;
@@ -1273,7 +1075,6 @@ SJ_DEV void chain_role(Smem *S, const ScanParams &p, const Carry &cin, unsigned 
     const uint32_t t = wait_ticket(S, j, p);
     if (t >= nelem) break;
     uint32_t s_in = (cin.state >> 1) & 1u, base = 0;
-#if SJB200_SCAN4_EARLY_LOOKBACK
     // The look-back needs the elements BEFORE t, not t itself: it runs while this CTA is still scanning t, so that the
     // element is resolved as soon as its own summary is there (with the look-back after the scan, an element was
     // resolved ~3.6 us after the last of its predecessors had been scanned: pick-up + poll round trips + fold).
@@ -1281,12 +1082,6 @@ SJ_DEV void chain_role(Smem *S, const ScanParams &p, const Carry &cin, unsigned 
     wait_bar(&S->scanned[ns], (j / kNS) & 1u, p, 64);
     if (!SJB200_SCAN4_TRACE && p.debug != nullptr && lane == 0) p.debug[uint64_t(t) * 8 + 6] = sj_globaltimer();
     const uint32_t par = S->elem[ns][0], b0 = S->elem[ns][1], b1 = S->elem[ns][2], hits = S->elem[ns][3];
-#else
-    wait_bar(&S->scanned[ns], (j / kNS) & 1u, p, 200);
-    if (!SJB200_SCAN4_TRACE && p.debug != nullptr && lane == 0) p.debug[uint64_t(t) * 8 + 6] = sj_globaltimer();
-    const uint32_t par = S->elem[ns][0], b0 = S->elem[ns][1], b1 = S->elem[ns][2], hits = S->elem[ns][3];
-    if (t > 0) look_back(p, t, lane, &s_in, &base);
-#endif
     const uint32_t mine_total = s_in ? b1 : b0;
     const uint32_t s_out = s_in ^ par;
     if (lane == 0) sj_st_relaxed_u64(p.count_desc + t, pack_inc(p.epoch, s_out, base + mine_total));
@@ -1346,7 +1141,7 @@ SJ_DEV void scan4_body(const sj_tensor_map *tmap, const ScanParams &p, uint8_t *
 #endif
   if (warp < unsigned(kScanWarps)) scan_role<kMode>(S, tmap, p, cin, warp, lane);
   else if (warp < unsigned(kScanWarps + kChainWarps)) chain_role(S, p, cin, lane, warp - unsigned(kScanWarps));
-  else if (kMode != 1) emit_role<kMode>(S, tmap, p, cin, warp - unsigned(kScanWarps + kChainWarps), lane);
+  else emit_role<kMode>(S, tmap, p, cin, warp - unsigned(kScanWarps + kChainWarps), lane);
 #if SJB200_SCAN4_TRACE
   if (tid == 0) S->trace_cta[2] = sj_globaltimer();
 #endif

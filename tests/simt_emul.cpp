@@ -33,7 +33,7 @@ struct LaunchArgs {
   unsigned grid;
   const sj_tensor_map *tmap;
   const ScanParams *p;
-  int mode;  // 0 stage 1 pipelined, 1 stage 1 deferred, 2 minify
+  int mode;  // 0 stage 1, 2 minify, 3 validate_utf8 (utf8v2)
 };
 
 void *thread_main(void *arg);
@@ -54,7 +54,6 @@ void *thread_main(void *arg) {
   const uint32_t sa = uint32_t(reinterpret_cast<uintptr_t>(a->cta->smem));
   if (a->la->mode == 3) utf8v2::utf8_body(a->la->tmap, *a->la->p, a->cta->smem, sa);
   else if (a->la->mode == 2) scan4::scan4_body<2>(a->la->tmap, *a->la->p, a->cta->smem, sa);
-  else if (a->la->mode == 1) scan4::scan4_body<1>(a->la->tmap, *a->la->p, a->cta->smem, sa);
   else scan4::scan4_body<0>(a->la->tmap, *a->la->p, a->cta->smem, sa);
   return nullptr;
 }
@@ -91,7 +90,6 @@ void emu_launch(unsigned grid, const sj_tensor_map &tmap, const ScanParams &p, i
   }
 }
 
-bool g_deferred = false;  // which variant of the kernel the next launches run
 
 // what sjb200_capi.cu keeps per context
 struct EmuCtx {
@@ -132,8 +130,7 @@ Result run_scan4(EmuCtx &cx, const uint8_t *buf, size_t len, uint32_t state_in, 
     p.buf = buf; p.len = len; p.pos_base = 0; p.prev_word = 0x20202020u;
     p.check_eof = (tb + nt == ntiles_total) ? 1u : 0u;
     p.use_tma = tma_ok ? 1u : 0u;
-    p.tile_begin = tb; p.ntiles = nt; p.sub_per_super = 1; p.nsuper = nt;
-    p.full_tiles = uint32_t((len / 128) / kTileRows);
+    p.tile_begin = tb; p.ntiles = nt;
     p.epoch = ++cx.epoch;
     p.idx_out = r.idx.data(); p.dst = minify_dst;
     p.write_sentinels = (sentinels && !minify_dst && tb + nt == ntiles_total) ? 1u : 0u;
@@ -144,7 +141,7 @@ Result run_scan4(EmuCtx &cx, const uint8_t *buf, size_t len, uint32_t state_in, 
     const unsigned g = std::min<unsigned>(grid, (nt * unsigned(kTileBytes) + scan4::kElemBytes - 1) / scan4::kElemBytes);
     cx.park.assign(size_t(g) * scan4::kParkRing * scan4::kParkSlotWords + 8, 0xDEADBEEFu);
     p.park = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(cx.park.data()) + 15) & ~uintptr_t(15));
-    emu_launch(g, tmap, p, minify_dst ? 2 : (g_deferred ? 1 : 0));
+    emu_launch(g, tmap, p, minify_dst ? 2 : 0);
     if (cx.ticket[0] != 0 || cx.ticket[1] != 0 || cx.ticket[2] != 0 || cx.flags != 0) { fprintf(stderr, "BUG: ticket/flags not re-armed\n"); exit(2); }
     flags |= cx.carry[slot + 1].flags;
     slot++;
@@ -437,8 +434,7 @@ int main(int argc, char **argv) {
     if (reinterpret_cast<uintptr_t>(buf0.data()) & 15u) { fprintf(stderr, "unaligned vector storage\n"); return 3; }
     const unsigned grid = 1 + unsigned(rng() % 3);
     const uint32_t state_in = (force_state != 0xFFFFFFFFu) ? force_state : ((rng() % 3 == 0) ? uint32_t(rng() % 8) : 0u);
-    g_deferred = (it & 1) != 0;  // alternate between the pipelined and the deferred variant
-    check(cx, buf0, 0, state_in, 0, grid, true, g_deferred ? "tma, deferred" : "tma, pipelined");
+    check(cx, buf0, 0, state_in, 0, grid, true, "tma");
     if (it % 3 == 0) check(cx, buf0, 0, state_in, 1 + uint32_t(rng() % 3), grid, true, "chunked");
     if (it % 2 == 0) check_minify(cx, buf0, 0, (it % 6 == 0) ? 1 + uint32_t(rng() % 3) : 0, grid, it % 4 != 0, rng() % 17);
     if (it % 5 == 1 && buf0.size() > 3) check_minify(cx, buf0, 1 + rng() % 3, 0, grid, true, rng() % 17);

@@ -25,11 +25,6 @@ rc, p = impl.create_dom_parser_implementation(len(doc))
 assert rc == 0, rc
 p.set_option("time_kernel", 1)
 p.set_option("use_tma", int(os.environ.get("PROBE_TMA", 1)))
-if os.environ.get("PROBE_DEFERRED"):
-    p.set_option("deferred", int(os.environ["PROBE_DEFERRED"]))
-if os.environ.get("PROBE_KERNEL"):
-    p.set_option("kernel", int(os.environ["PROBE_KERNEL"]))
-    tag += "/k" + os.environ["PROBE_KERNEL"]
 if os.environ.get("PROBE_GRID"):
     p.set_option("grid", int(os.environ["PROBE_GRID"]))
 d = torch.from_numpy(doc).cuda()

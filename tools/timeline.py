@@ -17,12 +17,6 @@ doc = corpus.random_json(size).copy()
 rc, p = sj.get_active_implementation().create_dom_parser_implementation(len(doc))
 p.set_option("debug_timeline", 1)
 p.set_option("time_kernel", 1)
-if os.environ.get("PROBE_DEFERRED"):
-    p.set_option("deferred", int(os.environ["PROBE_DEFERRED"]))
-if os.environ.get("PROBE_KERNEL"):
-    p.set_option("kernel", int(os.environ["PROBE_KERNEL"]))
-if os.environ.get("PROBE_R"):
-    p.set_option("sub_per_super", int(os.environ["PROBE_R"]))
 d = torch.from_numpy(doc).cuda()
 for _ in range(3):
     p.stage1_device(d, 0)
