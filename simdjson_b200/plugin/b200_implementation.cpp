@@ -1,6 +1,8 @@
 // b200_implementation.cpp -- see b200_implementation.h
 #include "b200_implementation.h"
 
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <new>
 
@@ -61,6 +63,20 @@ const implementation *get_implementation(int device) noexcept {
                                          implementation(4), implementation(5), implementation(6), implementation(7)};
   return &singletons[(device >= 0 && device < 8) ? device : 0];
 }
+
+// Selection by name without touching the reference: simdjson resolves SIMDJSON_FORCE_IMPLEMENTATION against its own
+// static list (src/implementation.cpp L211-242, L303), which an out-of-tree implementation cannot join.  When this
+// library is loaded (linked or LD_PRELOADed) and the variable names "b200", it installs itself as the active
+// implementation before the first use -- simdjson then never consults the list
+// (get_active_implementation(), src/implementation.cpp L321-332).  SJB200_DEVICE picks the GPU (default 0).
+namespace {
+__attribute__((constructor)) void activate_if_forced() {
+  const char *forced = std::getenv("SIMDJSON_FORCE_IMPLEMENTATION");
+  if (forced == nullptr || std::strcmp(forced, "b200") != 0) return;
+  const char *dev = std::getenv("SJB200_DEVICE");
+  simdjson::get_active_implementation() = get_implementation(dev ? std::atoi(dev) : 0);
+}
+}  // namespace
 
 // ---------------------------------------------------------------- dom_parser_implementation
 dom_parser_implementation::~dom_parser_implementation() {

@@ -40,6 +40,13 @@ HARNESS_API const char *dropin_active_name(int use_b200) {
   return s.c_str();
 }
 
+// the implementation simdjson would use right now (no override by the harness)
+HARNESS_API const char *dropin_default_active_name() {
+  static thread_local std::string s;
+  s = get_active_implementation()->name();
+  return s.c_str();
+}
+
 // dom::parser::parse -> simdjson::minify(element).  gpu_calls reports how many stage-1 calls the parser's
 // implementation sent to the GPU (0 for a CPU implementation).
 HARNESS_API int dropin_dom_roundtrip(int use_b200, const uint8_t *buf, size_t len, char *out, size_t cap, size_t *out_len,

@@ -153,3 +153,21 @@ def test_ondemand_minify_utf8_dropin(h):
     for s in (b'"', b'{"a" : 1 , "b":[ 1, 2 ,3 ] }', b"", b" ", b"\xff", b"\xe2\x82", b'"\\"  "  x'):
         assert h.minify(1, s) == h.minify(0, s), s
         assert h.utf8(1, s) == h.utf8(0, s), s
+
+
+@needs_plugin
+def test_force_implementation_by_name():
+    """SIMDJSON_FORCE_IMPLEMENTATION=b200 selects the plug-in once its library is loaded (doc/implementation-selection.md;
+    src/implementation.cpp L303 resolves the name against a static list an out-of-tree implementation cannot join, so the
+    plug-in installs itself from a load-time constructor).  Needs no GPU: nothing is created."""
+    import subprocess
+    import sys
+    code = ("import ctypes as C; L = C.CDLL(%r); L.dropin_default_active_name.restype = C.c_char_p; "
+            "print(L.dropin_default_active_name().decode())" % PLUGIN)
+    for env_value, want_b200 in (("b200", True), (None, False)):
+        env = dict(os.environ)
+        env.pop("SIMDJSON_FORCE_IMPLEMENTATION", None)
+        if env_value:
+            env["SIMDJSON_FORCE_IMPLEMENTATION"] = env_value
+        out = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, text=True, timeout=120).stdout.strip()
+        assert (out == "b200") == want_b200, (env_value, out)
