@@ -1,9 +1,22 @@
 """Summarise one `ncu --set full` report into the JSON kept under profiles/ (the .ncu-rep itself stays in gpurun_out/).
 usage: python tools/ncu_summary.py gpurun_out/scan4_full.ncu-rep profiles/NAME.json"""
 import csv
+import hashlib
 import json
+import os
 import subprocess
 import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KERNEL_SOURCES = ["sjb200_scan4.cuh", "sjb200_bits.cuh", "sjb200_simt.cuh", "sjb200_params.h", "sjb200_kernels.cu", "sjb200_utf8.cuh"]  # same list as bench.py
+
+
+def kernel_source_hash():
+    h = hashlib.sha256()
+    for f in KERNEL_SOURCES:
+        with open(os.path.join(ROOT, "simdjson_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
 
 KEYS = [
     "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
@@ -23,7 +36,7 @@ def main(rep, out):
     hdr, units = rows[0], rows[1]
     res = []
     for vals in rows[2:]:
-        d = {"Kernel Name": vals[hdr.index("Kernel Name")]}
+        d = {"Kernel Name": vals[hdr.index("Kernel Name")], "kernel_src_sha16": kernel_source_hash()}
         for i, h in enumerate(hdr):
             if h in KEYS or ("issue_stalled" in h and h.endswith("per_issue_active.ratio")):
                 d[h] = [vals[i], units[i]]
