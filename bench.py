@@ -78,26 +78,30 @@ def kernel_source_hash():
     return h.hexdigest()[:16]
 
 
-def ncu_traffic(kernel="scan4"):
-    """DRAM bytes of one launch of the kernel on the bench document, from an `ncu --set full` capture under profiles/
-    -- reported ONLY when that capture was taken from the kernel sources this run was built from (the summary records
-    their hash); otherwise null: a stale constant is worse than no number."""
+def ncu_traffic(kernel="scan4_kernel"):
+    """DRAM bytes of one launch of the kernel (substring of its name) on the bench document, from an `ncu --set full`
+    capture summarised under profiles/ -- reported ONLY when that capture was taken from the kernel sources this run was
+    built from (the summary records their hash); otherwise null: a stale constant is worse than no number."""
     want = kernel_source_hash()
     best = None
     pdir = os.path.join(ROOT, "profiles")
     for name in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
-        if not (name.endswith("_ncu_full.json") and kernel in name):
+        if not name.endswith("_ncu_full.json"):
             continue
         try:
             d = json.load(open(os.path.join(pdir, name)))
-            if d.get("kernel_src_sha16") != want:
-                continue
-            unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-            tot = 0.0
-            for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                v, u = d[k]
-                tot += float(v) * unit[u]
-            best = (int(tot), os.path.join("profiles", name))
+            for e in (d if isinstance(d, list) else [d]):
+                kn = e.get("Kernel Name", "")
+                if (kernel + "(") not in kn and not kn.startswith(kernel) and ("::" + kernel + "(") not in kn:
+                    continue
+                if e.get("kernel_src_sha16") != want:
+                    continue
+                unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                tot = 0.0
+                for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    v, u = e[k]
+                    tot += float(v) * unit[u]
+                best = (int(tot), os.path.join("profiles", name))
         except Exception:  # noqa: BLE001
             continue
     return best if best else (None, f"no ncu capture of kernel sources {want} under profiles/")
@@ -425,7 +429,7 @@ def run_ours(args, rank, world):
         nmean = float(np.mean(n_struct))
         algo_bytes = DOC_BYTES + 4.0 * nmean + 12.0
         achieved = algo_bytes / (kms * 1e-3) / 1e9
-        traffic, traffic_src = ncu_traffic("scan4")
+        traffic, traffic_src = ncu_traffic("scan4_kernel")
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
