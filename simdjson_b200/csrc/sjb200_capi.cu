@@ -88,6 +88,7 @@ struct sjb200_ctx {
   std::vector<cudaEvent_t> ring_events;
   CopyPool *pool = nullptr;
   long opt_force_grid = 0;
+  long opt_host_skip_scan = 0;  // tuning: the host-pointer pipeline copies only (no scan launches; results are meaningless)
   long opt_copy_threads = 4;        // 0: no staging (cudaMemcpyAsync straight from the caller's memory)
   long opt_ring_slots = 8;
   long opt_first_chunk_bytes = 512 << 10;  // first chunk of the host-pointer pipeline; the following ones double up to chunk_bytes
@@ -489,6 +490,7 @@ extern "C" int sjb200_set_option(sjb200_ctx *c, const char *key, long value) {
   else if (!strcmp(key, "debug_timeline")) c->opt_debug_timeline = value;
   else if (!strcmp(key, "chunk_bytes")) c->opt_chunk_bytes = std::max<long>(2 * kTileBytes, (value / (2 * kTileBytes)) * (2 * kTileBytes));
   else if (!strcmp(key, "force_grid")) c->opt_force_grid = value;
+  else if (!strcmp(key, "host_skip_scan")) c->opt_host_skip_scan = value;
   else if (!strcmp(key, "copy_threads")) c->opt_copy_threads = std::max<long>(0, std::min<long>(value, 64));
   else if (!strcmp(key, "ring_slots")) c->opt_ring_slots = std::max<long>(2, std::min<long>(value, 64));
   else if (!strcmp(key, "stage_min_bytes")) c->opt_stage_min_bytes = std::max<long>(0, value);
@@ -876,6 +878,7 @@ bool scan_host_document(sjb200_ctx *c, int kind, const uint8_t *buf, size_t len,
         !ok(c, cudaEventRecord(copied, c->copy_stream), "event record") || !ok(c, cudaStreamWaitEvent(c->stream, copied, 0), "wait event"))
       return false;
     const bool last = (k + 1 == nchunks);
+    if (c->opt_host_skip_scan) return true;
     if (!enqueue_scan(c, kind, &map, tma, c->d_in, len, uint32_t(off / kTileBytes), tiles_of(bytes), last, 0x20202020u, d_idx, d_dst,
                       k == 0 ? -1 : int(k), c->stream, int(k + 1), false, nullptr, c->h_carry + k + 1))
       return false;
