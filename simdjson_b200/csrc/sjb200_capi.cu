@@ -900,15 +900,14 @@ bool scan_host_document(sjb200_ctx *c, int kind, const uint8_t *buf, size_t len,
     c->t_wait_ms = c->t_issue_ms = c->t_sync_ms = 0;
     auto t_mark = now();
     while (good && issued < nchunks) {
-      while (released < issued && cudaEventQuery(c->ring_events[released % size_t(slots)]) == cudaSuccess) {
+      while (released < issued && cudaEventQuery(c->chunk_events[2 * released]) == cudaSuccess) {  // (the chunk's "copied" event: one event per copy on the copy stream)
         released++;
         pool.allow(released + size_t(slots));
       }
       if (pool.chunk_ready(issued)) {
         c->t_wait_ms += ms_since(t_mark);
         t_mark = now();
-        good = launch_chunk(issued, c->h_ring + (issued % size_t(slots)) * c->ring_slot_bytes) &&
-               ok(c, cudaEventRecord(c->ring_events[issued % size_t(slots)], c->copy_stream), "event record");
+        good = launch_chunk(issued, c->h_ring + (issued % size_t(slots)) * c->ring_slot_bytes);
         c->t_issue_ms += ms_since(t_mark);
         t_mark = now();
         issued++;
