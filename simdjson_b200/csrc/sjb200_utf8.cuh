@@ -6,9 +6,9 @@
 // UTF-8 validity needs no scan: byte i is judged from bytes i-3..i (SURVEY.md 8(a) equivalence note).  So this kernel has
 // no chain, no tickets and no CTA-wide barrier: warp g of the launch takes blocks g, g + G, g + 2G, ... (neighbouring
 // warps read neighbouring 4 KiB blocks), each through its own two-slot TMA ring (cp.async.bulk.tensor, 32 rows x 128 B,
-// 128B-swizzled: lane L owns row L and reads it with conflict-free LDS.128), the next block always in flight.  A lane
-// looks at its 128 bytes as four 32-byte units: a unit without a byte >= 0x80 in any lane (and nothing pending) costs
-// ~8 instructions, any other unit is transposed into bit planes and checked with the boolean rules of sjb200_bits.cuh.
+// 128B-swizzled: lane L owns row L and reads it with conflict-free LDS.128), the next block always in flight.  One
+// vote per block: without a byte >= 0x80 in any lane a block costs ~50 instructions; otherwise the lane's four 32-byte
+// units are transposed into bit planes and checked with the boolean rules of sjb200_bits.cuh, without further votes.
 // The three bytes before a lane's row come from the row before it (shared memory), those before a block from global
 // memory (one word, loaded one block ahead).  Errors are OR-ed in a register and reach memory once per warp.
 //
@@ -40,26 +40,32 @@ struct SmemU {
 };
 constexpr int kSmemBytesU = int(sizeof(SmemU)) + 1024;
 
-// one block: returns the OR of the error masks of the lane's four units
+// one block: returns the OR of the error masks of the lane's four units.  One vote per block: a block without a byte
+// >= 0x80 in any lane needs only the look at the four bytes before it; any other block is checked unit by unit without
+// further votes (on multi-byte text nearly every unit of a warp holds a non-ASCII byte somewhere).
 SJ_DEV uint32_t check_block(const uint8_t *T, uint32_t pw0, unsigned lane) {
   const uint32_t lane_off = lane * 128u;
+  uint32_t w[32];
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    const sj_u4 v = *reinterpret_cast<const sj_u4 *>(T + scan4::swz(lane_off + 16u * c));
+    w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+  }
+  uint32_t hi = 0;
+#pragma unroll
+  for (int i = 0; i < 32; i++) hi |= w[i];
+  if (!sj_any((hi & 0x80808080u) != 0)) {
+    // only the block before this one can have left a sequence open: it ends in ASCII here, which is an error
+    return (lane == 0 && utf8_carry_pending(utf8_carry_from_prev_word(pw0))) ? 1u : 0u;
+  }
   const uint32_t pw = (lane == 0) ? pw0 : *reinterpret_cast<const uint32_t *>(T + scan4::swz(lane_off - 4));
   utf8_carry uc = utf8_carry_from_prev_word(pw);
-  uint32_t pend = utf8_carry_pending(uc) ? 1u : 0u;
   uint32_t err = 0;
 #pragma unroll
   for (int u = 0; u < 4; u++) {
-    uint32_t w8[8];
-    scan4::load_unit(T, lane_off + 32u * u, w8);
-    const uint32_t hi = (w8[0] | w8[1] | w8[2] | w8[3] | w8[4] | w8[5] | w8[6] | w8[7]) & 0x80808080u;
-    if (sj_any((hi | pend) != 0)) {
-      uint32_t pl[8];
-      transpose32(w8, pl);
-      err |= utf8_check_unit(pl, uc);
-      pend = (uc.n1 >> 31) | (uc.n2 >> 30) | (uc.n3 >> 29);
-    } else {
-      uc = utf8_carry_zero();
-    }
+    uint32_t pl[8];
+    transpose32(w + 8 * u, pl);
+    err |= utf8_check_unit(pl, uc);
   }
   return err;
 }
