@@ -560,44 +560,56 @@ SJ_DEV void emit_from_smem(Smem *S, const ScanParams &p, uint64_t out_base, uint
 SJ_DEV uint32_t *park_slot(const ScanParams &p, uint32_t e) { return p.park + (size_t(sj_cta()) * kParkRing + (e % uint32_t(kParkRing))) * size_t(kParkSlotWords); }
 
 // ------------------------------------------------------------------------------------------------ minify: emit one block
-// kept bytes of a 4-byte word packed to its low end: PRMT selector (unused positions select a zero byte) | count << 16
+// kept bytes of a 4-byte word packed to its low end: the PRMT selector (unused positions select a zero byte)
 // (computed once per CTA into shared memory: 16 words in 16 banks, any mix of nibbles across the lanes is one access)
 SJ_DEV uint32_t compact_entry(uint32_t nib) {
   uint32_t sel = 0, cnt = 0;
   for (uint32_t b = 0; b < 4; b++)
     if ((nib >> b) & 1u) { sel |= b << (4 * cnt); cnt++; }
   for (uint32_t i = cnt; i < 4; i++) sel |= 4u << (4 * i);
-  return sel | (cnt << 16);
+  return sel;
 }
 
-// Block `warp` of this CTA's e-th element (resolved): fetch its bytes again (they are two scans old, still in L2) into
-// `slot`, pull the lane's row into registers, turn the slot into the staging area, pack the kept bytes of every word
-// with one PRMT, merge them into a running word with another, OR complete words into the (zeroed) staging area
-// (lanes share the words at their seams), and store the block's output as aligned 16-byte vectors.
-// Returns true when the slot's mbarrier completed a phase (the caller tracks parities).
+// minify: start fetching block `warp` of this CTA's e-th element again (two scans old, still in L2) into `slot`.
+// Returns true when it comes by TMA (completes `bar`); otherwise emit_minify_block fills the slot itself.
+SJ_DEV bool minify_fetch_issue(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, uint32_t e, unsigned warp, unsigned lane, uint8_t *slot, sj_mbar_t *bar,
+                               uint64_t launch_start) {
+  const uint64_t bstart = launch_start + uint64_t(S->ticket[e % kNS]) * kElemBytes + uint64_t(warp) * kBlockBytes;
+  const uint64_t row = bstart / 128;
+  const bool by_tma = p.use_tma && (row + kBlockRows <= p.len / 128);
+  sj_syncwarp();  // every lane is done with the slot
+  if (by_tma && lane == 0) {
+    sj_fence_proxy_async();
+    sj_mbar_arrive_expect_tx(bar, kBlockBytes);
+    sj_tma_load_rows(slot, tmap, bar, uint32_t(row));
+  }
+  return by_tma;
+}
+
+// Block `warp` of this CTA's e-th element (resolved): with its bytes back in `slot` (fetched < 0: not asked for yet;
+// 0 / 1: minify_fetch_issue ran and returned that), pull the lane's row into registers, turn the slot into the staging
+// area, pack the kept bytes of every word with one PRMT (independent look-ups), then string the packed words together
+// -- a shift, an OR and a select per word on the critical path -- storing complete words into the staging area (the
+// words at a lane's seams are OR-ed into the zeroed area, lanes share them), and store the block's output as aligned
+// 16-byte vectors.  Returns true when the slot's mbarrier completed a phase (the caller tracks parities).
 SJ_DEV bool emit_minify_block(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, uint64_t out_base, uint32_t e, unsigned warp, unsigned lane,
-                              const sj_u4 kv, uint32_t prew, uint8_t *slot, sj_mbar_t *bar, uint32_t parity, uint64_t launch_start) {
+                              const sj_u4 kv, uint32_t prew, uint8_t *slot, sj_mbar_t *bar, uint32_t parity, uint64_t launch_start, int fetched = -1) {
   const int ns = int(e % kNS);
   const uint32_t sum = S->summary[ns][warp];
   const uint32_t pol = S->res_pol[ns][warp] & 1u;
   const uint32_t total = pol ? ((sum >> 16) & 0x1FFFu) : (sum & 0xFFFFu);
-  if (total == 0) return false;
+  if (fetched < 0 && total == 0) return false;
   const uint32_t elem = S->ticket[ns];
   const uint64_t bstart = launch_start + uint64_t(elem) * kElemBytes + uint64_t(warp) * kBlockBytes;
-  const uint64_t row = bstart / 128;
-  const bool by_tma = p.use_tma && (row + kBlockRows <= p.len / 128);
-  sj_syncwarp();
+  const bool by_tma = fetched < 0 ? minify_fetch_issue(S, tmap, p, e, warp, lane, slot, bar, launch_start) : fetched != 0;
   if (by_tma) {
-    if (lane == 0) {
-      sj_fence_proxy_async();
-      sj_mbar_arrive_expect_tx(bar, kBlockBytes);
-      sj_tma_load_rows(slot, tmap, bar, uint32_t(row));
-    }
     wait_bar(bar, parity, p, 32);
   } else {
+    if (total == 0) return false;
     fill_block_guarded(slot, p, bstart, lane);
     sj_syncwarp();
   }
+  if (total == 0) return by_tma;
   uint32_t w[32];
 #pragma unroll
   for (int c = 0; c < 8; c++) {
@@ -611,27 +623,29 @@ SJ_DEV bool emit_minify_block(Smem *S, const sj_tensor_map *tmap, const ScanPara
   uint32_t *stg = reinterpret_cast<uint32_t *>(slot);
   const uint32_t off = (prew >> (16 * pol)) & 0xFFFFu;  // bytes of the block's output before this lane's
   const uint32_t keep[4] = {kv.x, kv.y, kv.z, kv.w};
-  uint32_t carry = 0, fill = off & 3u, wp = off >> 2;
+  // kept bytes per word: the nibble popcounts of the keep masks (0..4 each)
+  uint32_t cn[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) cn[q] = keep[q] - ((keep[q] >> 1) & 0x77777777u) - ((keep[q] >> 2) & 0x33333333u) - ((keep[q] >> 3) & 0x11111111u);
+#pragma unroll
+  for (int i = 0; i < 32; i++) w[i] = byte_perm(w[i], 0u, S->compact_lut[(keep[i >> 3] >> (4 * (i & 7))) & 15u]);
+  // carry holds sh/8 bytes at its low end (zero above them)
+  const uint32_t wp0 = off >> 2;
+  uint32_t carry = 0, sh = 8u * (off & 3u), wp = wp0;
 #pragma unroll
   for (int i = 0; i < 32; i++) {
-    const uint32_t ent = S->compact_lut[(keep[i >> 3] >> (4 * (i & 7))) & 15u];
-    const uint32_t comp = byte_perm(w[i], 0u, ent & 0xFFFFu);
-    const uint32_t cnt = ent >> 16;
-    // merged: the `fill` bytes waiting in carry, then the first bytes of comp
-    const uint32_t msel = uint32_t(0x4210541065407654ull >> (16 * fill)) & 0xFFFFu;
-    const uint32_t merged = byte_perm(carry, comp, msel);
-    const uint32_t tot = fill + cnt;
-    if (tot >= 4) {
-      sj_atomic_or(stg + wp, merged);
+    const uint32_t c8 = (i & 7) == 0 ? (cn[i >> 3] << 3) & 0x38u : (cn[i >> 3] >> (4 * (i & 7) - 3)) & 0x38u;  // 8 * kept bytes of word i
+    const uint32_t merged = carry | (w[i] << sh);
+    const uint32_t tot = sh + c8;
+    if (tot >= 32u) {
+      if (wp == wp0) sj_atomic_or(stg + wp, merged);  // may hold bytes of the lanes before this one
+      else stg[wp] = merged;
       wp++;
-      carry = fill ? (comp >> (8 * (4 - fill))) : 0u;
-      fill = tot - 4;
-    } else {
-      carry = merged;
-      fill = tot;
     }
+    carry = tot >= 32u ? sj_funnel_l(w[i], 0u, int(sh)) : merged;  // sh = 0: nothing of w[i] is left over
+    sh = tot & 31u;
   }
-  if (fill) sj_atomic_or(stg + wp, carry);
+  if (sh) sj_atomic_or(stg + wp, carry);
   sj_syncwarp();
   // ---- copy-out: the destination's 16-byte groups, whatever its alignment
   uint8_t *dst = p.dst + (out_base + S->res_base[ns][warp]);
@@ -812,6 +826,10 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
       }
     }
     if (!SJB200_SCAN4_TRACE && p.debug != nullptr && warp == 0 && lane == 0) p.debug[uint64_t(t) * 8 + 1] = sj_globaltimer();
+    // minify: the slot just scanned is free -- ask for the block that is emitted below now, the fetch (L2) runs while the
+    // element is composed and resolved
+    int fetched = -1;
+    if (kMin && !kEmitW && j >= uint32_t(kLag)) fetched = minify_fetch_issue(S, tmap, p, ne, warp, lane, T, &S->full[warp][r], launch_start) ? 1 : 0;
     SJ_TRACE4(5);
     {
       const int ns = int(j % kNS);
@@ -840,7 +858,7 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
       if (kMin) {
         const uint32_t pol = S->res_pol[ne % kNS][warp] & 1u;
         if (emit_minify_block(S, tmap, p, out_base, ne, warp, lane, S->park[kGPark > 0 ? 0 : ne % kPark][pol][kGPark > 0 ? 0 : warp * 32 + lane], S->parkpre[kGPark > 0 ? 0 : ne % kPark][kGPark > 0 ? 0 : warp * 32 + lane], T,
-                              &S->full[warp][r], (full_phase >> r) & 1u, launch_start))
+                              &S->full[warp][r], (full_phase >> r) & 1u, launch_start, fetched))
           full_phase ^= 1u << r;
       } else {
         emit_from_smem(S, p, out_base, ne, warp, lane, reinterpret_cast<uint32_t *>(T));
