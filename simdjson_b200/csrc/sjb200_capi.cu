@@ -202,7 +202,6 @@ bool make_tensor_map(sjb200_ctx *c, CUtensorMap *map, const uint8_t *d_buf, size
 
 // stage 1 and minify run on the scan4 structure (sjb200_scan4.cuh), validate_utf8 on utf8v2 (sjb200_utf8.cuh)
 bool use_scan4(const sjb200_ctx *, int kind) { return kind == kIndex || kind == kMinify; }
-bool use_utf8v2(const sjb200_ctx *, int kind) { return kind == kUtf8; }
 // the one tensor map the kernel selected for `kind` reads through (scan4: 4 KiB boxes; the tile-synchronous kernels: 32 KiB)
 bool map_for(sjb200_ctx *c, int kind, CUtensorMap *map, const uint8_t *d_buf, size_t len, bool *usable) {
   (void)kind;  // every kernel reads 4 KiB boxes of 32 rows

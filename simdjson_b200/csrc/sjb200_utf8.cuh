@@ -5,8 +5,9 @@
 //
 // UTF-8 validity needs no scan: byte i is judged from bytes i-3..i (SURVEY.md 8(a) equivalence note).  So this kernel has
 // no chain, no tickets and no CTA-wide barrier: warp g of the launch takes blocks g, g + G, g + 2G, ... (neighbouring
-// warps read neighbouring 4 KiB blocks), each through its own two-slot TMA ring (cp.async.bulk.tensor, 32 rows x 128 B,
-// 128B-swizzled: lane L owns row L and reads it with conflict-free LDS.128), the next block always in flight.  One
+// warps read neighbouring 4 KiB blocks), each through its own three-slot TMA ring (cp.async.bulk.tensor, 32 rows x 128 B,
+// 128B-swizzled: lane L owns row L and reads it with conflict-free LDS.128), the next two blocks always in flight
+// (with one block in flight per warp the kernel was bound by the load latency: ASCII and multi-byte text took the same time).  One
 // vote per block: without a byte >= 0x80 in any lane a block costs ~50 instructions; otherwise the lane's four 32-byte
 // units are transposed into bit planes and checked with the boolean rules of sjb200_bits.cuh, without further votes.
 // The three bytes before a lane's row come from the row before it (shared memory), those before a block from global
@@ -23,20 +24,24 @@ namespace sjb200 {
 namespace utf8v2 {
 
 #ifndef SJB200_UTF8_WARPS
-#define SJB200_UTF8_WARPS 8
+#define SJB200_UTF8_WARPS 6
 #endif
 #ifndef SJB200_UTF8_CTAS
 #define SJB200_UTF8_CTAS 3
 #endif
+#ifndef SJB200_UTF8_SLOTS
+#define SJB200_UTF8_SLOTS 3
+#endif
 constexpr int kWarpsU = SJB200_UTF8_WARPS;      // warps per CTA
-constexpr int kCtasPerSmU = SJB200_UTF8_CTAS;   // CTAs per SM the launch bounds aim for (8 KiB of shared memory per warp)
+constexpr int kCtasPerSmU = SJB200_UTF8_CTAS;   // CTAs per SM the launch bounds aim for
+constexpr int kSlotsU = SJB200_UTF8_SLOTS;      // ring slots per warp: kSlotsU - 1 blocks in flight while one is checked
 constexpr int kThreadsU = 32 * kWarpsU;
 constexpr int kBlockBytesU = scan4::kBlockBytes;  // 4 KiB = one TMA box of 32 rows
 constexpr int kBlockRowsU = scan4::kBlockRows;
 
 struct SmemU {
-  uint8_t ring[kWarpsU][2][kBlockBytesU];
-  sj_mbar_t full[kWarpsU][2];
+  uint8_t ring[kWarpsU][kSlotsU][kBlockBytesU];
+  sj_mbar_t full[kWarpsU][kSlotsU];
 };
 constexpr int kSmemBytesU = int(sizeof(SmemU)) + 1024;
 
@@ -74,8 +79,7 @@ SJ_DEV void utf8_body(const sj_tensor_map *tmap, const ScanParams &p, uint8_t *s
   SmemU *S = reinterpret_cast<SmemU *>(smem_raw + ((1024u - (smem_raw_addr & 1023u)) & 1023u));
   const unsigned tid = sj_tid(), lane = tid & 31u, warp = tid >> 5;
   if (lane == 0) {
-    sj_mbar_init(&S->full[warp][0], 1);
-    sj_mbar_init(&S->full[warp][1], 1);
+    for (int r = 0; r < kSlotsU; r++) sj_mbar_init(&S->full[warp][r], 1);
     sj_fence_mbar_init();
   }
   sj_syncwarp();
@@ -103,25 +107,39 @@ SJ_DEV void utf8_body(const sj_tensor_map *tmap, const ScanParams &p, uint8_t *s
     }
     return full;
   };
-  uint32_t pw_cur = 0x20202020u, pw_next = 0x20202020u;
-  bool tma_cur = false, tma_next = false;
-  uint64_t b = g;
-  if (b < nblocks) tma_cur = issue(b, 0, &pw_cur);
-  for (uint32_t it = 0; b < nblocks; it++, b += G) {
-    const int r = int(it & 1u);
-    const uint64_t bn = b + G;
-    if (bn < nblocks) tma_next = issue(bn, r ^ 1, &pw_next);
+  // the loads of the next kSlotsU - 1 blocks are always in flight; q = 0 is the block checked next
+  uint32_t pwq[kSlotsU - 1];
+  bool tmaq[kSlotsU - 1];
+#pragma unroll
+  for (int q = 0; q < kSlotsU - 1; q++) {
+    pwq[q] = 0x20202020u;
+    tmaq[q] = false;
+    if (g + uint64_t(q) * G < nblocks) tmaq[q] = issue(g + uint64_t(q) * G, q, &pwq[q]);
+  }
+  uint32_t r = 0, rn = kSlotsU - 1;  // slot of the block checked next / of the block asked for next
+  for (uint64_t b = g; b < nblocks; b += G) {
+    const uint64_t bn = b + uint64_t(kSlotsU - 1) * G;
+    uint32_t pw_new = 0x20202020u;
+    bool tma_new = false;
+    if (bn < nblocks) tma_new = issue(bn, int(rn), &pw_new);
     uint8_t *T = S->ring[warp][r];
-    if (tma_cur) {
+    if (tmaq[0]) {
       scan4::wait_bar(&S->full[warp][r], (phase >> r) & 1u, p, 32);
       phase ^= 1u << r;
     } else {
       scan4::fill_block_guarded(T, p, launch_start + b * kBlockBytesU, lane);
       sj_syncwarp();
     }
-    err |= check_block(T, sj_shfl(pw_cur, 0), lane);
-    tma_cur = tma_next;
-    pw_cur = pw_next;
+    err |= check_block(T, sj_shfl(pwq[0], 0), lane);
+#pragma unroll
+    for (int q = 0; q + 1 < kSlotsU - 1; q++) {
+      pwq[q] = pwq[q + 1];
+      tmaq[q] = tmaq[q + 1];
+    }
+    pwq[kSlotsU - 2] = pw_new;
+    tmaq[kSlotsU - 2] = tma_new;
+    r = (r + 1 == uint32_t(kSlotsU)) ? 0u : r + 1;
+    rn = (rn + 1 == uint32_t(kSlotsU)) ? 0u : rn + 1;
   }
   if (p.check_eof && g == 0 && lane == 0) {  // utf8_checker::check_eof (utf8_lookup4_algorithm.h L167-171): input must not end inside a sequence
     if (utf8_carry_pending(utf8_carry_from_prev_word(scan4::word_before(p, p.len)))) err |= 1u;
