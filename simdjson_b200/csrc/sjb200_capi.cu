@@ -168,17 +168,6 @@ bool next_epoch(sjb200_ctx *c, cudaStream_t launch_stream, uint32_t *epoch) {
   return true;
 }
 
-bool ensure_host_scratch(sjb200_ctx *c, uint8_t **p, size_t *have, size_t need) {
-  if (*have >= need) return true;
-  if (*p) cudaFreeHost(*p);
-  *p = nullptr; *have = 0;
-  void *q = nullptr;
-  if (!ok(c, cudaMallocHost(&q, need), "cudaMallocHost")) return false;
-  *p = static_cast<uint8_t *>(q);
-  *have = need;
-  return true;
-}
-
 bool make_tensor_map(sjb200_ctx *c, CUtensorMap *map, const uint8_t *d_buf, size_t len, bool *usable, int box_rows = kScan4BoxRows) {
   memset(map, 0, sizeof(*map));
   *usable = false;

@@ -620,7 +620,6 @@ SJ_DEV bool emit_minify_block(Smem *S, const sj_tensor_map *tmap, const ScanPara
 #pragma unroll
   for (int c = 0; c < 8; c++) *reinterpret_cast<sj_u4 *>(slot + lane * 128u + 16u * c) = sj_make_u4(0, 0, 0, 0);
   sj_syncwarp();
-  uint32_t *stg = reinterpret_cast<uint32_t *>(slot);
   const uint32_t off = (prew >> (16 * pol)) & 0xFFFFu;  // bytes of the block's output before this lane's
   const uint32_t keep[4] = {kv.x, kv.y, kv.z, kv.w};
   // kept bytes per word: the nibble popcounts of the keep masks (0..4 each)
@@ -638,31 +637,40 @@ SJ_DEV bool emit_minify_block(Smem *S, const sj_tensor_map *tmap, const ScanPara
     const uint32_t merged = carry | (w[i] << sh);
     const uint32_t tot = sh + c8;
     if (tot >= 32u) {
-      if (wp == wp0) sj_atomic_or(stg + wp, merged);  // may hold bytes of the lanes before this one
-      else stg[wp] = merged;
+      uint32_t *q = reinterpret_cast<uint32_t *>(slot + swz(4u * wp));
+      if (wp == wp0) sj_atomic_or(q, merged);  // may hold bytes of the lanes before this one
+      else *q = merged;
       wp++;
     }
     carry = tot >= 32u ? sj_funnel_l(w[i], 0u, int(sh)) : merged;  // sh = 0: nothing of w[i] is left over
     sh = tot & 31u;
   }
-  if (sh) sj_atomic_or(stg + wp, carry);
+  if (sh) sj_atomic_or(reinterpret_cast<uint32_t *>(slot + swz(4u * wp)), carry);
   sj_syncwarp();
-  // ---- copy-out: the destination's 16-byte groups, whatever its alignment
+  // ---- copy-out: the destination's 16-byte groups, whatever its alignment.  The staging area is swizzled like a block
+  // image (16-byte groups of a 128-byte row XOR-ed with the row number): a lane's output is ~24 words on this kind of
+  // input, and with a linear layout the lanes' stores above would hit the same 4 banks 8 at a time.
   uint8_t *dst = p.dst + (out_base + S->res_base[ns][warp]);
-  const uint8_t *stgb = slot;
   const uint32_t a = uint32_t(reinterpret_cast<uintptr_t>(dst) & 15u);
   const uint32_t head = (total < ((16u - a) & 15u)) ? total : ((16u - a) & 15u);
   const uint32_t nvec = (total - head) >> 4;
   const uint32_t tail = total - head - (nvec << 4);
-  if (lane < head) dst[lane] = stgb[lane];
+  if (lane < head) dst[lane] = slot[swz(lane)];
+  const uint32_t hw = head >> 2;
+  const int hs = int(8u * (head & 3u));
   for (uint32_t i = lane; i < nvec; i += 32) {
-    const uint32_t sb = head + 16u * i;       // staging byte offset of this vector (any alignment)
-    const uint32_t w0 = sb >> 2, sh = 8u * (sb & 3u);
-    const uint32_t x0 = stg[w0], x1 = stg[w0 + 1], x2 = stg[w0 + 2], x3 = stg[w0 + 3];
-    const uint32_t x4 = sh ? stg[w0 + 4] : 0u;  // (w0 + 4 <= 1023 whenever it is needed)
-    *reinterpret_cast<sj_u4 *>(dst + sb) = sj_make_u4(sj_funnel_r(x0, x1, int(sh)), sj_funnel_r(x1, x2, int(sh)), sj_funnel_r(x2, x3, int(sh)), sj_funnel_r(x3, x4, int(sh)));
+    // output vector i = staging bytes [head + 16 i, head + 16 i + 16): inside the aligned groups i and i + 1
+    const sj_u4 A = *reinterpret_cast<const sj_u4 *>(slot + swz(16u * i));
+    sj_u4 B = A;
+    if (head) B = *reinterpret_cast<const sj_u4 *>(slot + swz(16u * i + 16u));  // (exists: head + 16 i + 16 <= total <= 4096)
+    uint32_t x0, x1, x2, x3, x4;
+    if (hw == 0) { x0 = A.x; x1 = A.y; x2 = A.z; x3 = A.w; x4 = B.x; }
+    else if (hw == 1) { x0 = A.y; x1 = A.z; x2 = A.w; x3 = B.x; x4 = B.y; }
+    else if (hw == 2) { x0 = A.z; x1 = A.w; x2 = B.x; x3 = B.y; x4 = B.z; }
+    else { x0 = A.w; x1 = B.x; x2 = B.y; x3 = B.z; x4 = B.w; }
+    *reinterpret_cast<sj_u4 *>(dst + head + 16u * i) = sj_make_u4(sj_funnel_r(x0, x1, hs), sj_funnel_r(x1, x2, hs), sj_funnel_r(x2, x3, hs), sj_funnel_r(x3, x4, hs));
   }
-  if (lane < tail) dst[head + (nvec << 4) + lane] = stgb[head + (nvec << 4) + lane];
+  if (lane < tail) dst[head + (nvec << 4) + lane] = slot[swz(head + (nvec << 4) + lane)];
   sj_syncwarp();
   if (p.debug != nullptr && warp == 0 && lane == 0) p.debug[uint64_t(elem) * 8 + 5] = sj_globaltimer();
   return by_tma;

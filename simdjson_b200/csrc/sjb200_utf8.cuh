@@ -98,12 +98,12 @@ SJ_DEV void utf8_body(const sj_tensor_map *tmap, const ScanParams &p, uint8_t *s
     const bool full = p.use_tma && (row + kBlockRowsU <= p.len / 128);
     sj_syncwarp();  // every lane is done with the slot
     if (lane == 0) {
-      *pw = scan4::word_before(p, bstart);
       if (full) {
         sj_fence_proxy_async();
         sj_mbar_arrive_expect_tx(&S->full[warp][r], kBlockBytesU);
         sj_tma_load_rows(S->ring[warp][r], tmap, &S->full[warp][r], uint32_t(row));
       }
+      *pw = scan4::word_before(p, bstart);  // after the fence: it would wait for this load
     }
     return full;
   };
