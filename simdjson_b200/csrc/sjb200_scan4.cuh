@@ -628,24 +628,25 @@ SJ_DEV bool emit_minify_block(Smem *S, const sj_tensor_map *tmap, const ScanPara
   for (int q = 0; q < 4; q++) cn[q] = keep[q] - ((keep[q] >> 1) & 0x77777777u) - ((keep[q] >> 2) & 0x33333333u) - ((keep[q] >> 3) & 0x11111111u);
 #pragma unroll
   for (int i = 0; i < 32; i++) w[i] = byte_perm(w[i], 0u, S->compact_lut[(keep[i >> 3] >> (4 * (i & 7))) & 15u]);
-  // carry holds sh/8 bytes at its low end (zero above them)
-  const uint32_t wp0 = off >> 2;
-  uint32_t carry = 0, sh = 8u * (off & 3u), wp = wp0;
+  // carry holds sh/8 bytes at its low end (zero above them).  No branches: the first word a lane completes (it may hold
+  // bytes of the lanes before it) is kept in a register and OR-ed in after the loop, every other one is a plain store.
+  const uint32_t wa0 = off & ~3u;  // byte offset of the first word this lane contributes to
+  uint32_t carry = 0, sh = 8u * (off & 3u), wa = wa0, first = 0;
 #pragma unroll
   for (int i = 0; i < 32; i++) {
     const uint32_t c8 = (i & 7) == 0 ? (cn[i >> 3] << 3) & 0x38u : (cn[i >> 3] >> (4 * (i & 7) - 3)) & 0x38u;  // 8 * kept bytes of word i
     const uint32_t merged = carry | (w[i] << sh);
     const uint32_t tot = sh + c8;
-    if (tot >= 32u) {
-      uint32_t *q = reinterpret_cast<uint32_t *>(slot + swz(4u * wp));
-      if (wp == wp0) sj_atomic_or(q, merged);  // may hold bytes of the lanes before this one
-      else *q = merged;
-      wp++;
-    }
-    carry = tot >= 32u ? sj_funnel_l(w[i], 0u, int(sh)) : merged;  // sh = 0: nothing of w[i] is left over
+    const bool done = tot >= 32u;
+    const bool is_first = wa == wa0;
+    if (done && !is_first) *reinterpret_cast<uint32_t *>(slot + swz(wa)) = merged;
+    first = (done && is_first) ? merged : first;
+    carry = done ? sj_funnel_l(w[i], 0u, int(sh)) : merged;  // sh = 0: nothing of w[i] is left over
+    wa += done ? 4u : 0u;
     sh = tot & 31u;
   }
-  if (sh) sj_atomic_or(reinterpret_cast<uint32_t *>(slot + swz(4u * wp)), carry);
+  if (wa != wa0) sj_atomic_or(reinterpret_cast<uint32_t *>(slot + swz(wa0)), first);
+  if (sh) sj_atomic_or(reinterpret_cast<uint32_t *>(slot + swz(wa)), carry);
   sj_syncwarp();
   // ---- copy-out: the destination's 16-byte groups, whatever its alignment.  The staging area is swizzled like a block
   // image (16-byte groups of a 128-byte row XOR-ed with the row number): a lane's output is ~24 words on this kind of
