@@ -340,8 +340,24 @@ def run_check(args, rank, world, total=256 << 20):
     port = O.Port()
     nranks = world if world > 1 else max(2, args.gpus if args.gpus > 1 else 4)
     doc = corpus.ndjson_rows(total)
-    cuts = sharding.shard_cuts(doc, nranks)
-    report = {"ranks": nranks, "bytes": total, "cuts": "arbitrary character boundaries (sjb200_shard_cut)", "processes": world}
+    cuts = list(sharding.shard_cuts(doc, nranks))
+    # every odd cut is moved INTO a string value (the first byte after an opening quote): the rank behind it speculates
+    # "not in a string", is told otherwise in the first exchange round, re-scans and republishes in the second
+    raw = doc.tobytes() if hasattr(doc, "tobytes") else bytes(doc)
+    for k in range(1, nranks, 2):
+        pos = cuts[k]
+        for _ in range(64):
+            hit = raw.find(b',"', pos)
+            if hit < 0 or hit + 3 >= cuts[k + 1]:
+                break
+            cand = hit + 2
+            row0 = raw.rfind(b"\n", 0, cand) + 1
+            if B.raw_scan(O, port, doc[row0:cand], 0)[1] & 2:  # bit 1: in a string
+                cuts[k] = cand
+                break
+            pos = hit + 1
+    del raw
+    report = {"ranks": nranks, "bytes": total, "cuts": "character boundaries (sjb200_shard_cut), every odd cut moved inside a string value", "processes": world}
 
     def verify(r, res, got):
         want_all, state_before = B.raw_scan(O, port, doc[: cuts[r]], 0) if r else (np.zeros(0, np.uint32), 0)

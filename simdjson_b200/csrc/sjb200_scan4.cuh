@@ -748,6 +748,10 @@ SJ_DEV bool issue_load(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, 
   return full;
 }
 
+template <int kMode>
+SJ_DEV void emit_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, const Carry &cin, unsigned lane, uint8_t *stage, sj_mbar_t *fetch_bar,
+                      uint32_t fetch_phase);
+
 // kMode: 0 stage 1; 2 minify
 template <int kMode>
 SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, const Carry &cin, unsigned warp, unsigned lane) {
@@ -882,6 +886,9 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
   // drain: what this CTA scanned and has not emitted yet (no load is in flight: both ring slots are free)
   if (kEmitW) {
     if (warp == 0 && lane == 0) sj_st_release_u32(&S->scan_done, j);  // the emit warps stop after element j - 1
+    sj_syncwarp();
+    // nothing left to scan: help with what is left to emit (both ring slots are free: slot 0 is the staging area)
+    emit_role<kMode>(S, tmap, p, cin, lane, S->ring[warp][0], &S->full[warp][0], full_phase & 1u);
   } else {
     while (ne < j) {
       wait_bar(&S->resolved[ne % kNS], (ne / kNS) & 1u, p, 64);
@@ -903,11 +910,11 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
 // element is resolved, emits the block exactly as the scanning warp would have (same parked words, same staging scheme,
 // its own staging area), and reports it.  The last block of an element frees the element's parked masks.
 template <int kMode>
-SJ_DEV void emit_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, const Carry &cin, unsigned ewarp, unsigned lane) {
+SJ_DEV void emit_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, const Carry &cin, unsigned lane, uint8_t *stage, sj_mbar_t *fetch_bar,
+                      uint32_t fetch_phase) {  // stage: this warp's 4 KiB staging area; minify fetches blocks into it through fetch_bar (next parity: fetch_phase)
   const uint64_t out_base = cin.count;
   const uint64_t launch_start = uint64_t(p.tile_begin) * kTileBytes;
-  uint32_t *stg = reinterpret_cast<uint32_t *>(S->estage[ewarp]);
-  uint32_t fetch_phase = 0;  // minify: parity of the next completion of this warp's fetch barrier
+  uint32_t *stg = reinterpret_cast<uint32_t *>(stage);
   for (;;) {
     uint32_t q = 0;
     if (lane == 0) q = sj_atomic_add(&S->emit_next, 1u);
@@ -938,7 +945,7 @@ SJ_DEV void emit_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
       prew = S->parkpre[kGPark > 0 ? 0 : e % kPark][kGPark > 0 ? 0 : tid];
     }
     if (kMode == 2) {
-      if (emit_minify_block(S, tmap, p, out_base, e, b, lane, ev, prew, S->estage[ewarp], &S->efull[ewarp], fetch_phase, launch_start)) fetch_phase ^= 1u;
+      if (emit_minify_block(S, tmap, p, out_base, e, b, lane, ev, prew, stage, fetch_bar, fetch_phase, launch_start)) fetch_phase ^= 1u;
     } else {
       emit_block(S, p, out_base, e, b, lane, ev, prew, stg);
     }
@@ -1168,7 +1175,7 @@ SJ_DEV void scan4_body(const sj_tensor_map *tmap, const ScanParams &p, uint8_t *
 #endif
   if (warp < unsigned(kScanWarps)) scan_role<kMode>(S, tmap, p, cin, warp, lane);
   else if (warp < unsigned(kScanWarps + kChainWarps)) chain_role(S, p, cin, lane, warp - unsigned(kScanWarps));
-  else emit_role<kMode>(S, tmap, p, cin, warp - unsigned(kScanWarps + kChainWarps), lane);
+  else emit_role<kMode>(S, tmap, p, cin, lane, S->estage[warp - unsigned(kScanWarps + kChainWarps)], &S->efull[warp - unsigned(kScanWarps + kChainWarps)], 0u);
 #if SJB200_SCAN4_TRACE
   if (tid == 0) S->trace_cta[2] = sj_globaltimer();
 #endif
