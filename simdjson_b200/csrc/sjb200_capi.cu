@@ -82,12 +82,14 @@ struct sjb200_ctx {
   long opt_debug_timeline = 0;
   unsigned long long *d_debug = nullptr; size_t debug_tiles = 0; uint32_t debug_last_tiles = 0;
   unsigned long long launches = 0;               // kernels of ours launched by this context
+  unsigned long long ew_launches = 0;            // ... of which stage-1 launches on the emit-warp build
   PFN_encodeTiled encode = nullptr;
   // host-pointer pipeline: ring of page-locked staging slots filled by copy threads (sjb200_hostpipe.h)
   uint8_t *h_ring = nullptr; size_t ring_slot_bytes = 0; int ring_slots = 0;
   std::vector<cudaEvent_t> ring_events;
   CopyPool *pool = nullptr;
   long opt_force_grid = 0;
+  long opt_ew_min_bytes = 384l << 20;  // stage-1 launches of at least this many bytes run the emit-warp build of the kernel (0: never)
   long opt_host_skip_scan = 0;  // tuning: the host-pointer pipeline copies only (no scan launches; results are meaningless)
   long opt_copy_threads = 4;        // 0: no staging (cudaMemcpyAsync straight from the caller's memory)
   long opt_ring_slots = 8;
@@ -267,8 +269,9 @@ bool enqueue_scan(sjb200_ctx *c, int kind, const CUtensorMap *map, bool tma, con
     const uint32_t tpe = uint32_t(scan4_tiles_per_element());
     const uint32_t nelem = (ntiles + tpe - 1) / tpe;
     const int grid = grid_for(c, kind, nelem);
-    if (scan4_parks_in_global()) {  // emit-warp builds: the parked masks wait in an L2-resident ring of the context
-      const size_t need = scan4_park_words(grid_cap(c, kind));
+    const bool ew = kind == kIndex && c->opt_ew_min_bytes > 0 && uint64_t(ntiles) * kTileBytes >= uint64_t(c->opt_ew_min_bytes);
+    if (ew || scan4_parks_in_global()) {  // emit warps: the parked masks wait in an L2-resident ring of the context
+      const size_t need = std::max(ew ? scan4_ew_park_words(grid_cap(c, kind)) : 0, scan4_parks_in_global() ? scan4_park_words(grid_cap(c, kind)) : 0);
       if (c->d_park_words < need) {
         cudaStreamSynchronize(c->stream);
         cudaFree(c->d_park); c->d_park = nullptr; c->d_park_words = 0;
@@ -277,7 +280,8 @@ bool enqueue_scan(sjb200_ctx *c, int kind, const CUtensorMap *map, bool tma, con
       }
       p.park = c->d_park;
     }
-    launched = ok(c, launch_scan4(map, p, grid, kind == kMinify ? 2 : 0, stream), "launch scan4");
+    launched = ew ? ok(c, launch_scan4_ew(map, p, grid, stream), "launch scan4 (emit warps)") : ok(c, launch_scan4(map, p, grid, kind == kMinify ? 2 : 0, stream), "launch scan4");
+    c->ew_launches += (launched && ew) ? 1 : 0;
   } else {
     if (c->grid_u == 0) c->grid_u = utf8v2_max_ctas_per_sm() * c->sm_count;
     const uint64_t nblocks = (uint64_t(ntiles) * kTileBytes + 4095) / 4096;
@@ -460,6 +464,7 @@ extern "C" double sjb200_get_stat(sjb200_ctx *c, const char *key) {
     return n ? sum / double(n) : -1.0;
   }
   if (!strcmp(key, "launches")) return double(c->launches);
+  if (!strcmp(key, "ew_launches")) return double(c->ew_launches);
   if (!strcmp(key, "grid_index")) return double(grid_for(c, kIndex, 0xFFFFFFFFu));
   if (!strcmp(key, "sm_count")) return double(c->sm_count);
   if (!strcmp(key, "host_wait_ms")) return c->t_wait_ms;
@@ -478,6 +483,7 @@ extern "C" int sjb200_set_option(sjb200_ctx *c, const char *key, long value) {
   else if (!strcmp(key, "debug_timeline")) c->opt_debug_timeline = value;
   else if (!strcmp(key, "chunk_bytes")) c->opt_chunk_bytes = std::max<long>(2 * kTileBytes, (value / (2 * kTileBytes)) * (2 * kTileBytes));
   else if (!strcmp(key, "force_grid")) c->opt_force_grid = value;
+  else if (!strcmp(key, "ew_min_bytes")) c->opt_ew_min_bytes = value;
   else if (!strcmp(key, "host_skip_scan")) c->opt_host_skip_scan = value;
   else if (!strcmp(key, "copy_threads")) c->opt_copy_threads = std::max<long>(0, std::min<long>(value, 64));
   else if (!strcmp(key, "ring_slots")) c->opt_ring_slots = std::max<long>(2, std::min<long>(value, 64));

@@ -228,7 +228,7 @@ SJ_DEV void sj_tma_load_rows(uint8_t *dst, const sj_tensor_map *map, sj_mbar_t *
 #include <cuda_runtime.h>
 
 #define SJ_DEV __device__ __forceinline__
-#define SJ_DEV_NOINLINE __device__ __noinline__
+#define SJ_DEV_NOINLINE static __device__ __noinline__
 
 namespace sjb200 {
 

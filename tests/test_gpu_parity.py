@@ -195,6 +195,38 @@ def test_stage1_sizes_across_the_pipeline(port):
         parser.close()
 
 
+def test_emit_warp_kernel_for_large_launches(port):
+    """launches of at least `ew_min_bytes` run the emit-warp build of the stage-1 kernel (sjb200_kernels_ew.cu: scan warps
+    never emit, the masks wait in an L2-resident ring): same index arrays, all modes' scans, ring wrap (more elements per
+    CTA than the ring holds), partial last block, streaming mode, and back to the default kernel on the same context"""
+    rc, parser = sj.get_active_implementation().create_dom_parser_implementation(48 << 20)
+    assert rc == sj.SUCCESS
+    try:
+        parser.set_option("ew_min_bytes", 64 << 10)
+        rng = random.Random(corpus.SEED ^ 0xE3)
+        before = parser.get_stat("ew_launches")
+        for n, mode in [(2 * TILE, 0), (2 * TILE + 1, 0), (9 * TILE + 4100, 2), (40 << 20, 0), ((40 << 20) - 4097, 2)]:
+            doc = np.frombuffer((_big_adversarial(rng, 1 << 20) * 41)[:n], dtype=np.uint8) if n > (8 << 20) else np.frombuffer(_big_adversarial(rng, n), dtype=np.uint8)
+            d = torch.from_numpy(doc.copy()).cuda()
+            want = port.stage1(doc.tobytes(), mode)
+            parser.n_structural_indexes = O.N_SENTINEL
+            rc = parser.stage1_device(d, mode)
+            got = O.Stage1Result(rc, parser.n_structural_indexes, parser.device_index_buffer().cpu().numpy().view(np.uint32))
+            assert_same(got, want, (n, mode))
+        assert parser.get_stat("ew_launches") >= before + 5
+        parser.set_option("ew_min_bytes", 0)
+        doc = corpus.random_json(20 << 20)
+        d = torch.from_numpy(doc.copy()).cuda()
+        want = port.stage1(doc, 0)
+        mid = parser.get_stat("ew_launches")
+        rc = parser.stage1_device(d, 0)
+        got = parser.device_index_buffer().cpu().numpy().view(np.uint32)
+        assert rc == want.err and parser.n_structural_indexes == want.n and np.array_equal(got[: want.n + 3], want.words())
+        assert parser.get_stat("ew_launches") == mid
+    finally:
+        parser.close()
+
+
 def test_minify_sizes_and_alignments(port):
     """minify (scan4 structure: kept bytes compacted per block, output as aligned 16-byte vectors) over the same range of
     sizes, and with the device destination at every alignment class"""
