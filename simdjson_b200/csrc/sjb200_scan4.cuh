@@ -754,7 +754,7 @@ SJ_DEV void emit_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
 
 // kMode: 0 stage 1; 2 minify
 template <int kMode>
-SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, const Carry &cin, unsigned warp, unsigned lane) {
+SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, const Carry &cin, unsigned warp, unsigned lane, uint32_t first_ticket) {
   const uint32_t nelem = elements_of(p);
   const uint64_t launch_start = uint64_t(p.tile_begin) * kTileBytes;
   const uint64_t launch_end = launch_start + uint64_t(p.ntiles) * kTileBytes;
@@ -771,11 +771,7 @@ SJ_DEV void scan_role(Smem *S, const sj_tensor_map *tmap, const ScanParams &p, c
   // Tickets should be scanned in roughly the order they were taken (every element waits for ALL lower tickets): at
   // start-up the second ticket is therefore taken only once the first block has arrived, when every CTA of the launch
   // has drawn its first one.
-  if (warp == 0) {
-    uint32_t a0 = 0;
-    if (lane == 0) a0 = sj_atomic_add(p.ticket, 1u);
-    publish_ticket(S, 0, a0, lane);
-  }
+  if (warp == 0) publish_ticket(S, 0, first_ticket, lane);  // (thread 0 drew it at the top of the kernel)
   uint32_t t = wait_ticket(S, 0, p);
   if (t < nelem) tma_cur = issue_load(S, tmap, p, t, warp, lane, 0, &pw_cur, scan_limit);
   if (warp == 0) {
@@ -1147,33 +1143,38 @@ SJ_DEV void scan4_body(const sj_tensor_map *tmap, const ScanParams &p, uint8_t *
         for (int cc = 0; cc < kTracePoints; cc++) S->trace[a][b][cc] = 0;
   }
 #endif
+  // the CTA's first ticket: the atomic's round trip overlaps the set-up below
+  uint32_t first_ticket = 0;
+  if (tid == 0) first_ticket = sj_atomic_add(p.ticket, 1u);
   Carry cin;
   cin.count = 0; cin.state = 0; cin.ttable = 0; cin.flags = 0; cin.reserved = 0;
   if (p.carry_in != nullptr) cin = *p.carry_in;
+  // ~140 mbarriers: one thread each (a single thread took 1.3 us over them)
+  if (tid < unsigned(kNS)) {
+    sj_mbar_init(&S->ticket_ready[tid], 1);
+    sj_mbar_init(&S->scanned[tid], 1);
+    sj_mbar_init(&S->resolved[tid], 1);
+    S->arrived[tid] = 0;
+    S->emitted_cnt[tid] = 0;
+  } else if (tid < unsigned(kNS + 2 * kScanWarps)) {
+    const unsigned k = tid - unsigned(kNS);
+    sj_mbar_init(&S->full[k >> 1][k & 1u], 1);
+  } else if (tid < unsigned(kNS + 2 * kScanWarps + kParkFree)) {
+    sj_mbar_init(&S->park_free[tid - unsigned(kNS + 2 * kScanWarps)], 1);
+  } else if (tid < unsigned(kNS + 2 * kScanWarps + kParkFree + (kEmitWarps > 0 ? kEmitWarps : 1))) {
+    sj_mbar_init(&S->efull[tid - unsigned(kNS + 2 * kScanWarps + kParkFree)], 1);
+  }
   if (tid == 0) {
-    for (int w = 0; w < kScanWarps; w++) {
-      sj_mbar_init(&S->full[w][0], 1);
-      sj_mbar_init(&S->full[w][1], 1);
-    }
-    for (int i = 0; i < kNS; i++) {
-      sj_mbar_init(&S->ticket_ready[i], 1);
-      sj_mbar_init(&S->scanned[i], 1);
-      S->arrived[i] = 0;
-      S->emitted_cnt[i] = 0;
-      sj_mbar_init(&S->resolved[i], 1);
-    }
-    for (int i = 0; i < kParkFree; i++) sj_mbar_init(&S->park_free[i], 1);
-    for (int i = 0; i < (kEmitWarps > 0 ? kEmitWarps : 1); i++) sj_mbar_init(&S->efull[i], 1);
     S->emit_next = 0;
     S->scan_done = 0xFFFFFFFFu;
-    sj_fence_mbar_init();
   }
+  if (tid < unsigned(kNS + 2 * kScanWarps + kParkFree + (kEmitWarps > 0 ? kEmitWarps : 1))) sj_fence_mbar_init();
   if (kMode == 2 && tid < 16) S->compact_lut[tid] = compact_entry(tid);
   sj_syncthreads();
 #if SJB200_SCAN4_TRACE
   if (tid == 0) S->trace_cta[1] = sj_globaltimer();
 #endif
-  if (warp < unsigned(kScanWarps)) scan_role<kMode>(S, tmap, p, cin, warp, lane);
+  if (warp < unsigned(kScanWarps)) scan_role<kMode>(S, tmap, p, cin, warp, lane, first_ticket);
   else if (warp < unsigned(kScanWarps + kChainWarps)) chain_role(S, p, cin, lane, warp - unsigned(kScanWarps));
   else emit_role<kMode>(S, tmap, p, cin, lane, S->estage[warp - unsigned(kScanWarps + kChainWarps)], &S->efull[warp - unsigned(kScanWarps + kChainWarps)], 0u);
 #if SJB200_SCAN4_TRACE

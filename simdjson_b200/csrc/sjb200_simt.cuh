@@ -321,11 +321,9 @@ SJ_DEV void sj_mbar_init(sj_mbar_t *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sj_smem_u32(bar)), "r"(count) : "memory");
 }
 SJ_DEV void sj_fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-#ifdef SJB200_DIAG_NO_PROXY_FENCE  // measurement only: what the fence (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC) costs
-SJ_DEV void sj_fence_proxy_async() {}
-#else
+// (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC: waits for the thread's outstanding loads -- issue it before, not after, a global
+// load whose value is not needed yet.  Measured: a build without it is not faster, profiles/README.md)
 SJ_DEV void sj_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-#endif
 SJ_DEV void sj_mbar_arrive(sj_mbar_t *bar) {
   asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(sj_smem_u32(bar)) : "memory");
 }
