@@ -158,6 +158,9 @@ SJ_DEV Eff compose(const Eff &o, const Eff &n) {
 
 // A waiting warp must not spin at full speed: mbarrier.try_wait returns at once, and a busy loop takes issue slots
 // from the warps that do the work (measured: 20 % of all issued instructions).  `ns` = back-off between polls.
+#ifndef SJB200_SCAN4_POLL_SCALE
+#define SJB200_SCAN4_POLL_SCALE 1
+#endif
 SJ_DEV bool wait_bar(sj_mbar_t *bar, uint32_t parity, const ScanParams &p, unsigned ns) {
   uint32_t spins = 0;
   while (!sj_mbar_try_wait(bar, parity)) {
@@ -165,7 +168,7 @@ SJ_DEV bool wait_bar(sj_mbar_t *bar, uint32_t parity, const ScanParams &p, unsig
       sj_atomic_or(p.flags, kFlagInternal);
       return false;
     }
-    sj_nanosleep(ns);
+    sj_nanosleep(ns * SJB200_SCAN4_POLL_SCALE);
   }
   return true;
 }
