@@ -83,10 +83,12 @@ SJB200_API size_t sjb200_index_words(size_t capacity_bytes);
 SJB200_API int sjb200_device(const sjb200_ctx *ctx);
 /* last CUDA error string seen by this context ("" if none); for diagnostics only */
 SJB200_API const char *sjb200_last_cuda_error(const sjb200_ctx *ctx);
-/* tuning knobs, mostly for tests and bench: "use_tma" (0/1), "grid" (CTAs, 0 = auto), "chunk_bytes",
- * "time_kernel" (0/1: record CUDA events around the scan kernel on its launch stream) */
+/* tuning knobs, mostly for tests and bench: "use_tma" (0/1), "grid" (CTAs, 0 = auto), "chunk_bytes", "copy_threads",
+ * "ew_min_bytes" (stage-1 launches of at least this size use the emit-warp build of the kernel; 0 = never),
+ * "time_kernel" (0/1: record CUDA events around the scan kernel on its launch stream); none changes results */
 SJB200_API int sjb200_set_option(sjb200_ctx *ctx, const char *key, long value);
 /* "kernel_ms" (last scan kernel, needs time_kernel=1), "launches" (kernels launched by this context so far),
+ * "ew_launches" (of which on the emit-warp build),
  * "grid_index", "sm_count"; negative when unavailable */
 SJB200_API double sjb200_get_stat(sjb200_ctx *ctx, const char *key);
 
