@@ -116,6 +116,8 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.rows, self.stop, self.th, self.h = index, [], threading.Event(), None, None
         try:
+            if os.environ.get("SJB200_BENCH_NVML") == "0":  # diagnostic: no sampling thread at all
+                raise RuntimeError("disabled")
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
@@ -317,6 +319,7 @@ def run_ours(args, rank, world):
         comm.connect(all_gather_bytes)
 
     kernel_ms, n_struct, results = [], [], {}
+    host_ms = {"enqueue": 0.0, "finish": 0.0, "finish_max": 0.0}
 
     def run_steps(k, record):
         t_ev0, t_ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -340,12 +343,18 @@ def run_ours(args, rank, world):
             i = 0
             while i < k:
                 w = min(24, k - i)
+                th0 = time.perf_counter()
                 for j in range(i, i + w):
                     rcq = comm.enqueue(d_docs[j % ROTATE], d_idxs[j % ROTATE], rank == world - 1, stream)
                     if rcq != 0:
                         raise RuntimeError("sharded enqueue failed: " + parser.last_cuda_error())
+                host_ms["enqueue"] += (time.perf_counter() - th0) * 1e3
                 for j in range(i, i + w):
+                    th1 = time.perf_counter()
                     rcf, res = comm.finish()
+                    dt = (time.perf_counter() - th1) * 1e3
+                    host_ms["finish"] += dt
+                    host_ms["finish_max"] = max(host_ms["finish_max"], dt)
                     if rcf != 0:
                         raise RuntimeError("sharded finish failed: " + parser.last_cuda_error())
                     if record:
@@ -365,6 +374,13 @@ def run_ours(args, rank, world):
     with ClockSampler(local) as clocks:
         total_ms = run_steps(args.steps, True)
     launches2 = parser.get_stat("launches")
+    sharded_host = None
+    if world > 1:  # where the host's time went in the timed region (and the warm-up): per rank on stderr, rank 0's in the line
+        sharded_host = {"enqueue_ms": round(host_ms["enqueue"], 3), "finish_ms": round(host_ms["finish"], 3), "finish_max_ms": round(host_ms["finish_max"], 3),
+                        "window_polls": int(parser.get_stat("xchg_polls")), "poll_wait_ms": round(parser.get_stat("xchg_wait_ms"), 3),
+                        "own_scan_wait_ms": round(parser.get_stat("xchg_evsync_ms"), 3), "second_rounds": int(parser.get_stat("xchg_second_rounds")),
+                        "note": "host wall time over warm-up + timed passes of this rank"}
+        print(f"[rank {rank}] total_ms {total_ms:.3f} {sharded_host}", file=sys.stderr, flush=True)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -446,6 +462,8 @@ def run_ours(args, rank, world):
                          "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "sjb200::scan4_kernel (sjb200_scan4.cuh)", "kernel_ms": round(kms, 5), "algorithmic_bytes": int(algo_bytes),
                          "input_gbs_kernel_only": round(DOC_BYTES / (kms * 1e-3) / 1e9, 1), "kernel_src_sha16": kernel_source_hash()},
         }
+        if sharded_host is not None:
+            line["sharded_host"] = sharded_host
         line["cpu_baseline"] = cpu_baseline(shards[0])
         print(json.dumps(line), flush=True)
     if comm is not None:

@@ -96,6 +96,8 @@ struct sjb200_ctx {
   long opt_first_chunk_bytes = 512 << 10;  // first chunk of the host-pointer pipeline; the following ones double up to chunk_bytes
   long opt_stage_min_bytes = 1 << 20;  // smaller inputs go straight through the driver
   long opt_zero_copy_out = 1;       // stage 1 stores indexes straight into a page-locked, mapped caller array
+  unsigned long long xchg_polls = 0, xchg_second_rounds = 0;  // sharded passes: window polls / passes that needed the second round
+  double xchg_wait_ms = 0, xchg_evsync_ms = 0, xchg_enqueue_ms = 0;  // ... host time polling the window / waiting for the own scan / inside enqueue
   double t_wait_ms = 0, t_issue_ms = 0, t_sync_ms = 0;  // last host-pointer call: waiting for staged chunks / inside CUDA calls / final synchronise
   int last_input_path = 0, last_output_path = 0;  // stats: 0 driver copy, 1 staged ring, 2 caller memory is page-locked; 0 copy engine, 1 kernel stores
   PendingCall pending;
@@ -468,6 +470,11 @@ extern "C" double sjb200_get_stat(sjb200_ctx *c, const char *key) {
   if (!strcmp(key, "grid_index")) return double(grid_for(c, kIndex, 0xFFFFFFFFu));
   if (!strcmp(key, "sm_count")) return double(c->sm_count);
   if (!strcmp(key, "host_wait_ms")) return c->t_wait_ms;
+  if (!strcmp(key, "xchg_polls")) return double(c->xchg_polls);
+  if (!strcmp(key, "xchg_second_rounds")) return double(c->xchg_second_rounds);
+  if (!strcmp(key, "xchg_wait_ms")) return c->xchg_wait_ms;
+  if (!strcmp(key, "xchg_evsync_ms")) return c->xchg_evsync_ms;
+  if (!strcmp(key, "xchg_enqueue_ms")) return c->xchg_enqueue_ms;
   if (!strcmp(key, "host_issue_ms")) return c->t_issue_ms;
   if (!strcmp(key, "host_sync_ms")) return c->t_sync_ms;
   if (!strcmp(key, "input_path")) return double(c->last_input_path);
@@ -1103,9 +1110,13 @@ int comm_collect(sjb200_comm *m, uint32_t seq, int round) {
     if (!ok(c, cudaMemcpyAsync(m->h_rec, src, size_t(m->nranks) * 16, cudaMemcpyDeviceToHost, m->poll_stream), "D2H window") ||
         !ok(c, cudaStreamSynchronize(m->poll_stream), "sync"))
       return SJB200_UNEXPECTED_ERROR;
+    c->xchg_polls++;
     bool all = true;
     for (int r = 0; r < m->nranks; r++) all = all && xchg_complete(m->h_rec[2 * r], m->h_rec[2 * r + 1], seq);
-    if (all) return SJB200_SUCCESS;
+    if (all) {
+      c->xchg_wait_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      return SJB200_SUCCESS;
+    }
     if (std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count() > m->poll_timeout_ms) {
       c->last_error = "sharded scan: a peer's record did not arrive";
       return SJB200_UNEXPECTED_ERROR;
@@ -1199,6 +1210,7 @@ extern "C" int sjb200_stage1_sharded_enqueue(sjb200_comm *m, const uint8_t *d_sh
   sjb200_ctx *c = m->ctx;
   if (!use_scan4(c, kIndex)) return SJB200_UNEXPECTED_ERROR;
   DeviceGuard g(c->device);
+  const auto t_enq = std::chrono::steady_clock::now();
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
   if (!ensure_desc(c, len)) return SJB200_MEMALLOC;
   const uint32_t seq = m->head + 1;  // tags start at 1: a zeroed window never matches
@@ -1215,6 +1227,7 @@ extern "C" int sjb200_stage1_sharded_enqueue(sjb200_comm *m, const uint8_t *d_sh
       !ok(c, cudaEventRecord(m->done[m->head % uint32_t(kXchgSteps)], s), "event record"))
     return SJB200_UNEXPECTED_ERROR;
   m->head++;
+  c->xchg_enqueue_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enq).count();
   return SJB200_SUCCESS;
 }
 
@@ -1226,7 +1239,9 @@ extern "C" int sjb200_stage1_sharded_finish(sjb200_comm *m, sjb200_sharded_resul
   const sjb200_comm::Step st = m->steps[m->tail % uint32_t(kXchgSteps)];
   const uint32_t slot_i = m->tail % uint32_t(kXchgSteps);
   m->tail++;
+  const auto t_ev = std::chrono::steady_clock::now();
   if (!ok(c, cudaEventSynchronize(m->done[slot_i]), "event sync")) return SJB200_UNEXPECTED_ERROR;  // own scan (and its stores) done
+  c->xchg_evsync_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_ev).count();
   int rc = comm_collect(m, st.seq, 0);
   if (rc != SJB200_SUCCESS) return rc;
   uint32_t tt[kMaxRanks], flags_all = 0;
@@ -1244,6 +1259,7 @@ extern "C" int sjb200_stage1_sharded_finish(sjb200_comm *m, sjb200_sharded_resul
   uint64_t my_count = xchg_count(m->h_rec[2 * m->rank]);
   uint32_t my_flags = uint32_t(m->h_rec[2 * m->rank + 1] >> 16) & 0xFFu;
   if (any_wrong) {
+    c->xchg_second_rounds++;
     // second round: ranks whose speculation failed scan again with their true state; everybody republishes
     if (my_state != 0) {
       sjb200_shard_result sr;

@@ -619,11 +619,13 @@ SJ_DEV bool emit_minify_block(Smem *S, const sj_tensor_map *tmap, const ScanPara
     const sj_u4 v = *reinterpret_cast<const sj_u4 *>(slot + swz(lane * 128u + 16u * c));
     w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
   }
-  sj_syncwarp();  // every lane holds its row: the slot becomes the staging area (linear), zeroed because lanes OR into it
-#pragma unroll
-  for (int c = 0; c < 8; c++) *reinterpret_cast<sj_u4 *>(slot + lane * 128u + 16u * c) = sj_make_u4(0, 0, 0, 0);
-  sj_syncwarp();
   const uint32_t off = (prew >> (16 * pol)) & 0xFFFFu;  // bytes of the block's output before this lane's
+  sj_syncwarp();  // every lane holds its row: the slot becomes the staging area
+  // lanes OR into the words at their seams only -- a lane's first word is the previous lane's last one -- so only those
+  // are zeroed (complete words are plain stores)
+  if (off < uint32_t(kBlockBytes)) *reinterpret_cast<uint32_t *>(slot + swz(off & ~3u)) = 0u;
+  if (lane == 31 && total < uint32_t(kBlockBytes)) *reinterpret_cast<uint32_t *>(slot + swz(total & ~3u)) = 0u;
+  sj_syncwarp();
   const uint32_t keep[4] = {kv.x, kv.y, kv.z, kv.w};
   // kept bytes per word: the nibble popcounts of the keep masks (0..4 each)
   uint32_t cn[4];
