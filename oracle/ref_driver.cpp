@@ -254,3 +254,57 @@ SJR_API long sjr_dom_parse_many(const char *name, const uint8_t *buf, size_t len
   get_active_implementation() = saved;
   return ndocs;
 }
+
+// ---- stage-2-lite pinning: what the reference's stage 2 makes of tokens
+
+// dom_parser_implementation::parse_string (include/simdjson/internal/dom_parser_implementation.h L124) on a string whose
+// bytes AFTER the opening quote start at src (readable for SIMDJSON_PADDING bytes past the closing quote).
+// Returns the unescaped length, -1 when the reference rejects the string.
+SJR_API long sjr_parse_string(const char *name, const uint8_t *src, uint8_t *dst) {
+  auto impl = find_impl(name);
+  if (!impl) return -2;
+  std::unique_ptr<internal::dom_parser_implementation> p;
+  if (impl->create_dom_parser_implementation(64, 16, p)) return -2;
+  uint8_t *end = p->parse_string(src, dst, false);
+  return end ? long(end - dst) : -1;
+}
+
+// DOM-parse one document and dump its tape: for every tape word that starts a value, its type char and payload
+// (strings: offset into string_buf; 'l' / 'u' / 'd': the 64-bit word that follows; containers: 0), in tape order without
+// the root words; string_buf bytes up to the end of the last string record.  Returns the error_code of parse().
+SJR_API int sjr_dom_tape(const char *name, const uint8_t *buf, size_t len, uint8_t *types, uint64_t *payloads, size_t max_entries,
+                         size_t *n_entries, uint8_t *strbuf, size_t strbuf_cap, size_t *strbuf_len) {
+  auto impl = find_impl(name);
+  if (!impl) return -1;
+  const implementation *saved = get_active_implementation();
+  get_active_implementation() = impl;
+  dom::parser parser;
+  dom::element doc;
+  auto err = parser.parse(buf, len, true).get(doc);
+  *n_entries = 0;
+  *strbuf_len = 0;
+  if (!err) {
+    const uint64_t *tape = parser.doc.tape.get();
+    const size_t tape_len = size_t(tape[0] & 0x00FFFFFFFFFFFFFFull);  // root word: index one past the closing root word
+    size_t k = 0, sb_end = 0;
+    for (size_t i = 1; i + 1 < tape_len; i++) {
+      const uint8_t t = uint8_t(tape[i] >> 56);
+      uint64_t v = 0;
+      if (t == '"') {
+        v = tape[i] & 0x00FFFFFFFFFFFFFFull;
+        uint32_t sl;
+        std::memcpy(&sl, parser.doc.string_buf.get() + v, 4);
+        if (v + 5 + sl > sb_end) sb_end = size_t(v) + 5 + sl;
+      } else if (t == 'l' || t == 'u' || t == 'd') {
+        v = tape[++i];
+      }
+      if (k < max_entries) { types[k] = t; payloads[k] = v; }
+      k++;
+    }
+    *n_entries = k;
+    *strbuf_len = sb_end;
+    if (sb_end <= strbuf_cap) std::memcpy(strbuf, parser.doc.string_buf.get(), sb_end);
+  }
+  get_active_implementation() = saved;
+  return int(err);
+}

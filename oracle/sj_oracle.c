@@ -327,3 +327,189 @@ uint32_t sjo_transducer(const uint8_t *buf, size_t len) {
   }
   return T;
 }
+
+/* ------------------------------------------------------------ stage-2-lite
+ * What the reference's stage 2 decides about ONE token from its bytes alone -- the leaves of
+ * json_iterator::visit_primitive (src/generic/stage2/json_iterator.h L338-360):
+ *   strings  tape_builder::visit_string (src/generic/stage2/tape_builder.h L186-205) -> stringparsing::parse_string
+ *            (src/generic/stage2/stringparsing.h L146-190, handle_unicode_codepoint L55-98,
+ *            jsoncharutils::codepoint_to_utf8 include/simdjson/generic/jsoncharutils.h L37-62); the record a string
+ *            leaves in dom::document::string_buf is [uint32 length][bytes][0] (tape_builder.h on_start_string /
+ *            on_end_string), the tape payload its offset;
+ *   numbers  numberparsing::parse_number (include/simdjson/generic/numberparsing.h L860-961): grammar, int64 / uint64
+ *            decision and value; a float is only recognised (type 'd'), not converted -- the reference additionally
+ *            rejects floats whose VALUE is infinite (write_float L765-813), which this restatement does not model;
+ *   atoms    atomparsing::is_valid_{true,false,null}_atom (include/simdjson/generic/atomparsing.h L45-95).
+ * Written as plain sequential byte walks: no 32-byte chunks, no tables. */
+
+static int sjo_hex(uint8_t c) {
+  if (c >= '0' && c <= '9') return c - '0';
+  if (c >= 'a' && c <= 'f') return c - 'a' + 10;
+  if (c >= 'A' && c <= 'F') return c - 'A' + 10;
+  return -1;
+}
+static uint8_t sjo_at(const uint8_t *buf, size_t len, size_t i) { return i < len ? buf[i] : (uint8_t)0x20; } /* beyond the end: padding */
+static long sjo_hex4(const uint8_t *buf, size_t len, size_t i) {
+  long v = 0;
+  for (int k = 0; k < 4; k++) {
+    int h = sjo_hex(sjo_at(buf, len, i + (size_t)k));
+    if (h < 0) return -1;
+    v = v * 16 + h;
+  }
+  return v;
+}
+static int sjo_is_struct_or_ws(uint8_t c) {
+  return c == 0x20 || c == 0x09 || c == 0x0A || c == 0x0D || c == ',' || c == ':' || c == '[' || c == ']' || c == '{' || c == '}';
+}
+
+/* the string whose opening quote is at buf[pos]: unescaped bytes to dst (may be NULL: length only).
+ * returns the unescaped length, -1 for an invalid escape (STRING_ERROR), -2 when the input ends first */
+long sjo_parse_string(const uint8_t *buf, size_t len, size_t pos, uint8_t *dst) {
+  size_t q = pos + 1;
+  long out = 0;
+  for (;;) {
+    if (q >= len) return -2;
+    uint8_t b = buf[q];
+    if (b == '"') return out;
+    if (b != '\\') {
+      if (dst) dst[out] = b;
+      out++; q++;
+      continue;
+    }
+    uint8_t e = sjo_at(buf, len, q + 1);
+    if (e != 'u') {
+      uint8_t m = 0;
+      switch (e) {
+        case '"': m = 0x22; break; case '\\': m = 0x5C; break; case '/': m = 0x2F; break;
+        case 'b': m = 0x08; break; case 'f': m = 0x0C; break; case 'n': m = 0x0A; break;
+        case 'r': m = 0x0D; break; case 't': m = 0x09; break; default: break;
+      }
+      if (!m) return -1;
+      if (dst) dst[out] = m;
+      out++; q += 2;
+      continue;
+    }
+    long cp = sjo_hex4(buf, len, q + 2);
+    if (cp < 0) return -1;
+    q += 6;
+    if (cp >= 0xD800 && cp < 0xDC00) { /* high surrogate: a low one must follow as \uXXXX */
+      if (sjo_at(buf, len, q) != '\\' || sjo_at(buf, len, q + 1) != 'u') return -1;
+      long lo = sjo_hex4(buf, len, q + 2);
+      if (lo < 0xDC00 || lo > 0xDFFF) return -1;
+      cp = (((cp - 0xD800) << 10) | (lo - 0xDC00)) + 0x10000;
+      q += 6;
+    } else if (cp >= 0xDC00 && cp <= 0xDFFF) {
+      return -1;
+    }
+    uint8_t u[4];
+    int n;
+    if (cp <= 0x7F) { u[0] = (uint8_t)cp; n = 1; }
+    else if (cp <= 0x7FF) { u[0] = (uint8_t)(0xC0 | (cp >> 6)); u[1] = (uint8_t)(0x80 | (cp & 63)); n = 2; }
+    else if (cp <= 0xFFFF) { u[0] = (uint8_t)(0xE0 | (cp >> 12)); u[1] = (uint8_t)(0x80 | ((cp >> 6) & 63)); u[2] = (uint8_t)(0x80 | (cp & 63)); n = 3; }
+    else { u[0] = (uint8_t)(0xF0 | (cp >> 18)); u[1] = (uint8_t)(0x80 | ((cp >> 12) & 63)); u[2] = (uint8_t)(0x80 | ((cp >> 6) & 63)); u[3] = (uint8_t)(0x80 | (cp & 63)); n = 4; }
+    if (dst) for (int k = 0; k < n; k++) dst[out + k] = u[k];
+    out += n;
+  }
+}
+
+/* the number that starts at buf[pos]; returns the tape type ('l', 'u', 'd') or 0 with *value = error_code */
+static uint8_t sjo_number(const uint8_t *buf, size_t len, size_t pos, uint64_t *value) {
+  const int neg = buf[pos] == '-';
+  size_t q = pos + (size_t)neg;
+  const size_t start = q;
+  uint64_t i = 0;
+  while (sjo_at(buf, len, q) >= '0' && sjo_at(buf, len, q) <= '9') { i = i * 10u + (uint64_t)(sjo_at(buf, len, q) - '0'); q++; }
+  size_t digits = q - start;
+  if (digits == 0 || (sjo_at(buf, len, start) == '0' && digits > 1)) { *value = SJO_NUMBER_ERROR; return 0; }
+  int is_float = 0;
+  if (sjo_at(buf, len, q) == '.') {
+    is_float = 1;
+    q++;
+    const size_t fs = q;
+    while (sjo_at(buf, len, q) >= '0' && sjo_at(buf, len, q) <= '9') q++;
+    if (q == fs) { *value = SJO_NUMBER_ERROR; return 0; }
+  }
+  if (sjo_at(buf, len, q) == 'e' || sjo_at(buf, len, q) == 'E') {
+    is_float = 1;
+    q++;
+    if (sjo_at(buf, len, q) == '-' || sjo_at(buf, len, q) == '+') q++;
+    const size_t es = q;
+    while (sjo_at(buf, len, q) >= '0' && sjo_at(buf, len, q) <= '9') q++;
+    if (q == es) { *value = SJO_NUMBER_ERROR; return 0; }
+  }
+  const int dirty = !sjo_is_struct_or_ws(sjo_at(buf, len, q));
+  if (is_float) {
+    if (dirty) { *value = SJO_NUMBER_ERROR; return 0; }
+    *value = (uint64_t)q; /* one past the token: the consumer converts [pos, q) */
+    return 'd';
+  }
+  const size_t longest = neg ? 19 : 20;
+  if (digits > longest) { *value = SJO_BIGINT_ERROR; return 0; }
+  if (digits == longest) {
+    if (neg) {
+      if (i > ((uint64_t)1 << 63)) { *value = SJO_BIGINT_ERROR; return 0; }
+    } else if (buf[pos] != '1' || i <= (uint64_t)INT64_MAX) { *value = SJO_BIGINT_ERROR; return 0; }
+  }
+  if (dirty) { *value = SJO_NUMBER_ERROR; return 0; }
+  if (i > (uint64_t)INT64_MAX && !neg) { *value = i; return 'u'; }
+  *value = neg ? (~i + 1u) : i;
+  return 'l';
+}
+
+static int sjo_atom(const uint8_t *buf, size_t len, size_t pos, const char *word, size_t wl) {
+  for (size_t k = 0; k < wl; k++)
+    if (sjo_at(buf, len, pos + k) != (uint8_t)word[k]) return 0;
+  return sjo_is_struct_or_ws(sjo_at(buf, len, pos + wl));
+}
+
+int sjo_tokens(const uint8_t *buf, size_t len, const uint32_t *idx, uint32_t n, uint8_t *type, uint64_t *payload, uint8_t *strbuf,
+               size_t strbuf_cap, uint64_t *strbuf_len, uint32_t *n_strings, uint32_t *first_error_index) {
+  uint64_t sb = 0;
+  uint32_t ns = 0, first = 0xFFFFFFFFu;
+  int err = SJO_SUCCESS;
+  for (uint32_t k = 0; k < n; k++) {
+    const size_t p = idx[k];
+    const uint8_t c = buf[p];
+    uint8_t t = 0;
+    uint64_t v = 0;
+    if (c == '{' || c == '}' || c == '[' || c == ']' || c == ':' || c == ',') {
+      t = c;
+    } else if (c == '"') {
+      const long ul = sjo_parse_string(buf, len, p, NULL);
+      if (ul < 0) {
+        v = ul == -1 ? SJO_STRING_ERROR : SJO_UNCLOSED_STRING;
+      } else {
+        t = '"';
+        v = sb;
+        if (sb + (uint64_t)ul + 5 <= strbuf_cap) {
+          const uint32_t l32 = (uint32_t)ul;
+          for (int b = 0; b < 4; b++) strbuf[sb + (uint64_t)b] = (uint8_t)(l32 >> (8 * b));
+          sjo_parse_string(buf, len, p, strbuf + sb + 4);
+          strbuf[sb + 4 + (uint64_t)ul] = 0;
+        }
+        sb += (uint64_t)ul + 5;
+        ns++;
+      }
+    } else if (c <= '9' || c == '-') {
+      /* json_iterator.h L342: `(*value - '0') < 10` is evaluated in int, so EVERY byte up to '9' takes the number path
+       * (a stray '#' or 0x0C in value position is a NUMBER_ERROR, not a TAPE_ERROR) */
+      t = sjo_number(buf, len, p, &v);
+    } else if (c == 't') {
+      if (sjo_atom(buf, len, p, "true", 4)) t = 't'; else v = SJO_T_ATOM_ERROR;
+    } else if (c == 'f') {
+      if (sjo_atom(buf, len, p, "false", 5)) t = 'f'; else v = SJO_F_ATOM_ERROR;
+    } else if (c == 'n') {
+      if (sjo_atom(buf, len, p, "null", 4)) t = 'n'; else v = SJO_N_ATOM_ERROR;
+    } else {
+      v = SJO_TAPE_ERROR;
+    }
+    type[k] = t;
+    payload[k] = v;
+    if (t == 0 && first == 0xFFFFFFFFu) { first = k; err = (int)v; }
+  }
+  *strbuf_len = sb;
+  *n_strings = ns;
+  *first_error_index = first;
+  if (err == SJO_SUCCESS && sb > strbuf_cap) return SJO_CAPACITY;
+  return err;
+}

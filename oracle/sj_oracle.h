@@ -32,6 +32,13 @@ enum {
   SJO_SUCCESS = 0,
   SJO_CAPACITY = 1,
   SJO_MEMALLOC = 2,
+  SJO_TAPE_ERROR = 3,
+  SJO_STRING_ERROR = 5,
+  SJO_T_ATOM_ERROR = 6,
+  SJO_F_ATOM_ERROR = 7,
+  SJO_N_ATOM_ERROR = 8,
+  SJO_NUMBER_ERROR = 9,
+  SJO_BIGINT_ERROR = 10,
   SJO_UTF8_ERROR = 11,
   SJO_EMPTY = 13,
   SJO_UNESCAPED_CHARS = 14,
@@ -71,6 +78,16 @@ int sjo_minify(const uint8_t *buf, size_t len, uint8_t *dst, size_t *dst_len);
 /* validate_utf8: generic_validate_utf8 (src/generic/stage1/utf8_validator.h L18-34);
  * returns 1 for valid, 0 for invalid. */
 int sjo_validate_utf8(const uint8_t *buf, size_t len);
+
+/* stage-2-lite: per structural index what the reference's stage 2 decides from the token's
+ * bytes alone.  type[k]: the tape_type char ('{' '}' '[' ']' '"' 'l' 'u' 'd' 't' 'f' 'n'; ':' and ',' for those
+ * operators) or 0 for a token in error; payload[k]: string -> offset of its record ([u32 length][bytes][0], the layout of
+ * dom::document::string_buf) in strbuf, 'l' / 'u' -> the value, 'd' -> byte offset one past the number, type 0 -> the
+ * error_code.  Returns the error of the first token in error (document order), CAPACITY if strbuf is too small. */
+int sjo_tokens(const uint8_t *buf, size_t len, const uint32_t *idx, uint32_t n, uint8_t *type, uint64_t *payload, uint8_t *strbuf,
+               size_t strbuf_cap, uint64_t *strbuf_len, uint32_t *n_strings, uint32_t *first_error_index);
+/* one string (opening quote at buf[pos]): unescaped length (bytes to dst unless NULL), -1 invalid escape, -2 unterminated */
+long sjo_parse_string(const uint8_t *buf, size_t len, size_t pos, uint8_t *dst);
 
 /* helpers exposed for unit tests */
 uint64_t sjo_scan_shard(const uint8_t *buf, size_t len, uint32_t state_in, uint32_t *idx, uint32_t *state_out);

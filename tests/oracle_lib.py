@@ -72,8 +72,32 @@ class Port:
         L.sjo_validate_utf8.argtypes = [C.POINTER(C.c_uint8), C.c_size_t]
         L.sjo_trim_partial_utf8.restype = C.c_size_t
         L.sjo_trim_partial_utf8.argtypes = [C.POINTER(C.c_uint8), C.c_size_t]
+        L.sjo_tokens.restype = C.c_int
+        L.sjo_tokens.argtypes = [C.POINTER(C.c_uint8), C.c_size_t, C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64),
+                                 C.POINTER(C.c_uint8), C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.sjo_parse_string.restype = C.c_long
+        L.sjo_parse_string.argtypes = [C.POINTER(C.c_uint8), C.c_size_t, C.c_size_t, C.POINTER(C.c_uint8)]
         self.L = L
         self.name = "port"
+
+    def tokens(self, buf, idx, n, strbuf_cap=None):
+        """stage-2-lite: (err, types[n], payloads[n], string_buf bytes, n_strings, first_error_index)"""
+        a = _u8(buf)
+        ix = np.ascontiguousarray(idx[:n], dtype=np.uint32) if n else np.zeros(1, dtype=np.uint32)
+        types = np.zeros(max(n, 1), dtype=np.uint8)
+        pay = np.zeros(max(n, 1), dtype=np.uint64)
+        cap = (len(a) + 5 * n + 64) if strbuf_cap is None else strbuf_cap
+        sb = np.zeros(max(cap, 1), dtype=np.uint8)
+        sl, ns, fe = C.c_uint64(0), C.c_uint32(0), C.c_uint32(0)
+        err = self.L.sjo_tokens(_ptr(a), len(a), _ptr(ix, C.c_uint32), n, _ptr(types), _ptr(pay, C.c_uint64), _ptr(sb), cap, C.byref(sl), C.byref(ns), C.byref(fe))
+        return err, types[:n], pay[:n], sb[: min(sl.value, cap)], sl.value, ns.value, fe.value
+
+    def parse_string(self, buf, pos=0):
+        """the string whose opening quote is at buf[pos]: (length or -1 / -2, bytes)"""
+        a = _u8(buf)
+        dst = np.zeros(len(a) + 8, dtype=np.uint8)
+        r = self.L.sjo_parse_string(_ptr(a), len(a), pos, _ptr(dst))
+        return r, bytes(dst[: max(r, 0)])
 
     def stage1(self, buf, mode=REGULAR, capacity=None):
         a = _u8(buf)
@@ -119,6 +143,11 @@ class Ref:
         L.sjr_dom_roundtrip.argtypes = [C.c_char_p, C.POINTER(C.c_uint8), C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.sjr_dom_parse_many.restype = C.c_long
         L.sjr_dom_parse_many.argtypes = [C.c_char_p, C.POINTER(C.c_uint8), C.c_size_t, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
+        L.sjr_parse_string.restype = C.c_long
+        L.sjr_parse_string.argtypes = [C.c_char_p, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8)]
+        L.sjr_dom_tape.restype = C.c_int
+        L.sjr_dom_tape.argtypes = [C.c_char_p, C.POINTER(C.c_uint8), C.c_size_t, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64), C.c_size_t, C.POINTER(C.c_size_t),
+                                   C.POINTER(C.c_uint8), C.c_size_t, C.POINTER(C.c_size_t)]
         self.L = L
         self.impl = impl.encode()
         if not L.sjr_supported(self.impl):
@@ -170,6 +199,25 @@ class Ref:
         ol = C.c_size_t(0)
         err = self.L.sjr_dom_roundtrip(self.impl, _ptr(a), len(a), out, cap, C.byref(ol))
         return err, out.raw[: ol.value]
+
+    def parse_string(self, body):
+        """dom_parser_implementation::parse_string on the bytes after an opening quote (closing quote included in body)"""
+        a = np.concatenate([_u8(body), np.full(128, 0x20, dtype=np.uint8)])
+        dst = np.zeros(len(a) + 128, dtype=np.uint8)
+        r = self.L.sjr_parse_string(self.impl, _ptr(a), _ptr(dst))
+        return r, bytes(dst[: max(r, 0)])
+
+    def dom_tape(self, buf):
+        """(error_code, types, payloads, string_buf bytes) of dom::parser::parse: one entry per tape value, root words left out"""
+        a = _u8(buf)
+        cap = len(a) + 16
+        types = np.zeros(cap, dtype=np.uint8)
+        pay = np.zeros(cap, dtype=np.uint64)
+        sbc = 2 * len(a) + 64
+        sb = np.zeros(sbc, dtype=np.uint8)
+        ne, sl = C.c_size_t(0), C.c_size_t(0)
+        err = self.L.sjr_dom_tape(self.impl, _ptr(a), len(a), _ptr(types), _ptr(pay, C.c_uint64), cap, C.byref(ne), _ptr(sb), sbc, C.byref(sl))
+        return err, types[: ne.value], pay[: ne.value], sb[: sl.value]
 
     def dom_parse_many(self, buf, batch_size=1000000):
         a = _u8(buf)
