@@ -16,6 +16,7 @@ Configurations (`--config`, BASELINE.json `configs`):
   utf8_minify_256m  configs[3]: validate_utf8 on 256 MiB mixed ASCII / UTF-8 text, minify on 256 MiB pretty JSON
   concat_8g    configs[4]: twitter + citm repeated to 8 GiB, 8 shards of ~1 GiB with 64-bit index bases, round-robin
                over the N ranks
+  tokens_64m   SURVEY.md 8(f) row 4 (not a BASELINE config): stage-2-lite (sjb200_tokens_dev) on the 64 MiB document
 `--check` runs the parity gate of the multi-rank path on adversarial cuts (mid-row, mid-string: carry-in != 0, second
 round, re-scans) through the real IPC / NCCL plumbing and prints one JSON line; exit code 1 on a mismatch.
 
@@ -484,7 +485,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="stage1_64m", choices=["stage1_64m", "jsonexamples", "ndjson_1g", "utf8_minify_256m", "concat_8g"])
+    ap.add_argument("--config", default="stage1_64m", choices=["stage1_64m", "jsonexamples", "ndjson_1g", "utf8_minify_256m", "concat_8g", "tokens_64m"])
     ap.add_argument("--check", action="store_true", help="parity gate of the multi-rank path on adversarial cuts")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

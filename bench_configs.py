@@ -255,6 +255,66 @@ def run_utf8_minify(args, rank, world, size=256 << 20):
     return ok
 
 
+# =============================================================================== SURVEY 8(f) row 4: stage-2-lite on the 64 MiB document
+def run_tokens(args, rank, world, size=64 << 20):
+    """sjb200_tokens_dev behind stage 1 on BASELINE.json configs[1]'s document: token types / payloads / string buffer.
+    Timed with CUDA events around the three launches of one call (cold L2), whole-output parity against the oracle."""
+    torch, dist, sj, dev, local = _setup(rank, world)
+    if rank != 0:
+        return True
+    from simdjson_b200 import corpus
+    O = B.oracle()
+    port = O.Port()
+    steps = max(3, min(args.steps, 20))
+    doc = corpus.random_json(size).copy()
+    d = torch.from_numpy(doc).to(dev)
+    rc, parser = sj.get_active_implementation(local).create_dom_parser_implementation(size)
+    assert parser.stage1_device(d, sj.REGULAR) == 0
+    parser.set_option("tok_stage", int(os.environ.get("SJB200_TOK_STAGE", "1")))  # 0: A/B baseline without shared-memory staging
+    n = parser.n_structural_indexes
+    d_idx = parser.device_index_buffer()
+    cap = int(sj.lib().sjb200_string_buf_capacity(size))
+    d_type = torch.empty(n, dtype=torch.uint8, device=dev)
+    d_payload = torch.empty(n, dtype=torch.int64, device=dev)
+    d_strbuf = torch.empty(cap, dtype=torch.uint8, device=dev)
+    res = sj.capi.TokensResult()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+    ts = []
+    for it in range(steps + 1):
+        flush.fill_(it)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        sj.lib().sjb200_tokens_dev(parser._ctx, d.data_ptr(), size, d_idx.data_ptr(), n, d_type.data_ptr(), d_payload.data_ptr(), d_strbuf.data_ptr(), cap,
+                                   C.byref(res), C.c_void_p(stream.cuda_stream))
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = float(np.mean(ts[1:]))
+    r = port.stage1(doc)
+    t0 = time.time()
+    want = port.tokens(doc, r.idx, r.n, strbuf_cap=cap)
+    cpu_s = time.time() - t0
+    ok = (res.error == want[0] == 0 and n == r.n and bytes(d_type.cpu().numpy()) == bytes(want[1]) and np.array_equal(d_payload.cpu().numpy().view(np.uint64), want[2])
+          and res.string_bytes == want[4] and res.n_strings == want[5]
+          and bytes(d_strbuf[: res.string_bytes].cpu().numpy()) == bytes(want[3]))
+    # algorithmic bytes: the document once + the index array in, type + payload + string buffer out
+    algo = size + 4 * n + 9 * n + int(res.string_bytes)
+    line = _line(args, 1, size / (ms * 1e-3) / 1e9, ms,
+                 {"workload": "stage-2-lite (token types, integer values, string buffer) on the synthetic 64 MiB document of BASELINE.json configs[1], 1xB200 (SURVEY.md 8(f) row 4)",
+                  "bytes": size, "structurals": int(n), "strings": int(res.n_strings), "string_buf_bytes": int(res.string_bytes),
+                  "l2": "a 256 MiB buffer is written between calls (cold L2)", "value_is": "document bytes per second through sjb200_tokens_dev (3 launches + the 24-byte result)",
+                  "api": "sjb200_tokens_dev", "tok_stage": int(os.environ.get("SJB200_TOK_STAGE", "1"))},
+                 {"parity": {"ok": bool(ok), "against": "CPU oracle (sjo_tokens): every type, payload and string-buffer byte"}, "gpu_launches": 3 * (steps + 1),
+                  "roofline": dict(_roofline(algo, ms, "token_scan_kernel"), kernel="sjb200::token_scan_kernel + tile_scan_kernel + string_write_kernel (sjb200_tape.cu), one call",
+                                   note="the call's three launches together; strings are walked twice (length, then copy)"),
+                  "cpu_baseline": {"value": round(size / cpu_s / 1e9, 3), "unit": B.UNIT, "cores": 1, "kind": "port", "sample": "sjo_tokens (oracle/sj_oracle.c) on the whole 64 MiB document, one call"},
+                  "e2e": {"value": None, "unit": B.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "device-resident configuration"}})
+    print(json.dumps(line), flush=True)
+    parser.close()
+    return ok
+
+
 # =============================================================================== configs[4]: 8 GiB of twitter + citm, 8 shards
 def run_concat(args, rank, world, nshards=8, shard_target=1 << 30):
     torch, dist, sj, dev, local = _setup(rank, world)
@@ -422,6 +482,8 @@ def run(args, rank, world):
         ok = run_ndjson(args, rank, world)
     elif args.config == "utf8_minify_256m":
         ok = run_utf8_minify(args, rank, world)
+    elif args.config == "tokens_64m":
+        ok = run_tokens(args, rank, world)
     else:
         ok = run_concat(args, rank, world)
     _ = t0

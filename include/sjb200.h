@@ -147,6 +147,37 @@ typedef struct {
 SJB200_API int sjb200_document_table_dev(sjb200_ctx *ctx, const uint8_t *d_buf, const uint32_t *d_idx, uint32_t n, sjb200_doc_boundary *d_table,
                               uint32_t capacity, uint32_t *ndocs_out, void *stream);
 
+/* stage-2-lite on the device: from the device-resident output (d_idx, n) of a stage-1 call, what
+ * the reference's stage 2 decides about every token from its bytes alone -- the leaves of json_iterator::visit_primitive
+ * (src/generic/stage2/json_iterator.h L338-360) -- for all tokens at once:
+ *   d_type[k]     the tape_type char of structural k (include/simdjson/internal/tape_type.h L10-24): '{' '}' '[' ']'
+ *                 '"' 'l' (int64) 'u' (uint64) 'd' (float) 't' 'f' 'n'; ':' and ',' for those operators (they have no
+ *                 tape entry); 0 for a token in error
+ *   d_payload[k]  '"': offset of the string's record in d_strbuf (the tape payload of a string); 'l' / 'u': the value
+ *                 (numberparsing::parse_number, include/simdjson/generic/numberparsing.h L860-961); 'd': byte offset one
+ *                 past the number (floats are validated by grammar and delimited, not converted -- the reference also
+ *                 rejects floats whose value is infinite, L765-813); 0 type: the error_code (STRING_ERROR 5, T/F/N_ATOM
+ *                 _ERROR 6/7/8, NUMBER_ERROR 9, BIGINT_ERROR 10, TAPE_ERROR 3); other types: 0
+ *   d_strbuf      the document's string buffer, byte-identical to dom::document::string_buf after dom::parser::parse of
+ *                 the same document: per string, in document order, [uint32 length][unescaped bytes][0]
+ *                 (tape_builder::visit_string, src/generic/stage2/tape_builder.h L186-205; stringparsing::parse_string,
+ *                 stringparsing.h L146-190 -- the batched form of the dom_parser_implementation::parse_string virtual,
+ *                 include/simdjson/internal/dom_parser_implementation.h L124).  sjb200_string_buf_capacity(len) bytes
+ *                 always suffice (the reference's own sizing, include/simdjson/dom/document-inl.h L54).
+ * Scalars are judged as values inside an array or object (visit_primitive, not visit_root_primitive).  Not done here:
+ * the nesting grammar (the sequential part of stage 2).  Returns out->error: the error of the first token in error in
+ * document order (what a sequential stage 2 would have stopped at, token-level errors only), CAPACITY when d_strbuf is
+ * too small (nothing is written to it then; out->string_bytes says how much is needed), else SUCCESS. */
+typedef struct {
+  int error;
+  uint32_t first_error_index; /* structural index of the first token in error, 0xFFFFFFFF when none */
+  uint32_t n_strings;
+  uint64_t string_bytes;      /* bytes of d_strbuf in use */
+} sjb200_tokens_result;
+SJB200_API size_t sjb200_string_buf_capacity(size_t len);
+SJB200_API int sjb200_tokens_dev(sjb200_ctx *ctx, const uint8_t *d_buf, size_t len, const uint32_t *d_idx, uint32_t n, uint8_t *d_type, uint64_t *d_payload,
+                      uint8_t *d_strbuf, size_t strbuf_capacity, sjb200_tokens_result *out, void *stream);
+
 /* split form of the same calls for pipelining / timing: enqueue returns as soon as the work is on the
  * stream, finish waits for it and completes the reference's finish() logic. */
 SJB200_API int sjb200_stage1_dev_enqueue(sjb200_ctx *ctx, const uint8_t *d_buf, size_t len, int mode, uint32_t *d_idx, void *stream);

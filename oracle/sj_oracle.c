@@ -480,13 +480,7 @@ int sjo_tokens(const uint8_t *buf, size_t len, const uint32_t *idx, uint32_t n, 
         v = ul == -1 ? SJO_STRING_ERROR : SJO_UNCLOSED_STRING;
       } else {
         t = '"';
-        v = sb;
-        if (sb + (uint64_t)ul + 5 <= strbuf_cap) {
-          const uint32_t l32 = (uint32_t)ul;
-          for (int b = 0; b < 4; b++) strbuf[sb + (uint64_t)b] = (uint8_t)(l32 >> (8 * b));
-          sjo_parse_string(buf, len, p, strbuf + sb + 4);
-          strbuf[sb + 4 + (uint64_t)ul] = 0;
-        }
+        v = (uint64_t)ul; /* becomes the record's offset below, when the buffer is large enough */
         sb += (uint64_t)ul + 5;
         ns++;
       }
@@ -510,6 +504,16 @@ int sjo_tokens(const uint8_t *buf, size_t len, const uint32_t *idx, uint32_t n, 
   *strbuf_len = sb;
   *n_strings = ns;
   *first_error_index = first;
-  if (err == SJO_SUCCESS && sb > strbuf_cap) return SJO_CAPACITY;
+  if (sb > strbuf_cap) return err == SJO_SUCCESS ? SJO_CAPACITY : err; /* nothing written, payloads keep the lengths */
+  uint64_t off = 0;
+  for (uint32_t k = 0; k < n; k++) {
+    if (type[k] != '"') continue;
+    const uint32_t l32 = (uint32_t)payload[k];
+    for (int b = 0; b < 4; b++) strbuf[off + (uint64_t)b] = (uint8_t)(l32 >> (8 * b));
+    sjo_parse_string(buf, len, idx[k], strbuf + off + 4);
+    strbuf[off + 4 + l32] = 0;
+    payload[k] = off;
+    off += (uint64_t)l32 + 5;
+  }
   return err;
 }

@@ -20,12 +20,14 @@ EXPORTS = [
     "sjb200_stage1_shard_dev", "sjb200_stage1_shard_dev_enqueue", "sjb200_fold_state", "sjb200_shard_cut", "sjb200_shard_cut_line",
     "sjb200_comm_create", "sjb200_comm_destroy", "sjb200_comm_get_handle", "sjb200_comm_connect", "sjb200_comm_connect_local",
     "sjb200_stage1_sharded", "sjb200_stage1_sharded_enqueue", "sjb200_stage1_sharded_finish",
+    "sjb200_tokens_dev", "sjb200_string_buf_capacity",
 ]
 COMM_HANDLE_BYTES = 64
 
 # simdjson::error_code values of this path (include/simdjson/error.h L19-54)
 SUCCESS, CAPACITY, MEMALLOC, UTF8_ERROR, EMPTY, UNESCAPED_CHARS, UNCLOSED_STRING, UNSUPPORTED_ARCHITECTURE, UNEXPECTED_ERROR = 0, 1, 2, 11, 13, 14, 15, 16, 24
-ERROR_NAMES = {0: "SUCCESS", 1: "CAPACITY", 2: "MEMALLOC", 11: "UTF8_ERROR", 13: "EMPTY", 14: "UNESCAPED_CHARS", 15: "UNCLOSED_STRING",
+ERROR_NAMES = {0: "SUCCESS", 1: "CAPACITY", 2: "MEMALLOC", 3: "TAPE_ERROR", 5: "STRING_ERROR", 6: "T_ATOM_ERROR", 7: "F_ATOM_ERROR", 8: "N_ATOM_ERROR",
+               9: "NUMBER_ERROR", 10: "BIGINT_ERROR", 11: "UTF8_ERROR", 13: "EMPTY", 14: "UNESCAPED_CHARS", 15: "UNCLOSED_STRING",
                16: "UNSUPPORTED_ARCHITECTURE", 24: "UNEXPECTED_ERROR"}
 
 # simdjson::stage1_mode (include/simdjson/internal/dom_parser_implementation.h L22-27)
@@ -34,6 +36,10 @@ REGULAR, STREAMING_PARTIAL, STREAMING_FINAL, JSON_SEQUENCE_PARTIAL, JSON_SEQUENC
 
 class Doc(C.Structure):
     _fields_ = [("d_buf", C.c_void_p), ("len", C.c_size_t), ("d_idx", C.c_void_p), ("n_structural_indexes", C.c_uint32), ("error", C.c_int)]
+
+
+class TokensResult(C.Structure):
+    _fields_ = [("error", C.c_int), ("first_error_index", C.c_uint32), ("n_strings", C.c_uint32), ("string_bytes", C.c_uint64)]
 
 
 class ShardResult(C.Structure):
@@ -92,6 +98,8 @@ def load():
         "sjb200_stage1_sharded": (C.c_int, [vp, vp, sz, C.c_int, vp, C.POINTER(ShardedResult), vp]),
         "sjb200_stage1_sharded_enqueue": (C.c_int, [vp, vp, sz, C.c_int, vp, vp]),
         "sjb200_stage1_sharded_finish": (C.c_int, [vp, C.POINTER(ShardedResult)]),
+        "sjb200_tokens_dev": (C.c_int, [vp, vp, sz, vp, C.c_uint32, vp, vp, vp, sz, C.POINTER(TokensResult), vp]),
+        "sjb200_string_buf_capacity": (sz, [sz]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

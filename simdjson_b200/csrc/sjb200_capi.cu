@@ -16,6 +16,7 @@
 #include "../../include/sjb200.h"
 #include "sjb200_bits.cuh"
 #include "sjb200_docs.h"
+#include "sjb200_tape.h"
 #include "sjb200_finish.h"
 #include "sjb200_hostpipe.h"
 #include "sjb200_kernels.cuh"
@@ -64,6 +65,7 @@ struct sjb200_ctx {
   size_t desc_tiles = 0;
   StreamFinish *d_sfin = nullptr;  // [kCarrySlots] results of the device-side streaming epilogue
   uint32_t *d_doc_scratch = nullptr; size_t doc_scratch_words = 0; uint32_t *d_ndocs = nullptr;
+  void *d_tok_scratch = nullptr; size_t tok_scratch_bytes = 0; TokenTotals *d_tok_tot = nullptr;  // stage-2-lite (sjb200_tape.cu)
   uint32_t *d_park = nullptr; size_t d_park_words = 0;  // scan4 with emit warps: parked masks (a per-CTA ring, independent of the input size)
   int grid_u = 0;
   // pinned host mirrors
@@ -74,6 +76,7 @@ struct sjb200_ctx {
   uint8_t *h_tails = nullptr; uint8_t *d_tails = nullptr; const uint8_t **d_tail_ptrs = nullptr; size_t tails_cap = 0;  // batch: last 3 bytes of every document
   uint32_t epoch = 0;
   int grid4 = 0;
+  long opt_tok_stage = 1;
   long opt_use_tma = 1, opt_grid = 0, opt_chunk_bytes = 4 << 20, opt_time_kernel = 0;
   cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // around the last scan kernel when opt_time_kernel is set
   bool ev_valid = false;
@@ -389,7 +392,7 @@ extern "C" void sjb200_destroy(sjb200_ctx *c) {
   DeviceGuard g(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   free_sized(c);
-  cudaFree(c->d_carry); cudaFree(c->d_flags); cudaFree(c->d_ticket); cudaFree(c->d_sfin); cudaFree(c->d_doc_scratch); cudaFree(c->d_ndocs); cudaFree(c->d_tails); cudaFree(c->d_tail_ptrs); cudaFree(c->d_debug); cudaFree(c->d_park);
+  cudaFree(c->d_carry); cudaFree(c->d_flags); cudaFree(c->d_ticket); cudaFree(c->d_sfin); cudaFree(c->d_doc_scratch); cudaFree(c->d_ndocs); cudaFree(c->d_tok_scratch); cudaFree(c->d_tok_tot); cudaFree(c->d_tails); cudaFree(c->d_tail_ptrs); cudaFree(c->d_debug); cudaFree(c->d_park);
   if (c->h_carry) cudaFreeHost(c->h_carry);
   if (c->h_flags) cudaFreeHost(c->h_flags);
   if (c->h_small) cudaFreeHost(c->h_small);
@@ -486,6 +489,7 @@ extern "C" int sjb200_set_option(sjb200_ctx *c, const char *key, long value) {
   if (!c || !key) return SJB200_UNEXPECTED_ERROR;
   if (!strcmp(key, "use_tma")) c->opt_use_tma = value;
   else if (!strcmp(key, "grid")) c->opt_grid = value;
+  else if (!strcmp(key, "tok_stage")) c->opt_tok_stage = value ? 1 : 0;
   else if (!strcmp(key, "time_kernel")) c->opt_time_kernel = value;
   else if (!strcmp(key, "debug_timeline")) c->opt_debug_timeline = value;
   else if (!strcmp(key, "chunk_bytes")) c->opt_chunk_bytes = std::max<long>(2 * kTileBytes, (value / (2 * kTileBytes)) * (2 * kTileBytes));
@@ -689,6 +693,40 @@ extern "C" int sjb200_document_table_dev(sjb200_ctx *c, const uint8_t *d_buf, co
   c->launches += 3;
   memcpy(ndocs_out, c->h_small, sizeof(uint32_t));
   return SJB200_SUCCESS;
+}
+
+// stage-2-lite: type and payload of every token, the document's string buffer -- sjb200_tape.cu
+extern "C" size_t sjb200_string_buf_capacity(size_t len) { return ((5 * (len / 3) + 64) + 63) / 64 * 64; }  // dom/document-inl.h L54
+
+extern "C" int sjb200_tokens_dev(sjb200_ctx *c, const uint8_t *d_buf, size_t len, const uint32_t *d_idx, uint32_t n, uint8_t *d_type, uint64_t *d_payload,
+                                 uint8_t *d_strbuf, size_t strbuf_capacity, sjb200_tokens_result *out, void *stream) {
+  if (!c || !out || (n && (!d_buf || !d_idx || !d_type || !d_payload)) || (strbuf_capacity && !d_strbuf)) return SJB200_UNEXPECTED_ERROR;
+  out->error = SJB200_SUCCESS; out->first_error_index = 0xFFFFFFFFu; out->n_strings = 0; out->string_bytes = 0;
+  DeviceGuard g(c->device);
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+  const size_t need = tokens_scratch_bytes(n);
+  if (c->tok_scratch_bytes < need) {
+    cudaFree(c->d_tok_scratch); c->d_tok_scratch = nullptr; c->tok_scratch_bytes = 0;
+    if (cudaMalloc(&c->d_tok_scratch, need) != cudaSuccess) { c->last_error = "cudaMalloc(token scratch)"; return SJB200_MEMALLOC; }
+    c->tok_scratch_bytes = need;
+  }
+  if (!c->d_tok_tot && cudaMalloc(reinterpret_cast<void **>(&c->d_tok_tot), sizeof(TokenTotals)) != cudaSuccess) { c->last_error = "cudaMalloc(token totals)"; return SJB200_MEMALLOC; }
+  static_assert(sizeof(TokenTotals) <= 64, "h_small");
+  if (!ok(c, launch_tokens(d_buf, len, d_idx, n, d_type, d_payload, d_strbuf, strbuf_capacity, c->d_tok_scratch, c->d_tok_tot, int(c->opt_tok_stage), s), "tokens") ||
+      !ok(c, cudaMemcpyAsync(c->h_small, c->d_tok_tot, sizeof(TokenTotals), cudaMemcpyDeviceToHost, s), "D2H token totals") || !ok(c, cudaStreamSynchronize(s), "sync"))
+    return SJB200_UNEXPECTED_ERROR;
+  c->launches += n ? 3 : 1;
+  TokenTotals t;
+  memcpy(&t, c->h_small, sizeof(t));
+  out->n_strings = t.n_strings;
+  out->string_bytes = t.string_bytes;
+  if (t.first_error != ~0ull) {
+    out->first_error_index = uint32_t(t.first_error >> 8);
+    out->error = int(t.first_error & 0xFFull);
+  } else if (t.string_bytes > strbuf_capacity) {
+    out->error = SJB200_CAPACITY;
+  }
+  return out->error;
 }
 
 extern "C" int sjb200_stage1_dev(sjb200_ctx *c, const uint8_t *d_buf, size_t len, int mode, uint32_t *d_idx, uint32_t *n_inout,

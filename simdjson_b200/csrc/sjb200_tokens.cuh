@@ -1,0 +1,225 @@
+// sjb200_tokens.cuh -- what stage 2 decides about ONE token from its bytes (strings, numbers, atoms): the per-thread
+// functions of sjb200_tape.cu.  Pure functions of (byte source, len, pos), compiled for host and device, so that they are checked
+// on the CPU against the oracle (tests/tokens_emul.cpp) before the kernels around them run on a GPU.
+//
+// Reference: json_iterator::visit_primitive src/generic/stage2/json_iterator.h L338-360; stringparsing::parse_string
+// src/generic/stage2/stringparsing.h L146-190 (handle_unicode_codepoint L55-98, escape_map L22-48);
+// jsoncharutils::codepoint_to_utf8 include/simdjson/generic/jsoncharutils.h L37-62; numberparsing::parse_number
+// include/simdjson/generic/numberparsing.h L860-961; atomparsing include/simdjson/generic/atomparsing.h L45-95.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SJ_TOK __host__ __device__ __forceinline__
+#else
+#define SJ_TOK inline
+#endif
+
+namespace sjb200 {
+namespace tok {
+
+// simdjson::error_code values this file reports (include/simdjson/error.h L19-54)
+enum : uint32_t { kUnclosedStringError = 15, kTapeError = 3, kStringError = 5, kTAtomError = 6, kFAtomError = 7, kNAtomError = 8, kNumberError = 9, kBigintError = 10 };
+
+SJ_TOK uint8_t ld_byte(const uint8_t *p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+// A byte source: byte i of the document; beyond the end the reference reads padding (numbers and atoms look one byte
+// past the token).  Plain: straight from the document.  Windowed (the kernels): a span of the document staged in shared
+// memory by the whole CTA, anything outside it from global memory.
+struct PlainSrc {
+  const uint8_t *buf;
+  uint64_t len;
+  SJ_TOK uint32_t operator()(uint64_t i) const { return i < len ? uint32_t(ld_byte(buf + i)) : 0x20u; }
+};
+struct WindowSrc {
+  const uint8_t *buf;
+  uint64_t len;
+  const uint8_t *win;  // win[k] = document byte lo + k, for k < span
+  uint64_t lo, span;
+  SJ_TOK uint32_t operator()(uint64_t i) const {
+    const uint64_t k = i - lo;
+    if (k < span) return win[k];
+    return i < len ? uint32_t(ld_byte(buf + i)) : 0x20u;
+  }
+};
+SJ_TOK bool is_digit(uint32_t c) { return c - '0' < 10u; }
+// internal::structural_or_whitespace (src/internal/jsoncharutils_tables.cpp L31-45)
+SJ_TOK bool ends_scalar(uint32_t c) {
+  return c == 0x20u || c == 0x09u || c == 0x0Au || c == 0x0Du || c == ',' || c == ':' || c == '[' || c == ']' || c == '{' || c == '}';
+}
+SJ_TOK int hex_val(uint32_t c) {
+  if (c - '0' < 10u) return int(c - '0');
+  const uint32_t l = c | 0x20u;
+  if (l - 'a' < 6u) return int(l - 'a' + 10);
+  return -1;
+}
+// four hex digits at i..i+3, -1 if one of them is not a hex digit (hex_to_u32_nocheck's "high bits set")
+template <class S>
+SJ_TOK int hex4(const S &at, uint64_t i) {
+  const int a = hex_val(at(i)), b = hex_val(at(i + 1)), c = hex_val(at(i + 2)), d = hex_val(at(i + 3));
+  if ((a | b | c | d) < 0) return -1;
+  return (a << 12) | (b << 8) | (c << 4) | d;
+}
+
+// One string: opening quote at pos.  Returns its unescaped length, -1 invalid escape, -2 the input ends first.
+// kWrite: the unescaped bytes go to dst.
+template <bool kWrite, class S>
+SJ_TOK long long walk_string(const S &at, uint64_t len, uint64_t pos, uint8_t *dst) {
+  uint64_t q = pos + 1;
+  long long out = 0;
+  while (q < len) {
+    const uint32_t b = at(q);
+    if (b == '"') return out;
+    if (b != '\\') {
+      if (kWrite) dst[out] = uint8_t(b);
+      out++; q++;
+      continue;
+    }
+    const uint32_t e = at(q + 1);
+    if (e != 'u') {
+      uint32_t m;
+      switch (e) {  // stringparsing.h escape_map L22-48
+        case '"': m = 0x22; break;
+        case '\\': m = 0x5C; break;
+        case '/': m = 0x2F; break;
+        case 'b': m = 0x08; break;
+        case 'f': m = 0x0C; break;
+        case 'n': m = 0x0A; break;
+        case 'r': m = 0x0D; break;
+        case 't': m = 0x09; break;
+        default: return -1;
+      }
+      if (kWrite) dst[out] = uint8_t(m);
+      out++; q += 2;
+      continue;
+    }
+    int cp = hex4(at, q + 2);
+    if (cp < 0) return -1;
+    q += 6;
+    if (cp >= 0xD800 && cp < 0xDC00) {  // a high surrogate needs its low one as the next \uXXXX (no replacement character)
+      if (at(q) != '\\' || at(q + 1) != 'u') return -1;
+      const int lo = hex4(at, q + 2);
+      if (lo < 0xDC00 || lo > 0xDFFF) return -1;
+      cp = (((cp - 0xD800) << 10) | (lo - 0xDC00)) + 0x10000;
+      q += 6;
+    } else if (cp >= 0xDC00 && cp <= 0xDFFF) {
+      return -1;
+    }
+    if (cp <= 0x7F) {
+      if (kWrite) dst[out] = uint8_t(cp);
+      out += 1;
+    } else if (cp <= 0x7FF) {
+      if (kWrite) { dst[out] = uint8_t(0xC0 | (cp >> 6)); dst[out + 1] = uint8_t(0x80 | (cp & 63)); }
+      out += 2;
+    } else if (cp <= 0xFFFF) {
+      if (kWrite) { dst[out] = uint8_t(0xE0 | (cp >> 12)); dst[out + 1] = uint8_t(0x80 | ((cp >> 6) & 63)); dst[out + 2] = uint8_t(0x80 | (cp & 63)); }
+      out += 3;
+    } else {
+      if (kWrite) {
+        dst[out] = uint8_t(0xF0 | (cp >> 18)); dst[out + 1] = uint8_t(0x80 | ((cp >> 12) & 63));
+        dst[out + 2] = uint8_t(0x80 | ((cp >> 6) & 63)); dst[out + 3] = uint8_t(0x80 | (cp & 63));
+      }
+      out += 4;
+    }
+  }
+  return -2;
+}
+
+// The number that starts at pos (parse_number, numberparsing.h L860-961).  Returns the tape type, 0 with *value = error.
+template <class S>
+SJ_TOK uint32_t scan_number(const S &at, uint64_t pos, uint32_t first, unsigned long long *value) {
+  const bool neg = first == '-';
+  uint64_t q = pos + (neg ? 1 : 0);
+  const uint64_t start = q;
+  unsigned long long i = 0;
+  uint32_t c = at(q);
+  const uint32_t lead = c;
+  while (is_digit(c)) { i = i * 10ull + (c - '0'); c = at(++q); }
+  const uint64_t digits = q - start;
+  if (digits == 0 || (lead == '0' && digits > 1)) { *value = kNumberError; return 0; }
+  bool is_float = false;
+  if (c == '.') {
+    is_float = true;
+    const uint64_t fs = ++q;
+    c = at(q);
+    while (is_digit(c)) c = at(++q);
+    if (q == fs) { *value = kNumberError; return 0; }  // "1." is not a number
+  }
+  if ((c | 0x20u) == 'e') {
+    is_float = true;
+    c = at(++q);
+    if (c == '-' || c == '+') c = at(++q);
+    const uint64_t es = q;
+    while (is_digit(c)) c = at(++q);
+    if (q == es) { *value = kNumberError; return 0; }
+  }
+  const bool dirty = !ends_scalar(c);
+  if (is_float) {
+    if (dirty) { *value = kNumberError; return 0; }
+    *value = q;  // one past the token: the consumer converts [pos, q)
+    return 'd';
+  }
+  const uint64_t longest = neg ? 19 : 20;  // L920-946: the 64-bit limits
+  if (digits > longest) { *value = kBigintError; return 0; }
+  if (digits == longest) {
+    if (neg) {
+      if (i > (1ull << 63)) { *value = kBigintError; return 0; }
+    } else if (first != '1' || i <= 0x7FFFFFFFFFFFFFFFull) { *value = kBigintError; return 0; }  // wrapped around
+  }
+  if (dirty) { *value = kNumberError; return 0; }
+  if (!neg && i > 0x7FFFFFFFFFFFFFFFull) { *value = i; return 'u'; }
+  *value = neg ? (~i + 1ull) : i;
+  return 'l';
+}
+
+template <class S>
+SJ_TOK bool atom_is(const S &at, uint64_t pos, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, int wl) {
+  const uint32_t w[5] = {w0, w1, w2, w3, w4};
+  for (int k = 1; k < wl; k++)
+    if (at(pos + k) != w[k]) return false;
+  return ends_scalar(at(pos + wl));
+}
+
+// type and payload of the token at structural position p (see include/sjb200.h, sjb200_tokens_dev); a string's payload is
+// its unescaped length
+template <class S>
+SJ_TOK uint32_t classify_token(const S &at, uint64_t len, uint64_t p, unsigned long long *value) {
+  const uint32_t c = at(p);
+  *value = 0;
+  if (c == '{' || c == '}' || c == '[' || c == ']' || c == ':' || c == ',') return c;
+  if (c == '"') {
+    const long long ul = walk_string<false>(at, len, p, nullptr);
+    if (ul < 0) {
+      *value = ul == -1 ? uint32_t(kStringError) : uint32_t(kUnclosedStringError);
+      return 0;
+    }
+    *value = (unsigned long long)ul;
+    return '"';
+  }
+  if (c <= '9' || c == '-') return scan_number(at, p, c, value);  // json_iterator.h L342: `(*value - '0') < 10` in int -- every byte up to '9' takes the number path
+  if (c == 't') {
+    if (atom_is(at, p, 't', 'r', 'u', 'e', 0, 4)) return 't';
+    *value = kTAtomError;
+    return 0;
+  }
+  if (c == 'f') {
+    if (atom_is(at, p, 'f', 'a', 'l', 's', 'e', 5)) return 'f';
+    *value = kFAtomError;
+    return 0;
+  }
+  if (c == 'n') {
+    if (atom_is(at, p, 'n', 'u', 'l', 'l', 0, 4)) return 'n';
+    *value = kNAtomError;
+    return 0;
+  }
+  *value = kTapeError;
+  return 0;
+}
+
+}  // namespace tok
+}  // namespace sjb200

@@ -169,6 +169,24 @@ class dom_parser_implementation:
         self.n_structural_indexes = n.value
         return rc
 
+    def tokens_device(self, d_buf, d_idx=None, n=None, strbuf_capacity=None, stream=None):
+        """stage-2-lite (sjb200_tokens_dev) on the output of the last device-resident stage-1 call: returns
+        (capi.TokensResult, d_type uint8[n], d_payload int64[n] (bit pattern of the uint64), d_strbuf uint8[capacity])"""
+        import torch
+        if d_idx is None:
+            d_idx = self.device_index_buffer()
+        if n is None:
+            n = self.n_structural_indexes
+        cap = lib().sjb200_string_buf_capacity(d_buf.numel()) if strbuf_capacity is None else strbuf_capacity
+        dev = d_buf.device
+        d_type = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+        d_payload = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+        d_strbuf = torch.empty(max(cap, 1), dtype=torch.uint8, device=dev)
+        res = capi.TokensResult()
+        lib().sjb200_tokens_dev(self._ctx, d_buf.data_ptr(), d_buf.numel(), d_idx.data_ptr(), n, d_type.data_ptr(), d_payload.data_ptr(),
+                                d_strbuf.data_ptr() if cap else None, cap, C.byref(res), _stream_ptr(stream))
+        return res, d_type[:n], d_payload[:n], d_strbuf
+
     def stage1_shard_device(self, d_buf, state_in=0, last_shard=True, d_idx=None, stream=None):
         """one GPU's piece of a sharded scan; returns (error_code, capi.ShardResult)"""
         if d_idx is None:

@@ -690,3 +690,131 @@ def test_device_stream_epilogue_and_document_table(port):
             assert all(doc[b] in b'[{"0123456789-tfn' for b in t[:50, 1])
     finally:
         p.close()
+
+
+# --------------------------------------------------------------------------- stage-2-lite
+def _tokens_on_device(p, doc):
+    """stage 1 + sjb200_tokens_dev on a device-resident document; returns the oracle-shaped tuple"""
+    a = np.frombuffer(bytes(doc), dtype=np.uint8)
+    d = torch.from_numpy(a.copy()).cuda()
+    rc = p.stage1_device(d, sj.REGULAR)
+    return rc, d
+
+
+def _tokens_tuple(res, d_type, d_payload, d_strbuf, cap):
+    used = min(res.string_bytes, cap) if res.error != sj.CAPACITY else 0
+    return (res.error, d_type.cpu().numpy(), d_payload.cpu().numpy().view(np.uint64), d_strbuf[:used].cpu().numpy(), res.string_bytes, res.n_strings,
+            res.first_error_index)
+
+
+def _same_tokens(got, want, ctx):
+    assert got[0] == want[0], (ctx, got[0], want[0])
+    assert bytes(got[1]) == bytes(want[1]), (ctx, "types")
+    if not np.array_equal(got[2], want[2]):
+        k = int(np.argmax(got[2] != want[2]))
+        raise AssertionError((ctx, "payload", k, got[2][k], want[2][k], chr(want[1][k])))
+    assert got[4:] == want[4:], (ctx, got[4:], want[4:])
+    assert bytes(got[3]) == bytes(want[3]), (ctx, "string_buf")
+
+
+def test_tokens_device_matches_oracle(port):
+    import token_fuzz as TF
+    rng = random.Random(corpus.SEED ^ 0x70c3)
+    rc, p = sj.get_active_implementation().create_dom_parser_implementation(32 << 20)
+    assert rc == sj.SUCCESS
+    try:
+        docs = [bytes(corpus.random_json(rng.randrange(300, 300000), seed=5000 + i)) for i in range(8)]
+        docs += [open(os.path.join(O.JSONEXAMPLES, f), "rb").read() for f in ("twitter.json", "citm_catalog.json")]
+        docs += [bytes(corpus.random_json(16 << 20, seed=31337)), b"[]", b"7", b'""', b'{"a":"b"}']
+        for _ in range(40):  # documents of adversarial tokens: every scalar and string body the fuzzers produce, errors included
+            parts = []
+            for _ in range(rng.randrange(1, 3000)):
+                if rng.random() < 0.5:
+                    parts.append(b'"' + TF.string_body(rng)[0] + b'"')
+                else:
+                    tok = TF.scalar_token(rng)
+                    if b'"' not in tok and b"\\" not in tok:
+                        parts.append(tok)
+            docs.append(b"[" + rng.choice([b",", b" ,\n ", b", "]).join(parts) + b"]")
+        for k, doc in enumerate(docs):
+            r = port.stage1(doc)
+            assert r.err == 0
+            rc, d = _tokens_on_device(p, doc)
+            assert rc == 0 and p.n_structural_indexes == r.n
+            want = port.tokens(doc, r.idx, r.n, strbuf_cap=sj.lib().sjb200_string_buf_capacity(len(doc)))
+            for stage in ((1, 0) if k % 4 == 0 else (1,)):  # 0: the unstaged baseline path (every thread on global memory)
+                p.set_option("tok_stage", stage)
+                res, d_type, d_payload, d_strbuf = p.tokens_device(d)
+                _same_tokens(_tokens_tuple(res, d_type, d_payload, d_strbuf, d_strbuf.numel()), want, ("doc", k, stage, doc[:60]))
+            p.set_option("tok_stage", 1)
+            if k < 4:  # unaligned document and string buffer: the staging falls back to byte copies
+                du = torch.empty(len(doc) + 3, dtype=torch.uint8, device="cuda")[3:]
+                du.copy_(d)
+                assert p.stage1_device(du, sj.REGULAR) == 0
+                cap = int(sj.lib().sjb200_string_buf_capacity(len(doc)))
+                sb = torch.empty(cap + 5, dtype=torch.uint8, device="cuda")[5:]
+                ty = torch.empty(r.n, dtype=torch.uint8, device="cuda")
+                pl = torch.empty(r.n, dtype=torch.int64, device="cuda")
+                import ctypes as C
+                res2 = sj.capi.TokensResult()
+                sj.lib().sjb200_tokens_dev(p._ctx, du.data_ptr(), len(doc), p.device_index_buffer().data_ptr(), r.n, ty.data_ptr(), pl.data_ptr(), sb.data_ptr(), cap,
+                                           C.byref(res2), None)
+                _same_tokens(_tokens_tuple(res2, ty, pl, sb, cap), want, ("unaligned", k))
+        # too small a string buffer: CAPACITY, nothing written, payloads keep the lengths; and no structurals at all
+        doc = docs[0]
+        r = port.stage1(doc)
+        rc, d = _tokens_on_device(p, doc)
+        want = port.tokens(doc, r.idx, r.n, strbuf_cap=16)
+        res, d_type, d_payload, d_strbuf = p.tokens_device(d, strbuf_capacity=16)
+        assert res.error == sj.CAPACITY == want[0]
+        _same_tokens(_tokens_tuple(res, d_type, d_payload, d_strbuf, 16), (want[0], want[1], want[2], b"", want[4], want[5], want[6]), "capacity")
+        res, *_ = p.tokens_device(d, n=0)
+        assert res.error == 0 and res.n_strings == 0 and res.string_bytes == 0 and res.first_error_index == 0xFFFFFFFF
+    finally:
+        p.close()
+
+
+def test_tokens_device_matches_golden():
+    """the string buffer and the tape types / payloads the reference itself produced (tests/golden/tokens.json)"""
+    g = _load("tokens.json")
+    rc, p = sj.get_active_implementation().create_dom_parser_implementation(4 << 20)
+    assert rc == sj.SUCCESS
+    try:
+        for c in g["documents"]:
+            doc = bytes.fromhex(c["doc"])
+            rc, d = _tokens_on_device(p, doc)
+            assert rc == 0
+            res, d_type, d_payload, d_strbuf = p.tokens_device(d)
+            assert res.error == c["err"] == 0
+            types, pay = d_type.cpu().numpy(), d_payload.cpu().numpy().view(np.uint64)
+            keep = [i for i, t in enumerate(types) if chr(t) not in ":,"]
+            assert bytes(types[keep]) == c["types"].encode("latin1"), doc[:60]
+            for i, v in c["payloads"].items():
+                assert int(pay[keep][int(i)]) == int(v), (doc[:60], i)
+            assert bytes(d_strbuf[: res.string_bytes].cpu().numpy()) == bytes.fromhex(c["string_buf"]), doc[:60]
+        for c in g["scalars"]:
+            doc = bytes.fromhex(c["doc"])
+            rc, d = _tokens_on_device(p, doc)
+            if rc != 0:
+                assert rc == c["err"]
+                continue
+            res, d_type, d_payload, _sb = p.tokens_device(d)
+            k = c["index"]
+            if c["err"] == 0:
+                assert res.error == 0 and chr(int(d_type[k])) == c["type"], doc
+                if c["value"] is not None:
+                    assert int(d_payload[k].cpu().numpy().view(np.uint64)) == int(c["value"]), doc
+            else:
+                assert int(d_type[k]) == 0 and int(d_payload[k]) == c["err"] == res.error and res.first_error_index == k, doc
+        for f in g["files"]:
+            doc = open(os.path.join(O.JSONEXAMPLES, f["file"]), "rb").read()
+            rc, d = _tokens_on_device(p, doc)
+            res, d_type, d_payload, d_strbuf = p.tokens_device(d)
+            types, pay = d_type.cpu().numpy(), d_payload.cpu().numpy().view(np.uint64)
+            keep = np.array([chr(t) not in ":," for t in types])
+            t, pp = types[keep], pay[keep]
+            assert res.error == 0 and len(t) == f["entries"] and hashlib.sha256(bytes(t)).hexdigest() == f["types_sha256"]
+            assert hashlib.sha256(np.where(t == ord("d"), 0, pp).astype(np.uint64).tobytes()).hexdigest() == f["payloads_no_doubles_sha256"]
+            assert res.string_bytes == f["string_buf_bytes"] and hashlib.sha256(bytes(d_strbuf[: res.string_bytes].cpu().numpy())).hexdigest() == f["string_buf_sha256"]
+    finally:
+        p.close()
