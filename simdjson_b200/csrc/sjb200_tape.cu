@@ -31,6 +31,7 @@
 #include "sjb200_common.h"
 #include "sjb200_tape.h"
 #include "sjb200_tokens.cuh"
+#include "sjb200_tokens_warp.cuh"
 
 namespace sjb200 {
 
@@ -39,6 +40,8 @@ namespace {
 constexpr int kTokThreads = 512;           // structurals per tile, one per thread
 constexpr uint32_t kWinBytes = 20 * 1024;  // staged input span per tile (~5.6 KB on average)
 constexpr uint32_t kOutBytes = 20 * 1024;  // staged string records per tile (B only)
+constexpr uint64_t kLaneBudget = 96;       // a lane walks at most this many bytes of a string itself; longer strings go to the warp
+constexpr unsigned long long kLongFlag = 1ull << 63;  // payload between A and B: the string was measured by the warp, B copies it the same way
 
 __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long *sh) {
   for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
@@ -87,11 +90,26 @@ __global__ void __launch_bounds__(kTokThreads) token_scan_kernel(const uint8_t *
   } else {
     src.buf = buf; src.len = len; src.win = win; src.lo = 0; src.span = 0;
   }
+  const unsigned lane = threadIdx.x & 31u;
+  uint32_t t = 0xFFFFFFFFu;  // no token (beyond n)
+  unsigned long long v = 0;
+  const uint64_t p = i < n ? uint64_t(idx[i]) : 0;
+  if (i < n) t = tok::classify_token(src, len, p, &v, kLaneBudget);
+  // long strings: one after the other by the whole warp
+  uint32_t pending = __ballot_sync(0xFFFFFFFFu, t == tok::kLongString);
+  while (pending) {
+    const int l = __ffs(int(pending)) - 1;
+    pending &= pending - 1;
+    const uint64_t pl = __shfl_sync(0xFFFFFFFFu, (unsigned long long)p, l);
+    const long long ul = tok::warp_string<false>(src, len, pl, nullptr, lane);
+    if (int(lane) == l) {
+      if (ul < 0) { t = 0; v = ul == -1 ? uint32_t(tok::kStringError) : uint32_t(tok::kUnclosedStringError); }
+      else { t = '"'; v = (unsigned long long)ul | kLongFlag; }
+    }
+  }
   if (i < n) {
-    unsigned long long v = 0;
-    const uint32_t t = tok::classify_token(src, len, idx[i], &v);
     if (t == '"') {
-      bytes = v + 5;
+      bytes = (v & ~kLongFlag) + 5;
       nstr = 1;
     }
     type[i] = uint8_t(t);
@@ -170,8 +188,11 @@ __global__ void __launch_bounds__(kTokThreads) string_write_kernel(const uint8_t
   } else {
     src.buf = buf; src.len = len; src.win = win; src.lo = 0; src.span = 0;
   }
+  const unsigned lane = threadIdx.x & 31u;
   const bool mine_is_string = i < n && type[i] == '"';
-  const unsigned long long ul = mine_is_string ? payload[i] : 0ull;
+  const unsigned long long pl0 = mine_is_string ? payload[i] : 0ull;
+  const bool mine_is_long = (pl0 & kLongFlag) != 0;
+  const unsigned long long ul = pl0 & ~kLongFlag;
   const unsigned long long mine = mine_is_string ? ul + 5 : 0ull;
   // exclusive prefix over the CTA's threads (thread order = document order)
   unsigned long long x = mine;
@@ -188,12 +209,21 @@ __global__ void __launch_bounds__(kTokThreads) string_write_kernel(const uint8_t
   uint8_t *dst_tile = strbuf + t_off;
   const uint32_t phase = uint32_t(reinterpret_cast<uintptr_t>(dst_tile) & 15u);
   const bool staged_out = stage && t_bytes <= kOutBytes;
+  uint8_t *rec = staged_out ? outb + phase + rel : dst_tile + rel;
+  const uint64_t p = mine_is_string ? uint64_t(idx[i]) : 0;
   if (mine_is_string) {
-    uint8_t *rec = staged_out ? outb + phase + rel : dst_tile + rel;
     rec[0] = uint8_t(ul); rec[1] = uint8_t(ul >> 8); rec[2] = uint8_t(ul >> 16); rec[3] = uint8_t(ul >> 24);
-    tok::walk_string<true>(src, len, idx[i], rec + 4);
+    if (!mine_is_long) tok::walk_string<true>(src, len, p, rec + 4);
     rec[4 + ul] = 0;
     payload[i] = t_off + rel;
+  }
+  uint32_t pending = __ballot_sync(0xFFFFFFFFu, mine_is_long);
+  while (pending) {  // long strings: copied by the whole warp
+    const int l = __ffs(int(pending)) - 1;
+    pending &= pending - 1;
+    const uint64_t pl = __shfl_sync(0xFFFFFFFFu, (unsigned long long)p, l);
+    uint8_t *dl = reinterpret_cast<uint8_t *>(__shfl_sync(0xFFFFFFFFu, (unsigned long long)reinterpret_cast<uintptr_t>(rec + 4), l));
+    tok::warp_string<true>(src, len, pl, dl, lane);
   }
   if (!staged_out) return;
   __syncthreads();

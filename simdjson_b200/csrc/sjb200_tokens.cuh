@@ -66,13 +66,16 @@ SJ_TOK int hex4(const S &at, uint64_t i) {
   return (a << 12) | (b << 8) | (c << 4) | d;
 }
 
-// One string: opening quote at pos.  Returns its unescaped length, -1 invalid escape, -2 the input ends first.
+// One string: opening quote at pos.  Returns its unescaped length, -1 invalid escape, -2 the input ends first, -3 over budget.
 // kWrite: the unescaped bytes go to dst.
+// budget: give up (-3) once more than that many bytes have been looked at -- the caller hands such a string to the warp
+// (tok::warp_string, sjb200_tokens_warp.cuh).
 template <bool kWrite, class S>
-SJ_TOK long long walk_string(const S &at, uint64_t len, uint64_t pos, uint8_t *dst) {
+SJ_TOK long long walk_string(const S &at, uint64_t len, uint64_t pos, uint8_t *dst, uint64_t budget = ~0ull) {
   uint64_t q = pos + 1;
   long long out = 0;
   while (q < len) {
+    if (q - pos > budget) return -3;
     const uint32_t b = at(q);
     if (b == '"') return out;
     if (b != '\\') {
@@ -187,13 +190,15 @@ SJ_TOK bool atom_is(const S &at, uint64_t pos, uint32_t w0, uint32_t w1, uint32_
 
 // type and payload of the token at structural position p (see include/sjb200.h, sjb200_tokens_dev); a string's payload is
 // its unescaped length
+constexpr uint32_t kLongString = 1;  // classify_token: a string longer than the budget, length not known yet
 template <class S>
-SJ_TOK uint32_t classify_token(const S &at, uint64_t len, uint64_t p, unsigned long long *value) {
+SJ_TOK uint32_t classify_token(const S &at, uint64_t len, uint64_t p, unsigned long long *value, uint64_t string_budget = ~0ull) {
   const uint32_t c = at(p);
   *value = 0;
   if (c == '{' || c == '}' || c == '[' || c == ']' || c == ':' || c == ',') return c;
   if (c == '"') {
-    const long long ul = walk_string<false>(at, len, p, nullptr);
+    const long long ul = walk_string<false>(at, len, p, nullptr, string_budget);
+    if (ul == -3) return kLongString;
     if (ul < 0) {
       *value = ul == -1 ? uint32_t(kStringError) : uint32_t(kUnclosedStringError);
       return 0;

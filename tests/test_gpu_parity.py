@@ -736,6 +736,12 @@ def test_tokens_device_matches_oracle(port):
                     if b'"' not in tok and b"\\" not in tok:
                         parts.append(tok)
             docs.append(b"[" + rng.choice([b",", b" ,\n ", b", "]).join(parts) + b"]")
+        for _ in range(12):  # long strings (handled by whole warps): plain runs, dense escapes, at every phase of the 32-byte steps
+            parts = [b'"' + TF.long_body(rng, rng.choice([90, 97, 200, 513, 3000, 40000]), rng.choice([0.0, 0.05, 0.3, 1.0])) + b'"' for _ in range(rng.randrange(1, 40))]
+            parts += [b'"' + b"q" * rng.randrange(0, 200) + bad + b'tail"' for bad in (b"\\uD800", b"\\uDC00 ", b"\\u12", b"\\q")][: rng.randrange(0, 5)]
+            rng.shuffle(parts)
+            docs.append(b"[" + b" , ".join(parts) + b"]")
+        docs.append(b'{"blob":"' + TF.long_body(rng, 3 << 20, 0.0) + b'","esc":"' + TF.long_body(rng, 1 << 20, 1.0) + b'"}')
         for k, doc in enumerate(docs):
             r = port.stage1(doc)
             assert r.err == 0

@@ -87,3 +87,18 @@ def wrap_scalar(tok, rng):
     if style == 2:
         return b'{"a":' + tok + b"}", 3
     return b"[0,\n" + tok + b"\n]", 3
+
+
+def long_body(rng, n, esc_rate):
+    """a string body of about n bytes: plain runs (so that 512-byte blocks without specials occur) mixed with escapes at esc_rate"""
+    out = bytearray()
+    while len(out) < n:
+        r = rng.random()
+        if r < esc_rate:
+            b, _ = string_body(rng, bad_rate=0.0, maxlen=40)
+            out += b
+        elif r < esc_rate + 0.02:
+            out += rng.choice([b"\\\\" * rng.randrange(1, 40), b"\\\\\\\"", b"\\ud83d\\ude00" * rng.randrange(1, 8), b"\\u0041", b"\\n\\t\\\\u0041"])
+        else:
+            out += bytes(rng.choice(b"abcdefghijklmnopqrstuvwxyz 0123456789,.:;{}[]") for _ in range(rng.choice([1, 7, 31, 32, 33, 100, 511, 512, 513, 700, 1500])))
+    return bytes(out)
