@@ -177,8 +177,11 @@ __global__ void __launch_bounds__(kTokThreads) string_write_kernel(const uint8_t
   __shared__ __align__(16) uint8_t outb[kOutBytes + 16];
   __shared__ unsigned long long sh[kTokThreads / 32];
   const unsigned long long total = tot->string_bytes;
-  if (total > capacity) return;  // CAPACITY: nothing is written, payloads keep the lengths
   const uint32_t i0 = blockIdx.x * uint32_t(kTokThreads), i = i0 + threadIdx.x;
+  if (total > capacity) {  // CAPACITY: nothing is written, payloads keep the lengths (without the marker of the long ones)
+    if (i < n && type[i] == '"') payload[i] &= ~kLongFlag;
+    return;
+  }
   const unsigned long long t_off = tile_off[blockIdx.x];
   const unsigned long long t_bytes = (blockIdx.x + 1 < ntiles ? tile_off[blockIdx.x + 1] : total) - t_off;  // this tile's records
   if (t_bytes == 0) return;  // (uniform) no string in this tile

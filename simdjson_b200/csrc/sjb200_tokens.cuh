@@ -31,10 +31,36 @@ SJ_TOK uint8_t ld_byte(const uint8_t *p) {
 // A byte source: byte i of the document; beyond the end the reference reads padding (numbers and atoms look one byte
 // past the token).  Plain: straight from the document.  Windowed (the kernels): a span of the document staged in shared
 // memory by the whole CTA, anything outside it from global memory.
+// word(i, &w): the four bytes i..i+3 as a little-endian word when they can be had with ONE aligned load (false otherwise:
+// the caller goes byte by byte); vec16(i, w): likewise sixteen bytes from an address that is 16-byte aligned.
+SJ_TOK uint32_t ld_word(const uint8_t *p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(reinterpret_cast<const uint32_t *>(p));
+#else
+  uint32_t v;
+  __builtin_memcpy(&v, p, 4);
+  return v;
+#endif
+}
 struct PlainSrc {
   const uint8_t *buf;
   uint64_t len;
   SJ_TOK uint32_t operator()(uint64_t i) const { return i < len ? uint32_t(ld_byte(buf + i)) : 0x20u; }
+  SJ_TOK bool word(uint64_t i, uint32_t *w) const {
+    if (i + 4 > len || ((reinterpret_cast<uintptr_t>(buf) + i) & 3u)) return false;
+    *w = ld_word(buf + i);
+    return true;
+  }
+  SJ_TOK bool vec16(uint64_t i, uint32_t w[4]) const {
+    if (i + 16 > len || ((reinterpret_cast<uintptr_t>(buf) + i) & 15u)) return false;
+#if defined(__CUDA_ARCH__)
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(buf + i));
+    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+#else
+    __builtin_memcpy(w, buf + i, 16);
+#endif
+    return true;
+  }
 };
 struct WindowSrc {
   const uint8_t *buf;
@@ -46,7 +72,22 @@ struct WindowSrc {
     if (k < span) return win[k];
     return i < len ? uint32_t(ld_byte(buf + i)) : 0x20u;
   }
+  SJ_TOK bool word(uint64_t i, uint32_t *w) const {
+    const uint64_t k = i - lo;
+    if (k < span) {  // (k + 4 > span: straddles the window's end)
+      if (k + 4 > span || (reinterpret_cast<uintptr_t>(win + k) & 3u)) return false;
+      *w = *reinterpret_cast<const uint32_t *>(win + k);
+      return true;
+    }
+    return PlainSrc{buf, len}.word(i, w);
+  }
+  SJ_TOK bool vec16(uint64_t i, uint32_t w[4]) const { return PlainSrc{buf, len}.vec16(i, w); }  // long strings: straight from global memory
 };
+// a byte of the word equals c
+SJ_TOK bool word_has(uint32_t w, uint32_t c) {
+  const uint32_t x = w ^ (c * 0x01010101u);
+  return ((x - 0x01010101u) & ~x & 0x80808080u) != 0;
+}
 SJ_TOK bool is_digit(uint32_t c) { return c - '0' < 10u; }
 // internal::structural_or_whitespace (src/internal/jsoncharutils_tables.cpp L31-45)
 SJ_TOK bool ends_scalar(uint32_t c) {
@@ -76,6 +117,12 @@ SJ_TOK long long walk_string(const S &at, uint64_t len, uint64_t pos, uint8_t *d
   long long out = 0;
   while (q < len) {
     if (q - pos > budget) return -3;
+    uint32_t w;
+    if (at.word(q, &w) && !word_has(w, '"') && !word_has(w, '\\')) {  // four ordinary bytes at once
+      if (kWrite) { dst[out] = uint8_t(w); dst[out + 1] = uint8_t(w >> 8); dst[out + 2] = uint8_t(w >> 16); dst[out + 3] = uint8_t(w >> 24); }
+      out += 4; q += 4;
+      continue;
+    }
     const uint32_t b = at(q);
     if (b == '"') return out;
     if (b != '\\') {

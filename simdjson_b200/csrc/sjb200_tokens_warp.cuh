@@ -11,7 +11,7 @@
 //     code point (handle_unicode_codepoint L55-98: a high surrogate takes the low one that must follow and contributes
 //     4, the low one 0 -- a low surrogate is legal exactly when the escape six bytes before it is a high one); the four
 //     hex digits 0; any other byte 1 -- so the output offset of a byte is a warp prefix sum;
-//   * blocks of 512 bytes without a backslash or a quote (the common case in a long string) are copied without any of that.
+//   * blocks of 1 KiB without a backslash or a quote (the common case in a long string) are copied without any of that.
 // Same results as tok::walk_string (the sequential walk): checked against the oracle under the host SIMT emulation
 // (tests/tokens_warp_emul.cpp) -- written against the primitive layer of sjb200_simt.cuh for that purpose.
 #pragma once
@@ -32,24 +32,43 @@ SJ_DEV long long warp_string(const S &at, uint64_t len, uint64_t pos, uint8_t *d
   uint32_t prev_uchar = 0;    // the previous step's escaped 'u' lanes (their hex digits / a low surrogate may lie in this step)
   for (;;) {
     if (q >= len) return esc_carry ? -1 : -2;  // (a backslash as the last byte: its "escaped character" is padding)
-    // ---- 512 bytes at once when nothing in them needs a decision
-    if (!esc_carry && (prev_uchar >> 28) == 0 && q + 512 <= len) {
-      uint32_t w[16];
-      bool special = false;
+    // ---- 1 KiB at once when nothing in it needs a decision: two aligned 16-byte loads per lane, both in flight together
+    // (a single warp is latency-bound: one round trip to memory per step).  The block starts at the 16-byte boundary
+    // at or below q; the bytes before q (first block only) are lane 0's and ignored.
+    if (!esc_carry && (prev_uchar >> 28) == 0) {
+      const uint64_t mis = (reinterpret_cast<uintptr_t>(at.buf) + q) & 15u;
+      if (q >= mis && q - mis + 1024 <= len) {
+        const uint64_t a0 = q - mis;
+        uint32_t w[8];
+        const bool got = at.vec16(a0 + 16u * lane, w) && at.vec16(a0 + 512u + 16u * lane, w + 4);
+        bool special = !got;
+        if (got) {
 #pragma unroll
-      for (int k = 0; k < 16; k++) {
-        w[k] = at(q + 16u * lane + uint32_t(k));
-        special = special || w[k] == '\\' || w[k] == '"';
-      }
-      if (!sj_any(special)) {
-        if (kWrite) {
-#pragma unroll
-          for (int k = 0; k < 16; k++) dst[out + 16u * lane + uint32_t(k)] = uint8_t(w[k]);
+          for (int j = 0; j < 8; j++) {
+            uint32_t x = w[j];
+            if (j < 4 && lane == 0 && mis > uint64_t(4 * j)) {  // bytes before q: neutral
+              const uint32_t nb = mis - 4 * j >= 4 ? 4u : uint32_t(mis - 4 * j);
+              const uint32_t low = nb >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nb)) - 1u);
+              x = (x & ~low) | (0x20202020u & low);
+            }
+            special = special || word_has(x, '"') || word_has(x, '\\');
+          }
         }
-        out += 512;
-        q += 512;
-        prev_uchar = 0;
-        continue;
+        if (!sj_any(special)) {
+          if (kWrite) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              const uint64_t off = uint64_t(j < 4 ? 0 : 512) + 16u * lane + 4u * uint32_t(j & 3);  // of this word inside the block
+#pragma unroll
+              for (int t = 0; t < 4; t++)
+                if (off + uint64_t(t) >= mis) dst[out + (long long)(off + uint64_t(t) - mis)] = uint8_t(w[j] >> (8 * t));
+            }
+          }
+          out += (long long)(1024 - mis);
+          q = a0 + 1024;
+          prev_uchar = 0;
+          continue;
+        }
       }
     }
     // ---- 32 bytes, one per lane
