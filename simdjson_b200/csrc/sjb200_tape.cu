@@ -37,9 +37,10 @@ namespace sjb200 {
 
 namespace {
 
-constexpr int kTokThreads = 512;           // structurals per tile, one per thread
-constexpr uint32_t kWinBytes = 20 * 1024;  // staged input span per tile (~5.6 KB on average)
-constexpr uint32_t kOutBytes = 20 * 1024;  // staged string records per tile (B only)
+constexpr int kTokThreads = 256;           // structurals per tile, one per thread (4 CTAs per SM: a CTA's warps finish at different
+                                           // times and wait at its barriers -- 2 CTAs of 512 left a third of the issue slots idle)
+constexpr uint32_t kWinBytes = 12 * 1024;  // staged input span per tile (~2.8 KB on average)
+constexpr uint32_t kOutBytes = 12 * 1024;  // staged string records per tile (B only)
 constexpr uint64_t kLaneBudget = 96;       // a lane walks at most this many bytes of a string itself; longer strings go to the warp
 constexpr unsigned long long kLongFlag = 1ull << 63;  // payload between A and B: the string was measured by the warp, B copies it the same way
 
@@ -55,14 +56,18 @@ __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v
 
 // Stage the span of the document this tile's tokens live in: win[k] = buf[lo + k] for k < span (span <= kWinBytes).
 // lo is rounded down so that buf + lo is 16-byte aligned (whole vectors, never beyond len: the last bytes come one by one).
-__device__ tok::WindowSrc stage_window(const uint8_t *buf, uint64_t len, const uint32_t *idx, uint32_t n, uint32_t i0, uint8_t *win) {
+// The span reaches kWinMargin bytes past the next tile's first structural (what a token of this tile may look at:
+// tok::FastWin); *fast: all of that fits, and win is padded with spaces past the end of the document.
+constexpr uint32_t kWinMargin = 16;
+__device__ tok::WindowSrc stage_window(const uint8_t *buf, uint64_t len, const uint32_t *idx, uint32_t n, uint32_t i0, uint8_t *win, bool *fast) {
   tok::WindowSrc src;
   src.buf = buf; src.len = len; src.win = win;
   const uint64_t first = idx[i0];
   const uint64_t next = (uint64_t(i0) + kTokThreads < n) ? uint64_t(idx[i0 + kTokThreads]) : len;
   const uint64_t mis = (reinterpret_cast<uintptr_t>(buf) + first) & 15u;
   const uint64_t lo = first >= mis ? first - mis : first;  // (first < mis: an unaligned buffer's first bytes; byte loads below)
-  uint64_t span = next - lo;
+  uint64_t span = next + kWinMargin - lo;
+  *fast = span + kWinMargin <= kWinBytes;
   if (span > kWinBytes) span = kWinBytes;
   if (lo + span > len) span = len - lo;
   src.lo = lo; src.span = span;
@@ -72,6 +77,7 @@ __device__ tok::WindowSrc stage_window(const uint8_t *buf, uint64_t len, const u
   uint4 *w = reinterpret_cast<uint4 *>(win);
   for (uint32_t v = threadIdx.x; v < nvec; v += kTokThreads) w[v] = __ldg(g + v);
   for (uint32_t k = (nvec << 4) + threadIdx.x; k < uint32_t(span); k += kTokThreads) win[k] = __ldg(buf + lo + k);
+  if (*fast && threadIdx.x < kWinMargin) win[uint32_t(span) + threadIdx.x] = 0x20;  // (only the end of the document is ever looked at there)
   __syncthreads();
   return src;
 }
@@ -80,13 +86,14 @@ __device__ tok::WindowSrc stage_window(const uint8_t *buf, uint64_t len, const u
 __global__ void __launch_bounds__(kTokThreads) token_scan_kernel(const uint8_t *buf, uint64_t len, const uint32_t *idx, uint32_t n, uint8_t *type,
                                                                 unsigned long long *payload, unsigned long long *tile_bytes, uint32_t *tile_strings,
                                                                 TokenTotals *tot, int stage) {
-  __shared__ __align__(16) uint8_t win[kWinBytes];
+  __shared__ __align__(16) uint8_t win[kWinBytes];  // (stage_window: span + margin <= kWinBytes when it pads)
   __shared__ unsigned long long sh[kTokThreads / 32];
   const uint32_t i0 = blockIdx.x * uint32_t(kTokThreads), i = i0 + threadIdx.x;
   unsigned long long bytes = 0, nstr = 0;
   tok::WindowSrc src;
+  bool fast = false;
   if (stage) {
-    src = stage_window(buf, len, idx, n, i0, win);
+    src = stage_window(buf, len, idx, n, i0, win, &fast);
   } else {
     src.buf = buf; src.len = len; src.win = win; src.lo = 0; src.span = 0;
   }
@@ -94,7 +101,15 @@ __global__ void __launch_bounds__(kTokThreads) token_scan_kernel(const uint8_t *
   uint32_t t = 0xFFFFFFFFu;  // no token (beyond n)
   unsigned long long v = 0;
   const uint64_t p = i < n ? uint64_t(idx[i]) : 0;
-  if (i < n) t = tok::classify_token(src, len, p, &v, kLaneBudget);
+  if (i < n) {
+    if (fast) {  // (uniform) the usual case: 32-bit offsets into the window, nothing to check
+      const tok::FastWin f{win, uint32_t(src.span)};
+      t = tok::classify_token(f, f.limit, uint32_t(p - src.lo), &v, uint32_t(kLaneBudget));
+      if (t == 'd') v += src.lo;  // (a float's payload is a document offset)
+    } else {
+      t = tok::classify_token(src, len, p, &v, kLaneBudget);
+    }
+  }
   // long strings: one after the other by the whole warp
   uint32_t pending = __ballot_sync(0xFFFFFFFFu, t == tok::kLongString);
   while (pending) {
@@ -173,7 +188,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(unsigned long long *til
 __global__ void __launch_bounds__(kTokThreads) string_write_kernel(const uint8_t *buf, uint64_t len, const uint32_t *idx, uint32_t n, const uint8_t *type,
                                                                   unsigned long long *payload, const unsigned long long *tile_off, uint32_t ntiles,
                                                                   uint8_t *strbuf, unsigned long long capacity, const TokenTotals *tot, int stage) {
-  __shared__ __align__(16) uint8_t win[kWinBytes];
+  __shared__ __align__(16) uint8_t win[kWinBytes];  // (stage_window: span + margin <= kWinBytes when it pads)
   __shared__ __align__(16) uint8_t outb[kOutBytes + 16];
   __shared__ unsigned long long sh[kTokThreads / 32];
   const unsigned long long total = tot->string_bytes;
@@ -186,8 +201,9 @@ __global__ void __launch_bounds__(kTokThreads) string_write_kernel(const uint8_t
   const unsigned long long t_bytes = (blockIdx.x + 1 < ntiles ? tile_off[blockIdx.x + 1] : total) - t_off;  // this tile's records
   if (t_bytes == 0) return;  // (uniform) no string in this tile
   tok::WindowSrc src;
+  bool fast = false;
   if (stage) {
-    src = stage_window(buf, len, idx, n, i0, win);
+    src = stage_window(buf, len, idx, n, i0, win, &fast);
   } else {
     src.buf = buf; src.len = len; src.win = win; src.lo = 0; src.span = 0;
   }
@@ -216,7 +232,14 @@ __global__ void __launch_bounds__(kTokThreads) string_write_kernel(const uint8_t
   const uint64_t p = mine_is_string ? uint64_t(idx[i]) : 0;
   if (mine_is_string) {
     rec[0] = uint8_t(ul); rec[1] = uint8_t(ul >> 8); rec[2] = uint8_t(ul >> 16); rec[3] = uint8_t(ul >> 24);
-    if (!mine_is_long) tok::walk_string<true>(src, len, p, rec + 4);
+    if (!mine_is_long) {
+      if (fast) {
+        const tok::FastWin f{win, uint32_t(src.span)};
+        tok::walk_string<true>(f, f.limit, uint32_t(p - src.lo), rec + 4);
+      } else {
+        tok::walk_string<true>(src, len, p, rec + 4);
+      }
+    }
     rec[4 + ul] = 0;
     payload[i] = t_off + rel;
   }

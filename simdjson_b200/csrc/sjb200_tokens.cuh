@@ -43,6 +43,7 @@ SJ_TOK uint32_t ld_word(const uint8_t *p) {
 #endif
 }
 struct PlainSrc {
+  typedef uint64_t pos_t;
   const uint8_t *buf;
   uint64_t len;
   SJ_TOK uint32_t operator()(uint64_t i) const { return i < len ? uint32_t(ld_byte(buf + i)) : 0x20u; }
@@ -63,6 +64,7 @@ struct PlainSrc {
   }
 };
 struct WindowSrc {
+  typedef uint64_t pos_t;
   const uint8_t *buf;
   uint64_t len;
   const uint8_t *win;  // win[k] = document byte lo + k, for k < span
@@ -83,10 +85,29 @@ struct WindowSrc {
   }
   SJ_TOK bool vec16(uint64_t i, uint32_t w[4]) const { return PlainSrc{buf, len}.vec16(i, w); }  // long strings: straight from global memory
 };
+// The whole tile inside the staged window (the usual case): positions are 32-bit offsets into it and nothing is checked --
+// the CTA stages the tile's span plus 16 bytes (or 0x20 padding beyond the end of the document), and no token looks
+// further than 10 bytes past the closing quote / the end of its scalar, which lie before the next tile's first structural.
+struct FastWin {
+  typedef uint32_t pos_t;
+  const uint8_t *win;  // 16-byte aligned
+  uint32_t limit;      // bytes of the document in the window (the walk's "len")
+  SJ_TOK uint32_t operator()(uint32_t r) const { return win[r]; }
+  SJ_TOK bool word(uint32_t r, uint32_t *w) const {
+    if ((r & 3u) || r + 4 > limit) return false;
+    *w = *reinterpret_cast<const uint32_t *>(win + r);
+    return true;
+  }
+};
 // a byte of the word equals c
 SJ_TOK bool word_has(uint32_t w, uint32_t c) {
   const uint32_t x = w ^ (c * 0x01010101u);
   return ((x - 0x01010101u) & ~x & 0x80808080u) != 0;
+}
+// ... a quote or a backslash
+SJ_TOK bool word_has_special(uint32_t w) {
+  const uint32_t x = w ^ 0x22222222u, y = w ^ 0x5C5C5C5Cu;
+  return ((((x - 0x01010101u) & ~x) | ((y - 0x01010101u) & ~y)) & 0x80808080u) != 0;
 }
 SJ_TOK bool is_digit(uint32_t c) { return c - '0' < 10u; }
 // internal::structural_or_whitespace (src/internal/jsoncharutils_tables.cpp L31-45)
@@ -101,7 +122,7 @@ SJ_TOK int hex_val(uint32_t c) {
 }
 // four hex digits at i..i+3, -1 if one of them is not a hex digit (hex_to_u32_nocheck's "high bits set")
 template <class S>
-SJ_TOK int hex4(const S &at, uint64_t i) {
+SJ_TOK int hex4(const S &at, typename S::pos_t i) {
   const int a = hex_val(at(i)), b = hex_val(at(i + 1)), c = hex_val(at(i + 2)), d = hex_val(at(i + 3));
   if ((a | b | c | d) < 0) return -1;
   return (a << 12) | (b << 8) | (c << 4) | d;
@@ -112,21 +133,23 @@ SJ_TOK int hex4(const S &at, uint64_t i) {
 // budget: give up (-3) once more than that many bytes have been looked at -- the caller hands such a string to the warp
 // (tok::warp_string, sjb200_tokens_warp.cuh).
 template <bool kWrite, class S>
-SJ_TOK long long walk_string(const S &at, uint64_t len, uint64_t pos, uint8_t *dst, uint64_t budget = ~0ull) {
-  uint64_t q = pos + 1;
-  long long out = 0;
-  while (q < len) {
-    if (q - pos > budget) return -3;
+SJ_TOK long long walk_string(const S &at, typename S::pos_t len, typename S::pos_t pos, uint8_t *dst, typename S::pos_t budget = ~(typename S::pos_t)0) {
+  typedef typename S::pos_t P;
+  P q = pos + 1;
+  uint32_t out = 0;  // (a string is < 4 GiB: stage 1's limit)
+  uint8_t *o = dst;  // kWrite: where the next unescaped byte goes (one pointer, bumped: the stores need no address arithmetic)
+  const P stop = (budget < len && pos + 1 < len - budget) ? P(pos + 1 + budget) : len;  // the walk looks at bytes below stop
+  while (q < stop) {
     uint32_t w;
-    if (at.word(q, &w) && !word_has(w, '"') && !word_has(w, '\\')) {  // four ordinary bytes at once
-      if (kWrite) { dst[out] = uint8_t(w); dst[out + 1] = uint8_t(w >> 8); dst[out + 2] = uint8_t(w >> 16); dst[out + 3] = uint8_t(w >> 24); }
+    if (at.word(q, &w) && !word_has_special(w)) {  // four ordinary bytes at once
+      if (kWrite) { o[0] = uint8_t(w); o[1] = uint8_t(w >> 8); o[2] = uint8_t(w >> 16); o[3] = uint8_t(w >> 24); o += 4; }
       out += 4; q += 4;
       continue;
     }
     const uint32_t b = at(q);
     if (b == '"') return out;
     if (b != '\\') {
-      if (kWrite) dst[out] = uint8_t(b);
+      if (kWrite) *o++ = uint8_t(b);
       out++; q++;
       continue;
     }
@@ -144,7 +167,7 @@ SJ_TOK long long walk_string(const S &at, uint64_t len, uint64_t pos, uint8_t *d
         case 't': m = 0x09; break;
         default: return -1;
       }
-      if (kWrite) dst[out] = uint8_t(m);
+      if (kWrite) *o++ = uint8_t(m);
       out++; q += 2;
       continue;
     }
@@ -161,41 +184,43 @@ SJ_TOK long long walk_string(const S &at, uint64_t len, uint64_t pos, uint8_t *d
       return -1;
     }
     if (cp <= 0x7F) {
-      if (kWrite) dst[out] = uint8_t(cp);
+      if (kWrite) *o++ = uint8_t(cp);
       out += 1;
     } else if (cp <= 0x7FF) {
-      if (kWrite) { dst[out] = uint8_t(0xC0 | (cp >> 6)); dst[out + 1] = uint8_t(0x80 | (cp & 63)); }
+      if (kWrite) { o[0] = uint8_t(0xC0 | (cp >> 6)); o[1] = uint8_t(0x80 | (cp & 63)); o += 2; }
       out += 2;
     } else if (cp <= 0xFFFF) {
-      if (kWrite) { dst[out] = uint8_t(0xE0 | (cp >> 12)); dst[out + 1] = uint8_t(0x80 | ((cp >> 6) & 63)); dst[out + 2] = uint8_t(0x80 | (cp & 63)); }
+      if (kWrite) { o[0] = uint8_t(0xE0 | (cp >> 12)); o[1] = uint8_t(0x80 | ((cp >> 6) & 63)); o[2] = uint8_t(0x80 | (cp & 63)); o += 3; }
       out += 3;
     } else {
       if (kWrite) {
-        dst[out] = uint8_t(0xF0 | (cp >> 18)); dst[out + 1] = uint8_t(0x80 | ((cp >> 12) & 63));
-        dst[out + 2] = uint8_t(0x80 | ((cp >> 6) & 63)); dst[out + 3] = uint8_t(0x80 | (cp & 63));
+        o[0] = uint8_t(0xF0 | (cp >> 18)); o[1] = uint8_t(0x80 | ((cp >> 12) & 63));
+        o[2] = uint8_t(0x80 | ((cp >> 6) & 63)); o[3] = uint8_t(0x80 | (cp & 63));
+        o += 4;
       }
       out += 4;
     }
   }
-  return -2;
+  return q < len ? -3 : -2;  // over budget / the input ends first
 }
 
 // The number that starts at pos (parse_number, numberparsing.h L860-961).  Returns the tape type, 0 with *value = error.
 template <class S>
-SJ_TOK uint32_t scan_number(const S &at, uint64_t pos, uint32_t first, unsigned long long *value) {
+SJ_TOK uint32_t scan_number(const S &at, typename S::pos_t pos, uint32_t first, unsigned long long *value) {
+  typedef typename S::pos_t P;
   const bool neg = first == '-';
-  uint64_t q = pos + (neg ? 1 : 0);
-  const uint64_t start = q;
+  P q = pos + (neg ? 1 : 0);
+  const P start = q;
   unsigned long long i = 0;
   uint32_t c = at(q);
   const uint32_t lead = c;
   while (is_digit(c)) { i = i * 10ull + (c - '0'); c = at(++q); }
-  const uint64_t digits = q - start;
+  const uint32_t digits = uint32_t(q - start);
   if (digits == 0 || (lead == '0' && digits > 1)) { *value = kNumberError; return 0; }
   bool is_float = false;
   if (c == '.') {
     is_float = true;
-    const uint64_t fs = ++q;
+    const P fs = ++q;
     c = at(q);
     while (is_digit(c)) c = at(++q);
     if (q == fs) { *value = kNumberError; return 0; }  // "1." is not a number
@@ -204,7 +229,7 @@ SJ_TOK uint32_t scan_number(const S &at, uint64_t pos, uint32_t first, unsigned 
     is_float = true;
     c = at(++q);
     if (c == '-' || c == '+') c = at(++q);
-    const uint64_t es = q;
+    const P es = q;
     while (is_digit(c)) c = at(++q);
     if (q == es) { *value = kNumberError; return 0; }
   }
@@ -214,7 +239,7 @@ SJ_TOK uint32_t scan_number(const S &at, uint64_t pos, uint32_t first, unsigned 
     *value = q;  // one past the token: the consumer converts [pos, q)
     return 'd';
   }
-  const uint64_t longest = neg ? 19 : 20;  // L920-946: the 64-bit limits
+  const uint32_t longest = neg ? 19 : 20;  // L920-946: the 64-bit limits
   if (digits > longest) { *value = kBigintError; return 0; }
   if (digits == longest) {
     if (neg) {
@@ -228,7 +253,7 @@ SJ_TOK uint32_t scan_number(const S &at, uint64_t pos, uint32_t first, unsigned 
 }
 
 template <class S>
-SJ_TOK bool atom_is(const S &at, uint64_t pos, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, int wl) {
+SJ_TOK bool atom_is(const S &at, typename S::pos_t pos, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, int wl) {
   const uint32_t w[5] = {w0, w1, w2, w3, w4};
   for (int k = 1; k < wl; k++)
     if (at(pos + k) != w[k]) return false;
@@ -239,7 +264,8 @@ SJ_TOK bool atom_is(const S &at, uint64_t pos, uint32_t w0, uint32_t w1, uint32_
 // its unescaped length
 constexpr uint32_t kLongString = 1;  // classify_token: a string longer than the budget, length not known yet
 template <class S>
-SJ_TOK uint32_t classify_token(const S &at, uint64_t len, uint64_t p, unsigned long long *value, uint64_t string_budget = ~0ull) {
+SJ_TOK uint32_t classify_token(const S &at, typename S::pos_t len, typename S::pos_t p, unsigned long long *value,
+                                typename S::pos_t string_budget = ~(typename S::pos_t)0) {
   const uint32_t c = at(p);
   *value = 0;
   if (c == '{' || c == '}' || c == '[' || c == ']' || c == ':' || c == ',') return c;

@@ -62,6 +62,11 @@ def test_token_functions_match_oracle(emu):
                     continue
                 parts.append(tok)
         docs.append(b"[" + rng.choice([b",", b" ,\n ", b", "]).join(parts) + b"]")
+    for _ in range(10):  # long strings: over the lane budget (handed to the warp on the GPU), tiles that do not fit the window
+        parts = [b'"' + TF.long_body(rng, rng.choice([90, 97, 200, 513, 3000, 30000]), rng.choice([0.0, 0.05, 0.3, 1.0])) + b'"' for _ in range(rng.randrange(1, 30))]
+        parts += [str(rng.randrange(10 ** 9)).encode() for _ in range(rng.randrange(0, 900))]
+        rng.shuffle(parts)
+        docs.append(b"[" + b" , ".join(parts) + b"]")
     for d in docs:
         r = port.stage1(d)
         assert r.err == 0
