@@ -489,7 +489,7 @@ extern "C" int sjb200_set_option(sjb200_ctx *c, const char *key, long value) {
   if (!c || !key) return SJB200_UNEXPECTED_ERROR;
   if (!strcmp(key, "use_tma")) c->opt_use_tma = value;
   else if (!strcmp(key, "grid")) c->opt_grid = value;
-  else if (!strcmp(key, "tok_stage")) c->opt_tok_stage = value & 3;  // 0: no staging, 1: staged tiles, 3: staged + tokens compacted by kind
+  else if (!strcmp(key, "tok_stage")) c->opt_tok_stage = value ? 1 : 0;
   else if (!strcmp(key, "time_kernel")) c->opt_time_kernel = value;
   else if (!strcmp(key, "debug_timeline")) c->opt_debug_timeline = value;
   else if (!strcmp(key, "chunk_bytes")) c->opt_chunk_bytes = std::max<long>(2 * kTileBytes, (value / (2 * kTileBytes)) * (2 * kTileBytes));

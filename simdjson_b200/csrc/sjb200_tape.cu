@@ -264,200 +264,6 @@ __global__ void __launch_bounds__(kTokThreads) string_write_kernel(const uint8_t
   if (threadIdx.x < tail) dst_tile[head + (nvec << 4) + threadIdx.x] = outb[phase + head + (nvec << 4) + threadIdx.x];
 }
 
-// =============================================================================== compacted variants (option tok_kernel = 2)
-// The same two passes with the tokens of a tile sorted by kind first: in a warp of the kernels above ~10 lanes hold
-// strings of different lengths, ~8 hold numbers, the rest operators, and every lane waits for the slowest of every kind
-// (1 275 warp instructions per 32 tokens, of which a lane's own token needs a tenth).  Here the CTA lists its strings and
-// its other scalars (ballot / popcount offsets, order preserved), then thread s takes the s-th string: the first warps
-// walk strings in every lane, the next ones scan numbers, the rest have nothing to do and yield their issue slots to the
-// other CTAs of the SM.  Long strings go to the CTA's warps round-robin instead of waiting for one warp.
-constexpr int kTokWarps = kTokThreads / 32;
-
-// lists the threads for which `flag` is set, in thread order: list[k] = thread index; returns how many (CTA-uniform)
-__device__ uint32_t cta_list(bool flag, uint16_t *list, uint32_t *wcnt) {
-  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t b = __ballot_sync(0xFFFFFFFFu, flag);
-  __syncthreads();  // (wcnt may still be read from a previous call)
-  if (lane == 0) wcnt[warp] = uint32_t(__popc(b));
-  __syncthreads();
-  uint32_t before = 0, total = 0;
-  for (int w = 0; w < kTokWarps; w++) {
-    const uint32_t c = wcnt[w];
-    if (w < int(warp)) before += c;
-    total += c;
-  }
-  if (flag) list[before + uint32_t(__popc(b & ((1u << lane) - 1u)))] = uint16_t(threadIdx.x);
-  __syncthreads();
-  return total;
-}
-
-__global__ void __launch_bounds__(kTokThreads) token_scan_kernel2(const uint8_t *buf, uint64_t len, const uint32_t *idx, uint32_t n, uint8_t *type,
-                                                                 unsigned long long *payload, unsigned long long *tile_bytes, uint32_t *tile_strings,
-                                                                 TokenTotals *tot) {
-  __shared__ __align__(16) uint8_t win[kWinBytes];
-  __shared__ unsigned long long sh[kTokThreads / 32];
-  __shared__ unsigned long long rval[kTokThreads];
-  __shared__ uint8_t rtype[kTokThreads];
-  __shared__ uint16_t slist[kTokThreads], olist[kTokThreads], llist[kTokThreads];
-  __shared__ uint32_t wcnt[kTokWarps];
-  __shared__ uint32_t nlong;
-  const uint32_t i0 = blockIdx.x * uint32_t(kTokThreads), i = i0 + threadIdx.x;
-  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  bool fast = false;
-  const tok::WindowSrc src = stage_window(buf, len, idx, n, i0, win, &fast);
-  const tok::FastWin f{win, uint32_t(src.span)};
-  if (threadIdx.x == 0) nlong = 0;
-  // kinds
-  const uint64_t p = i < n ? uint64_t(idx[i]) : 0;
-  const uint32_t c = i < n ? src(p) : 0u;
-  const bool is_op = c == '{' || c == '}' || c == '[' || c == ']' || c == ':' || c == ',';
-  const bool is_str = i < n && c == '"';
-  const bool is_oth = i < n && !is_op && !is_str;
-  rtype[threadIdx.x] = is_op ? uint8_t(c) : uint8_t(0);
-  rval[threadIdx.x] = 0;
-  const uint32_t ns = cta_list(is_str, slist, wcnt);
-  const uint32_t no = cta_list(is_oth, olist, wcnt);
-  // strings: thread s takes the s-th one
-  if (threadIdx.x < ns) {
-    const uint32_t t = slist[threadIdx.x];
-    const uint64_t pt = idx[i0 + t];
-    const long long ul = fast ? tok::walk_string<false>(f, f.limit, uint32_t(pt - src.lo), nullptr, uint32_t(kLaneBudget))
-                              : tok::walk_string<false>(src, len, pt, nullptr, kLaneBudget);
-    if (ul == -3) {
-      llist[atomicAdd(&nlong, 1u)] = uint16_t(t);
-    } else if (ul < 0) {
-      rval[t] = ul == -1 ? uint32_t(tok::kStringError) : uint32_t(tok::kUnclosedStringError);
-    } else {
-      rtype[t] = '"';
-      rval[t] = (unsigned long long)ul;
-    }
-  }
-  // numbers, atoms, anything else: thread s takes the s-th one
-  if (threadIdx.x < no) {
-    const uint32_t t = olist[threadIdx.x];
-    const uint64_t pt = idx[i0 + t];
-    unsigned long long v = 0;
-    uint32_t ty;
-    if (fast) {
-      ty = tok::classify_token(f, f.limit, uint32_t(pt - src.lo), &v);
-      if (ty == 'd') v += src.lo;
-    } else {
-      ty = tok::classify_token(src, len, pt, &v);
-    }
-    rtype[t] = uint8_t(ty);
-    rval[t] = v;
-  }
-  __syncthreads();
-  // long strings: the CTA's warps take them in turn
-  const uint32_t nl = nlong;
-  for (uint32_t k = warp; k < nl; k += uint32_t(kTokWarps)) {
-    const uint32_t t = llist[k];
-    const long long ul = tok::warp_string<false>(src, len, uint64_t(idx[i0 + t]), nullptr, lane);
-    if (lane == 0) {
-      if (ul < 0) { rtype[t] = 0; rval[t] = ul == -1 ? uint32_t(tok::kStringError) : uint32_t(tok::kUnclosedStringError); }
-      else { rtype[t] = '"'; rval[t] = (unsigned long long)ul | kLongFlag; }
-    }
-  }
-  __syncthreads();
-  unsigned long long bytes = 0, nstr = 0;
-  if (i < n) {
-    const uint32_t t = rtype[threadIdx.x];
-    const unsigned long long v = rval[threadIdx.x];
-    if (t == '"') {
-      bytes = (v & ~kLongFlag) + 5;
-      nstr = 1;
-    }
-    type[i] = uint8_t(t);
-    payload[i] = v;
-    if (t == 0) atomicMin(&tot->first_error, ((unsigned long long)i << 8) | (v & 0xFFull));
-  }
-  const unsigned long long tb = block_sum_u64(bytes, sh);
-  const unsigned long long ts = block_sum_u64(nstr, sh);
-  if (threadIdx.x == 0) {
-    tile_bytes[blockIdx.x] = tb;
-    tile_strings[blockIdx.x] = uint32_t(ts);
-  }
-}
-
-__global__ void __launch_bounds__(kTokThreads) string_write_kernel2(const uint8_t *buf, uint64_t len, const uint32_t *idx, uint32_t n, const uint8_t *type,
-                                                                   unsigned long long *payload, const unsigned long long *tile_off, uint32_t ntiles,
-                                                                   uint8_t *strbuf, unsigned long long capacity, const TokenTotals *tot) {
-  __shared__ __align__(16) uint8_t win[kWinBytes];
-  __shared__ __align__(16) uint8_t outb[kOutBytes + 16];
-  __shared__ unsigned long long sh[kTokThreads / 32];
-  __shared__ unsigned long long srel[kTokThreads];
-  __shared__ uint32_t sul[kTokThreads];
-  __shared__ uint16_t slist[kTokThreads], llist[kTokThreads];
-  __shared__ uint32_t wcnt[kTokWarps];
-  const unsigned long long total = tot->string_bytes;
-  const uint32_t i0 = blockIdx.x * uint32_t(kTokThreads), i = i0 + threadIdx.x;
-  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  if (total > capacity) {  // CAPACITY: nothing is written, payloads keep the lengths (without the marker of the long ones)
-    if (i < n && type[i] == '"') payload[i] &= ~kLongFlag;
-    return;
-  }
-  const unsigned long long t_off = tile_off[blockIdx.x];
-  const unsigned long long t_bytes = (blockIdx.x + 1 < ntiles ? tile_off[blockIdx.x + 1] : total) - t_off;
-  if (t_bytes == 0) return;  // (uniform) no string in this tile
-  bool fast = false;
-  const tok::WindowSrc src = stage_window(buf, len, idx, n, i0, win, &fast);
-  const tok::FastWin f{win, uint32_t(src.span)};
-  const bool mine_is_string = i < n && type[i] == '"';
-  const unsigned long long pl0 = mine_is_string ? payload[i] : 0ull;
-  const bool mine_is_long = (pl0 & kLongFlag) != 0;
-  const unsigned long long ul = pl0 & ~kLongFlag;
-  const unsigned long long mine = mine_is_string ? ul + 5 : 0ull;
-  unsigned long long x = mine;  // exclusive prefix over the CTA's threads (thread order = document order)
-  for (int d = 1; d < 32; d <<= 1) {
-    const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, x, d);
-    if (int(lane) >= d) x += y;
-  }
-  if (lane == 31) sh[warp] = x;
-  __syncthreads();
-  unsigned long long rel = x - mine;
-  for (uint32_t w = 0; w < warp; w++) rel += sh[w];
-  srel[threadIdx.x] = rel;
-  sul[threadIdx.x] = uint32_t(ul);
-  if (mine_is_string) payload[i] = t_off + rel;
-  const uint32_t ns = cta_list(mine_is_string && !mine_is_long, slist, wcnt);
-  const uint32_t nl = cta_list(mine_is_long, llist, wcnt);
-  uint8_t *dst_tile = strbuf + t_off;
-  const uint32_t phase = uint32_t(reinterpret_cast<uintptr_t>(dst_tile) & 15u);
-  const bool staged_out = t_bytes <= kOutBytes;
-  uint8_t *base = staged_out ? outb + phase : dst_tile;
-  if (threadIdx.x < ns) {  // thread s copies the s-th string of the tile
-    const uint32_t t = slist[threadIdx.x];
-    const uint32_t l = sul[t];
-    uint8_t *rec = base + srel[t];
-    const uint64_t pt = idx[i0 + t];
-    rec[0] = uint8_t(l); rec[1] = uint8_t(l >> 8); rec[2] = uint8_t(l >> 16); rec[3] = uint8_t(l >> 24);
-    if (fast) tok::walk_string<true>(f, f.limit, uint32_t(pt - src.lo), rec + 4);
-    else tok::walk_string<true>(src, len, pt, rec + 4);
-    rec[4 + l] = 0;
-  }
-  for (uint32_t k = warp; k < nl; k += uint32_t(kTokWarps)) {  // long strings: the CTA's warps take them in turn
-    const uint32_t t = llist[k];
-    const uint32_t l = sul[t];
-    uint8_t *rec = base + srel[t];
-    if (lane == 0) {
-      rec[0] = uint8_t(l); rec[1] = uint8_t(l >> 8); rec[2] = uint8_t(l >> 16); rec[3] = uint8_t(l >> 24);
-      rec[4 + l] = 0;
-    }
-    tok::warp_string<true>(src, len, uint64_t(idx[i0 + t]), rec + 4, lane);
-  }
-  if (!staged_out) return;
-  __syncthreads();
-  const uint32_t nb = uint32_t(t_bytes);
-  const uint32_t head = (nb < ((16u - phase) & 15u)) ? nb : ((16u - phase) & 15u);
-  const uint32_t nvec = (nb - head) >> 4;
-  const uint32_t tail = nb - head - (nvec << 4);
-  if (threadIdx.x < head) dst_tile[threadIdx.x] = outb[phase + threadIdx.x];
-  const uint4 *sv = reinterpret_cast<const uint4 *>(outb + phase + head);
-  uint4 *gv = reinterpret_cast<uint4 *>(dst_tile + head);
-  for (uint32_t v = threadIdx.x; v < nvec; v += kTokThreads) gv[v] = sv[v];
-  if (threadIdx.x < tail) dst_tile[head + (nvec << 4) + threadIdx.x] = outb[phase + head + (nvec << 4) + threadIdx.x];
-}
-
 }  // namespace
 
 size_t tokens_scratch_bytes(uint32_t n) {
@@ -476,15 +282,11 @@ cudaError_t launch_tokens(const uint8_t *buf, uint64_t len, const uint32_t *idx,
     tile_scan_kernel<<<1, 1024, 0, stream>>>(tile_bytes, tile_strings, 0, tot_dev);
     return cudaGetLastError();
   }
-  const bool compact = (stage & 2) != 0;  // bit 1: the compacted variants (they always stage)
-  if (compact) token_scan_kernel2<<<tiles, kTokThreads, 0, stream>>>(buf, len, idx, n, type, reinterpret_cast<unsigned long long *>(payload), tile_bytes, tile_strings, tot_dev);
-  else token_scan_kernel<<<tiles, kTokThreads, 0, stream>>>(buf, len, idx, n, type, reinterpret_cast<unsigned long long *>(payload), tile_bytes, tile_strings, tot_dev,
-                                                            stage & 1);
+  token_scan_kernel<<<tiles, kTokThreads, 0, stream>>>(buf, len, idx, n, type, reinterpret_cast<unsigned long long *>(payload), tile_bytes, tile_strings, tot_dev,
+                                                       stage);
   tile_scan_kernel<<<1, 1024, 0, stream>>>(tile_bytes, tile_strings, tiles, tot_dev);
-  if (compact) string_write_kernel2<<<tiles, kTokThreads, 0, stream>>>(buf, len, idx, n, type, reinterpret_cast<unsigned long long *>(payload), tile_bytes, tiles, strbuf,
-                                                                      strbuf_capacity, tot_dev);
-  else string_write_kernel<<<tiles, kTokThreads, 0, stream>>>(buf, len, idx, n, type, reinterpret_cast<unsigned long long *>(payload), tile_bytes, tiles, strbuf,
-                                                              strbuf_capacity, tot_dev, stage & 1);
+  string_write_kernel<<<tiles, kTokThreads, 0, stream>>>(buf, len, idx, n, type, reinterpret_cast<unsigned long long *>(payload), tile_bytes, tiles, strbuf,
+                                                         strbuf_capacity, tot_dev, stage);
   return cudaGetLastError();
 }
 

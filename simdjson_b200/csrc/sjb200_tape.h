@@ -15,8 +15,8 @@ struct TokenTotals {
 
 size_t tokens_scratch_bytes(uint32_t n);
 // type[n], payload[n], strbuf[strbuf_capacity]: device memory; scratch: tokens_scratch_bytes(n) bytes, 8-byte aligned;
-// stage (option tok_stage): 0 = every thread reads / writes global memory (the A/B baseline of the staging), 1 = tiles staged
-// through shared memory, 3 = staged and the tokens of a tile compacted by kind before they are walked
+// stage: 1 = tiles staged through shared memory (the product path), 0 = every thread reads / writes global memory (kept as
+// the A/B baseline of the staging, option tok_stage)
 cudaError_t launch_tokens(const uint8_t *buf, uint64_t len, const uint32_t *idx, uint32_t n, uint8_t *type, uint64_t *payload, uint8_t *strbuf,
                           uint64_t strbuf_capacity, void *scratch, TokenTotals *tot_dev, int stage, cudaStream_t stream);
 

@@ -748,7 +748,7 @@ def test_tokens_device_matches_oracle(port):
             rc, d = _tokens_on_device(p, doc)
             assert rc == 0 and p.n_structural_indexes == r.n
             want = port.tokens(doc, r.idx, r.n, strbuf_cap=sj.lib().sjb200_string_buf_capacity(len(doc)))
-            for stage in ((1, 3, 0) if k % 4 == 0 else (1, 3)):  # 3: tokens compacted by kind; 0: the unstaged baseline path (every thread on global memory)
+            for stage in ((1, 0) if k % 4 == 0 else (1,)):  # 0: the unstaged baseline path (every thread on global memory)
                 p.set_option("tok_stage", stage)
                 res, d_type, d_payload, d_strbuf = p.tokens_device(d)
                 _same_tokens(_tokens_tuple(res, d_type, d_payload, d_strbuf, d_strbuf.numel()), want, ("doc", k, stage, doc[:60]))
@@ -771,12 +771,9 @@ def test_tokens_device_matches_oracle(port):
         r = port.stage1(doc)
         rc, d = _tokens_on_device(p, doc)
         want = port.tokens(doc, r.idx, r.n, strbuf_cap=16)
-        for stage in (1, 3):
-            p.set_option("tok_stage", stage)
-            res, d_type, d_payload, d_strbuf = p.tokens_device(d, strbuf_capacity=16)
-            assert res.error == sj.CAPACITY == want[0]
-            _same_tokens(_tokens_tuple(res, d_type, d_payload, d_strbuf, 16), (want[0], want[1], want[2], b"", want[4], want[5], want[6]), ("capacity", stage))
-        p.set_option("tok_stage", 1)
+        res, d_type, d_payload, d_strbuf = p.tokens_device(d, strbuf_capacity=16)
+        assert res.error == sj.CAPACITY == want[0]
+        _same_tokens(_tokens_tuple(res, d_type, d_payload, d_strbuf, 16), (want[0], want[1], want[2], b"", want[4], want[5], want[6]), "capacity")
         res, *_ = p.tokens_device(d, n=0)
         assert res.error == 0 and res.n_strings == 0 and res.string_bytes == 0 and res.first_error_index == 0xFFFFFFFF
     finally:
@@ -788,8 +785,6 @@ def test_tokens_device_matches_golden():
     g = _load("tokens.json")
     rc, p = sj.get_active_implementation().create_dom_parser_implementation(4 << 20)
     assert rc == sj.SUCCESS
-    if os.environ.get("SJB200_TEST_TOK_STAGE"):  # (memcheck runs of the other kernel variants)
-        p.set_option("tok_stage", int(os.environ["SJB200_TEST_TOK_STAGE"]))
     try:
         for c in g["documents"]:
             doc = bytes.fromhex(c["doc"])
