@@ -193,6 +193,77 @@ def make_stream(world, k):
     return doc
 
 
+STREAM_PIECE = 8 << 20
+
+
+def _stream_layout(world):
+    """(number of 8 MiB pieces, end of the last piece, total) of make_stream(world, k): piece i occupies
+    [1 + i * (P + 2), ... + P), ',\n' in front of every piece but the first"""
+    total = world * DOC_BYTES
+    size, i = 1, 0
+    while True:
+        extra = STREAM_PIECE + (2 if i else 0)
+        if size + extra + 64 > total:
+            break
+        size += extra
+        i += 1
+    return i, size, total
+
+
+def stream_range(world, k, lo, hi, cache=None):
+    """bytes [lo, hi) of make_stream(world, k) without building the rest: only the 8 MiB pieces that overlap are generated
+    (a rank of an N-GPU run needs its own 64 MiB shard, not N x 64 MiB -- at N = 8 the full stream costs minutes of Python per rank)"""
+    from simdjson_b200 import corpus
+    npieces, end_pieces, total = _stream_layout(world)
+    lo, hi = max(0, lo), min(total, hi)
+    out = np.empty(hi - lo, dtype=np.uint8)
+    cache = {} if cache is None else cache
+
+    def put(start, data):  # data = stream bytes [start, start + len(data))
+        a, b = max(lo, start), min(hi, start + len(data))
+        if a < b:
+            out[a - lo: b - lo] = np.frombuffer(data, dtype=np.uint8)[a - start: b - start] if isinstance(data, (bytes, bytearray)) else data[a - start: b - start]
+    put(0, b"[")
+    for i in range(npieces):
+        start = 1 + i * (STREAM_PIECE + 2)
+        if i:
+            put(start - 2, b",\n")
+        if start < hi and start + STREAM_PIECE > lo:
+            if i not in cache:
+                cache[i] = np.asarray(corpus.random_json(STREAM_PIECE, seed=corpus.SEED + 104729 * k + 31 * i), dtype=np.uint8)
+                assert len(cache[i]) == STREAM_PIECE
+            put(start, cache[i])
+    tail_head = b',\n"'
+    put(end_pieces, tail_head)
+    xs, xe = end_pieces + len(tail_head), total - 2  # the padding string's body
+    a, b = max(lo, xs), min(hi, xe)
+    if a < b:
+        out[a - lo: b - lo] = ord("x")
+    put(total - 2, b'"]')
+    return out
+
+
+def make_shard(world, k, rank, window=1 << 20):
+    """rank's shard of make_stream(world, k) cut the way sharding.shard_cuts_at_lines cuts it, built from the pieces around it only"""
+    from simdjson_b200 import sharding
+    L = sharding._lib()
+    total = world * DOC_BYTES
+    cache = {}
+
+    def cut(j):
+        if j == 0:
+            return 0
+        if j >= world:
+            return total
+        nominal = (total * j) // world
+        base = max(0, nominal - window)
+        loc = np.ascontiguousarray(stream_range(world, k, base, min(total, nominal + 8), cache))
+        return base + int(L.sjb200_shard_cut_line(loc.ctypes.data, len(loc), nominal - base, window))
+    c0 = cut(rank)
+    c1 = max(c0, cut(rank + 1))  # (shard_cuts_at_lines keeps cuts monotonic the same way; nominal cuts are 64 MiB apart, the window is 1 MiB)
+    return np.ascontiguousarray(stream_range(world, k, c0, c1, cache))
+
+
 def oracle():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
@@ -303,10 +374,8 @@ def run_ours(args, rank, world):
         docs = [make_doc(k) for k in range(ROTATE)]
         shards, cuts = docs, None
     else:
-        streams = [make_stream(world, k) for k in range(ROTATE)]
-        cuts = [sharding.shard_cuts_at_lines(s, world) for s in streams]
-        shards = [np.ascontiguousarray(s[c[rank]: c[rank + 1]]) for s, c in zip(streams, cuts)]
-        del streams
+        shards = [make_shard(world, k, rank) for k in range(ROTATE)]  # = make_stream(world, k) cut by sharding.shard_cuts_at_lines, rank's part
+        cuts = None
     d_docs = [torch.from_numpy(d.copy()).to(dev) for d in shards]
     comm = None
     if world > 1:
